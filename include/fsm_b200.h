@@ -1,0 +1,127 @@
+/* fsm_b200.h — C ABI of the B200-native pseudo-spectral stepper (libfsm_b200.so).
+ *
+ * Drop-in boundary for ONE path of qiauil/torchfsm (v0.0.4): the per-step update behind
+ * Operator.integrate(u_0, mesh, dt, step). The reference has no FFI; its seams are Python
+ * protocols. Each entry point below names the reference code it replaces
+ * (paths relative to the reference root). INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every device buffer is allocated and owned by the caller
+ *    (PyTorch); the library never allocates or frees device memory and keeps no pointer beyond
+ *    those stored in the plan descriptor (tables), which the caller must keep alive.
+ *  - all work is enqueued on the caller's stream, asynchronously; no device synchronisation.
+ *  - return 0 on success, negative errno-style codes otherwise: -EINVAL bad argument,
+ *    -ENOSYS unsupported configuration, -ENOMEM workspace too small, -EIO CUDA error;
+ *    fsm_last_error() returns a thread-local message. No C++ exception crosses the ABI.
+ *
+ * Spectral layout ("rot-half"): real fields are stored as half spectra (Hermitian redundancy
+ * removed along the last physical axis) with the x wavenumber fastest:
+ *     1-D  [kx < n0/2+1]
+ *     2-D  [ky < n1/2+1][kx < n0]
+ *     3-D  [ky < n1][kz < n2/2+1][kx < n0]
+ * per (batch, channel), complex interleaved (re, im) in the plan dtype. fsm_half_to_full /
+ * fsm_full_to_half convert from/to the reference's full C2C layout (B, C, n0, n1, n2).
+ */
+#ifndef FSM_B200_H
+#define FSM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FSM_ABI_VERSION 1
+
+typedef struct fsm_plan fsm_plan;
+
+enum fsm_dtype { FSM_F32 = 0, FSM_F64 = 1 };
+
+/* Nonlinear program = the fused form of the reference's nonlinear core(s). */
+enum fsm_program {
+    FSM_PROG_LINEAR = 0,      /* no nonlinear term (operator/_base.py:451-453 -> ETDRK0)            */
+    FSM_PROG_CONVECTION = 1,  /* u.grad(u), channels == ndim   (operator/generic/_convection.py:18-48) */
+    FSM_PROG_KS = 2,          /* 1/2|grad phi|^2 - mean        (operator/dedicated/_ks_convection.py:18-38) */
+    FSM_PROG_NS2D_VORT = 3,   /* vorticity convection, 2-D     (operator/dedicated/_navier_stokes.py:27-46) */
+    FSM_PROG_NS3D = 4         /* convection + pressure projection (operator/dedicated/_navier_stokes.py:231-254) */
+};
+
+/* Time integrators (integrator/_etdrk.py:10-93, integrator/_stable_etdrk/_uncached.py:18-228,
+ * integrator/_stable_etdrk/_setdrk_step.py:5-82, integrator/_rk.py:43-58,142-155). */
+enum fsm_integrator {
+    FSM_INT_ETDRK0 = 0, FSM_INT_ETDRK1 = 1, FSM_INT_ETDRK2 = 2,
+    FSM_INT_SETDRK1 = 3, FSM_INT_SETDRK2 = 4, FSM_INT_SETDRK3 = 5, FSM_INT_SETDRK4 = 6,
+    FSM_INT_RK4 = 7
+};
+
+/* Plan descriptor. All pointers are DEVICE pointers in the plan dtype unless stated otherwise.
+ * Tables are real arrays in the rot-half layout, shape [tab_channels][modes], built by the
+ * caller with the reference's own expressions (the plain-ETDRK tables cancel
+ * catastrophically in fp32, so they are inputs, not something the library may "improve"). */
+typedef struct fsm_desc {
+    int32_t struct_size;      /* sizeof(fsm_desc), ABI guard                                        */
+    int32_t dtype;            /* enum fsm_dtype                                                     */
+    int32_t ndim;             /* 1..3                                                               */
+    int32_t n[3];             /* grid points per axis (powers of two, 8..1024); unused = 1           */
+    int32_t batch;            /* B                                                                  */
+    int32_t channels;         /* C                                                                  */
+    int32_t program;          /* enum fsm_program                                                   */
+    int32_t integrator;       /* enum fsm_integrator                                                */
+    int32_t kmax[3];          /* dealiasing: modes with |m_i| <= kmax[i] are kept (mesh.py:443-461)  */
+    int32_t ks_remove_mean;   /* KS: subtract the batch+space mean (_ks_convection.py:34-36)         */
+    int32_t tab_channels;     /* 1 = one table for all channels, or == channels                      */
+    int32_t chunk;            /* samples processed per pass launch; 0 = choose automatically         */
+    double dt;                /* time step (RK4 only uses it; ETD tables already contain it)         */
+    double nl_coef;           /* scalar coefficient of the convective nonlinear term                 */
+    double ks_ext_sum;        /* multi-GPU KS: sum of zero modes of the OTHER ranks (0 if single)    */
+    int32_t ks_ext_count;     /* multi-GPU KS: number of samples on the other ranks                  */
+    int32_t reserved;
+    const void* dk[3];        /* per-axis 2*pi*f(m), Nyquist entry zeroed (length n[i])  mesh.py:399-404 */
+    const void* dkraw[3];     /* per-axis 2*pi*f(m) as the reference has it (length n[i])           */
+    const void* tab_exp;      /* exp(dt L)            _etdrk.py:21 / _uncached.py:30                 */
+    const void* tab_half_exp; /* exp(dt L / 2)        _uncached.py:135,191                           */
+    const void* tab_coef[6];  /* coef_1..coef_6       _etdrk.py:43-45,66-70 / _uncached.py:72-211    */
+    const void* tab_lin;      /* L itself (RK4 and fsm_rhs)   operator/_base.py:339-357              */
+    const void* source_hat;   /* optional constant source spectrum, complex [C][modes], coefficient
+                                 folded in (operator/_base.py:994-1015)                              */
+} fsm_desc;
+
+/* replaces: OperatorLike._build_integrator (operator/_base.py:441-526) */
+int fsm_plan_create(fsm_plan** out, const fsm_desc* desc);
+void fsm_plan_destroy(fsm_plan* plan);
+/* bytes of caller-provided device workspace every call below needs */
+size_t fsm_workspace_bytes(const fsm_plan* plan);
+
+/* replaces: the hot loop `for i in range(step): u_hat = integrator.forward(u_hat, dt)`
+ * (operator/_base.py:732-735). u_hat is updated in place (rot-half layout, [B][C][modes]). */
+int fsm_step(fsm_plan* plan, void* u_hat, void* workspace, size_t ws_bytes, int n_steps, void* stream);
+
+/* replaces: the operator closure L*u_hat + N(u_hat) (operator/_base.py:408-439), used by
+ * Operator.__call__ (operator/_base.py:753-790). out_hat must not alias u_hat. */
+int fsm_rhs(fsm_plan* plan, const void* u_hat, void* out_hat, void* workspace, size_t ws_bytes, void* stream);
+
+/* replaces: FourierMesh.fft on a real field (mesh.py:481-485): u (B,C,n0,n1,n2) real -> rot-half */
+int fsm_r2c(fsm_plan* plan, const void* u, void* u_hat, void* workspace, size_t ws_bytes, void* stream);
+/* replaces: FourierMesh.ifft(...).real (mesh.py:487-491): rot-half -> (B,C,n0,n1,n2) real */
+int fsm_c2r(fsm_plan* plan, const void* u_hat, void* u, void* workspace, size_t ws_bytes, void* stream);
+
+/* rot-half <-> the reference's full complex spectrum (B,C,n0,n1,n2): u_0_fft input,
+ * return_in_fourier and recorder frames (operator/_base.py:727-751, traj_recorder.py:46-55) */
+int fsm_half_to_full(fsm_plan* plan, const void* u_hat, void* full_hat, void* stream);
+int fsm_full_to_half(fsm_plan* plan, const void* full_hat, void* u_hat, void* stream);
+
+/* introspection for benchmarks: kernels launched per step, algorithmic bytes per step
+ * (transform-pass model), modes per field, chunk size */
+int fsm_plan_info(const fsm_plan* plan, int64_t* launches_per_step, int64_t* algo_bytes_per_step,
+                  int64_t* modes_per_field, int32_t* chunk);
+
+const char* fsm_last_error(void);
+int fsm_abi_version(void);
+/* 0 = CUDA sm_100a build (the product); 1 = host emulator build used only by the CPU test-suite */
+int fsm_backend(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSM_B200_H */

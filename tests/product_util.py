@@ -1,0 +1,73 @@
+"""Build torchfsm_b200 operators from golden-fixture specs (shared by emulator and GPU tests)."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU_LIB = os.path.join(ROOT, "tests", "emu", "_build", "libfsm_emu.so")
+
+
+def build_emulator():
+    import subprocess
+    subprocess.run(["make", "-s", "-j8", "-C", os.path.join(ROOT, "torchfsm_b200", "csrc"), "emu"], check=True)
+    return EMU_LIB
+
+
+def product_operator(terms, sources=None):
+    """terms = [(kind, coef, params)] -> torchfsm_b200 Operator built from its public classes."""
+    import torchfsm_b200 as fsm
+    op = None
+    for i, (kind, coef, params) in enumerate(terms):
+        if kind == "laplacian":
+            t = fsm.Laplacian()
+        elif kind == "biharmonic":
+            t = fsm.Biharmonic()
+        elif kind == "spatial_derivative":
+            t = fsm.SpatialDerivative(params["dim_index"], params["order"])
+        elif kind == "implicit_unit_source":
+            t = fsm.ImplicitSource()
+        elif kind == "convection":
+            t = fsm.Convection()
+        elif kind == "ks_convection":
+            t = fsm.KSConvection(params.get("remove_mean", True))
+        elif kind == "vorticity_convection":
+            t = fsm.VorticityConvection()
+        elif kind == "ns_pressure_convection":
+            t = fsm.NSPressureConvection()
+        elif kind == "explicit_source":
+            t = fsm.ExplicitSource(params["source"])
+        else:
+            raise ValueError(kind)
+        t = coef * t
+        op = t if op is None else op + t
+    return op
+
+
+def integrator_enum(name):
+    import torchfsm_b200 as fsm
+    if name == "auto":
+        return "auto"
+    for enum in (fsm.ETDRKIntegrator, fsm.SETDRKIntegrator, fsm.RKIntegrator):
+        if name in enum.__members__:
+            return enum[name]
+    raise ValueError(name)
+
+
+def product_from_golden(g, device):
+    """Operator + mesh + u0 tensor for a golden fixture on `device`."""
+    import torchfsm_b200 as fsm
+    spec = g["spec"]
+    dtype = torch.float32 if spec["dtype"] == "float32" else torch.float64
+    terms = []
+    for i, (kind, coef, params) in enumerate(spec["terms"]):
+        params = dict(params)
+        if kind == "explicit_source":
+            params["source"] = torch.from_numpy(g[f"src_{i}"]).to(device)
+        terms.append((kind, coef, params))
+    op = product_operator(terms)
+    op.set_integrator(integrator_enum(spec["integrator"]))
+    mesh = fsm.MeshGrid([tuple(m) for m in spec["mesh"]], device=device, dtype=dtype)
+    u0 = torch.from_numpy(g["u0"]).to(device)
+    return op, mesh, u0

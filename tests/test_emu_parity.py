@@ -1,0 +1,110 @@
+"""CPU checks of the product's host logic and kernel logic.
+
+The kernels of torchfsm_b200/csrc are compiled for the host by a fiber-based emulator
+(tests/emu) and driven through the SAME C ABI and Python plugin layer as on the GPU, then
+compared with the reference's golden vectors. This is test infrastructure: the product never
+loads the emulator build (see test_product_boundary.py)."""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import golden_names, load_golden, rel_l2
+from product_util import build_emulator, product_from_golden
+
+TOL = {"f32": 1e-5, "f64": 1e-12}
+SUPPORTED = [n for n in golden_names() if "1d" not in n]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def emulator():
+    from torchfsm_b200 import _cabi
+    _cabi.use_library(build_emulator())
+    assert _cabi.is_emulator()
+    yield
+    _cabi._lib = None
+
+
+@pytest.mark.parametrize("name", SUPPORTED)
+def test_emulated_kernels_match_reference_golden(name):
+    g = load_golden(name)
+    spec, tol = g["spec"], TOL[name[-3:]]
+    op, mesh, u0 = product_from_golden(g, "cpu")
+    u1 = op.integrate(u0, mesh=mesh, dt=spec["dt"], step=1)
+    assert rel_l2(u1.numpy(), g["u1"]) <= tol
+    uT = op.integrate(u0, dt=spec["dt"], step=spec["steps"])
+    assert rel_l2(uT.numpy(), g["uT"]) <= tol
+    uT_hat = op.integrate(u0, dt=spec["dt"], step=spec["steps"], return_in_fourier=True)
+    assert uT_hat.shape == g["uT_hat"].shape
+    # the drop-in returns the Hermitian projection of the reference's spectrum:
+    # identical after .real(ifft(.))
+    back = torch.fft.ifftn(uT_hat, dim=tuple(range(2, uT_hat.dim()))).real
+    assert rel_l2(back.numpy(), g["uT"]) <= tol
+    assert rel_l2(op(u0).numpy(), g["rhs0"]) <= 10 * tol
+
+
+def test_transforms_roundtrip_and_full_spectrum():
+    g = load_golden("burgers2d_32x64_etdrk2_f64")
+    op, mesh, u0 = product_from_golden(g, "cpu")
+    op.integrate(u0, mesh=mesh, dt=g["spec"]["dt"], step=1)
+    st = op._state_dict["integrator"]
+    u_hat = st.r2c(u0)
+    assert rel_l2(st.c2r(u_hat).numpy(), u0.numpy()) < 1e-14
+    full = st.half_to_full(u_hat)
+    ref = torch.fft.fftn(u0, dim=(2, 3))
+    assert rel_l2(full.numpy(), ref.numpy()) < 1e-14
+    assert rel_l2(st.full_to_half(ref).numpy(), u_hat.numpy()) < 1e-14
+
+
+def test_u0_fft_input_and_recorder_protocol():
+    import torchfsm_b200 as fsm
+    g = load_golden("c3_ns2d_32_etdrk2_f64")
+    spec = g["spec"]
+    op, mesh, u0 = product_from_golden(g, "cpu")
+    u0_fft = torch.fft.fftn(u0, dim=(2, 3))
+    uT = op.integrate(u_0_fft=u0_fft, mesh=mesh, dt=spec["dt"], step=spec["steps"])
+    assert rel_l2(uT.numpy(), g["uT"]) <= 1e-12
+    rec = fsm.AutoRecorder(fsm.IntervalController(interval=2))
+    traj = op.integrate(u0, dt=spec["dt"], step=4, trajectory_recorder=rec)
+    assert traj.shape == (u0.shape[0], 3) + tuple(u0.shape[1:])          # steps 0, 2, 4
+    assert rel_l2(traj[:, 0].numpy(), g["u0"]) <= 1e-12
+
+
+def test_stepper_speaks_the_integrator_protocol():
+    """_state_dict['integrator'] exposes .dt/.step/.forward on full spectra (operator/_base.py:462-491)."""
+    g = load_golden("ns2d_32_setdrk4_f64")
+    spec = g["spec"]
+    op, mesh, u0 = product_from_golden(g, "cpu")
+    op.integrate(u0, mesh=mesh, dt=spec["dt"], step=1)
+    st = op._state_dict["integrator"]
+    assert st.dt == spec["dt"]
+    u1_full = st.forward(torch.fft.fftn(u0, dim=(2, 3)), spec["dt"])
+    assert rel_l2(torch.fft.ifftn(u1_full, dim=(2, 3)).real.numpy(), g["u1"]) <= 1e-12
+
+
+def test_reference_tables_can_be_injected():
+    """The ETD tables are inputs of the C ABI: feeding the reference's own tables reproduces its step."""
+    from golden_util import golden_tables
+    g = load_golden("c3_ns2d_32_etdrk2_f32")
+    spec = g["spec"]
+    op, mesh, u0 = product_from_golden(g, "cpu")
+    m, c = op._pre_check(u0, None, mesh)
+    op.register_mesh(m, c)
+    tabs = {k: torch.from_numpy(v) for k, v in golden_tables(g).items()}
+    st = op._build_integrator(spec["dt"], u0.shape[0], tables=tabs)
+    u_hat = st.step_half(st.r2c(u0), spec["steps"])
+    assert rel_l2(st.c2r(u_hat).numpy(), g["uT"]) <= 1e-5
+
+
+def test_unsupported_requests_fail_loudly():
+    import torchfsm_b200 as fsm
+    u = torch.zeros(1, 1, 24, 24, dtype=torch.float64)
+    with pytest.raises(NotImplementedError):
+        (fsm.Laplacian() - fsm.KSConvection()).integrate(u, mesh=[(0, 1, 24), (0, 1, 24)], dt=0.1, step=1)
+    u = torch.zeros(1, 2, 32, 32, dtype=torch.float64)
+    with pytest.raises(NotImplementedError):
+        (fsm.Laplacian() - fsm.Convection() - fsm.KSConvection()).integrate(
+            u, mesh=[(0, 1, 32), (0, 1, 32)], dt=0.1, step=1)
+    with pytest.raises(NotImplementedError):
+        fsm.ImplicitSource(lambda x: x ** 2)
+    with pytest.raises(ValueError):
+        fsm.VorticityConvection().integrate(u, mesh=[(0, 1, 32), (0, 1, 32)], dt=0.1, step=1)

@@ -1,0 +1,72 @@
+"""Boundary hygiene: the product never touches the oracle or the emulator, the C-ABI library
+exports what include/fsm_b200.h declares, and a missing CUDA library is a loud error."""
+import ctypes
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "torchfsm_b200")
+
+
+def _product_sources():
+    for base, _, files in os.walk(PKG):
+        if "_build" in base:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                yield os.path.join(base, f)
+
+
+def test_product_does_not_import_oracle_or_emulator():
+    for path in _product_sources():
+        src = open(path).read()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), path
+        assert "tests.emu" not in src and "libfsm_emu" not in src, path
+        assert "/root/reference" not in src, path
+
+
+def test_header_symbols_are_exported_by_the_cuda_library():
+    lib_path = os.path.join(PKG, "libfsm_b200.so")
+    if not os.path.exists(lib_path):
+        if shutil.which("nvcc") is None:
+            pytest.skip("nvcc not available and libfsm_b200.so not built")
+        subprocess.run(["make", "-s", "-j8", "-C", os.path.join(PKG, "csrc"), "cuda"], check=True)
+    header = open(os.path.join(ROOT, "include", "fsm_b200.h")).read()
+    declared = set(re.findall(r"\b(fsm_[a-z0-9_]+)\s*\(", header))
+    assert {"fsm_plan_create", "fsm_step", "fsm_r2c", "fsm_c2r", "fsm_rhs"} <= declared
+    lib = ctypes.CDLL(lib_path)                       # loads without a GPU; no compute call is made
+    for sym in sorted(declared):
+        assert hasattr(lib, sym), f"{sym} declared in include/fsm_b200.h but not exported"
+    from torchfsm_b200 import _cabi
+    assert set(_cabi.EXPORTS) == declared
+    lib.fsm_abi_version.restype = ctypes.c_int
+    lib.fsm_backend.restype = ctypes.c_int
+    assert lib.fsm_abi_version() == 1 and lib.fsm_backend() == 0
+
+
+def test_missing_cuda_library_is_a_loud_error(monkeypatch, tmp_path):
+    from torchfsm_b200 import _cabi
+    monkeypatch.setattr(_cabi, "_lib", None)
+    monkeypatch.setattr(_cabi, "DEFAULT_LIB", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU/torch fallback"):
+        _cabi.lib()
+
+
+def test_cpu_tensors_are_rejected_by_the_cuda_build():
+    import torch
+    import torchfsm_b200 as fsm
+    from torchfsm_b200 import _cabi
+    lib_path = os.path.join(PKG, "libfsm_b200.so")
+    if not os.path.exists(lib_path):
+        pytest.skip("libfsm_b200.so not built")
+    _cabi.use_library(lib_path)
+    try:
+        u = torch.zeros(1, 1, 32, 32)
+        with pytest.raises(RuntimeError, match="CUDA devices only"):
+            (0.1 * fsm.Laplacian()).integrate(u, mesh=[(0, 1, 32), (0, 1, 32)], dt=0.1, step=1)
+    finally:
+        _cabi._lib = None

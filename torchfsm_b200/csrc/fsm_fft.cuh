@@ -1,0 +1,284 @@
+// In-register radix butterflies and the per-line multi-stage Stockham FFT.
+//
+// Data distribution of one line of length N handled by TL = N/EPT threads:
+//   thread tau owns positions  p = tau + m*TL,  m = 0..EPT-1   (register v[m])
+// both on entry (natural-order input) and on exit (natural-order output). With that
+// ownership a warp's global loads/stores of consecutive tau are fully coalesced and
+// point-wise products between several transformed lines need no data movement.
+// Stages exchange data through one padded shared-memory line buffer.
+#pragma once
+#include "fsm_compat.h"
+#include <type_traits>
+
+namespace fsm {
+
+template <typename T>
+struct alignas(2 * sizeof(T)) cplx {
+    T x, y;
+};
+
+template <typename T> FSM_HD __forceinline__ cplx<T> mk(T x, T y) { cplx<T> r; r.x = x; r.y = y; return r; }
+template <typename T> FSM_HD __forceinline__ cplx<T> operator+(cplx<T> a, cplx<T> b) { return mk<T>(a.x + b.x, a.y + b.y); }
+template <typename T> FSM_HD __forceinline__ cplx<T> operator-(cplx<T> a, cplx<T> b) { return mk<T>(a.x - b.x, a.y - b.y); }
+template <typename T> FSM_HD __forceinline__ cplx<T> cmul(cplx<T> a, cplx<T> b) {
+    return mk<T>(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// a * conj(b)
+template <typename T> FSM_HD __forceinline__ cplx<T> cmulc(cplx<T> a, cplx<T> b) {
+    return mk<T>(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+template <typename T> FSM_HD __forceinline__ cplx<T> cscale(cplx<T> a, T s) { return mk<T>(a.x * s, a.y * s); }
+template <typename T> FSM_HD __forceinline__ cplx<T> cconj(cplx<T> a) { return mk<T>(a.x, -a.y); }
+// multiply by i*s (s real)
+template <typename T> FSM_HD __forceinline__ cplx<T> cmul_i(cplx<T> a, T s) { return mk<T>(-a.y * s, a.x * s); }
+
+// compile-time loop with a constexpr index
+template <int I, int E, class F>
+FSM_HD __forceinline__ void static_for(F&& f) {
+    if constexpr (I < E) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, E>(f);
+    }
+}
+
+// cos / sin of 2*pi*j/32, j = 0..16
+FSM_HD constexpr double cos32(int j) {
+    constexpr double t[17] = {1.0,
+                              0.98078528040323044913,
+                              0.92387953251128675613,
+                              0.83146961230254523708,
+                              0.70710678118654752440,
+                              0.55557023301960222474,
+                              0.38268343236508977173,
+                              0.19509032201612826785,
+                              0.0,
+                              -0.19509032201612826785,
+                              -0.38268343236508977173,
+                              -0.55557023301960222474,
+                              -0.70710678118654752440,
+                              -0.83146961230254523708,
+                              -0.92387953251128675613,
+                              -0.98078528040323044913,
+                              -1.0};
+    return t[j];
+}
+FSM_HD constexpr double sin32(int j) { return j <= 8 ? cos32(8 - j) : cos32(j - 8); }
+
+// DIR = -1: forward (exp(-2 pi i jk/R)); DIR = +1: inverse (unnormalised).
+template <int R, int DIR, typename T>
+struct Dft {
+    static_assert(R == 4 || R == 8 || R == 16 || R == 32, "radix");
+    static FSM_HD __forceinline__ void run(cplx<T>* a) {
+        cplx<T> e[R / 2], o[R / 2];
+        static_for<0, R / 2>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
+            e[k] = a[2 * k];
+            o[k] = a[2 * k + 1];
+        });
+        Dft<R / 2, DIR, T>::run(e);
+        Dft<R / 2, DIR, T>::run(o);
+        static_for<0, R / 2>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
+            constexpr int j = k * (32 / R);  // W_R^k = W_32^j, 0 <= j < 16
+            cplx<T> t;
+            if constexpr (j == 0) {
+                t = o[k];
+            } else if constexpr (j == 8) {  // W = (0, DIR)
+                t = mk<T>(-T(DIR) * o[k].y, T(DIR) * o[k].x);
+            } else if constexpr (j == 4) {  // W = h (1, DIR)
+                constexpr T h = T(0.70710678118654752440);
+                t = mk<T>(h * (o[k].x - T(DIR) * o[k].y), h * (o[k].y + T(DIR) * o[k].x));
+            } else if constexpr (j == 12) {  // W = h (-1, DIR)
+                constexpr T h = T(0.70710678118654752440);
+                t = mk<T>(-h * (o[k].x + T(DIR) * o[k].y), h * (T(DIR) * o[k].x - o[k].y));
+            } else {
+                constexpr T c = T(cos32(j));
+                constexpr T s = T(DIR) * T(sin32(j));
+                t = mk<T>(c * o[k].x - s * o[k].y, c * o[k].y + s * o[k].x);
+            }
+            a[k] = e[k] + t;
+            a[k + R / 2] = e[k] - t;
+        });
+    }
+};
+template <int DIR, typename T>
+struct Dft<2, DIR, T> {
+    static FSM_HD __forceinline__ void run(cplx<T>* a) {
+        cplx<T> t = a[0];
+        a[0] = t + a[1];
+        a[1] = t - a[1];
+    }
+};
+template <int DIR, typename T>
+struct Dft<1, DIR, T> {
+    static FSM_HD __forceinline__ void run(cplx<T>*) {}
+};
+
+// ------------------------------------------------------------------------------------
+// FFT configuration: N = R0*R1*R2, every radix divides EPT, TL = N/EPT threads per line.
+// ------------------------------------------------------------------------------------
+template <int N_, int EPT_, int R0_, int R1_ = 1, int R2_ = 1>
+struct FftCfg {
+    static constexpr int N = N_, EPT = EPT_, TL = N_ / EPT_;
+    static constexpr int R0 = R0_, R1 = R1_, R2 = R2_;
+    static constexpr int NST = (R2_ > 1) ? 3 : ((R1_ > 1) ? 2 : 1);
+    static_assert(R0_ * R1_ * R2_ == N_, "radix product");
+    static_assert(EPT_ % R0_ == 0 && EPT_ % R1_ == 0 && EPT_ % R2_ == 0, "radix must divide EPT");
+    static constexpr int PADSHIFT = (R0_ >= 32) ? 5 : 4;
+    // padded index inside a line buffer
+    static FSM_HD constexpr int pad(int i) { return i + (i >> PADSHIFT); }
+    // complex elements per line buffer, rounded so that LINE_PITCH % 16 == 2: eight lines
+    // read "column-wise" by consecutive lanes (transposed stores) hit distinct banks.
+    static constexpr int RAWLEN = N_ + (N_ >> PADSHIFT) + 1;
+    static constexpr int LINE_PITCH = RAWLEN + ((2 - RAWLEN % 16) + 16) % 16;
+    // twiddle tables (complex entries): stage 1 uses (R1-1)*R0, stage 2 uses (R2-1)*R0*R1
+    static constexpr int TW1 = (R1_ > 1) ? (R1_ - 1) * R0_ : 0;
+    static constexpr int TW2 = (R2_ > 1) ? (R2_ - 1) * R0_ * R1_ : 0;
+    static constexpr int TW_TOTAL = TW1 + TW2;
+};
+
+// Synchronisation among the TL threads of one line.
+template <int TL>
+struct LineSync {
+    int bar_id;  // named barrier id when the line spans several warps
+    __device__ __forceinline__ void operator()() const {
+        if constexpr (TL <= 32) {
+            __syncwarp();
+        } else {
+            FSM_NAMED_BARRIER(bar_id, TL);
+        }
+    }
+};
+
+// v[m] holds x[tau + m*TL] on entry and X[tau + m*TL] on exit. `buf` is this line's
+// shared-memory buffer (Cfg::LINE_PITCH complex); `tw` the forward twiddle tables.
+// The caller must make sure every thread of the line is done with `buf` before calling.
+template <class Cfg, int DIR, typename T>
+__device__ __forceinline__ void line_fft(cplx<T>* v, cplx<T>* buf, const cplx<T>* tw, int tau,
+                                         const LineSync<Cfg::TL>& sync) {
+    constexpr int N = Cfg::N, EPT = Cfg::EPT, TL = Cfg::TL;
+    constexpr int R0 = Cfg::R0, R1 = Cfg::R1, R2 = Cfg::R2;
+    // ---- stage 0: Ns = 1, no twiddles
+    static_for<0, EPT / R0>([&](auto qc) {
+        constexpr int q = decltype(qc)::value;
+        cplx<T> a[R0];
+        static_for<0, R0>([&](auto tc) {
+            constexpr int t = decltype(tc)::value;
+            a[t] = v[q + t * (EPT / R0)];
+        });
+        Dft<R0, DIR, T>::run(a);
+        if constexpr (Cfg::NST == 1) {
+            static_for<0, R0>([&](auto tc) {
+                constexpr int t = decltype(tc)::value;
+                v[q + t * (EPT / R0)] = a[t];
+            });
+        } else {
+            const int w = tau + q * TL;
+            static_for<0, R0>([&](auto tc) {
+                constexpr int t = decltype(tc)::value;
+                buf[Cfg::pad(w * R0 + t)] = a[t];
+            });
+        }
+    });
+    if constexpr (Cfg::NST == 1) return;
+    sync();
+    // ---- stage 1: Ns = R0
+    {
+        constexpr int Ns = R0;
+        static_for<0, EPT / R1>([&](auto qc) {
+            constexpr int q = decltype(qc)::value;
+            const int w = tau + q * TL;
+            static_for<0, R1>([&](auto tc) {
+                constexpr int t = decltype(tc)::value;
+                v[q * R1 + t] = buf[Cfg::pad(w + t * (N / R1))];
+            });
+        });
+        if constexpr (Cfg::NST == 3) sync();  // everyone has read before anyone overwrites
+        cplx<T> out[EPT];
+        static_for<0, EPT / R1>([&](auto qc) {
+            constexpr int q = decltype(qc)::value;
+            const int w = tau + q * TL;
+            const int j = w & (Ns - 1);
+            cplx<T> a[R1];
+            a[0] = v[q * R1];
+            static_for<1, R1>([&](auto tc) {
+                constexpr int t = decltype(tc)::value;
+                const cplx<T> wv = tw[(t - 1) * Ns + j];
+                a[t] = (DIR < 0) ? cmul(v[q * R1 + t], wv) : cmulc(v[q * R1 + t], wv);
+            });
+            Dft<R1, DIR, T>::run(a);
+            if constexpr (Cfg::NST == 2) {
+                static_for<0, R1>([&](auto tc) {
+                    constexpr int t = decltype(tc)::value;
+                    out[q + t * (EPT / R1)] = a[t];
+                });
+            } else {
+                const int base = (w / Ns) * Ns * R1 + j;
+                static_for<0, R1>([&](auto tc) {
+                    constexpr int t = decltype(tc)::value;
+                    buf[Cfg::pad(base + t * Ns)] = a[t];
+                });
+            }
+        });
+        if constexpr (Cfg::NST == 2) {
+            static_for<0, EPT>([&](auto mc) {
+                constexpr int m = decltype(mc)::value;
+                v[m] = out[m];
+            });
+            return;
+        }
+    }
+    if constexpr (Cfg::NST == 3) {
+        sync();
+        // ---- stage 2: Ns = R0*R1, last
+        constexpr int Ns = R0 * R1;
+        const cplx<T>* tw2 = tw + Cfg::TW1;
+        cplx<T> out[EPT];
+        static_for<0, EPT / R2>([&](auto qc) {
+            constexpr int q = decltype(qc)::value;
+            const int w = tau + q * TL;  // w < N/R2 == Ns
+            cplx<T> a[R2];
+            a[0] = buf[Cfg::pad(w)];
+            static_for<1, R2>([&](auto tc) {
+                constexpr int t = decltype(tc)::value;
+                const cplx<T> x = buf[Cfg::pad(w + t * (N / R2))];
+                const cplx<T> wv = tw2[(t - 1) * Ns + w];
+                a[t] = (DIR < 0) ? cmul(x, wv) : cmulc(x, wv);
+            });
+            Dft<R2, DIR, T>::run(a);
+            static_for<0, R2>([&](auto tc) {
+                constexpr int t = decltype(tc)::value;
+                out[q + t * (EPT / R2)] = a[t];
+            });
+        });
+        static_for<0, EPT>([&](auto mc) {
+            constexpr int m = decltype(mc)::value;
+            v[m] = out[m];
+        });
+    }
+}
+
+// Host-side twiddle table for a configuration (forward sign), layout described above.
+template <class Cfg, typename T>
+inline void fill_twiddles(cplx<T>* tw) {
+    const double two_pi = 6.283185307179586476925286766559;
+    if (Cfg::R1 > 1) {
+        const int Ns = Cfg::R0;
+        for (int t = 1; t < Cfg::R1; ++t)
+            for (int j = 0; j < Ns; ++j) {
+                double ang = -two_pi * (double)(j * t) / (double)(Ns * Cfg::R1);
+                tw[(t - 1) * Ns + j] = mk<T>((T)__builtin_cos(ang), (T)__builtin_sin(ang));
+            }
+    }
+    if (Cfg::R2 > 1) {
+        const int Ns = Cfg::R0 * Cfg::R1;
+        cplx<T>* tw2 = tw + Cfg::TW1;
+        for (int t = 1; t < Cfg::R2; ++t)
+            for (int j = 0; j < Ns; ++j) {
+                double ang = -two_pi * (double)(j * t) / (double)(Ns * Cfg::R2);
+                tw2[(t - 1) * Ns + j] = mk<T>((T)__builtin_cos(ang), (T)__builtin_sin(ang));
+            }
+    }
+}
+
+}  // namespace fsm

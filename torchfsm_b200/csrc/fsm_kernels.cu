@@ -1,0 +1,142 @@
+// Kernel instantiations for ONE line length: compile with -DFSM_N=<N> (8..1024).
+#include "fsm_launch.h"
+#include <cerrno>
+
+#ifndef FSM_N
+#error "compile with -DFSM_N=<line length>"
+#endif
+
+namespace fsm {
+
+// FFT decomposition per line length: N = R0*R1*R2, EPT elements per thread, TL = N/EPT threads per line.
+template <int N> struct CfgFor;
+template <> struct CfgFor<8> { using type = FftCfg<8, 4, 4, 2>; };
+template <> struct CfgFor<16> { using type = FftCfg<16, 4, 4, 4>; };
+template <> struct CfgFor<32> { using type = FftCfg<32, 8, 8, 4>; };
+template <> struct CfgFor<64> { using type = FftCfg<64, 8, 8, 8>; };
+template <> struct CfgFor<128> { using type = FftCfg<128, 16, 16, 8>; };
+template <> struct CfgFor<256> { using type = FftCfg<256, 16, 16, 16>; };
+template <> struct CfgFor<512> { using type = FftCfg<512, 16, 16, 16, 2>; };
+template <> struct CfgFor<1024> { using type = FftCfg<1024, 32, 32, 32>; };
+
+
+#ifndef FSM_EMU
+template <class K>
+static inline int set_smem(K kern, size_t bytes) {
+    if (bytes > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return -EIO;
+    }
+    return 0;
+}
+static inline int check_launch() { return cudaGetLastError() == cudaSuccess ? 0 : -EIO; }
+#else
+template <class K> static inline int set_smem(K, size_t) { return 0; }
+static inline int check_launch() { return 0; }
+#endif
+
+template <typename T, int N, int PROG>
+static int launch_ix_p(const IxArgs<T>& a, cudaStream_t s) {
+    using Cfg = typename CfgFor<N>::type;
+    auto kern = k_pass_ix<T, Cfg, PROG>;
+    const size_t smem = Smem<Cfg, T>::bytes(kKL);
+    if (int e = set_smem(kern, smem)) return e;
+    dim3 grid((a.n_t + kKL - 1) / kKL, a.n_outer, a.nbc), block(kKL * Cfg::TL);
+    FSM_LAUNCH(kern, grid, block, smem, s, a.g, a.state, a.w1, a.state_bstride, a.w1_fstride, kKL, a.in_t_stride,
+               a.in_o_stride, a.out_o_stride, a.out_e_stride, a.n_t);
+    return check_launch();
+}
+template <typename T, int N>
+static int launch_ix(int prog, const IxArgs<T>& a, cudaStream_t s) {
+    switch (prog) {
+        case PROG_NS2D: return launch_ix_p<T, N, PROG_NS2D>(a, s);
+        case PROG_C2R: return launch_ix_p<T, N, PROG_C2R>(a, s);
+        case PROG_CONV: case PROG_KS: case PROG_NS3D: return launch_ix_p<T, N, PROG_CONV>(a, s);
+        default: return -ENOSYS;
+    }
+}
+
+template <typename T, int N, int DIR>
+static int launch_mid_d(const MidArgs<T>& a, cudaStream_t s) {
+    using Cfg = typename CfgFor<N>::type;
+    auto kern = k_pass_mid<T, Cfg, DIR>;
+    const size_t smem = Smem<Cfg, T>::bytes(kKL);
+    if (int e = set_smem(kern, smem)) return e;
+    dim3 grid((a.n_t + kKL - 1) / kKL, a.n_outer, a.nb), block(kKL * Cfg::TL);
+    FSM_LAUNCH(kern, grid, block, smem, s, a.g, a.in, a.out, a.in_fstride, a.out_fstride, a.nfi, a.spec, kKL,
+               a.in_t_stride, a.in_o_stride, a.out_o_stride, a.out_e_stride, a.n_t);
+    return check_launch();
+}
+template <typename T, int N>
+static int launch_mid(int dir, const MidArgs<T>& a, cudaStream_t s) {
+    return dir > 0 ? launch_mid_d<T, N, +1>(a, s) : launch_mid_d<T, N, -1>(a, s);
+}
+
+template <typename T, int N, int PROG, int NDIM>
+static int launch_phys_p(const PhysArgs<T>& a, cudaStream_t s) {
+    using Cfg = typename CfgFor<N>::type;
+    using PT = PhysTraits<PROG, NDIM>;
+    constexpr int NFW = (PT::NOUT * PT::RPT + 1) / 2;
+    auto kern = k_pass_phys<T, Cfg, PROG, NDIM>;
+    const int K = kKL * PT::RPT;
+    const size_t smem = Smem<Cfg, T>::bytes(kKL * (1 + (NFW > 0 ? NFW : 0)));
+    if (int e = set_smem(kern, smem)) return e;
+    dim3 grid((a.n_t + K - 1) / K, a.n_outer, a.nb), block(kKL * Cfg::TL);
+    FSM_LAUNCH(kern, grid, block, smem, s, a.g, a.win, a.wout, a.phys_in, a.phys_out, a.win_fstride, a.wout_fstride, K,
+               a.in_t_stride, a.in_o_stride, a.out_o_stride, a.out_e_stride, a.n_t, 1);
+    return check_launch();
+}
+template <typename T, int N>
+static int launch_phys(int prog, int ndim, const PhysArgs<T>& a, cudaStream_t s) {
+    if (prog == PROG_C2R) return launch_phys_p<T, N, PROG_C2R, 2>(a, s);
+    if (prog == PROG_R2C) return launch_phys_p<T, N, PROG_R2C, 2>(a, s);
+    if (ndim == 2) {
+        if (prog == PROG_NS2D) return launch_phys_p<T, N, PROG_NS2D, 2>(a, s);
+        if (prog == PROG_KS) return launch_phys_p<T, N, PROG_KS, 2>(a, s);
+        if (prog == PROG_CONV) return launch_phys_p<T, N, PROG_CONV, 2>(a, s);
+    } else if (ndim == 3) {
+        if (prog == PROG_KS) return launch_phys_p<T, N, PROG_KS, 3>(a, s);
+        if constexpr (N <= 512) {
+            if (prog == PROG_CONV || prog == PROG_NS3D) return launch_phys_p<T, N, PROG_CONV, 3>(a, s);
+        }
+    }
+    return -ENOSYS;
+}
+
+template <typename T, int N, int C>
+static int launch_fx_c(const FxArgs<T>& a, cudaStream_t s) {
+    using Cfg = typename CfgFor<N>::type;
+    auto kern = k_pass_fx<T, Cfg, C>;
+    const size_t smem = Smem<Cfg, T>::bytes(kKL);
+    if (int e = set_smem(kern, smem)) return e;
+    dim3 grid((a.nlines + kKL - 1) / kKL, 1, a.nb), block(kKL * Cfg::TL);
+    FSM_LAUNCH(kern, grid, block, smem, s, a.g, a.win, a.win_fstride, a.cb, a.ep, a.nlines, a.b0);
+    return check_launch();
+}
+template <typename T, int N>
+static int launch_fx(int C, const FxArgs<T>& a, cudaStream_t s) {
+    using Cfg = typename CfgFor<N>::type;
+    if (C == 1) return launch_fx_c<T, N, 1>(a, s);
+    if constexpr (Cfg::EPT * 2 <= 32) {
+        if (C == 2) return launch_fx_c<T, N, 2>(a, s);
+    }
+    if constexpr (Cfg::EPT * 3 <= 48) {
+        if (C == 3) return launch_fx_c<T, N, 3>(a, s);
+    }
+    return -ENOSYS;
+}
+
+#define FSM_CAT2(a, b) a##b
+#define FSM_CAT(a, b) FSM_CAT2(a, b)
+const LaunchTable<float>* FSM_CAT(table_f32_, FSM_N)() {
+    static const LaunchTable<float> t = {FSM_N, launch_ix<float, FSM_N>, launch_mid<float, FSM_N>,
+                                         launch_phys<float, FSM_N>, launch_fx<float, FSM_N>};
+    return &t;
+}
+const LaunchTable<double>* FSM_CAT(table_f64_, FSM_N)() {
+    static const LaunchTable<double> t = {FSM_N, launch_ix<double, FSM_N>, launch_mid<double, FSM_N>,
+                                          launch_phys<double, FSM_N>, launch_fx<double, FSM_N>};
+    return &t;
+}
+
+}  // namespace fsm

@@ -1,0 +1,720 @@
+// Line-pass kernels of the fused pseudo-spectral step (2-D and 3-D grids).
+//
+// Layouts (complex unless noted; B = batch, F = field index, C = channels):
+//   physical   (B, C, n0, n1[, n2])   real, last axis contiguous ("rows")
+//   spectral   "rot-half": 2-D [ky<nh][kx<n0];  3-D [ky<n1][kz<nh][kx<n0]   (nh = nlast/2+1)
+//   W1  (after inverse-x)   2-D [x][ky<ph];      3-D [kz][x][ky]
+//   W3  (after inverse-y)   3-D [x][y][kz<ph]
+//   W2a (after forward-last) 2-D [ky][x];        3-D [kz][x][y]
+//   W2b (after forward-y)   3-D [ky][kz][x]
+// Every pass reads contiguous lines, transforms them in registers/shared memory and writes
+// either contiguous lines or "rotated" (line index becomes the fastest output index), so no
+// pass ever makes strided global accesses.
+//
+// One nonlinear evaluation = IX -> [MID inverse] -> PHYS -> [MID forward] -> FX(+combine).
+#pragma once
+#include "fsm_fft.cuh"
+
+namespace fsm {
+
+constexpr int kKL = 8;  // thread-lines per CTA in every line pass
+
+enum Prog : int {
+    PROG_NONE = 0,
+    PROG_CONV = 1,     // u.grad(u), C == ndim            (reference: generic/_convection.py:43-46)
+    PROG_KS = 2,       // 1/2 |grad phi|^2, C == 1         (dedicated/_ks_convection.py:33-38)
+    PROG_NS2D = 3,     // vorticity convection, 2-D, C == 1 (dedicated/_navier_stokes.py:41-46)
+    PROG_NS3D = 4,     // conv + pressure projection, 3-D   (dedicated/_navier_stokes.py:241-254)
+    PROG_C2R = 5,      // plain inverse transform to physical space (mesh.py:487-491, .real)
+    PROG_R2C = 6,      // plain forward transform of a real field   (mesh.py:481-485)
+};
+
+template <typename T>
+struct Geom {
+    int ndim;
+    int n[3];      // physical sizes (x, y, z); unused entries = 1
+    int nh;        // nlast/2 + 1
+    int ph;        // padded pitch of the half axis in W1 (2-D) / W3 (3-D)
+    int kmax[3];   // dealiasing: keep |m_i| <= kmax[i]
+    long nmodes;   // complex modes per field in the rot-half layout
+    T inv_ntot;    // 1 / (n0*n1*n2)
+    const T* dk[3];     // 2*pi*f_i(m), Nyquist entry zeroed (Hermitian projection of i*k)
+    const T* dkraw[3];  // 2*pi*f_i(m) as the reference computes it (Nyquist kept, negative)
+};
+
+template <int N>
+__device__ __forceinline__ int signed_mode(int p) { return (p <= N / 2) ? p : p - N; }
+__device__ __forceinline__ int signed_mode_rt(int p, int n) { return (p <= n / 2) ? p : p - n; }
+__device__ __forceinline__ int iabs(int a) { return a < 0 ? -a : a; }
+
+// Stage twiddles are generated once per CTA with sincospi (no global table, no allocation).
+__device__ __forceinline__ void fsm_sincospi(float x, float* s, float* c) {
+#ifdef FSM_EMU
+    *s = (float)std::sin(3.14159265358979323846 * (double)x);
+    *c = (float)std::cos(3.14159265358979323846 * (double)x);
+#else
+    sincospif(x, s, c);
+#endif
+}
+__device__ __forceinline__ void fsm_sincospi(double x, double* s, double* c) {
+#ifdef FSM_EMU
+    *s = std::sin(3.14159265358979323846 * x);
+    *c = std::cos(3.14159265358979323846 * x);
+#else
+    sincospi(x, s, c);
+#endif
+}
+
+template <class Cfg, typename T>
+__device__ __forceinline__ void make_twiddles(cplx<T>* tw) {
+    if constexpr (Cfg::R1 > 1) {
+        constexpr int Ns = Cfg::R0;
+        for (int i = threadIdx.x; i < Cfg::TW1; i += blockDim.x) {
+            const int t = i / Ns + 1, j = i % Ns;
+            T s, c;
+            fsm_sincospi(T(-2) * T(j * t) / T(Ns * Cfg::R1), &s, &c);
+            tw[i] = mk<T>(c, s);
+        }
+    }
+    if constexpr (Cfg::R2 > 1) {
+        constexpr int Ns = Cfg::R0 * Cfg::R1;
+        for (int i = threadIdx.x; i < Cfg::TW2; i += blockDim.x) {
+            const int t = i / Ns + 1, j = i % Ns;
+            T s, c;
+            fsm_sincospi(T(-2) * T(j * t) / T(Ns * Cfg::R2), &s, &c);
+            tw[Cfg::TW1 + i] = mk<T>(c, s);
+        }
+    }
+    __syncthreads();
+}
+
+// Shared-memory carve-up used by every pass: [twiddles][NBUF line buffers]
+template <class Cfg, typename T>
+struct Smem {
+    static constexpr int TWPAD = (Cfg::TW_TOTAL + 1) & ~1;
+    static size_t bytes(int nbuf) { return sizeof(cplx<T>) * (size_t)(TWPAD + nbuf * Cfg::LINE_PITCH); }
+};
+
+// Rotated ("transposed") store of K line buffers that hold natural-order results:
+//   dst[e * e_stride + t]  for e < n_e, t < K (t = line slot, fastest)
+template <class Cfg, typename T>
+__device__ __forceinline__ void rotated_store(const cplx<T>* bufs, int K, int k_valid, cplx<T>* dst, long e_stride,
+                                              int n_e) {
+    const int total = K * n_e;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int t = i % K, e = i / K;
+        if (t < k_valid) dst[(long)e * e_stride + t] = bufs[t * Cfg::LINE_PITCH + e];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Pass IX: inverse transform along x of symbol-multiplied spectra (dealias mask, 1/N scale and
+// the x-derivative / stream-function symbols are applied while loading).
+//   grid = (tiles of K lines over the line-minor index, outer index, batch*channels)
+// Line-minor index t: ky (2-D and 3-D). Outer index: kz (3-D). Output rotated: [.. x][ky].
+// Derived fields per channel (NF):
+//   PROG_CONV/NS3D/KS: {u_hat, i kx u_hat}                       (2 fields)
+//   PROG_NS2D:         {i ky psi, -i kx psi, i kx w, i ky w}     (4 fields), psi = -w / lap
+//   PROG_C2R:          {u_hat} without mask                       (1 field)
+// ------------------------------------------------------------------------------------------
+template <int PROG>
+struct IxFields {
+    static constexpr int NF = (PROG == PROG_NS2D) ? 4 : ((PROG == PROG_C2R) ? 1 : 2);
+};
+
+template <typename T, class Cfg, int PROG>
+__global__ void __launch_bounds__(kKL * Cfg::TL) k_pass_ix(Geom<T> g, const cplx<T>* __restrict__ state, cplx<T>* __restrict__ w1,
+                                                  long state_bstride /*per (b,c)*/, long w1_fstride, int K,
+                                                  long in_t_stride, long in_o_stride, long out_o_stride,
+                                                  long out_e_stride, int n_t) {
+    constexpr int N = Cfg::N, EPT = Cfg::EPT, TL = Cfg::TL;
+    constexpr int NF = IxFields<PROG>::NF;
+    FSM_DYN_SMEM(smem_raw);
+    cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);
+    cplx<T>* bufs = tw + Smem<Cfg, T>::TWPAD;
+    make_twiddles<Cfg, T>(tw);
+
+    const int lt = threadIdx.x / TL, tau = threadIdx.x % TL;
+    const int t0 = blockIdx.x * K;
+    const int o = blockIdx.y;
+    const long bc = blockIdx.z;
+    const int t = t0 + lt;  // ky index of this thread-line
+    const int k_valid = (K < n_t - t0) ? K : (n_t - t0);
+    // dealias test on the line coordinates
+    const int my = signed_mode_rt(t < n_t ? t : 0, g.n[1]);
+    bool line_kept = (t < n_t);
+    if (PROG != PROG_C2R) {
+        line_kept = line_kept && (iabs(my) <= g.kmax[1]);
+        if (g.ndim == 3) line_kept = line_kept && (o <= g.kmax[2]);
+    }
+    const T dky = (t < n_t) ? g.dk[1][t] : T(0);
+    const T dkyraw = (t < n_t) ? g.dkraw[1][t] : T(0);
+
+    cplx<T> u[EPT];
+    const cplx<T>* src = state + bc * state_bstride + (long)t * in_t_stride + (long)o * in_o_stride;
+    FSM_UNROLL
+    for (int m = 0; m < EPT; ++m) {
+        const int p = tau + m * TL;
+        bool kept = line_kept;
+        if (PROG != PROG_C2R) kept = kept && (iabs(signed_mode<N>(p)) <= g.kmax[0]);
+        u[m] = kept ? cscale(src[p], g.inv_ntot) : mk<T>(T(0), T(0));
+    }
+    LineSync<TL> sync{1 + lt};
+    cplx<T>* mybuf = bufs + lt * Cfg::LINE_PITCH;
+
+    static_for<0, NF>([&](auto fc) {
+        constexpr int f = decltype(fc)::value;
+        cplx<T> v[EPT];
+        FSM_UNROLL
+        for (int m = 0; m < EPT; ++m) {
+            const int p = tau + m * TL;
+            if constexpr (PROG == PROG_NS2D) {
+                const T dkx = g.dk[0][p];
+                const T dkxraw = g.dkraw[0][p];
+                // lap = (i dkxraw)^2 + (i dkyraw)^2 (mesh.py:406-426); psi = -w * where(lap==0, 1, 1/lap)
+                const T lap = -(dkxraw * dkxraw) - (dkyraw * dkyraw);
+                const T ninv = (lap == T(0)) ? T(-1) : T(-1) / lap;
+                if constexpr (f == 0) v[m] = cmul_i(u[m], dky * ninv);          // u_x = d_y psi
+                else if constexpr (f == 1) v[m] = cmul_i(u[m], -dkx * ninv);    // u_y = -d_x psi
+                else if constexpr (f == 2) v[m] = cmul_i(u[m], dkx);            // d_x w
+                else v[m] = cmul_i(u[m], dky);                                  // d_y w
+            } else {
+                if constexpr (f == 0) v[m] = u[m];
+                else v[m] = cmul_i(u[m], g.dk[0][p]);                           // d_x
+            }
+        }
+        line_fft<Cfg, +1, T>(v, mybuf, tw, tau, sync);
+        sync();
+        FSM_UNROLL
+        for (int m = 0; m < EPT; ++m) mybuf[tau + m * TL] = v[m];
+        __syncthreads();
+        cplx<T>* dst = w1 + (bc * NF + f) * w1_fstride + (long)o * out_o_stride + t0;
+        rotated_store<Cfg, T>(bufs, K, k_valid, dst, out_e_stride, N);
+        __syncthreads();
+    });
+}
+
+// ------------------------------------------------------------------------------------------
+// Pass MID (3-D only): C2C transform along y on NFI input fields, producing NFO output fields;
+// output field j = transform(in[src[j]] * (deriv[j] ? i*dk_y : 1)). Rotated output.
+//   inverse: W1 [kz][x][ky] -> W3 [x][y][kz];   forward: W2a [kz][x][y] -> W2b [ky][kz][x]
+// ------------------------------------------------------------------------------------------
+struct MidSpec {
+    int nfo;
+    int src[12];
+    int deriv[12];
+};
+
+template <typename T, class Cfg, int DIR>
+__global__ void __launch_bounds__(kKL * Cfg::TL) k_pass_mid(Geom<T> g, const cplx<T>* __restrict__ in, cplx<T>* __restrict__ out,
+                                                   long in_fstride, long out_fstride, int nfi, MidSpec spec, int K,
+                                                   long in_t_stride, long in_o_stride, long out_o_stride,
+                                                   long out_e_stride, int n_t) {
+    constexpr int N = Cfg::N, EPT = Cfg::EPT, TL = Cfg::TL;
+    FSM_DYN_SMEM(smem_raw);
+    cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);
+    cplx<T>* bufs = tw + Smem<Cfg, T>::TWPAD;
+    make_twiddles<Cfg, T>(tw);
+    const int lt = threadIdx.x / TL, tau = threadIdx.x % TL;
+    const int t0 = blockIdx.x * K;
+    const int o = blockIdx.y;
+    const long b = blockIdx.z;
+    const int t = t0 + lt;
+    const int k_valid = (K < n_t - t0) ? K : (n_t - t0);
+    const bool line_ok = t < n_t;
+    LineSync<TL> sync{1 + lt};
+    cplx<T>* mybuf = bufs + lt * Cfg::LINE_PITCH;
+    for (int j = 0; j < spec.nfo; ++j) {
+        const cplx<T>* src = in + (b * nfi + spec.src[j]) * in_fstride + (long)t * in_t_stride + (long)o * in_o_stride;
+        cplx<T> v[EPT];
+        FSM_UNROLL
+        for (int m = 0; m < EPT; ++m) {
+            const int p = tau + m * TL;
+            bool kept = line_ok;
+            if (DIR > 0) kept = kept && (iabs(signed_mode<N>(p)) <= g.kmax[1]);
+            cplx<T> x = kept ? src[p] : mk<T>(T(0), T(0));
+            if (spec.deriv[j]) x = cmul_i(x, g.dk[1][p]);
+            v[m] = x;
+        }
+        line_fft<Cfg, DIR, T>(v, mybuf, tw, tau, sync);
+        sync();
+        FSM_UNROLL
+        for (int m = 0; m < EPT; ++m) mybuf[tau + m * TL] = v[m];
+        __syncthreads();
+        cplx<T>* dst = out + (b * spec.nfo + j) * out_fstride + (long)o * out_o_stride + t0;
+        rotated_store<Cfg, T>(bufs, K, k_valid, dst, out_e_stride, N);
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Pass PHYS: last-axis pass. Two real fields ride in one complex transform:
+//   inverse: Z = A_hat + i B_hat (mirrored/conjugated for the negative half) -> (a, b) = (Re, Im)
+//   forward: z = s0 + i s1 -> Z; S0(k) = (Z(k)+conj Z(N-k))/2, S1(k) = (Z(k)-conj Z(N-k))/(2i)
+// The nonlinear product is formed in registers between the two.
+//   rows: 2-D x;  3-D (x, y) with y the line-minor index. Output rotated.
+// ------------------------------------------------------------------------------------------
+template <int PROG, int NDIM>
+struct PhysTraits;
+// NFI = input fields per sample, NOUT = output fields per sample, RPT = rows per thread-line
+template <> struct PhysTraits<PROG_NS2D, 2> { static constexpr int NFI = 4, NOUT = 1, RPT = 2; };
+template <> struct PhysTraits<PROG_KS, 2> { static constexpr int NFI = 2, NOUT = 1, RPT = 2; };
+template <> struct PhysTraits<PROG_KS, 3> { static constexpr int NFI = 3, NOUT = 1, RPT = 2; };
+template <> struct PhysTraits<PROG_CONV, 2> { static constexpr int NFI = 4, NOUT = 2, RPT = 1; };
+template <> struct PhysTraits<PROG_CONV, 3> { static constexpr int NFI = 9, NOUT = 3, RPT = 2; };
+template <int NDIM> struct PhysTraits<PROG_C2R, NDIM> { static constexpr int NFI = 1, NOUT = 0, RPT = 2; };
+template <int NDIM> struct PhysTraits<PROG_R2C, NDIM> { static constexpr int NFI = 0, NOUT = 1, RPT = 2; };
+
+// Build Z(p) = A + iB from half-lines (k <= kmax kept; DC/Nyquist imaginary parts dropped as a C2R does).
+template <typename T, int N>
+__device__ __forceinline__ cplx<T> pair_load(const cplx<T>* a, const cplx<T>* b, bool da, bool db, const T* dk, int p,
+                                             int kmax, bool row_ok) {
+    const int k = (p <= N / 2) ? p : N - p;
+    cplx<T> A = mk<T>(T(0), T(0)), B = mk<T>(T(0), T(0));
+    if (row_ok && k <= kmax) {
+        if (a) A = a[k];
+        if (b) B = b[k];
+        const T d = dk[k];
+        if (da) A = cmul_i(A, d);
+        if (db) B = cmul_i(B, d);
+        if (k == 0 || k == N / 2) { A.y = T(0); B.y = T(0); }
+        if (p > N / 2) { A.y = -A.y; B.y = -B.y; }
+    }
+    return mk<T>(A.x - B.y, A.y + B.x);
+}
+
+template <typename T, class Cfg, int PROG, int NDIM>
+__global__ void __launch_bounds__(kKL * Cfg::TL) k_pass_phys(Geom<T> g, const cplx<T>* __restrict__ win, cplx<T>* __restrict__ wout,
+                                                    const T* __restrict__ phys_in, T* __restrict__ phys_out,
+                                                    long win_fstride, long wout_fstride, int K /*rows per CTA*/,
+                                                    long in_t_stride, long in_o_stride, long out_o_stride,
+                                                    long out_e_stride, int n_t, int nsamp_fields /*C2R/R2C: fields per z*/) {
+    constexpr int N = Cfg::N, EPT = Cfg::EPT, TL = Cfg::TL;
+    using PT = PhysTraits<PROG, NDIM>;
+    constexpr int RPT = PT::RPT, NFI = PT::NFI, NOUT = PT::NOUT;
+    constexpr int NFW = (NOUT * RPT + 1) / 2;  // forward transforms (= staging lines) per thread-line
+    FSM_DYN_SMEM(smem_raw);
+    cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);
+    cplx<T>* bufs = tw + Smem<Cfg, T>::TWPAD;
+    make_twiddles<Cfg, T>(tw);
+    const int NL = K / RPT;  // thread-lines per CTA
+    const int lt = threadIdx.x / TL, tau = threadIdx.x % TL;
+    const int t0 = blockIdx.x * K;
+    const int o = blockIdx.y;
+    const long b = blockIdx.z;
+    const int kmaxl = (PROG == PROG_C2R) ? N / 2 : g.kmax[NDIM - 1];
+    const T* dkl = g.dk[NDIM - 1];
+    LineSync<TL> sync{1 + lt};
+    // smem: NL fft buffers, then NL*NFW staging lines
+    cplx<T>* mybuf = bufs + lt * Cfg::LINE_PITCH;
+    cplx<T>* stage = bufs + (NL + lt * (NFW > 0 ? NFW : 1)) * Cfg::LINE_PITCH;
+    const cplx<T>* wb = win + b * NFI * win_fstride + (long)o * in_o_stride;
+
+    T keep2[EPT];   // CONV3D: third component of row 0 waits for row 1
+    T acc[(NOUT > 0 ? NOUT : 1)][EPT];
+    (void)keep2;
+    static_for<0, RPT>([&](auto rc) {
+        constexpr int r = decltype(rc)::value;
+        const int row = t0 + lt * RPT + r;
+        const bool row_ok = row < n_t;
+        const long roff = (long)row * in_t_stride;
+        cplx<T> v[EPT];
+        auto inverse_pair = [&](int fa, int fb, bool da, bool db) {
+            const cplx<T>* pa = (fa >= 0) ? wb + fa * win_fstride + roff : nullptr;
+            const cplx<T>* pb = (fb >= 0) ? wb + fb * win_fstride + roff : nullptr;
+            FSM_UNROLL
+            for (int m = 0; m < EPT; ++m) v[m] = pair_load<T, N>(pa, pb, da, db, dkl, tau + m * TL, kmaxl, row_ok);
+            sync();
+            line_fft<Cfg, +1, T>(v, mybuf, tw, tau, sync);
+        };
+        if constexpr (PROG == PROG_NS2D) {
+            // fields: 0 u_x, 1 u_y, 2 d_x w, 3 d_y w  ->  u_x d_x w + u_y d_y w
+            inverse_pair(0, 2, false, false);
+            FSM_UNROLL
+            for (int m = 0; m < EPT; ++m) acc[0][m] = v[m].x * v[m].y;
+            inverse_pair(1, 3, false, false);
+            FSM_UNROLL
+            for (int m = 0; m < EPT; ++m) acc[0][m] += v[m].x * v[m].y;
+        } else if constexpr (PROG == PROG_KS && NDIM == 2) {
+            // fields: 0 phi (x-transformed), 1 d_x phi  ->  1/2 (phi_x^2 + phi_y^2)
+            inverse_pair(1, 0, false, true);
+            FSM_UNROLL
+            for (int m = 0; m < EPT; ++m) acc[0][m] = T(0.5) * (v[m].x * v[m].x + v[m].y * v[m].y);
+        } else if constexpr (PROG == PROG_KS && NDIM == 3) {
+            // fields: 0 phi, 1 d_x phi, 2 d_y phi
+            inverse_pair(1, 2, false, false);
+            FSM_UNROLL
+            for (int m = 0; m < EPT; ++m) acc[0][m] = v[m].x * v[m].x + v[m].y * v[m].y;
+            inverse_pair(0, -1, true, false);
+            FSM_UNROLL
+            for (int m = 0; m < EPT; ++m) acc[0][m] = T(0.5) * (acc[0][m] + v[m].x * v[m].x);
+        } else if constexpr (PROG == PROG_CONV && NDIM == 2) {
+            // fields per channel c: 2c = u_c, 2c+1 = d_x u_c ; d_y applied here
+            T u0[EPT], u1[EPT];
+            inverse_pair(0, 2, false, false);
+            FSM_UNROLL
+            for (int m = 0; m < EPT; ++m) { u0[m] = v[m].x; u1[m] = v[m].y; }
+            inverse_pair(1, 3, false, false);
+            FSM_UNROLL
+            for (int m = 0; m < EPT; ++m) { acc[0][m] = u0[m] * v[m].x; acc[1][m] = u0[m] * v[m].y; }
+            inverse_pair(0, 2, true, true);
+            FSM_UNROLL
+            for (int m = 0; m < EPT; ++m) { acc[0][m] += u1[m] * v[m].x; acc[1][m] += u1[m] * v[m].y; }
+        } else if constexpr (PROG == PROG_CONV && NDIM == 3) {
+            // fields: c = u_c (0..2), 3+c = d_x u_c, 6+c = d_y u_c ; d_z applied here.
+            // direction j: (d_j u_2, u_j) then (d_j u_0, d_j u_1)
+            T uj[EPT];
+            static_for<0, 3>([&](auto jc) {
+                constexpr int j = decltype(jc)::value;
+                constexpr int base = (j == 0) ? 3 : ((j == 1) ? 6 : 0);
+                constexpr bool dz = (j == 2);
+                inverse_pair(base + 2, j, dz, false);
+                FSM_UNROLL
+                for (int m = 0; m < EPT; ++m) {
+                    uj[m] = v[m].y;
+                    acc[2][m] = (j == 0) ? uj[m] * v[m].x : acc[2][m] + uj[m] * v[m].x;
+                }
+                inverse_pair(base + 0, base + 1, dz, dz);
+                FSM_UNROLL
+                for (int m = 0; m < EPT; ++m) {
+                    acc[0][m] = (j == 0) ? uj[m] * v[m].x : acc[0][m] + uj[m] * v[m].x;
+                    acc[1][m] = (j == 0) ? uj[m] * v[m].y : acc[1][m] + uj[m] * v[m].y;
+                }
+            });
+        } else if constexpr (PROG == PROG_C2R) {
+            // one field, rows r (real part) and r+1 (imag part) of the same field share a transform
+        } else if constexpr (PROG == PROG_R2C) {
+            const T* prow = phys_in + (b * (long)n_t * gridDim.y + ((long)o * n_t + row)) * N;
+            FSM_UNROLL
+            for (int m = 0; m < EPT; ++m) acc[0][m] = row_ok ? prow[tau + m * TL] : T(0);
+        }
+
+        // ---- forward side: pack real results pairwise into complex lines and transform
+        if constexpr (NOUT == 1) {
+            if constexpr (r == 0) {
+                FSM_UNROLL
+                for (int m = 0; m < EPT; ++m) keep2[m] = acc[0][m];
+            } else {
+                FSM_UNROLL
+                for (int m = 0; m < EPT; ++m) v[m] = mk<T>(keep2[m], acc[0][m]);
+                sync();
+                line_fft<Cfg, -1, T>(v, mybuf, tw, tau, sync);
+                FSM_UNROLL
+                for (int m = 0; m < EPT; ++m) stage[tau + m * TL] = v[m];
+            }
+        } else if constexpr (NOUT == 2) {
+            FSM_UNROLL
+            for (int m = 0; m < EPT; ++m) v[m] = mk<T>(acc[0][m], acc[1][m]);
+            sync();
+            line_fft<Cfg, -1, T>(v, mybuf, tw, tau, sync);
+            FSM_UNROLL
+            for (int m = 0; m < EPT; ++m) stage[tau + m * TL] = v[m];
+        } else if constexpr (NOUT == 3) {
+            // staging line r*? : line 0 = (c0,c1) of row 0, line 1 = (c2 row0, c2 row1), line 2 = (c0,c1) of row 1
+            FSM_UNROLL
+            for (int m = 0; m < EPT; ++m) v[m] = mk<T>(acc[0][m], acc[1][m]);
+            sync();
+            line_fft<Cfg, -1, T>(v, mybuf, tw, tau, sync);
+            FSM_UNROLL
+            for (int m = 0; m < EPT; ++m) stage[(r == 0 ? 0 : 2) * Cfg::LINE_PITCH + tau + m * TL] = v[m];
+            if constexpr (r == 0) {
+                FSM_UNROLL
+                for (int m = 0; m < EPT; ++m) keep2[m] = acc[2][m];
+            } else {
+                FSM_UNROLL
+                for (int m = 0; m < EPT; ++m) v[m] = mk<T>(keep2[m], acc[2][m]);
+                sync();
+                line_fft<Cfg, -1, T>(v, mybuf, tw, tau, sync);
+                FSM_UNROLL
+                for (int m = 0; m < EPT; ++m) stage[1 * Cfg::LINE_PITCH + tau + m * TL] = v[m];
+            }
+        }
+    });
+
+    if constexpr (PROG == PROG_C2R) {
+        // rows (lt*2, lt*2+1) of field f = blockIdx.z % nsamp_fields handled as one complex inverse transform
+        const int row = t0 + lt * 2;
+        const bool ok0 = row < n_t, ok1 = row + 1 < n_t;
+        const cplx<T>* p0 = win + b * win_fstride + (long)o * in_o_stride + (long)row * in_t_stride;
+        cplx<T> v[EPT];
+        FSM_UNROLL
+        for (int m = 0; m < EPT; ++m) {
+            const int p = tau + m * TL;
+            const int k = (p <= N / 2) ? p : N - p;
+            cplx<T> A = ok0 ? p0[k] : mk<T>(T(0), T(0));
+            cplx<T> B = ok1 ? p0[in_t_stride + k] : mk<T>(T(0), T(0));
+            if (k == 0 || k == N / 2) { A.y = T(0); B.y = T(0); }
+            if (p > N / 2) { A.y = -A.y; B.y = -B.y; }
+            v[m] = mk<T>(A.x - B.y, A.y + B.x);
+        }
+        line_fft<Cfg, +1, T>(v, mybuf, tw, tau, sync);
+        T* prow = phys_out + (b * (long)n_t * gridDim.y + ((long)o * n_t + row)) * N;
+        FSM_UNROLL
+        for (int m = 0; m < EPT; ++m) {
+            if (ok0) prow[tau + m * TL] = v[m].x;
+            if (ok1) prow[N + tau + m * TL] = v[m].y;
+        }
+        (void)nsamp_fields;
+        return;
+    }
+
+    if constexpr (NOUT > 0) {
+        __syncthreads();
+        // ---- split the packed spectra and store rotated: wout[f][k * out_e_stride + row]
+        const int nh = N / 2 + 1;
+        cplx<T>* ob = wout + b * NOUT * wout_fstride + (long)o * out_o_stride + t0;
+        const cplx<T>* st0 = bufs + NL * Cfg::LINE_PITCH;
+        const int total = NL * nh;
+        for (int i = threadIdx.x; i < total; i += blockDim.x) {
+            const int l = i % NL, k = i / NL;
+            const int kn = (k == 0) ? 0 : N - k;
+            const cplx<T>* sl = st0 + l * NFW * Cfg::LINE_PITCH;
+            auto split = [&](const cplx<T>* line, cplx<T>& s0, cplx<T>& s1) {
+                const cplx<T> zk = line[k], zn = line[kn];
+                s0 = mk<T>(T(0.5) * (zk.x + zn.x), T(0.5) * (zk.y - zn.y));
+                s1 = mk<T>(T(0.5) * (zk.y + zn.y), T(0.5) * (zn.x - zk.x));
+            };
+            cplx<T> s0, s1;
+            if constexpr (NOUT == 1) {
+                split(sl, s0, s1);
+                const int row = l * 2;
+                if (t0 + row < n_t) ob[(long)k * out_e_stride + row] = s0;
+                if (t0 + row + 1 < n_t) ob[(long)k * out_e_stride + row + 1] = s1;
+            } else if constexpr (NOUT == 2) {
+                split(sl, s0, s1);
+                if (t0 + l < n_t) {
+                    ob[(long)k * out_e_stride + l] = s0;
+                    ob[wout_fstride + (long)k * out_e_stride + l] = s1;
+                }
+            } else {
+                const int row = l * 2;
+                const bool ok0 = t0 + row < n_t, ok1 = t0 + row + 1 < n_t;
+                split(sl, s0, s1);
+                if (ok0) { ob[(long)k * out_e_stride + row] = s0; ob[wout_fstride + (long)k * out_e_stride + row] = s1; }
+                split(sl + 2 * Cfg::LINE_PITCH, s0, s1);
+                if (ok1) { ob[(long)k * out_e_stride + row + 1] = s0; ob[wout_fstride + (long)k * out_e_stride + row + 1] = s1; }
+                split(sl + Cfg::LINE_PITCH, s0, s1);
+                if (ok0) ob[2 * wout_fstride + (long)k * out_e_stride + row] = s0;
+                if (ok1) ob[2 * wout_fstride + (long)k * out_e_stride + row + 1] = s1;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Pass FX: forward transform along x of the C nonlinear components, spectral epilogue
+// (coefficient, NS pressure projection, constant source, KS zero-mode capture) and the
+// data-driven integrator combine. Contiguous in, contiguous out (rot-half layout).
+// ------------------------------------------------------------------------------------------
+#define FSM_MAX_IN 3
+#define FSM_MAX_OUT 3
+template <typename T>
+struct Combine {
+    int n_in, n_out, n_tab;
+    int use_fresh;                 // 0: no nonlinear term (pure linear step)
+    const cplx<T>* in[FSM_MAX_IN];
+    cplx<T>* out[FSM_MAX_OUT];
+    const T* tab[8];               // real tables [tab_channels][nmodes]
+    long tab_cstride;              // 0 if one table serves every channel
+    // out[r] = sum_m (ca[r][m] + cb[r][m] * tab[ct[r][m]]) * X_m,  X_0 = fresh N, X_{1+i} = in[i]
+    int ct[FSM_MAX_OUT][FSM_MAX_IN + 1];   // table index, -1 = scalar only, -2 = term absent
+    T ca[FSM_MAX_OUT][FSM_MAX_IN + 1];
+    T cb[FSM_MAX_OUT][FSM_MAX_IN + 1];
+};
+
+template <typename T>
+struct FxEpilogue {
+    T nl_coef;                     // scalar coefficient of the convective term
+    const cplx<T>* source;         // optional constant source spectrum [C][nmodes] (coef folded in)
+    T* dc_out;                     // KS: per-sample zero-mode of the nonlinear term (captured, then zeroed)
+    int project;                   // NS3D pressure projection
+};
+
+template <typename T>
+__device__ __forceinline__ void combine_mode(const Combine<T>& cb, cplx<T> fresh, long bc_off, long tab_off, long mode) {
+    cplx<T> X[FSM_MAX_IN + 1];
+    X[0] = fresh;
+    FSM_UNROLL
+    for (int i = 0; i < FSM_MAX_IN; ++i)
+        if (i < cb.n_in) X[1 + i] = cb.in[i][bc_off + mode];
+    T tv[8];
+    FSM_UNROLL
+    for (int i = 0; i < 8; ++i)
+        if (i < cb.n_tab) tv[i] = cb.tab[i][tab_off + mode];
+    FSM_UNROLL
+    for (int r = 0; r < FSM_MAX_OUT; ++r) {
+        if (r < cb.n_out) {
+            cplx<T> s = mk<T>(T(0), T(0));
+            FSM_UNROLL
+            for (int m = 0; m < FSM_MAX_IN + 1; ++m) {
+                const int ti = cb.ct[r][m];
+                if (ti != -2) {
+                    T coef = cb.ca[r][m];
+                    FSM_UNROLL
+                    for (int q = 0; q < 8; ++q)
+                        if (ti == q) coef = fsm_fma(cb.cb[r][m], tv[q], coef);
+                    s.x = fsm_fma(coef, X[m].x, s.x);
+                    s.y = fsm_fma(coef, X[m].y, s.y);
+                }
+            }
+            cb.out[r][bc_off + mode] = s;
+        }
+    }
+}
+
+template <typename T, class Cfg, int C>
+__global__ void __launch_bounds__(kKL * Cfg::TL) k_pass_fx(Geom<T> g, const cplx<T>* __restrict__ win, long win_fstride,
+                                                  Combine<T> cb, FxEpilogue<T> ep, int nlines, int b0) {
+    constexpr int N = Cfg::N, EPT = Cfg::EPT, TL = Cfg::TL;
+    FSM_DYN_SMEM(smem_raw);
+    cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);
+    cplx<T>* bufs = tw + Smem<Cfg, T>::TWPAD;
+    make_twiddles<Cfg, T>(tw);
+    const int K = blockDim.x / TL;
+    const int lt = threadIdx.x / TL, tau = threadIdx.x % TL;
+    const int line = blockIdx.x * K + lt;
+    const long bl = blockIdx.z;          // sample index inside the chunk (W buffers)
+    const long b = b0 + bl;              // global sample index (state arrays)
+    if (line >= nlines) return;
+    LineSync<TL> sync{1 + lt};
+    cplx<T>* mybuf = bufs + lt * Cfg::LINE_PITCH;
+    cplx<T> nhat[C][EPT];
+    static_for<0, C>([&](auto cc) {
+        constexpr int c = decltype(cc)::value;
+        const cplx<T>* src = win + (bl * C + c) * win_fstride + (long)line * N;
+        FSM_UNROLL
+        for (int m = 0; m < EPT; ++m) nhat[c][m] = src[tau + m * TL];
+        if (c > 0) sync();
+        line_fft<Cfg, -1, T>(nhat[c], mybuf, tw, tau, sync);
+    });
+    // line coordinates
+    int ky, kz = 0;
+    if (g.ndim == 3) { ky = line / g.nh; kz = line % g.nh; } else { ky = line; }
+    FSM_UNROLL
+    for (int m = 0; m < EPT; ++m) {
+        const int p = tau + m * TL;
+        const long mode = (long)line * N + p;
+        cplx<T> f[C];
+        FSM_UNROLL
+        for (int c = 0; c < C; ++c) f[c] = cscale(nhat[c][m], ep.nl_coef);
+        if constexpr (C == 3) {
+            if (ep.project) {
+                // result_i = (ik_i) lap^-1 sum_j (ik_j) c_j - c_i   (_navier_stokes.py:249-254), with the
+                // Hermitian projection of the composite symbol: a cross term is dropped when exactly one
+                // of its two axes sits on its Nyquist index.
+                const T d0 = g.dkraw[0][p], d1 = g.dkraw[1][ky], d2 = g.dkraw[2][kz];
+                const bool q0 = (p == g.n[0] / 2), q1 = (ky == g.n[1] / 2), q2 = (kz == g.n[2] / 2);
+                const T k2 = d0 * d0 + d1 * d1 + d2 * d2;
+                const T ik2 = (k2 == T(0)) ? T(0) : T(1) / k2;
+                const T dd[3] = {d0, d1, d2};
+                const bool qq[3] = {q0, q1, q2};
+                cplx<T> r[3];
+                FSM_UNROLL
+                for (int i = 0; i < 3; ++i) {
+                    cplx<T> s = mk<T>(T(0), T(0));
+                    FSM_UNROLL
+                    for (int j = 0; j < 3; ++j) {
+                        const T w = (i == j || qq[i] == qq[j]) ? dd[i] * dd[j] * ik2 : T(0);
+                        s.x = fsm_fma(w, f[j].x, s.x);
+                        s.y = fsm_fma(w, f[j].y, s.y);
+                    }
+                    r[i] = s - f[i];
+                }
+                FSM_UNROLL
+                for (int i = 0; i < 3; ++i) f[i] = r[i];
+            }
+        }
+        FSM_UNROLL
+        for (int c = 0; c < C; ++c) {
+            if (ep.source) f[c] = f[c] + ep.source[(long)c * g.nmodes + mode];
+            if (ep.dc_out && mode == 0 && c == 0) { ep.dc_out[b] = f[c].x; f[c] = mk<T>(T(0), T(0)); }
+            combine_mode<T>(cb, f[c], (b * C + c) * g.nmodes, c * cb.tab_cstride, mode);
+        }
+    }
+}
+
+// Combine without a nonlinear term (ETDRK0) or point-wise fix-ups: one thread per mode.
+template <typename T>
+__global__ void k_combine_only(Combine<T> cb, long nmodes, int C, long total /*B*C*nmodes*/) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long mode = i % nmodes;
+    const long bc = i / nmodes;
+    const int c = (int)(bc % C);
+    combine_mode<T>(cb, mk<T>(T(0), T(0)), bc * nmodes, c * cb.tab_cstride, mode);
+}
+
+// KS: N_hat_b(0) = coef * (S_b - mean_b S_b). The FX pass stored coef*S_b in dc[b] and combined a zero.
+// This kernel adds the missing contribution (coefficient of the fresh term at mode 0) to every output.
+template <typename T>
+__global__ void k_ks_dc_fix(Combine<T> cb, const T* dc, int B, long nmodes, T ext_sum, int ext_count) {
+    FSM_DYN_SMEM(smem_raw);
+    T* s_mean = reinterpret_cast<T*>(smem_raw);
+    if (threadIdx.x == 0) {
+        T s = ext_sum;
+        for (int b = 0; b < B; ++b) s += dc[b];
+        s_mean[0] = s / T(B + ext_count);
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        const T delta = dc[b] - s_mean[0];
+        for (int r = 0; r < cb.n_out; ++r) {
+            const int ti = cb.ct[r][0];
+            if (ti == -2) continue;
+            T coef = cb.ca[r][0];
+            if (ti >= 0) coef += cb.cb[r][0] * cb.tab[ti][0];
+            cplx<T>* o = cb.out[r] + (long)b * nmodes;  // C == 1
+            o[0].x += coef * delta;
+        }
+    }
+}
+
+// half (rot) <-> full complex spectrum (reference layout (B*C, n0, n1[, n2])), used for u_0_fft input,
+// return_in_fourier and recorder frames. Hermitian completion of the missing half.
+template <typename T>
+__global__ void k_half_to_full(Geom<T> g, const cplx<T>* __restrict__ half, cplx<T>* __restrict__ full, long nfields) {
+    const long ntot = (long)g.n[0] * g.n[1] * g.n[2];
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nfields * ntot) return;
+    const long f = i / ntot;
+    long rem = i % ntot;
+    int idx[3];
+    idx[2] = (int)(rem % g.n[2]); rem /= g.n[2];
+    idx[1] = (int)(rem % g.n[1]); rem /= g.n[1];
+    idx[0] = (int)rem;
+    // physical index order (x, y, z) -> for 2-D the arrays are (n0, n1, 1)
+    const int last = g.ndim - 1;
+    const int nl = g.n[last];
+    bool conj = idx[last] > nl / 2;
+    int q[3] = {idx[0], idx[1], idx[2]};
+    if (conj)
+        for (int d = 0; d < g.ndim; ++d) q[d] = (g.n[d] - idx[d]) % g.n[d];
+    long mode;
+    if (g.ndim == 1) mode = q[0];
+    else if (g.ndim == 2) mode = (long)q[1] * g.n[0] + q[0];
+    else mode = ((long)q[1] * g.nh + q[2]) * g.n[0] + q[0];
+    cplx<T> v = half[f * g.nmodes + mode];
+    if (conj) v.y = -v.y;
+    full[i] = v;
+}
+
+template <typename T>
+__global__ void k_full_to_half(Geom<T> g, const cplx<T>* __restrict__ full, cplx<T>* __restrict__ half, long nfields) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nfields * g.nmodes) return;
+    const long f = i / g.nmodes;
+    long mode = i % g.nmodes;
+    int q[3] = {0, 0, 0};
+    if (g.ndim == 1) q[0] = (int)mode;
+    else if (g.ndim == 2) { q[0] = (int)(mode % g.n[0]); q[1] = (int)(mode / g.n[0]); }
+    else { q[0] = (int)(mode % g.n[0]); mode /= g.n[0]; q[2] = (int)(mode % g.nh); q[1] = (int)(mode / g.nh); }
+    // Hermitian projection of the real-field spectrum: (U(k) + conj U(-k)) / 2
+    const long ntot = (long)g.n[0] * g.n[1] * g.n[2];
+    const long a = ((long)q[0] * g.n[1] + q[1]) * g.n[2] + q[2];
+    const int m0 = (g.n[0] - q[0]) % g.n[0], m1 = (g.n[1] - q[1]) % g.n[1], m2 = (g.n[2] - q[2]) % g.n[2];
+    const long bidx = ((long)m0 * g.n[1] + m1) * g.n[2] + m2;
+    const cplx<T> u = full[f * ntot + a], w = full[f * ntot + bidx];
+    half[i] = mk<T>(T(0.5) * (u.x + w.x), T(0.5) * (u.y - w.y));
+}
+
+}  // namespace fsm

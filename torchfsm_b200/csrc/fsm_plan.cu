@@ -1,0 +1,727 @@
+// Plan, stage programs and the C ABI (include/fsm_b200.h) of libfsm_b200.so.
+#include "fsm_b200.h"
+#include "fsm_launch.h"
+
+#include <cerrno>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+namespace fsm {
+
+#define FSM_DECL_TABLE(N)                      \
+    const LaunchTable<float>* table_f32_##N(); \
+    const LaunchTable<double>* table_f64_##N();
+FSM_DECL_TABLE(8)
+FSM_DECL_TABLE(16)
+FSM_DECL_TABLE(32)
+FSM_DECL_TABLE(64)
+FSM_DECL_TABLE(128)
+FSM_DECL_TABLE(256)
+FSM_DECL_TABLE(512)
+FSM_DECL_TABLE(1024)
+
+template <> const LaunchTable<float>* launch_table<float>(int N) {
+    switch (N) {
+        case 8: return table_f32_8();
+        case 16: return table_f32_16();
+        case 32: return table_f32_32();
+        case 64: return table_f32_64();
+        case 128: return table_f32_128();
+        case 256: return table_f32_256();
+        case 512: return table_f32_512();
+        case 1024: return table_f32_1024();
+        default: return nullptr;
+    }
+}
+template <> const LaunchTable<double>* launch_table<double>(int N) {
+    switch (N) {
+        case 8: return table_f64_8();
+        case 16: return table_f64_16();
+        case 32: return table_f64_32();
+        case 64: return table_f64_64();
+        case 128: return table_f64_128();
+        case 256: return table_f64_256();
+        case 512: return table_f64_512();
+        case 1024: return table_f64_1024();
+        default: return nullptr;
+    }
+}
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+// --------------------------------------------------------------------------------------------
+// Stage programs. Arrays: 0 = U (caller state, updated in place), 1..4 = scratch state arrays,
+// 5 = external output (fsm_rhs). Tables: see enum below. X_0 is the fresh nonlinear term.
+// --------------------------------------------------------------------------------------------
+enum { ARR_U = 0, ARR_S1 = 1, ARR_S2 = 2, ARR_S3 = 3, ARR_S4 = 4, ARR_EXT = 5, ARR_COUNT = 6 };
+enum { TAB_EXP = 0, TAB_HALF = 1, TAB_C1 = 2, TAB_C2, TAB_C3, TAB_C4, TAB_C5, TAB_C6, TAB_LIN = 8, TAB_COUNT = 9 };
+constexpr int NO_TERM = -2, SCALAR = -1;
+
+struct Coef {
+    int tab = NO_TERM;
+    double a = 0, b = 0;  // coefficient = a + b * table
+};
+struct Stage {
+    int input = ARR_U;          // array the nonlinear term is evaluated on
+    int n_in = 0, in[FSM_MAX_IN] = {0, 0, 0};
+    int n_out = 0, out[FSM_MAX_OUT] = {0, 0, 0};
+    Coef c[FSM_MAX_OUT][FSM_MAX_IN + 1];
+};
+static Coef tabc(int tab, double b = 1.0) { Coef c; c.tab = tab; c.a = 0; c.b = b; return c; }
+static Coef scal(double a) { Coef c; c.tab = SCALAR; c.a = a; c.b = 0; return c; }
+static Coef affine(double a, int tab, double b) { Coef c; c.tab = tab; c.a = a; c.b = b; return c; }
+
+static std::vector<Stage> build_stages(int integ, double dt, bool has_lin) {
+    std::vector<Stage> st;
+    auto mk_stage = [](int input, std::initializer_list<int> ins, std::initializer_list<int> outs) {
+        Stage s;
+        s.input = input;
+        for (int a : ins) s.in[s.n_in++] = a;
+        for (int a : outs) s.out[s.n_out++] = a;
+        return s;
+    };
+    switch (integ) {
+        case FSM_INT_ETDRK0: {  // u' = E u                      (_etdrk.py:23-27)
+            Stage s = mk_stage(ARR_U, {ARR_U}, {ARR_U});
+            s.c[0][1] = tabc(TAB_EXP);
+            st.push_back(s);
+            break;
+        }
+        case FSM_INT_ETDRK1:
+        case FSM_INT_SETDRK1: {  // u' = E u + c1 N(u)            (_etdrk.py:47-51, _setdrk_step.py:5-11)
+            Stage s = mk_stage(ARR_U, {ARR_U}, {ARR_U});
+            s.c[0][0] = tabc(TAB_C1);
+            s.c[0][1] = tabc(TAB_EXP);
+            st.push_back(s);
+            break;
+        }
+        case FSM_INT_ETDRK2:
+        case FSM_INT_SETDRK2: {  // a = E u + c1 N0; u' = a + c2 (N(a) - N0)   (_etdrk.py:72-82)
+            Stage s1 = mk_stage(ARR_U, {ARR_U}, {ARR_S1, ARR_S2});
+            s1.c[0][0] = tabc(TAB_C1);
+            s1.c[0][1] = tabc(TAB_EXP);
+            s1.c[1][0] = scal(1.0);
+            Stage s2 = mk_stage(ARR_S1, {ARR_S1, ARR_S2}, {ARR_U});
+            s2.c[0][0] = tabc(TAB_C2);
+            s2.c[0][1] = scal(1.0);
+            s2.c[0][2] = tabc(TAB_C2, -1.0);
+            st.push_back(s1);
+            st.push_back(s2);
+            break;
+        }
+        case FSM_INT_SETDRK3: {  // _setdrk_step.py:28-52 ; S1 = stage state, S2 = N0, S3 = running sum
+            Stage s1 = mk_stage(ARR_U, {ARR_U}, {ARR_S1, ARR_S2, ARR_S3});
+            s1.c[0][0] = tabc(TAB_C1); s1.c[0][1] = tabc(TAB_HALF);
+            s1.c[1][0] = scal(1.0);
+            s1.c[2][0] = tabc(TAB_C3); s1.c[2][1] = tabc(TAB_EXP);
+            Stage s2 = mk_stage(ARR_S1, {ARR_U, ARR_S2, ARR_S3}, {ARR_S1, ARR_S3});
+            s2.c[0][0] = tabc(TAB_C2, 2.0); s2.c[0][1] = tabc(TAB_EXP); s2.c[0][2] = tabc(TAB_C2, -1.0);
+            s2.c[1][0] = tabc(TAB_C4); s2.c[1][3] = scal(1.0);
+            Stage s3 = mk_stage(ARR_S1, {ARR_S3}, {ARR_U});
+            s3.c[0][0] = tabc(TAB_C5); s3.c[0][1] = scal(1.0);
+            st.push_back(s1); st.push_back(s2); st.push_back(s3);
+            break;
+        }
+        case FSM_INT_SETDRK4: {  // _setdrk_step.py:55-82 ; S1 = a, S2 = N0, S3 = running sum, S4 = b then c
+            Stage s1 = mk_stage(ARR_U, {ARR_U}, {ARR_S1, ARR_S2, ARR_S3});
+            s1.c[0][0] = tabc(TAB_C1); s1.c[0][1] = tabc(TAB_HALF);
+            s1.c[1][0] = scal(1.0);
+            s1.c[2][0] = tabc(TAB_C4); s1.c[2][1] = tabc(TAB_EXP);
+            Stage s2 = mk_stage(ARR_S1, {ARR_U, ARR_S3}, {ARR_S4, ARR_S3});
+            s2.c[0][0] = tabc(TAB_C2); s2.c[0][1] = tabc(TAB_HALF);
+            s2.c[1][0] = tabc(TAB_C5, 2.0); s2.c[1][2] = scal(1.0);
+            Stage s3 = mk_stage(ARR_S4, {ARR_S1, ARR_S2, ARR_S3}, {ARR_S4, ARR_S3});
+            s3.c[0][0] = tabc(TAB_C3, 2.0); s3.c[0][1] = tabc(TAB_HALF); s3.c[0][2] = tabc(TAB_C3, -1.0);
+            s3.c[1][0] = tabc(TAB_C5, 2.0); s3.c[1][3] = scal(1.0);
+            Stage s4 = mk_stage(ARR_S4, {ARR_S3}, {ARR_U});
+            s4.c[0][0] = tabc(TAB_C6); s4.c[0][1] = scal(1.0);
+            st.push_back(s1); st.push_back(s2); st.push_back(s3); st.push_back(s4);
+            break;
+        }
+        case FSM_INT_RK4: {  // k = L s + N(s)  (_rk.py:43-58,142-155); S1 = stage state, S2 = running sum
+            auto lin = [&](double a, double b) { return has_lin ? affine(a, TAB_LIN, b) : scal(a); };
+            Stage s1 = mk_stage(ARR_U, {ARR_U}, {ARR_S1, ARR_S2});
+            s1.c[0][0] = scal(dt / 2); s1.c[0][1] = lin(1.0, dt / 2);
+            s1.c[1][0] = scal(dt / 6); s1.c[1][1] = lin(1.0, dt / 6);
+            Stage s2 = mk_stage(ARR_S1, {ARR_U, ARR_S1, ARR_S2}, {ARR_S1, ARR_S2});
+            s2.c[0][0] = scal(dt / 2); s2.c[0][1] = scal(1.0); s2.c[0][2] = lin(0.0, dt / 2);
+            s2.c[1][0] = scal(dt / 3); s2.c[1][2] = lin(0.0, dt / 3); s2.c[1][3] = scal(1.0);
+            Stage s3 = s2;
+            s3.c[0][0] = scal(dt); s3.c[0][2] = lin(0.0, dt);
+            Stage s4 = mk_stage(ARR_S1, {ARR_S1, ARR_S2}, {ARR_U});
+            s4.c[0][0] = scal(dt / 6); s4.c[0][1] = lin(0.0, dt / 6); s4.c[0][2] = scal(1.0);
+            st.push_back(s1); st.push_back(s2); st.push_back(s3); st.push_back(s4);
+            break;
+        }
+        default: break;
+    }
+    return st;
+}
+
+}  // namespace fsm
+
+using namespace fsm;
+
+struct fsm_plan {
+    fsm_desc d;
+    int ndim, n[3], nh, ph, B, C, prog, kprog;  // kprog = kernel-side Prog enum
+    bool f64;
+    long nmodes, ntot;
+    int chunk;
+    int nf_ix, nfi, nout;  // fields: IX per channel, PHYS inputs per sample, PHYS outputs per sample
+    std::vector<Stage> stages;
+    Stage rhs_stage;
+    // workspace (offsets in bytes)
+    size_t off_arr[ARR_COUNT], off_w1, off_w2, off_w3, off_w2b, off_dc, ws_bytes;
+    size_t cap_fields;  // how many independent fields the W buffers can hold at once (r2c/c2r)
+    int64_t launches_per_step, algo_bytes_per_step;
+};
+
+namespace {
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
+
+template <typename T>
+Geom<T> make_geom(const fsm_plan* p, bool nomask) {
+    Geom<T> g;
+    g.ndim = p->ndim;
+    for (int i = 0; i < 3; ++i) {
+        g.n[i] = p->n[i];
+        g.kmax[i] = nomask ? p->n[i] / 2 : p->d.kmax[i];
+        g.dk[i] = static_cast<const T*>(p->d.dk[i]);
+        g.dkraw[i] = static_cast<const T*>(p->d.dkraw[i]);
+    }
+    g.nh = p->nh;
+    g.ph = p->ph;
+    g.nmodes = p->nmodes;
+    g.inv_ntot = T(1.0 / (double)p->ntot);
+    return g;
+}
+
+template <typename T>
+const void* table_ptr(const fsm_plan* p, int tab) {
+    switch (tab) {
+        case TAB_EXP: return p->d.tab_exp;
+        case TAB_HALF: return p->d.tab_half_exp;
+        case TAB_LIN: return p->d.tab_lin;
+        default: return (tab >= TAB_C1 && tab <= TAB_C6) ? p->d.tab_coef[tab - TAB_C1] : nullptr;
+    }
+}
+
+// Translate a stage into the device-side Combine descriptor.
+template <typename T>
+int make_combine(const fsm_plan* p, const Stage& s, cplx<T>* const* arr, bool fresh, Combine<T>* out) {
+    Combine<T> cb;
+    memset(&cb, 0, sizeof(cb));
+    cb.n_in = s.n_in;
+    cb.n_out = s.n_out;
+    cb.use_fresh = fresh ? 1 : 0;
+    cb.tab_cstride = (p->d.tab_channels > 1) ? p->nmodes : 0;
+    int slot_of[TAB_COUNT];
+    for (int i = 0; i < TAB_COUNT; ++i) slot_of[i] = -1;
+    for (int i = 0; i < s.n_in; ++i) cb.in[i] = arr[s.in[i]];
+    for (int r = 0; r < s.n_out; ++r) cb.out[r] = arr[s.out[r]];
+    for (int r = 0; r < FSM_MAX_OUT; ++r)
+        for (int m = 0; m < FSM_MAX_IN + 1; ++m) {
+            const Coef& c = s.c[r][m];
+            cb.ct[r][m] = NO_TERM;
+            if (r >= s.n_out || c.tab == NO_TERM) continue;
+            if (m == 0 && !fresh) continue;
+            if (m > s.n_in) return fail(-EINVAL, "stage coefficient refers to a missing input");
+            cb.ca[r][m] = (T)c.a;
+            cb.cb[r][m] = (T)c.b;
+            if (c.tab == SCALAR) {
+                cb.ct[r][m] = -1;
+            } else {
+                if (slot_of[c.tab] < 0) {
+                    const void* tp = table_ptr<T>(p, c.tab);
+                    if (!tp) return fail(-EINVAL, "integrator needs table %d but the descriptor has none", c.tab);
+                    if (cb.n_tab >= 8) return fail(-EINVAL, "too many tables in one stage");
+                    slot_of[c.tab] = cb.n_tab;
+                    cb.tab[cb.n_tab++] = static_cast<const T*>(tp);
+                }
+                cb.ct[r][m] = slot_of[c.tab];
+            }
+        }
+    *out = cb;
+    return 0;
+}
+
+template <typename T>
+struct Buffers {
+    cplx<T>* arr[ARR_COUNT];
+    cplx<T>*w1, *w2, *w3, *w2b;
+    T* dc;
+};
+
+template <typename T>
+Buffers<T> carve(const fsm_plan* p, void* u_hat, void* ws, void* ext) {
+    Buffers<T> b;
+    char* base = static_cast<char*>(ws);
+    b.arr[ARR_U] = static_cast<cplx<T>*>(u_hat);
+    for (int i = ARR_S1; i <= ARR_S4; ++i) b.arr[i] = reinterpret_cast<cplx<T>*>(base + p->off_arr[i]);
+    b.arr[ARR_EXT] = static_cast<cplx<T>*>(ext);
+    b.w1 = reinterpret_cast<cplx<T>*>(base + p->off_w1);
+    b.w2 = reinterpret_cast<cplx<T>*>(base + p->off_w2);
+    b.w3 = reinterpret_cast<cplx<T>*>(base + p->off_w3);
+    b.w2b = reinterpret_cast<cplx<T>*>(base + p->off_w2b);
+    b.dc = reinterpret_cast<T*>(base + p->off_dc);
+    return b;
+}
+
+MidSpec mid_spec_inverse(const fsm_plan* p) {
+    MidSpec s;
+    memset(&s, 0, sizeof(s));
+    if (p->kprog == PROG_KS) {          // in: phi, dx phi -> phi, dx phi, dy phi
+        s.nfo = 3;
+        s.src[0] = 0; s.src[1] = 1; s.src[2] = 0; s.deriv[2] = 1;
+    } else {                            // CONV / NS3D: in [c][u, dx u] -> u_c, dx u_c, dy u_c
+        s.nfo = 9;
+        for (int c = 0; c < 3; ++c) {
+            s.src[c] = 2 * c;
+            s.src[3 + c] = 2 * c + 1;
+            s.src[6 + c] = 2 * c; s.deriv[6 + c] = 1;
+        }
+    }
+    return s;
+}
+MidSpec mid_spec_identity(int nf) {
+    MidSpec s;
+    memset(&s, 0, sizeof(s));
+    s.nfo = nf;
+    for (int i = 0; i < nf; ++i) s.src[i] = i;
+    return s;
+}
+
+// forward half of an evaluation: [MID forward] -> FX + combine, for `nb` samples starting at b0
+template <typename T>
+int run_forward_tail(const fsm_plan* p, const Buffers<T>& bf, const Geom<T>& g, int nfields_per_sample, int C,
+                     const Combine<T>& cb, const FxEpilogue<T>& ep, int b0, int nb, cudaStream_t st) {
+    const cplx<T>* fx_in = bf.w2;
+    if (p->ndim == 3) {
+        const LaunchTable<T>* ty = launch_table<T>(p->n[1]);
+        MidArgs<T> m;
+        m.g = g; m.in = bf.w2; m.out = bf.w2b;
+        m.in_fstride = (long)p->nh * p->n[0] * p->n[1]; m.out_fstride = p->nmodes;
+        m.in_t_stride = p->n[1]; m.in_o_stride = (long)p->n[0] * p->n[1];
+        m.out_o_stride = p->n[0]; m.out_e_stride = (long)p->nh * p->n[0];
+        m.nfi = nfields_per_sample; m.n_t = p->n[0]; m.n_outer = p->nh; m.nb = nb;
+        m.spec = mid_spec_identity(nfields_per_sample);
+        if (int e = ty->mid(-1, m, st)) return fail(e, "MID forward launch failed");
+        fx_in = bf.w2b;
+    }
+    const LaunchTable<T>* tx = launch_table<T>(p->n[0]);
+    FxArgs<T> f;
+    f.g = g; f.win = fx_in; f.win_fstride = p->nmodes; f.cb = cb; f.ep = ep;
+    f.nlines = (int)(p->nmodes / p->n[0]); f.b0 = b0; f.nb = nb;
+    if (int e = tx->fx(C, f, st)) return fail(e, "FX launch failed (channels=%d, n0=%d)", C, p->n[0]);
+    return 0;
+}
+
+// One nonlinear evaluation of `stage_in` followed by the stage combine.
+template <typename T>
+int run_stage(const fsm_plan* p, const Buffers<T>& bf, const Stage& s, cudaStream_t st) {
+    Combine<T> cb;
+    const bool fresh = p->prog != FSM_PROG_LINEAR;
+    if (int e = make_combine<T>(p, s, bf.arr, fresh, &cb)) return e;
+    if (!fresh) {
+        const long total = (long)p->B * p->C * p->nmodes;
+        auto kern = k_combine_only<T>;
+        FSM_LAUNCH(kern, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, cb, p->nmodes, p->C, total);
+        return 0;
+    }
+    const Geom<T> g = make_geom<T>(p, false);
+    const cplx<T>* stage_in = bf.arr[s.input];
+    const LaunchTable<T>* tx = launch_table<T>(p->n[0]);
+    const LaunchTable<T>* tl = launch_table<T>(p->n[p->ndim - 1]);
+    const LaunchTable<T>* ty = (p->ndim == 3) ? launch_table<T>(p->n[1]) : nullptr;
+    FxEpilogue<T> ep;
+    ep.nl_coef = (T)p->d.nl_coef;
+    ep.source = static_cast<const cplx<T>*>(p->d.source_hat);
+    ep.dc_out = (p->prog == FSM_PROG_KS && p->d.ks_remove_mean) ? bf.dc : nullptr;
+    ep.project = (p->prog == FSM_PROG_NS3D) ? 1 : 0;
+    for (int b0 = 0; b0 < p->B; b0 += p->chunk) {
+        const int nb = (p->B - b0 < p->chunk) ? (p->B - b0) : p->chunk;
+        IxArgs<T> a;
+        a.g = g; a.state = stage_in + (long)b0 * p->C * p->nmodes; a.w1 = bf.w1;
+        a.state_bstride = p->nmodes; a.nbc = nb * p->C;
+        PhysArgs<T> ph;
+        ph.g = g; ph.wout = bf.w2; ph.phys_in = nullptr; ph.phys_out = nullptr; ph.nb = nb;
+        if (p->ndim == 2) {
+            a.w1_fstride = (long)p->n[0] * p->ph;
+            a.in_t_stride = p->n[0]; a.in_o_stride = 0; a.out_o_stride = 0; a.out_e_stride = p->ph;
+            a.n_t = (p->d.kmax[1] + 1 < p->nh) ? p->d.kmax[1] + 1 : p->nh; a.n_outer = 1;
+            if (int e = tx->ix(p->kprog, a, st)) return fail(e, "IX launch failed");
+            ph.win = bf.w1; ph.win_fstride = a.w1_fstride; ph.wout_fstride = p->nmodes;
+            ph.in_t_stride = p->ph; ph.in_o_stride = 0; ph.out_o_stride = 0; ph.out_e_stride = p->n[0];
+            ph.n_t = p->n[0]; ph.n_outer = 1;
+        } else {
+            const long plane = (long)p->n[0] * p->n[1];
+            a.w1_fstride = (long)p->nh * plane;
+            a.in_t_stride = (long)p->nh * p->n[0]; a.in_o_stride = p->n[0];
+            a.out_o_stride = plane; a.out_e_stride = p->n[1];
+            a.n_t = p->n[1]; a.n_outer = (p->d.kmax[2] + 1 < p->nh) ? p->d.kmax[2] + 1 : p->nh;
+            if (int e = tx->ix(p->kprog, a, st)) return fail(e, "IX launch failed");
+            MidArgs<T> m;
+            m.g = g; m.in = bf.w1; m.out = bf.w3;
+            m.in_fstride = a.w1_fstride; m.out_fstride = plane * p->ph;
+            m.in_t_stride = plane; m.in_o_stride = p->n[1];
+            m.out_o_stride = (long)p->n[1] * p->ph; m.out_e_stride = p->ph;
+            m.nfi = p->C * p->nf_ix; m.n_t = a.n_outer; m.n_outer = p->n[0]; m.nb = nb;
+            m.spec = mid_spec_inverse(p);
+            if (int e = ty->mid(+1, m, st)) return fail(e, "MID inverse launch failed");
+            ph.win = bf.w3; ph.win_fstride = m.out_fstride; ph.wout_fstride = (long)p->nh * plane;
+            ph.in_t_stride = p->ph; ph.in_o_stride = (long)p->n[1] * p->ph;
+            ph.out_o_stride = p->n[1]; ph.out_e_stride = plane;
+            ph.n_t = p->n[1]; ph.n_outer = p->n[0];
+        }
+        if (int e = tl->phys(p->kprog, p->ndim, ph, st)) return fail(e, "PHYS launch failed");
+        if (int e = run_forward_tail<T>(p, bf, g, p->nout, p->C, cb, ep, b0, nb, st)) return e;
+    }
+    if (ep.dc_out) {
+        auto kern = k_ks_dc_fix<T>;
+        FSM_LAUNCH(kern, dim3(1), dim3(128), sizeof(T) * 2, st, cb, (const T*)bf.dc, p->B, p->nmodes,
+                   (T)p->d.ks_ext_sum, (int)p->d.ks_ext_count);
+    }
+    return 0;
+}
+
+template <typename T>
+int do_step(fsm_plan* p, void* u_hat, void* ws, int n_steps, cudaStream_t st) {
+    Buffers<T> bf = carve<T>(p, u_hat, ws, nullptr);
+    for (int i = 0; i < n_steps; ++i)
+        for (const Stage& s : p->stages)
+            if (int e = run_stage<T>(p, bf, s, st)) return e;
+    return 0;
+}
+
+template <typename T>
+int do_rhs(fsm_plan* p, const void* u_hat, void* out, void* ws, cudaStream_t st) {
+    Buffers<T> bf = carve<T>(p, const_cast<void*>(u_hat), ws, out);
+    return run_stage<T>(p, bf, p->rhs_stage, st);
+}
+
+template <typename T>
+int do_r2c(fsm_plan* p, const void* u, void* u_hat, void* ws, cudaStream_t st) {
+    Buffers<T> bf = carve<T>(p, u_hat, ws, nullptr);
+    const Geom<T> g = make_geom<T>(p, true);
+    const LaunchTable<T>* tl = launch_table<T>(p->n[p->ndim - 1]);
+    const long nfields = (long)p->B * p->C;
+    const long nreal = p->ntot;
+    Stage s;  // out = fresh
+    s.input = ARR_U; s.n_in = 0; s.n_out = 1; s.out[0] = ARR_U;
+    s.c[0][0] = scal(1.0);
+    for (long f0 = 0; f0 < nfields; f0 += (long)p->cap_fields) {
+        const int nf = (int)((nfields - f0 < (long)p->cap_fields) ? nfields - f0 : (long)p->cap_fields);
+        PhysArgs<T> ph;
+        ph.g = g; ph.win = nullptr; ph.wout = bf.w2; ph.phys_in = static_cast<const T*>(u) + f0 * nreal;
+        ph.phys_out = nullptr; ph.win_fstride = 0; ph.nb = nf;
+        if (p->ndim == 2) {
+            ph.wout_fstride = p->nmodes; ph.in_t_stride = 0; ph.in_o_stride = 0; ph.out_o_stride = 0;
+            ph.out_e_stride = p->n[0]; ph.n_t = p->n[0]; ph.n_outer = 1;
+        } else {
+            const long plane = (long)p->n[0] * p->n[1];
+            ph.wout_fstride = (long)p->nh * plane; ph.in_t_stride = 0; ph.in_o_stride = 0;
+            ph.out_o_stride = p->n[1]; ph.out_e_stride = plane; ph.n_t = p->n[1]; ph.n_outer = p->n[0];
+        }
+        if (int e = tl->phys(PROG_R2C, p->ndim, ph, st)) return fail(e, "R2C PHYS launch failed");
+        // every field is an independent single-channel "sample" for the tail
+        cplx<T>* arr[ARR_COUNT] = {bf.arr[ARR_U] + f0 * p->nmodes, nullptr, nullptr, nullptr, nullptr, nullptr};
+        Combine<T> cb;
+        fsm_plan tmp = *p;  // tables unused; channel stride irrelevant
+        tmp.d.tab_channels = 1;
+        if (int e = make_combine<T>(&tmp, s, arr, true, &cb)) return e;
+        FxEpilogue<T> ep;
+        ep.nl_coef = T(1); ep.source = nullptr; ep.dc_out = nullptr; ep.project = 0;
+        if (int e = run_forward_tail<T>(p, bf, g, 1, 1, cb, ep, 0, nf, st)) return e;
+    }
+    return 0;
+}
+
+template <typename T>
+int do_c2r(fsm_plan* p, const void* u_hat, void* u, void* ws, cudaStream_t st) {
+    Buffers<T> bf = carve<T>(p, const_cast<void*>(u_hat), ws, nullptr);
+    const Geom<T> g = make_geom<T>(p, true);
+    const LaunchTable<T>* tx = launch_table<T>(p->n[0]);
+    const LaunchTable<T>* tl = launch_table<T>(p->n[p->ndim - 1]);
+    const long nfields = (long)p->B * p->C;
+    for (long f0 = 0; f0 < nfields; f0 += (long)p->cap_fields) {
+        const int nf = (int)((nfields - f0 < (long)p->cap_fields) ? nfields - f0 : (long)p->cap_fields);
+        IxArgs<T> a;
+        a.g = g; a.state = static_cast<const cplx<T>*>(u_hat) + f0 * p->nmodes; a.w1 = bf.w1;
+        a.state_bstride = p->nmodes; a.nbc = nf;
+        PhysArgs<T> ph;
+        ph.g = g; ph.wout = nullptr; ph.phys_in = nullptr; ph.phys_out = static_cast<T*>(u) + f0 * p->ntot;
+        ph.wout_fstride = 0; ph.out_o_stride = 0; ph.out_e_stride = 0; ph.nb = nf;
+        if (p->ndim == 2) {
+            a.w1_fstride = (long)p->n[0] * p->ph;
+            a.in_t_stride = p->n[0]; a.in_o_stride = 0; a.out_o_stride = 0; a.out_e_stride = p->ph;
+            a.n_t = p->nh; a.n_outer = 1;
+            if (int e = tx->ix(PROG_C2R, a, st)) return fail(e, "C2R IX launch failed");
+            ph.win = bf.w1; ph.win_fstride = a.w1_fstride; ph.in_t_stride = p->ph; ph.in_o_stride = 0;
+            ph.n_t = p->n[0]; ph.n_outer = 1;
+        } else {
+            const long plane = (long)p->n[0] * p->n[1];
+            const LaunchTable<T>* ty = launch_table<T>(p->n[1]);
+            a.w1_fstride = (long)p->nh * plane;
+            a.in_t_stride = (long)p->nh * p->n[0]; a.in_o_stride = p->n[0];
+            a.out_o_stride = plane; a.out_e_stride = p->n[1];
+            a.n_t = p->n[1]; a.n_outer = p->nh;
+            if (int e = tx->ix(PROG_C2R, a, st)) return fail(e, "C2R IX launch failed");
+            MidArgs<T> m;
+            m.g = g; m.in = bf.w1; m.out = bf.w3;
+            m.in_fstride = a.w1_fstride; m.out_fstride = plane * p->ph;
+            m.in_t_stride = plane; m.in_o_stride = p->n[1];
+            m.out_o_stride = (long)p->n[1] * p->ph; m.out_e_stride = p->ph;
+            m.nfi = 1; m.n_t = p->nh; m.n_outer = p->n[0]; m.nb = nf;
+            m.spec = mid_spec_identity(1);
+            if (int e = ty->mid(+1, m, st)) return fail(e, "C2R MID launch failed");
+            ph.win = bf.w3; ph.win_fstride = m.out_fstride;
+            ph.in_t_stride = p->ph; ph.in_o_stride = (long)p->n[1] * p->ph;
+            ph.n_t = p->n[1]; ph.n_outer = p->n[0];
+        }
+        if (int e = tl->phys(PROG_C2R, p->ndim, ph, st)) return fail(e, "C2R PHYS launch failed");
+    }
+    return 0;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int fsm_abi_version(void) { return FSM_ABI_VERSION; }
+int fsm_backend(void) {
+#ifdef FSM_EMU
+    return 1;
+#else
+    return 0;
+#endif
+}
+const char* fsm_last_error(void) { return g_err; }
+
+int fsm_plan_create(fsm_plan** out, const fsm_desc* d) {
+    if (!out || !d) return fail(-EINVAL, "null argument");
+    if (d->struct_size != (int32_t)sizeof(fsm_desc))
+        return fail(-EINVAL, "fsm_desc size mismatch: caller %d, library %d", d->struct_size, (int)sizeof(fsm_desc));
+    if (d->ndim < 2 || d->ndim > 3) return fail(-ENOSYS, "ndim=%d: only 2-D and 3-D grids are supported by this build", d->ndim);
+    if (d->dtype != FSM_F32 && d->dtype != FSM_F64) return fail(-EINVAL, "bad dtype %d", d->dtype);
+    if (d->batch < 1 || d->channels < 1) return fail(-EINVAL, "batch and channels must be positive");
+    fsm_plan* p = new fsm_plan();
+    p->d = *d;
+    p->ndim = d->ndim;
+    p->f64 = d->dtype == FSM_F64;
+    p->B = d->batch;
+    p->C = d->channels;
+    p->prog = d->program;
+    p->ntot = 1;
+    for (int i = 0; i < 3; ++i) {
+        p->n[i] = (i < d->ndim) ? d->n[i] : 1;
+        p->ntot *= p->n[i];
+        if (i < d->ndim) {
+            const bool ok = p->f64 ? (launch_table<double>(p->n[i]) != nullptr) : (launch_table<float>(p->n[i]) != nullptr);
+            if (!is_pow2(p->n[i]) || !ok) {
+                delete p;
+                return fail(-ENOSYS, "axis %d has %d points: only powers of two in [8, 1024] are supported", i, d->n[i]);
+            }
+            if (!d->dk[i] || !d->dkraw[i]) { delete p; return fail(-EINVAL, "missing wavenumber table for axis %d", i); }
+            if (d->kmax[i] < 0 || d->kmax[i] > p->n[i] / 2) { delete p; return fail(-EINVAL, "bad kmax[%d]=%d", i, d->kmax[i]); }
+        }
+    }
+    const int nlast = p->n[p->ndim - 1];
+    p->nh = nlast / 2 + 1;
+    p->ph = (p->nh + 7) / 8 * 8;
+    p->nmodes = (long)p->nh * (p->ntot / nlast);
+    // program -> kernel program and field counts
+    switch (p->prog) {
+        case FSM_PROG_LINEAR: p->kprog = PROG_NONE; p->nf_ix = 1; p->nfi = 1; p->nout = 1; break;
+        case FSM_PROG_CONVECTION:
+            if (p->C != p->ndim) { delete p; return fail(-EINVAL, "convection needs channels == ndim"); }
+            p->kprog = PROG_CONV; p->nf_ix = 2; p->nfi = (p->ndim == 2) ? 4 : 9; p->nout = p->C; break;
+        case FSM_PROG_KS:
+            if (p->C != 1) { delete p; return fail(-EINVAL, "KS convection needs one channel"); }
+            p->kprog = PROG_KS; p->nf_ix = 2; p->nfi = (p->ndim == 2) ? 2 : 3; p->nout = 1; break;
+        case FSM_PROG_NS2D_VORT:
+            if (p->C != 1 || p->ndim != 2) { delete p; return fail(-EINVAL, "vorticity convection needs a 2-D scalar field"); }
+            p->kprog = PROG_NS2D; p->nf_ix = 4; p->nfi = 4; p->nout = 1; break;
+        case FSM_PROG_NS3D:
+            if (p->C != 3 || p->ndim != 3) { delete p; return fail(-EINVAL, "NS pressure convection needs a 3-D, 3-channel field"); }
+            p->kprog = PROG_NS3D; p->nf_ix = 2; p->nfi = 9; p->nout = 3; break;
+        default: delete p; return fail(-ENOSYS, "unknown program %d", p->prog);
+    }
+    if (p->prog == FSM_PROG_LINEAR && d->integrator != FSM_INT_ETDRK0 && d->integrator != FSM_INT_RK4) {
+        // a purely linear operator under an ETD scheme: the nonlinear term is identically zero
+    }
+    if (p->prog != FSM_PROG_LINEAR && d->integrator == FSM_INT_ETDRK0) {
+        delete p;
+        return fail(-EINVAL, "The ETDRK0 integrator only supports linear term");
+    }
+    p->stages = build_stages(d->integrator, d->dt, d->tab_lin != nullptr);
+    if (p->stages.empty()) { delete p; return fail(-ENOSYS, "unknown integrator %d", d->integrator); }
+    // right-hand side L u + N(u)
+    {
+        Stage s;
+        s.input = ARR_U; s.n_in = 1; s.in[0] = ARR_U; s.n_out = 1; s.out[0] = ARR_EXT;
+        s.c[0][0] = scal(1.0);
+        s.c[0][1] = d->tab_lin ? tabc(TAB_LIN) : scal(0.0);
+        p->rhs_stage = s;
+    }
+    // chunking: keep the per-chunk intermediates of 2-D runs inside the 126 MB L2
+    const size_t esz = p->f64 ? 16 : 8;
+    const long plane = (long)p->n[0] * p->n[1];
+    size_t w1_per, w2_per, w3_per = 0, w2b_per = 0;
+    if (p->ndim == 2) {
+        w1_per = (size_t)p->C * p->nf_ix * p->n[0] * p->ph * esz;
+        w2_per = (size_t)p->nout * p->nmodes * esz;
+    } else {
+        w1_per = (size_t)p->C * p->nf_ix * p->nh * plane * esz;
+        w3_per = (size_t)p->nfi * plane * p->ph * esz;
+        w2_per = (size_t)p->nout * p->nh * plane * esz;
+        w2b_per = (size_t)p->nout * p->nmodes * esz;
+    }
+    int chunk = d->chunk;
+    if (chunk <= 0) {
+        const size_t per = w1_per + w2_per + w3_per + w2b_per;
+        const size_t budget = (size_t)48 << 20;
+        chunk = (int)(budget / (per ? per : 1));
+        if (chunk < 1) chunk = 1;
+    }
+    if (chunk > p->B) chunk = p->B;
+    p->chunk = chunk;
+    // workspace layout
+    size_t off = 0;
+    const size_t state_bytes = (size_t)p->B * p->C * p->nmodes * esz;
+    int n_scratch = 0;
+    for (const Stage& s : p->stages) {
+        for (int i = 0; i < s.n_out; ++i) if (s.out[i] >= ARR_S1 && s.out[i] <= ARR_S4 && s.out[i] > n_scratch) n_scratch = s.out[i];
+    }
+    for (int i = 0; i < ARR_COUNT; ++i) p->off_arr[i] = 0;
+    for (int i = ARR_S1; i <= ARR_S4; ++i) {
+        p->off_arr[i] = off;
+        if (i <= n_scratch) off = align_up(off + state_bytes, 256);
+    }
+    p->off_w1 = off; off = align_up(off + w1_per * chunk, 256);
+    p->off_w2 = off; off = align_up(off + w2_per * chunk, 256);
+    p->off_w3 = off; off = align_up(off + w3_per * chunk, 256);
+    p->off_w2b = off; off = align_up(off + w2b_per * chunk, 256);
+    p->off_dc = off; off = align_up(off + (size_t)p->B * (p->f64 ? 8 : 4), 256);
+    p->ws_bytes = off;
+    // generic transforms process this many independent fields per launch
+    size_t cap = (size_t)chunk * p->C * p->nf_ix;
+    if ((size_t)chunk * p->nout < cap) cap = (size_t)chunk * p->nout;
+    if (p->ndim == 3 && (size_t)chunk * p->nfi < cap) cap = (size_t)chunk * p->nfi;
+    p->cap_fields = cap < 1 ? 1 : cap;
+    // bookkeeping for benchmarks (SURVEY.md §8d transform-pass model)
+    {
+        const int nchunks = (p->B + chunk - 1) / chunk;
+        int64_t launches = 0, units = 0;  // units of one real field
+        for (const Stage& s : p->stages) {
+            if (p->prog == FSM_PROG_LINEAR) {
+                launches += 1;
+            } else {
+                launches += (int64_t)nchunks * (p->ndim == 2 ? 3 : 5) + ((p->prog == FSM_PROG_KS && d->ks_remove_mean) ? 1 : 0);
+                const int cnf = p->C * p->nf_ix;
+                if (p->ndim == 2) units += (p->C + cnf) + (p->nfi + p->nout) + p->nout;
+                else units += (p->C + cnf) + (cnf + p->nfi) + (p->nfi + p->nout) + 2 * p->nout + p->nout;
+            }
+            units += (int64_t)(s.n_in + s.n_out) * p->C;
+        }
+        p->launches_per_step = launches;
+        p->algo_bytes_per_step = units * (int64_t)p->ntot * (p->f64 ? 8 : 4) * p->B;
+    }
+    *out = p;
+    return 0;
+}
+
+void fsm_plan_destroy(fsm_plan* plan) { delete plan; }
+
+size_t fsm_workspace_bytes(const fsm_plan* plan) { return plan ? plan->ws_bytes : 0; }
+
+int fsm_plan_info(const fsm_plan* plan, int64_t* launches_per_step, int64_t* algo_bytes_per_step,
+                  int64_t* modes_per_field, int32_t* chunk) {
+    if (!plan) return fail(-EINVAL, "null plan");
+    if (launches_per_step) *launches_per_step = plan->launches_per_step;
+    if (algo_bytes_per_step) *algo_bytes_per_step = plan->algo_bytes_per_step;
+    if (modes_per_field) *modes_per_field = plan->nmodes;
+    if (chunk) *chunk = plan->chunk;
+    return 0;
+}
+
+#define FSM_CHECK_WS(plan, ws, bytes)                                                        \
+    if (!(plan)) return fail(-EINVAL, "null plan");                                          \
+    if (!(ws) || (bytes) < (plan)->ws_bytes)                                                 \
+        return fail(-ENOMEM, "workspace too small: %zu bytes given, %zu needed", (size_t)(bytes), (plan)->ws_bytes);
+
+int fsm_step(fsm_plan* plan, void* u_hat, void* workspace, size_t ws_bytes, int n_steps, void* stream) {
+    FSM_CHECK_WS(plan, workspace, ws_bytes);
+    if (!u_hat || n_steps < 0) return fail(-EINVAL, "bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return plan->f64 ? do_step<double>(plan, u_hat, workspace, n_steps, st) : do_step<float>(plan, u_hat, workspace, n_steps, st);
+}
+
+int fsm_rhs(fsm_plan* plan, const void* u_hat, void* out_hat, void* workspace, size_t ws_bytes, void* stream) {
+    FSM_CHECK_WS(plan, workspace, ws_bytes);
+    if (!u_hat || !out_hat || u_hat == out_hat) return fail(-EINVAL, "bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return plan->f64 ? do_rhs<double>(plan, u_hat, out_hat, workspace, st) : do_rhs<float>(plan, u_hat, out_hat, workspace, st);
+}
+
+int fsm_r2c(fsm_plan* plan, const void* u, void* u_hat, void* workspace, size_t ws_bytes, void* stream) {
+    FSM_CHECK_WS(plan, workspace, ws_bytes);
+    if (!u || !u_hat) return fail(-EINVAL, "bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return plan->f64 ? do_r2c<double>(plan, u, u_hat, workspace, st) : do_r2c<float>(plan, u, u_hat, workspace, st);
+}
+
+int fsm_c2r(fsm_plan* plan, const void* u_hat, void* u, void* workspace, size_t ws_bytes, void* stream) {
+    FSM_CHECK_WS(plan, workspace, ws_bytes);
+    if (!u || !u_hat) return fail(-EINVAL, "bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return plan->f64 ? do_c2r<double>(plan, u_hat, u, workspace, st) : do_c2r<float>(plan, u_hat, u, workspace, st);
+}
+
+int fsm_half_to_full(fsm_plan* plan, const void* u_hat, void* full_hat, void* stream) {
+    if (!plan || !u_hat || !full_hat) return fail(-EINVAL, "bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long nf = (long)plan->B * plan->C;
+    const long total = nf * plan->ntot;
+    dim3 grid((unsigned)((total + 255) / 256)), block(256);
+    if (plan->f64) {
+        auto kern = k_half_to_full<double>;
+        FSM_LAUNCH(kern, grid, block, 0, st, make_geom<double>(plan, true), (const cplx<double>*)u_hat, (cplx<double>*)full_hat, nf);
+    } else {
+        auto kern = k_half_to_full<float>;
+        FSM_LAUNCH(kern, grid, block, 0, st, make_geom<float>(plan, true), (const cplx<float>*)u_hat, (cplx<float>*)full_hat, nf);
+    }
+    return 0;
+}
+
+int fsm_full_to_half(fsm_plan* plan, const void* full_hat, void* u_hat, void* stream) {
+    if (!plan || !u_hat || !full_hat) return fail(-EINVAL, "bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long nf = (long)plan->B * plan->C;
+    const long total = nf * plan->nmodes;
+    dim3 grid((unsigned)((total + 255) / 256)), block(256);
+    if (plan->f64) {
+        auto kern = k_full_to_half<double>;
+        FSM_LAUNCH(kern, grid, block, 0, st, make_geom<double>(plan, true), (const cplx<double>*)full_hat, (cplx<double>*)u_hat, nf);
+    } else {
+        auto kern = k_full_to_half<float>;
+        FSM_LAUNCH(kern, grid, block, 0, st, make_geom<float>(plan, true), (const cplx<float>*)full_hat, (cplx<float>*)u_hat, nf);
+    }
+    return 0;
+}
+
+}  // extern "C"

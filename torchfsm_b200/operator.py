@@ -1,0 +1,577 @@
+"""Operator algebra and the ``integrate`` driver — the reference-facing plugin surface.
+
+Same names, argument meaning and error behaviour as the reference's operator layer for the hot
+path (``torchfsm/operator/_base.py``): operators are sums of generator terms, ``integrate(u_0,
+u_0_fft, dt, step, mesh, progressive, trajectory_recorder, return_in_fourier)`` advances a
+state, ``__call__`` evaluates the right-hand side, ``set_integrator`` picks the scheme.
+What differs is what ``_build_integrator`` installs: instead of a torch integrator object the
+operator is lowered to a *fused step program* executed by the CUDA library through the C ABI
+(``include/fsm_b200.h``). Anything the fused programs cannot express raises
+``NotImplementedError`` — there is no torch/CPU fallback on this path.
+"""
+import ctypes
+import os
+from typing import Callable, List, Optional, Sequence, Union
+
+import torch
+
+from . import _cabi
+from .integrator import (ETDRKIntegrator, SETDRKIntegrator, RKIntegrator, integrator_name, build_tables)
+from .mesh import FourierMesh, MeshGrid
+
+_LINEAR_KINDS = ("laplacian", "biharmonic", "spatial_derivative", "implicit_unit_source")
+_PROGRAM_OF = {"convection": _cabi.PROG_CONVECTION, "ks_convection": _cabi.PROG_KS,
+               "vorticity_convection": _cabi.PROG_NS2D_VORT, "ns_pressure_convection": _cabi.PROG_NS3D}
+
+
+class _Term:
+    __slots__ = ("kind", "coef", "params")
+
+    def __init__(self, kind, coef=1, params=None):
+        self.kind, self.coef, self.params = kind, coef, dict(params or {})
+
+    def scaled(self, s):
+        return _Term(self.kind, self.coef * s, self.params)
+
+
+# ------------------------------------------------------------------------------------------------
+# rot-half layout helpers (see include/fsm_b200.h)
+# ------------------------------------------------------------------------------------------------
+def _rot_half(t: torch.Tensor, shape) -> torch.Tensor:
+    """(X, n0[, n1[, n2]]) full-layout tensor -> (X, rot-half modes) contiguous."""
+    nd = len(shape)
+    nh = shape[-1] // 2 + 1
+    t = t[..., :nh]
+    if nd == 2:
+        t = t.permute(0, 2, 1)
+    elif nd == 3:
+        t = t.permute(0, 2, 3, 1)
+    return t.contiguous()
+
+
+def _expand_table(t: torch.Tensor, shape) -> torch.Tensor:
+    """Broadcastable (1|B, 1|C, ...) reference-layout table -> (Ct, *shape)."""
+    if t.shape[0] != 1:
+        raise NotImplementedError("batched (per-sample) coefficients are not supported by the fused CUDA path")
+    t = t[0]
+    return t.expand(t.shape[0], *shape)
+
+
+class FusedStepper:
+    """What ``_build_integrator`` installs: a plan of the CUDA library plus the buffers it needs.
+
+    Exposes the reference's integrator protocol on full-spectrum tensors (``.dt``, ``.step(u_hat)``,
+    ``.forward(u_hat, dt)``; operator/_base.py:462-491) and the native half-spectrum entry points
+    used by ``integrate``.
+    """
+
+    def __init__(self, f_mesh: FourierMesh, batch: int, n_channel: int, program: int, integrator: str, dt: float,
+                 linear_coef: Optional[torch.Tensor], nl_coef: float, source_hat: Optional[torch.Tensor],
+                 kmax: Sequence[int], ks_remove_mean: bool, integrator_cfg: dict, chunk: int = 0,
+                 tables: Optional[dict] = None):
+        lib = _cabi.lib()
+        self.f_mesh, self.B, self.C, self.dt = f_mesh, batch, n_channel, dt
+        self.shape = tuple(f_mesh.shape)
+        self.n_dim = len(self.shape)
+        self.device, self.rdtype, self.cdtype = f_mesh.device, f_mesh.dtype, f_mesh.cdtype
+        if self.device.type != "cuda" and not _cabi.is_emulator():
+            raise RuntimeError("torchfsm_b200 runs on CUDA devices only (tensor is on %s)" % self.device)
+        nh = self.shape[-1] // 2 + 1
+        self.nmodes = nh
+        for n in self.shape[:-1]:
+            self.nmodes *= n
+        self.integrator = integrator
+        self._keep = []  # tensors referenced by the plan descriptor
+
+        def real_table(t):
+            t = _expand_table(t, self.shape)
+            if t.is_complex():
+                if float(t.imag.abs().max()) != 0.0:
+                    raise NotImplementedError(
+                        "complex linear coefficients (odd-order linear terms) are not supported by the fused CUDA path")
+                t = t.real
+            if t.shape[0] > 1 and bool((t == t[:1]).all()):
+                t = t[:1]
+            return t.to(self.rdtype)
+
+        desc = _cabi.FsmDesc()
+        desc.struct_size = ctypes.sizeof(_cabi.FsmDesc)
+        desc.dtype = _cabi.FSM_F32 if self.rdtype == torch.float32 else _cabi.FSM_F64
+        desc.ndim = self.n_dim
+        for i in range(3):
+            desc.n[i] = self.shape[i] if i < self.n_dim else 1
+            desc.kmax[i] = int(kmax[i]) if i < self.n_dim else 0
+        desc.batch, desc.channels = batch, n_channel
+        desc.program = program
+        desc.integrator = _cabi.INTEGRATOR_IDS[integrator]
+        desc.ks_remove_mean = 1 if ks_remove_mean else 0
+        desc.chunk = int(chunk or int(os.environ.get("FSM_CHUNK", "0")))
+        desc.dt = float(dt)
+        desc.nl_coef = float(nl_coef)
+        dk, dkraw = f_mesh.wavenumber_tables()
+        for i in range(self.n_dim):
+            self._keep += [dk[i], dkraw[i]]
+            desc.dk[i] = dk[i].data_ptr()
+            desc.dkraw[i] = dkraw[i].data_ptr()
+        # ---- coefficient tables (reference expressions, then re-laid out)
+        self.tables_full = {}
+        tab_channels = 1
+        if tables is None:
+            L = linear_coef
+            if L is None:                                    # operator/_base.py:473-478
+                L = torch.tensor([0.0], dtype=self.cdtype, device=self.device).reshape([1] * (self.n_dim + 2))
+            tables = build_tables(integrator, dt, L, **integrator_cfg)
+        self.tables_full = tables
+        rot = {}
+        for k, t in tables.items():
+            rt = real_table(t)
+            rot[k] = rt
+            tab_channels = max(tab_channels, rt.shape[0])
+        if linear_coef is not None:
+            rot["lin"] = real_table(linear_coef)
+            tab_channels = max(tab_channels, rot["lin"].shape[0])
+        for k in list(rot):
+            t = rot[k]
+            if t.shape[0] != tab_channels:
+                t = t.expand(tab_channels, *t.shape[1:])
+            rot[k] = _rot_half(t, self.shape)
+            self._keep.append(rot[k])
+        desc.tab_channels = tab_channels
+        if "exp" in rot:
+            desc.tab_exp = rot["exp"].data_ptr()
+        if "half_exp" in rot:
+            desc.tab_half_exp = rot["half_exp"].data_ptr()
+        for i in range(6):
+            if f"coef_{i + 1}" in rot:
+                desc.tab_coef[i] = rot[f"coef_{i + 1}"].data_ptr()
+        if "lin" in rot:
+            desc.tab_lin = rot["lin"].data_ptr()
+        if source_hat is not None:
+            s = _expand_table(source_hat, self.shape)
+            if s.shape[0] not in (1, n_channel):
+                raise ValueError("explicit source has an incompatible channel count")
+            s = s.expand(n_channel, *self.shape).to(self.cdtype)
+            self.source_rot = _rot_half(s, self.shape)
+            self._keep.append(self.source_rot)
+            desc.source_hat = self.source_rot.data_ptr()
+        self.rot_tables = rot
+        self._desc = desc
+        plan = ctypes.c_void_p()
+        _cabi.check(lib.fsm_plan_create(ctypes.byref(plan), ctypes.byref(desc)), "plan_create")
+        self._plan = plan
+        self._lib = lib
+        ws = lib.fsm_workspace_bytes(plan)
+        self.workspace = torch.empty(max(ws, 16), dtype=torch.uint8, device=self.device)
+        self.ws_bytes = ws
+
+    # ---- plumbing ---------------------------------------------------------------------------
+    def __del__(self):
+        try:
+            if getattr(self, "_plan", None):
+                self._lib.fsm_plan_destroy(self._plan)
+                self._plan = None
+        except Exception:
+            pass
+
+    def _stream(self):
+        if self.device.type == "cuda":
+            return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        return ctypes.c_void_p(0)
+
+    def info(self):
+        a, b, c, d = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int32()
+        _cabi.check(self._lib.fsm_plan_info(self._plan, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c),
+                                            ctypes.byref(d)), "plan_info")
+        return {"launches_per_step": a.value, "algo_bytes_per_step": b.value, "modes_per_field": c.value,
+                "chunk": d.value}
+
+    def empty_half(self):
+        return torch.empty((self.B, self.C, self.nmodes), dtype=self.cdtype, device=self.device)
+
+    # ---- native entry points (rot-half state) -------------------------------------------------
+    def r2c(self, u: torch.Tensor) -> torch.Tensor:
+        u = u.to(self.rdtype).contiguous()
+        out = self.empty_half()
+        _cabi.check(self._lib.fsm_r2c(self._plan, u.data_ptr(), out.data_ptr(), self.workspace.data_ptr(),
+                                      self.ws_bytes, self._stream()), "r2c")
+        return out
+
+    def c2r(self, u_hat: torch.Tensor) -> torch.Tensor:
+        out = torch.empty((self.B, self.C) + self.shape, dtype=self.rdtype, device=self.device)
+        _cabi.check(self._lib.fsm_c2r(self._plan, u_hat.data_ptr(), out.data_ptr(), self.workspace.data_ptr(),
+                                      self.ws_bytes, self._stream()), "c2r")
+        return out
+
+    def half_to_full(self, u_hat: torch.Tensor) -> torch.Tensor:
+        out = torch.empty((self.B, self.C) + self.shape, dtype=self.cdtype, device=self.device)
+        _cabi.check(self._lib.fsm_half_to_full(self._plan, u_hat.data_ptr(), out.data_ptr(), self._stream()),
+                    "half_to_full")
+        return out
+
+    def full_to_half(self, full_hat: torch.Tensor) -> torch.Tensor:
+        full_hat = full_hat.to(self.cdtype).contiguous()
+        out = self.empty_half()
+        _cabi.check(self._lib.fsm_full_to_half(self._plan, full_hat.data_ptr(), out.data_ptr(), self._stream()),
+                    "full_to_half")
+        return out
+
+    def step_half(self, u_hat: torch.Tensor, n_steps: int = 1) -> torch.Tensor:
+        """Advance the rot-half state in place by ``n_steps``."""
+        _cabi.check(self._lib.fsm_step(self._plan, u_hat.data_ptr(), self.workspace.data_ptr(), self.ws_bytes,
+                                       int(n_steps), self._stream()), "step")
+        return u_hat
+
+    def rhs_half(self, u_hat: torch.Tensor) -> torch.Tensor:
+        out = self.empty_half()
+        _cabi.check(self._lib.fsm_rhs(self._plan, u_hat.data_ptr(), out.data_ptr(), self.workspace.data_ptr(),
+                                      self.ws_bytes, self._stream()), "rhs")
+        return out
+
+    # ---- reference integrator protocol (full spectra) -------------------------------------------
+    def step(self, u_hat_full: torch.Tensor) -> torch.Tensor:
+        h = self.full_to_half(u_hat_full)
+        return self.half_to_full(self.step_half(h, 1))
+
+    def forward(self, u_hat_full: torch.Tensor, dt: float) -> torch.Tensor:
+        return self.step(u_hat_full)
+
+
+# ------------------------------------------------------------------------------------------------
+# Operators
+# ------------------------------------------------------------------------------------------------
+class OperatorLike:
+    """Sum of generator terms (mirror of ``OperatorLike``/``Operator``, operator/_base.py:286-850)."""
+
+    def __init__(self, terms: Optional[List[_Term]] = None):
+        self.terms: List[_Term] = list(terms or [])
+        self._de_aliasing_rate = 2 / 3
+        self._integrator = "auto"
+        self._integrator_config = {}
+        self._value_mesh_check_func: Callable[[int, int], bool] = lambda dim_value, dim_mesh: True
+        self._state_dict = {"f_mesh": None, "n_channel": None, "linear_coef": None, "integrator": None}
+        self._lowered = None
+        self._chunk = 0
+
+    # ---- algebra (operator/_base.py:170-206, 826-850) ------------------------------------------
+    def _new(self, terms):
+        op = Operator(terms)
+        op._value_mesh_check_func = self._value_mesh_check_func
+        return op
+
+    def __add__(self, other):
+        if isinstance(other, OperatorLike):
+            return self._new(self.terms + other.terms)
+        if isinstance(other, torch.Tensor):
+            return self._new(self.terms + [_Term("explicit_source", 1, {"source": other})])
+        return NotImplemented
+
+    __radd__ = __add__
+    __iadd__ = __add__
+
+    def __mul__(self, other):
+        if isinstance(other, OperatorLike):
+            return NotImplemented
+        return self._new([t.scaled(other) for t in self.terms])
+
+    __rmul__ = __mul__
+    __imul__ = __mul__
+
+    def __neg__(self):
+        return self._new([t.scaled(-1) for t in self.terms])
+
+    def __sub__(self, other):
+        try:
+            return self + (-1 * other)
+        except Exception:
+            return NotImplemented
+
+    def __rsub__(self, other):
+        try:
+            return other + (-1 * self)
+        except Exception:
+            return NotImplemented
+
+    def __truediv__(self, other):
+        try:
+            return self * (1 / other)
+        except Exception:
+            return NotImplemented
+
+    # ---- configuration ------------------------------------------------------------------------------
+    def set_integrator(self, integrator, **integrator_config):
+        """operator/_base.py:646-674"""
+        if isinstance(integrator, str):
+            assert integrator == "auto", ("The integrator should be 'auto' or an instance of ETDRKIntegrator, "
+                                          "SETDRKIntegrator or RKIntegrator")
+        else:
+            assert isinstance(integrator, (ETDRKIntegrator, SETDRKIntegrator, RKIntegrator)), (
+                "The integrator should be 'auto' or an instance of ETDRKIntegrator, SETDRKIntegrator or RKIntegrator")
+        self._integrator = integrator
+        self._integrator_config = integrator_config
+        self._state_dict["integrator"] = None
+
+    def set_de_aliasing_rate(self, de_aliasing_rate: float):
+        """operator/_base.py:273-281 (the reference's version breaks the next call; this one re-registers)."""
+        self._de_aliasing_rate = de_aliasing_rate
+        self._state_dict["integrator"] = None
+        self._lowered = None
+
+    def set_chunk(self, chunk: int):
+        """Samples per pass launch (0 = library default); a tuning knob of the CUDA path."""
+        self._chunk = int(chunk)
+        self._state_dict["integrator"] = None
+
+    def register_additional_check(self, func: Callable[[int, int], bool]):
+        self._value_mesh_check_func = func
+
+    @property
+    def is_linear(self) -> bool:
+        return all(t.kind in _LINEAR_KINDS for t in self.terms)
+
+    # ---- lowering ----------------------------------------------------------------------------------
+    def register_mesh(self, mesh, n_channel: int, device=None, dtype=None):
+        """operator/_base.py:581-624: build L and classify the nonlinear part into a fused program."""
+        f_mesh = mesh if isinstance(mesh, FourierMesh) and device is None and dtype is None \
+            else FourierMesh(mesh, device=device, dtype=dtype)
+        self._state_dict = {"f_mesh": f_mesh, "n_channel": n_channel, "linear_coef": None, "integrator": None}
+        lin = []
+        program, nl_coef, ks_remove_mean = _cabi.PROG_LINEAR, 0.0, True
+        source_hat = None
+        for t in self.terms:
+            if t.kind in _LINEAR_KINDS:
+                lin.append(t)
+            elif t.kind in _PROGRAM_OF:
+                if program != _cabi.PROG_LINEAR:
+                    raise NotImplementedError("only one convective nonlinear term per operator is supported "
+                                              "by the fused CUDA path")
+                if isinstance(t.coef, torch.Tensor):
+                    raise NotImplementedError("tensor-valued coefficients on nonlinear terms are not supported")
+                program, nl_coef = _PROGRAM_OF[t.kind], float(t.coef)
+                if t.kind == "convection" and f_mesh.n_dim != n_channel:
+                    raise ValueError("convection operator only works for vector field with the same dimension as mesh")
+                if t.kind == "vorticity_convection" and (f_mesh.n_dim != 2 or n_channel != 1):
+                    raise ValueError("Only vorticity in 2Dmesh is supported")
+                if t.kind == "ks_convection":
+                    if n_channel != 1:
+                        raise NotImplementedError("KSConvection only supports scalar field")
+                    ks_remove_mean = bool(t.params.get("remove_mean", True))
+                if t.kind == "ns_pressure_convection" and t.params.get("external_force") is not None:
+                    raise NotImplementedError("NSPressureConvection with an external force is not supported "
+                                              "by the fused CUDA path")
+            elif t.kind == "explicit_source":
+                src = t.params["source"].to(device=f_mesh.device)
+                s_hat = torch.fft.fftn(src, dim=list(range(2, src.dim())))        # operator/_base.py:1002-1005
+                s_hat = t.coef * s_hat
+                source_hat = s_hat if source_hat is None else source_hat + s_hat
+            else:
+                raise ValueError(f"Operator {t.kind} is not supported")
+        L = None
+        if lin:                                                                   # operator/_base.py:339-357
+            L = sum(t.coef * self._linear_core(t, f_mesh, n_channel) for t in lin)
+        if program == _cabi.PROG_LINEAR and source_hat is not None:
+            raise NotImplementedError("an explicit source without a convective term is not supported "
+                                      "by the fused CUDA path")
+        kmax = f_mesh.low_pass_kmax(self._de_aliasing_rate) if program != _cabi.PROG_LINEAR \
+            else [n // 2 for n in f_mesh.shape]
+        self._state_dict["linear_coef"] = L
+        self._lowered = dict(program=program, nl_coef=nl_coef, ks_remove_mean=ks_remove_mean,
+                             source_hat=source_hat, kmax=kmax)
+
+    @staticmethod
+    def _linear_core(t: _Term, f_mesh: FourierMesh, n_channel: int) -> torch.Tensor:
+        if t.kind == "laplacian":                                                 # generic/_laplacian.py:12-15
+            return torch.cat([f_mesh.laplacian()] * n_channel, dim=1)
+        if t.kind == "biharmonic":                                                # generic/_biharmonic.py:13-16
+            return torch.cat([f_mesh.laplacian() * f_mesh.laplacian()] * n_channel, dim=1)
+        if t.kind == "spatial_derivative":                                        # generic/_spatial_derivative.py
+            if n_channel != 1:
+                raise ValueError("The SpatialDerivative operator only supports scalar field.")
+            return f_mesh.grad(t.params["dim_index"], t.params["order"])
+        if t.kind == "implicit_unit_source":                                      # generic/_source.py:14-17
+            return torch.ones_like(f_mesh.bf(0))
+        raise ValueError(t.kind)
+
+    def _pre_check(self, u, u_fft, mesh):
+        """operator/_base.py:528-579"""
+        if u_fft is None and u is None:
+            raise ValueError("Either u or u_fft should be given")
+        if u_fft is not None and u is not None:
+            assert u.shape == u_fft.shape, "The shape of u and u_fft should be the same"
+        assert mesh is not None, "Mesh should be given"
+        value = u if u is not None else u_fft
+        if value.requires_grad:
+            raise NotImplementedError("the fused CUDA path is forward-only; detach the input first")
+        if not isinstance(mesh, FourierMesh):
+            if isinstance(mesh, MeshGrid):
+                mesh = FourierMesh(mesh, device=value.device, dtype=mesh.dtype)
+            else:
+                mesh = FourierMesh(mesh, device=value.device, dtype=value.dtype)
+        n_channel = value.shape[1]
+        assert len(value.shape) == mesh.n_dim + 2, \
+            f"the value shape {tuple(value.shape)} is not compatible with mesh dim {mesh.n_dim}"
+        for i in range(mesh.n_dim):
+            assert value.shape[i + 2] == mesh.mesh_info[i][2], \
+                f"Expect to have {mesh.mesh_info[i][2]} points in dim {i} but got {value.shape[i + 2]}"
+        assert value.device == mesh.device, \
+            "The device of mesh {} and the device of value {} are not the same".format(mesh.device, value.device)
+        assert self._value_mesh_check_func(len(value.shape) - 2, mesh.n_dim), \
+            "Value and mesh do not match the requirement"
+        return mesh, n_channel
+
+    def _build_integrator(self, dt: float, batch: int, tables: Optional[dict] = None, rhs_only: bool = False):
+        """operator/_base.py:441-526: installs a FusedStepper in ``_state_dict['integrator']``.
+
+        ``rhs_only`` plans the bare right-hand side (no ETD tables needed) and does not install it."""
+        sd, lo = self._state_dict, self._lowered
+        if rhs_only:
+            name, cfg = "RK4", {}
+        else:
+            name, cfg = integrator_name(self._integrator, lo["program"] == _cabi.PROG_LINEAR), self._integrator_config
+        if name == "ETDRK0":
+            assert lo["program"] == _cabi.PROG_LINEAR, "The ETDRK0 integrator only supports linear term"
+        try:
+            st = FusedStepper(sd["f_mesh"], batch, sd["n_channel"], lo["program"], name, dt, sd["linear_coef"],
+                              lo["nl_coef"], lo["source_hat"], lo["kmax"], lo["ks_remove_mean"], cfg,
+                              chunk=self._chunk, tables=tables)
+        except torch.cuda.OutOfMemoryError as e:
+            raise RuntimeError(os.linesep.join([
+                "Cuda out of memory when building the integrator.",
+                "Original error message: {}".format(str(e)),
+                "Please try to use a smaller mesh or a low-order integrator."]))
+        if rhs_only:
+            self._rhs_stepper = st
+        else:
+            sd["integrator"] = st
+        return st
+
+    def _stepper_for(self, value, mesh, dt):
+        if self._state_dict["f_mesh"] is None or mesh is not None or self._lowered is None:
+            mesh, n_channel = self._pre_check(value[0], value[1], mesh if mesh is not None else self._state_dict["f_mesh"])
+            self.register_mesh(mesh, n_channel)
+        else:
+            self._pre_check(value[0], value[1], self._state_dict["f_mesh"])
+        v = value[0] if value[0] is not None else value[1]
+        st = self._state_dict["integrator"]
+        if st is None or st.dt != dt or st.B != v.shape[0]:
+            st = self._build_integrator(dt, v.shape[0])
+        return st
+
+    # ---- the hot path ----------------------------------------------------------------------------------
+    def integrate(self, u_0: Optional[torch.Tensor] = None, u_0_fft: Optional[torch.Tensor] = None, dt: float = 1,
+                  step: int = 1, mesh=None, progressive: bool = False, trajectory_recorder=None,
+                  return_in_fourier: bool = False):
+        """operator/_base.py:676-751 — same signature and return conventions."""
+        st = self._stepper_for((u_0, u_0_fft), mesh, dt)
+        try:
+            u_hat = st.r2c(u_0) if u_0_fft is None else st.full_to_half(u_0_fft)
+            bar = None
+            if progressive:
+                from tqdm.auto import tqdm
+                bar = tqdm(total=step, desc="Integrating")
+            if trajectory_recorder is None and bar is None:
+                st.step_half(u_hat, step)
+            else:
+                i = 0
+                control = getattr(trajectory_recorder, "control_func", None) if trajectory_recorder is not None else None
+                while i < step:
+                    if trajectory_recorder is not None and (control is None or control(i)):
+                        trajectory_recorder.record(i, st.half_to_full(u_hat))
+                    # fuse the steps up to the next frame the recorder may want
+                    j = i + 1
+                    if control is not None or trajectory_recorder is None:
+                        limit = min(step, i + (max(1, step // 100) if bar is not None else step))
+                        while j < limit and not (control is not None and control(j)):
+                            j += 1
+                    st.step_half(u_hat, j - i)
+                    if bar is not None:
+                        bar.update(j - i)
+                    i = j
+            if bar is not None:
+                bar.close()
+            if trajectory_recorder is not None:
+                trajectory_recorder.record(step, st.half_to_full(u_hat))
+                trajectory_recorder.return_in_fourier = return_in_fourier
+                return trajectory_recorder.trajectory
+            return st.half_to_full(u_hat) if return_in_fourier else st.c2r(u_hat)
+        except torch.cuda.OutOfMemoryError as e:
+            raise RuntimeError(os.linesep.join([
+                "Cuda out of memory when integrating the operator.",
+                "Original error message: {}".format(str(e)),
+                "Please try to use a smaller mesh or a low-order integrator."]))
+
+    def __call__(self, u: Optional[torch.Tensor] = None, u_fft: Optional[torch.Tensor] = None, mesh=None,
+                 return_in_fourier: bool = False):
+        """operator/_base.py:753-790 — evaluate L u + N(u) once."""
+        if self._state_dict["f_mesh"] is None or mesh is not None or self._lowered is None:
+            m, n_channel = self._pre_check(u, u_fft, mesh if mesh is not None else self._state_dict["f_mesh"])
+            self.register_mesh(m, n_channel)
+            self._rhs_stepper = None
+        else:
+            self._pre_check(u, u_fft, self._state_dict["f_mesh"])
+        v = u if u is not None else u_fft
+        st = getattr(self, "_rhs_stepper", None)
+        if st is None or st.B != v.shape[0] or st.f_mesh is not self._state_dict["f_mesh"]:
+            st = self._build_integrator(1.0, v.shape[0], rhs_only=True)
+        u_hat = st.r2c(u) if u_fft is None else st.full_to_half(u_fft)
+        out = st.rhs_half(u_hat)
+        return st.half_to_full(out) if return_in_fourier else st.c2r(out)
+
+
+class Operator(OperatorLike):
+    pass
+
+
+class LinearOperator(OperatorLike):
+    pass
+
+
+class NonlinearOperator(OperatorLike):
+    pass
+
+
+# ---- generator wrappers with the reference's class names ------------------------------------------
+def Laplacian() -> Operator:
+    """operator/generic/_laplacian.py:17-25"""
+    return Operator([_Term("laplacian")])
+
+
+def Biharmonic() -> Operator:
+    """operator/generic/_biharmonic.py:19-28"""
+    return Operator([_Term("biharmonic")])
+
+
+def SpatialDerivative(dim_index: int, order: int) -> Operator:
+    """operator/generic/_spatial_derivative.py:42-55"""
+    return Operator([_Term("spatial_derivative", 1, {"dim_index": dim_index, "order": order})])
+
+
+def ImplicitSource(source_func=None, non_linear: bool = True) -> Operator:
+    """operator/generic/_source.py:45-74 (unit form only on the fused path)"""
+    if source_func is not None:
+        raise NotImplementedError("ImplicitSource(source_func) is not supported by the fused CUDA path")
+    return Operator([_Term("implicit_unit_source")])
+
+
+def ExplicitSource(source: torch.Tensor) -> Operator:
+    """operator/_base.py:1018-1028"""
+    return Operator([_Term("explicit_source", 1, {"source": source})])
+
+
+def Convection() -> Operator:
+    """operator/generic/_convection.py:66-76"""
+    return Operator([_Term("convection")])
+
+
+def KSConvection(remove_mean: bool = True) -> Operator:
+    """operator/dedicated/_ks_convection.py:54-67"""
+    return Operator([_Term("ks_convection", 1, {"remove_mean": remove_mean})])
+
+
+def VorticityConvection() -> Operator:
+    """operator/dedicated/_navier_stokes.py:61-72"""
+    return Operator([_Term("vorticity_convection")])
+
+
+def NSPressureConvection(external_force=None) -> Operator:
+    """operator/dedicated/_navier_stokes.py:257-268"""
+    return Operator([_Term("ns_pressure_convection", 1, {"external_force": external_force})])
