@@ -116,6 +116,13 @@ int fsm_full_to_half(fsm_plan* plan, const void* full_hat, void* u_hat, void* st
 int fsm_plan_info(const fsm_plan* plan, int64_t* launches_per_step, int64_t* algo_bytes_per_step,
                   int64_t* modes_per_field, int32_t* chunk);
 
+/* per-pass device timing for benchmarks: when enabled every pass launch is bracketed by CUDA
+ * events on the caller's stream. fsm_profile_read waits for the recorded events, returns summed
+ * milliseconds and launch counts per pass class {0: IX, 1: MID, 2: PHYS, 3: FX+combine} since the
+ * last read, and the algorithmic bytes each class moves per step (SURVEY.md §8d model). */
+int fsm_profile_enable(fsm_plan* plan, int on);
+int fsm_profile_read(fsm_plan* plan, double* ms4, int64_t* launches4, int64_t* algo_bytes_per_step4);
+
 const char* fsm_last_error(void);
 int fsm_abi_version(void);
 /* 0 = CUDA sm_100a build (the product); 1 = host emulator build used only by the CPU test-suite */

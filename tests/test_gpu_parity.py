@@ -1,0 +1,186 @@
+"""GPU parity tests (run with -m gpu on a B200). Everything goes through the public plugin layer
+and the C ABI of libfsm_b200.so; the numpy oracle and the golden fixtures are the checkers.
+Nothing here reads /root/reference."""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import golden_names, load_golden, golden_tables, rel_l2
+from product_util import product_from_golden, product_operator
+
+pytestmark = pytest.mark.gpu
+TOL = {"f32": 1e-5, "f64": 1e-12}
+SUPPORTED = [n for n in golden_names() if "1d" not in n]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def cuda_library():
+    from torchfsm_b200 import _cabi
+    _cabi._lib = None
+    lib = _cabi.lib()
+    assert lib.fsm_backend() == 0, "GPU tests must run on the CUDA build, not the emulator"
+    assert torch.cuda.is_available()
+    yield
+
+
+@pytest.mark.parametrize("name", SUPPORTED)
+def test_cuda_matches_reference_golden(name):
+    g = load_golden(name)
+    spec, tol = g["spec"], TOL[name[-3:]]
+    op, mesh, u0 = product_from_golden(g, "cuda")
+    u1 = op.integrate(u0, mesh=mesh, dt=spec["dt"], step=1)
+    assert rel_l2(u1.cpu().numpy(), g["u1"]) <= tol
+    uT = op.integrate(u0, dt=spec["dt"], step=spec["steps"])
+    assert rel_l2(uT.cpu().numpy(), g["uT"]) <= tol
+    assert rel_l2(op(u0).cpu().numpy(), g["rhs0"]) <= 10 * tol
+    st = op._state_dict["integrator"]
+    full = st.half_to_full(st.r2c(u0))
+    ref = torch.fft.fftn(torch.from_numpy(g["u0"]), dim=tuple(range(2, u0.dim())))
+    assert rel_l2(full.cpu().numpy(), ref.numpy()) <= tol
+
+
+@pytest.mark.parametrize("name", ["c3_ns2d_32_etdrk2_f32", "c2_ks2d_32_f32", "c4_burgers3d_16_f32"])
+def test_cuda_step_with_reference_tables(name):
+    """Same inputs INCLUDING the reference's own coefficient tables."""
+    g = load_golden(name)
+    spec = g["spec"]
+    op, mesh, u0 = product_from_golden(g, "cuda")
+    m, c = op._pre_check(u0, None, mesh)
+    op.register_mesh(m, c)
+    tabs = {k: torch.from_numpy(v).cuda() for k, v in golden_tables(g).items()}
+    st = op._build_integrator(spec["dt"], u0.shape[0], tables=tabs)
+    u_hat = st.step_half(st.r2c(u0), spec["steps"])
+    assert rel_l2(st.c2r(u_hat).cpu().numpy(), g["uT"]) <= 1e-5
+
+
+def _ns2d_terms(n, dtype):
+    ax = torch.arange(n, dtype=dtype) * (2 * np.pi / n)
+    y = ax.reshape(1, 1, 1, n).expand(1, 1, n, n)
+    src = 4.0 * torch.cos(4.0 * y)
+    return [("vorticity_convection", -1, {}), ("laplacian", 1 / 100, {}), ("implicit_unit_source", -0.1, {}),
+            ("explicit_source", -1, {"source": src})]
+
+
+def _smooth(shape, dtype, seed):
+    g = torch.Generator().manual_seed(seed)
+    u = torch.randn(*shape, generator=g, dtype=dtype)
+    dims = tuple(range(2, len(shape)))
+    u_hat = torch.fft.fftn(u, dim=dims)
+    for d in dims:
+        n = shape[d]
+        f = torch.fft.fftfreq(n, 1.0 / n).abs()
+        keep = (f <= n // 8).to(u_hat.dtype)
+        view = [1] * len(shape)
+        view[d] = n
+        u_hat = u_hat * keep.reshape(view)
+    u = torch.fft.ifftn(u_hat, dim=dims).real
+    return u / u.abs().amax(dim=tuple(range(1, len(shape))), keepdim=True)
+
+
+def _conv(terms, fn):
+    return [(k, c, {kk: (fn(vv) if isinstance(vv, torch.Tensor) else vv) for kk, vv in p.items()}) for k, c, p in terms]
+
+
+@pytest.mark.parametrize("n,batch,dtype,tol", [(256, 3, torch.float32, 1e-5), (128, 2, torch.float64, 1e-12),
+                                               (1024, 1, torch.float32, 1e-5)])
+def test_ns2d_vs_oracle_seeded(n, batch, dtype, tol):
+    """C3-shaped problem at sizes the oracle finishes in seconds; per-step parity over 5 steps."""
+    import torchfsm_b200 as fsm
+    from oracle import OracleOperator
+    mesh_info = [(0, 2 * np.pi, n), (0, 2 * np.pi, n)]
+    terms = _ns2d_terms(n, dtype)
+    u0 = _smooth((batch, 1, n, n), dtype, seed=7)
+    dt = 0.01
+    ora = OracleOperator(_conv(terms, lambda t: t.numpy()))
+    ora.register_mesh(mesh_info, 1, dtype="float32" if dtype == torch.float32 else "float64", workers=8)
+    ora.set_integrator("ETDRK2")
+    integ = ora.build_integrator(dt)
+    op = product_operator(_conv(terms, lambda t: t.cuda()))
+    op.set_integrator(fsm.ETDRKIntegrator.ETDRK2)
+    mesh = fsm.MeshGrid(mesh_info, device="cuda", dtype=dtype)
+    m, c = op._pre_check(u0.cuda(), None, mesh)
+    op.register_mesh(m, c)
+    tabs = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in integ.tables.items()}
+    st = op._build_integrator(dt, batch, tables=tabs)
+    u_hat = st.r2c(u0.cuda())
+    ref_hat = ora.mesh.fft(u0.numpy())
+    for step in range(5):
+        u_hat = st.step_half(u_hat, 1)
+        ref_hat = integ.step(ref_hat)
+        got = st.c2r(u_hat).cpu().numpy()
+        want = ora.mesh.ifft(ref_hat).real
+        assert rel_l2(got, want) <= tol, f"step {step}"
+
+
+@pytest.mark.parametrize("n,batch", [(128, 2)])
+def test_burgers3d_vs_oracle_seeded(n, batch):
+    import torchfsm_b200 as fsm
+    from oracle import OracleOperator
+    mesh_info = [(0, 1, n)] * 3
+    terms = [("laplacian", 0.01, {}), ("convection", -1, {})]
+    u0 = _smooth((batch, 3, n, n, n), torch.float32, seed=11)
+    dt = 0.002
+    ora = OracleOperator(terms).register_mesh(mesh_info, 3, dtype="float32", workers=8)
+    ora.set_integrator("ETDRK2")
+    integ = ora.build_integrator(dt)
+    op = product_operator(terms)
+    op.set_integrator(fsm.ETDRKIntegrator.ETDRK2)
+    mesh = fsm.MeshGrid(mesh_info, device="cuda", dtype=torch.float32)
+    m, c = op._pre_check(u0.cuda(), None, mesh)
+    op.register_mesh(m, c)
+    tabs = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in integ.tables.items()}
+    st = op._build_integrator(dt, batch, tables=tabs)
+    u_hat = st.step_half(st.r2c(u0.cuda()), 2)
+    ref_hat = integ.step(integ.step(ora.mesh.fft(u0.numpy())))
+    assert rel_l2(st.c2r(u_hat).cpu().numpy(), ora.mesh.ifft(ref_hat).real) <= 1e-5
+
+
+# ---------------------------------------------------------------- full-size, size-independent properties
+def test_c3_full_size_properties():
+    """1024^2 x 64 (BASELINE config C3): transform round trip, Parseval, batch independence, Taylor-Green."""
+    import torchfsm_b200 as fsm
+    n, B = 1024, 64
+    mesh = fsm.MeshGrid([(0, 2 * np.pi, n)] * 2, device="cuda", dtype=torch.float32)
+    x, y = mesh.bc_mesh_grid()
+    op = fsm.pde.NavierStokesVorticity(Re=100, force=fsm.field.kolm_force(y))
+    op.set_integrator(fsm.ETDRKIntegrator.ETDRK2)
+    u0 = fsm.field.diffused_noise(mesh, batch_size=B, generator=torch.Generator().manual_seed(0))
+    assert u0.shape == (B, 1, n, n) and torch.isfinite(u0).all()
+    uT = op.integrate(u0, mesh=mesh, dt=0.01, step=3)
+    assert torch.isfinite(uT).all()
+    st = op._state_dict["integrator"]
+    back = st.c2r(st.r2c(u0))
+    assert float((back - u0).norm() / u0.norm()) < 5e-7
+    full = st.half_to_full(st.r2c(u0))
+    assert abs(float((full.abs().double() ** 2).sum() / (n * n) / (u0.double() ** 2).sum()) - 1) < 1e-5
+    del full, back
+    uT2 = op.integrate(u0[:2].contiguous(), dt=0.01, step=3)
+    assert float((uT2 - uT[:2]).norm() / uT[:2].norm()) < 1e-6
+    tg = fsm.pde.NavierStokesVorticity(Re=50)
+    tg.set_integrator(fsm.ETDRKIntegrator.ETDRK2)
+    w0 = (2 * torch.cos(x) * torch.cos(y)).repeat(2, 1, 1, 1)
+    wT = tg.integrate(w0, mesh=mesh, dt=0.05, step=10)
+    assert float((wT - w0 * np.exp(-2 * 0.5 / 50)).abs().max()) < 2e-5
+
+
+def test_c2_ks_batch_mean_property():
+    """KS 256^2: the batch mean couples samples only through the k=0 bin."""
+    import torchfsm_b200 as fsm
+    n = 256
+    mesh = fsm.MeshGrid([(0, 60, n)] * 2, device="cuda", dtype=torch.float32)
+    u0 = torch.randn(8, 1, n, n, generator=torch.Generator().manual_seed(0)).cuda()
+    both = fsm.pde.KuramotoSivashinskyHighDim().integrate(u0, mesh=mesh, dt=0.1, step=3)
+    alone = fsm.pde.KuramotoSivashinskyHighDim().integrate(u0[:1].contiguous(), mesh=mesh, dt=0.1, step=3)
+    diff = (both[:1] - alone).double()
+    assert float(diff.std()) < 1e-5 * float(alone.abs().max()) and torch.isfinite(both).all()
+
+
+def test_pure_diffusion_is_exact_on_gpu():
+    import torchfsm_b200 as fsm
+    n, nu, dt, steps = 512, 0.03, 0.1, 7
+    mesh = fsm.MeshGrid([(0, 1, n), (0, 1, n)], device="cuda", dtype=torch.float64)
+    x, y = mesh.bc_mesh_grid()
+    u0 = torch.sin(2 * np.pi * 3 * x) * torch.cos(2 * np.pi * 2 * y)
+    uT = (nu * fsm.Laplacian()).integrate(u0, mesh=mesh, dt=dt, step=steps)
+    want = np.exp(-nu * (2 * np.pi) ** 2 * 13 * dt * steps) * u0
+    assert float((uT - want).abs().max()) < 1e-12

@@ -32,7 +32,7 @@ class FsmDesc(ctypes.Structure):
 
 
 EXPORTS = ["fsm_plan_create", "fsm_plan_destroy", "fsm_workspace_bytes", "fsm_step", "fsm_rhs", "fsm_r2c",
-           "fsm_c2r", "fsm_half_to_full", "fsm_full_to_half", "fsm_plan_info", "fsm_last_error",
+           "fsm_c2r", "fsm_half_to_full", "fsm_full_to_half", "fsm_plan_info", "fsm_profile_enable", "fsm_profile_read", "fsm_last_error",
            "fsm_abi_version", "fsm_backend"]
 
 _lib = None
@@ -61,6 +61,10 @@ def _declare(lib):
     lib.fsm_full_to_half.restype = i32
     lib.fsm_plan_info.argtypes = [vp, i64p, i64p, i64p, ctypes.POINTER(ctypes.c_int32)]
     lib.fsm_plan_info.restype = i32
+    lib.fsm_profile_enable.argtypes = [vp, i32]
+    lib.fsm_profile_enable.restype = i32
+    lib.fsm_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), i64p, i64p]
+    lib.fsm_profile_read.restype = i32
     lib.fsm_last_error.argtypes = []
     lib.fsm_last_error.restype = ctypes.c_char_p
     lib.fsm_abi_version.restype = i32

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <vector>
+#include <utility>
 
 namespace fsm {
 
@@ -184,9 +185,39 @@ struct fsm_plan {
     size_t off_arr[ARR_COUNT], off_w1, off_w2, off_w3, off_w2b, off_dc, ws_bytes;
     size_t cap_fields;  // how many independent fields the W buffers can hold at once (r2c/c2r)
     int64_t launches_per_step, algo_bytes_per_step;
+    int64_t pass_units[4];  // algorithmic field-units moved per step by each pass class (IX, MID, PHYS, FX)
+    // optional per-pass device timing
+    bool profile = false;
+#ifndef FSM_EMU
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev_used;
+#endif
 };
 
 namespace {
+
+enum { PASS_IX = 0, PASS_MID = 1, PASS_PHYS = 2, PASS_FX = 3 };
+
+#ifndef FSM_EMU
+struct ProfScope {
+    fsm_plan* p;
+    int cls;
+    cudaStream_t st;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    static cudaEvent_t get(fsm_plan* p) {
+        if (!p->ev_pool.empty()) { cudaEvent_t e = p->ev_pool.back(); p->ev_pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+    ProfScope(const fsm_plan* cp, int c, cudaStream_t s) : p(const_cast<fsm_plan*>(cp)), cls(c), st(s) {
+        if (p->profile) { e0 = get(p); e1 = get(p); cudaEventRecord(e0, st); }
+    }
+    ~ProfScope() {
+        if (e0) { cudaEventRecord(e1, st); p->ev_used.push_back({cls, {e0, e1}}); }
+    }
+};
+#else
+struct ProfScope { ProfScope(const fsm_plan*, int, cudaStream_t) {} };
+#endif
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
@@ -317,14 +348,14 @@ int run_forward_tail(const fsm_plan* p, const Buffers<T>& bf, const Geom<T>& g, 
         m.out_o_stride = p->n[0]; m.out_e_stride = (long)p->nh * p->n[0];
         m.nfi = nfields_per_sample; m.n_t = p->n[0]; m.n_outer = p->nh; m.nb = nb;
         m.spec = mid_spec_identity(nfields_per_sample);
-        if (int e = ty->mid(-1, m, st)) return fail(e, "MID forward launch failed");
+        { ProfScope ps(p, PASS_MID, st); if (int e = ty->mid(-1, m, st)) return fail(e, "MID forward launch failed"); }
         fx_in = bf.w2b;
     }
     const LaunchTable<T>* tx = launch_table<T>(p->n[0]);
     FxArgs<T> f;
     f.g = g; f.win = fx_in; f.win_fstride = p->nmodes; f.cb = cb; f.ep = ep;
     f.nlines = (int)(p->nmodes / p->n[0]); f.b0 = b0; f.nb = nb;
-    if (int e = tx->fx(C, f, st)) return fail(e, "FX launch failed (channels=%d, n0=%d)", C, p->n[0]);
+    { ProfScope ps(p, PASS_FX, st); if (int e = tx->fx(C, f, st)) return fail(e, "FX launch failed (channels=%d, n0=%d)", C, p->n[0]); }
     return 0;
 }
 
@@ -361,7 +392,7 @@ int run_stage(const fsm_plan* p, const Buffers<T>& bf, const Stage& s, cudaStrea
             a.w1_fstride = (long)p->n[0] * p->ph;
             a.in_t_stride = p->n[0]; a.in_o_stride = 0; a.out_o_stride = 0; a.out_e_stride = p->ph;
             a.n_t = (p->d.kmax[1] + 1 < p->nh) ? p->d.kmax[1] + 1 : p->nh; a.n_outer = 1;
-            if (int e = tx->ix(p->kprog, a, st)) return fail(e, "IX launch failed");
+            { ProfScope ps(p, PASS_IX, st); if (int e = tx->ix(p->kprog, a, st)) return fail(e, "IX launch failed"); }
             ph.win = bf.w1; ph.win_fstride = a.w1_fstride; ph.wout_fstride = p->nmodes;
             ph.in_t_stride = p->ph; ph.in_o_stride = 0; ph.out_o_stride = 0; ph.out_e_stride = p->n[0];
             ph.n_t = p->n[0]; ph.n_outer = 1;
@@ -371,7 +402,7 @@ int run_stage(const fsm_plan* p, const Buffers<T>& bf, const Stage& s, cudaStrea
             a.in_t_stride = (long)p->nh * p->n[0]; a.in_o_stride = p->n[0];
             a.out_o_stride = plane; a.out_e_stride = p->n[1];
             a.n_t = p->n[1]; a.n_outer = (p->d.kmax[2] + 1 < p->nh) ? p->d.kmax[2] + 1 : p->nh;
-            if (int e = tx->ix(p->kprog, a, st)) return fail(e, "IX launch failed");
+            { ProfScope ps(p, PASS_IX, st); if (int e = tx->ix(p->kprog, a, st)) return fail(e, "IX launch failed"); }
             MidArgs<T> m;
             m.g = g; m.in = bf.w1; m.out = bf.w3;
             m.in_fstride = a.w1_fstride; m.out_fstride = plane * p->ph;
@@ -379,13 +410,13 @@ int run_stage(const fsm_plan* p, const Buffers<T>& bf, const Stage& s, cudaStrea
             m.out_o_stride = (long)p->n[1] * p->ph; m.out_e_stride = p->ph;
             m.nfi = p->C * p->nf_ix; m.n_t = a.n_outer; m.n_outer = p->n[0]; m.nb = nb;
             m.spec = mid_spec_inverse(p);
-            if (int e = ty->mid(+1, m, st)) return fail(e, "MID inverse launch failed");
+            { ProfScope ps(p, PASS_MID, st); if (int e = ty->mid(+1, m, st)) return fail(e, "MID inverse launch failed"); }
             ph.win = bf.w3; ph.win_fstride = m.out_fstride; ph.wout_fstride = (long)p->nh * plane;
             ph.in_t_stride = p->ph; ph.in_o_stride = (long)p->n[1] * p->ph;
             ph.out_o_stride = p->n[1]; ph.out_e_stride = plane;
             ph.n_t = p->n[1]; ph.n_outer = p->n[0];
         }
-        if (int e = tl->phys(p->kprog, p->ndim, ph, st)) return fail(e, "PHYS launch failed");
+        { ProfScope ps(p, PASS_PHYS, st); if (int e = tl->phys(p->kprog, p->ndim, ph, st)) return fail(e, "PHYS launch failed"); }
         if (int e = run_forward_tail<T>(p, bf, g, p->nout, p->C, cb, ep, b0, nb, st)) return e;
     }
     if (ep.dc_out) {
@@ -627,17 +658,21 @@ int fsm_plan_create(fsm_plan** out, const fsm_desc* d) {
     {
         const int nchunks = (p->B + chunk - 1) / chunk;
         int64_t launches = 0, units = 0;  // units of one real field
+        for (int i = 0; i < 4; ++i) p->pass_units[i] = 0;
         for (const Stage& s : p->stages) {
             if (p->prog == FSM_PROG_LINEAR) {
                 launches += 1;
             } else {
                 launches += (int64_t)nchunks * (p->ndim == 2 ? 3 : 5) + ((p->prog == FSM_PROG_KS && d->ks_remove_mean) ? 1 : 0);
                 const int cnf = p->C * p->nf_ix;
-                if (p->ndim == 2) units += (p->C + cnf) + (p->nfi + p->nout) + p->nout;
-                else units += (p->C + cnf) + (cnf + p->nfi) + (p->nfi + p->nout) + 2 * p->nout + p->nout;
+                p->pass_units[PASS_IX] += p->C + cnf;
+                p->pass_units[PASS_PHYS] += p->nfi + p->nout;
+                p->pass_units[PASS_FX] += p->nout;
+                if (p->ndim == 3) p->pass_units[PASS_MID] += (cnf + p->nfi) + 2 * p->nout;
             }
-            units += (int64_t)(s.n_in + s.n_out) * p->C;
+            p->pass_units[PASS_FX] += (int64_t)(s.n_in + s.n_out) * p->C;
         }
+        for (int i = 0; i < 4; ++i) units += p->pass_units[i];
         p->launches_per_step = launches;
         p->algo_bytes_per_step = units * (int64_t)p->ntot * (p->f64 ? 8 : 4) * p->B;
     }
@@ -645,7 +680,14 @@ int fsm_plan_create(fsm_plan** out, const fsm_desc* d) {
     return 0;
 }
 
-void fsm_plan_destroy(fsm_plan* plan) { delete plan; }
+void fsm_plan_destroy(fsm_plan* plan) {
+    if (!plan) return;
+#ifndef FSM_EMU
+    for (auto& u : plan->ev_used) { cudaEventDestroy(u.second.first); cudaEventDestroy(u.second.second); }
+    for (auto e : plan->ev_pool) cudaEventDestroy(e);
+#endif
+    delete plan;
+}
 
 size_t fsm_workspace_bytes(const fsm_plan* plan) { return plan ? plan->ws_bytes : 0; }
 
@@ -656,6 +698,33 @@ int fsm_plan_info(const fsm_plan* plan, int64_t* launches_per_step, int64_t* alg
     if (algo_bytes_per_step) *algo_bytes_per_step = plan->algo_bytes_per_step;
     if (modes_per_field) *modes_per_field = plan->nmodes;
     if (chunk) *chunk = plan->chunk;
+    return 0;
+}
+
+int fsm_profile_enable(fsm_plan* plan, int on) {
+    if (!plan) return fail(-EINVAL, "null plan");
+    plan->profile = on != 0;
+    return 0;
+}
+
+int fsm_profile_read(fsm_plan* plan, double* ms, int64_t* launches, int64_t* algo_bytes_per_step) {
+    if (!plan || !ms || !launches) return fail(-EINVAL, "bad argument");
+    for (int i = 0; i < 4; ++i) { ms[i] = 0; launches[i] = 0; }
+    if (algo_bytes_per_step)
+        for (int i = 0; i < 4; ++i)
+            algo_bytes_per_step[i] = plan->pass_units[i] * (int64_t)plan->ntot * (plan->f64 ? 8 : 4) * plan->B;
+#ifndef FSM_EMU
+    for (auto& u : plan->ev_used) {
+        cudaEventSynchronize(u.second.second);
+        float t = 0;
+        cudaEventElapsedTime(&t, u.second.first, u.second.second);
+        ms[u.first] += t;
+        launches[u.first] += 1;
+        plan->ev_pool.push_back(u.second.first);
+        plan->ev_pool.push_back(u.second.second);
+    }
+    plan->ev_used.clear();
+#endif
     return 0;
 }
 

@@ -185,6 +185,15 @@ class FusedStepper:
         return {"launches_per_step": a.value, "algo_bytes_per_step": b.value, "modes_per_field": c.value,
                 "chunk": d.value}
 
+    def profile(self, on: bool):
+        _cabi.check(self._lib.fsm_profile_enable(self._plan, 1 if on else 0), "profile_enable")
+
+    def profile_read(self):
+        ms, n, by = (ctypes.c_double * 4)(), (ctypes.c_int64 * 4)(), (ctypes.c_int64 * 4)()
+        _cabi.check(self._lib.fsm_profile_read(self._plan, ms, n, by), "profile_read")
+        names = ("IX", "MID", "PHYS", "FX")
+        return {k: {"ms": ms[i], "launches": n[i], "algo_bytes_per_step": by[i]} for i, k in enumerate(names)}
+
     def empty_half(self):
         return torch.empty((self.B, self.C, self.nmodes), dtype=self.cdtype, device=self.device)
 
