@@ -17,7 +17,7 @@ template <> struct CfgFor<64> { using type = FftCfg<64, 8, 8, 8>; };
 template <> struct CfgFor<128> { using type = FftCfg<128, 16, 16, 8>; };
 template <> struct CfgFor<256> { using type = FftCfg<256, 16, 16, 16>; };
 template <> struct CfgFor<512> { using type = FftCfg<512, 16, 16, 16, 2>; };
-template <> struct CfgFor<1024> { using type = FftCfg<1024, 32, 32, 32>; };
+template <> struct CfgFor<1024> { using type = FftCfg<1024, 16, 16, 16, 4>; };
 
 
 #ifndef FSM_EMU

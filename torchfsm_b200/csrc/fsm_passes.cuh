@@ -98,12 +98,16 @@ struct Smem {
 // Rotated ("transposed") store of K line buffers that hold natural-order results:
 //   dst[e * e_stride + t]  for e < n_e, t < K (t = line slot, fastest)
 template <class Cfg, typename T>
-__device__ __forceinline__ void rotated_store(const cplx<T>* bufs, int K, int k_valid, cplx<T>* dst, long e_stride,
-                                              int n_e) {
-    const int total = K * n_e;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int t = i % K, e = i / K;
-        if (t < k_valid) dst[(long)e * e_stride + t] = bufs[t * Cfg::LINE_PITCH + e];
+__device__ __forceinline__ void rotated_store(const cplx<T>* bufs, int k_valid, cplx<T>* dst, long e_stride) {
+    constexpr int K = kKL, NT = kKL * Cfg::TL, N = Cfg::N;
+    static_assert((N * K) % NT == 0, "store loop must divide evenly");
+    const int t = threadIdx.x % K;
+    const int e0 = threadIdx.x / K;
+    const cplx<T>* src = bufs + t * Cfg::LINE_PITCH + e0;
+    cplx<T>* d = dst + (long)e0 * e_stride + t;
+    if (t < k_valid) {
+        FSM_UNROLL
+        for (int j = 0; j < (N * K) / NT; ++j) d[(long)j * (NT / K) * e_stride] = src[j * (NT / K)];
     }
 }
 
@@ -189,7 +193,7 @@ __global__ void __launch_bounds__(kKL * Cfg::TL) k_pass_ix(Geom<T> g, const cplx
         for (int m = 0; m < EPT; ++m) mybuf[tau + m * TL] = v[m];
         __syncthreads();
         cplx<T>* dst = w1 + (bc * NF + f) * w1_fstride + (long)o * out_o_stride + t0;
-        rotated_store<Cfg, T>(bufs, K, k_valid, dst, out_e_stride, N);
+        rotated_store<Cfg, T>(bufs, k_valid, dst, out_e_stride);
         __syncthreads();
     });
 }
@@ -242,7 +246,7 @@ __global__ void __launch_bounds__(kKL * Cfg::TL) k_pass_mid(Geom<T> g, const cpl
         for (int m = 0; m < EPT; ++m) mybuf[tau + m * TL] = v[m];
         __syncthreads();
         cplx<T>* dst = out + (b * spec.nfo + j) * out_fstride + (long)o * out_o_stride + t0;
-        rotated_store<Cfg, T>(bufs, K, k_valid, dst, out_e_stride, N);
+        rotated_store<Cfg, T>(bufs, k_valid, dst, out_e_stride);
         __syncthreads();
     }
 }
@@ -464,9 +468,10 @@ __global__ void __launch_bounds__(kKL * Cfg::TL) k_pass_phys(Geom<T> g, const cp
         const int nh = N / 2 + 1;
         cplx<T>* ob = wout + b * NOUT * wout_fstride + (long)o * out_o_stride + t0;
         const cplx<T>* st0 = bufs + NL * Cfg::LINE_PITCH;
-        const int total = NL * nh;
-        for (int i = threadIdx.x; i < total; i += blockDim.x) {
-            const int l = i % NL, k = i / NL;
+        constexpr int NLc = kKL;
+        const int total = NLc * nh;
+        for (int i = threadIdx.x; i < total; i += kKL * TL) {
+            const int l = i % NLc, k = i / NLc;
             const int kn = (k == 0) ? 0 : N - k;
             const cplx<T>* sl = st0 + l * NFW * Cfg::LINE_PITCH;
             auto split = [&](const cplx<T>* line, cplx<T>& s0, cplx<T>& s1) {
@@ -530,36 +535,56 @@ struct FxEpilogue {
     int project;                   // NS3D pressure projection
 };
 
-template <typename T>
-__device__ __forceinline__ void combine_mode(const Combine<T>& cb, cplx<T> fresh, long bc_off, long tab_off, long mode) {
-    cplx<T> X[FSM_MAX_IN + 1];
-    X[0] = fresh;
+// Evaluate the combine for NB modes (mode0 + j*mstride): every global load of the block is issued
+// before the first store so the memory system sees them all in flight.
+template <typename T, int NB>
+__device__ __forceinline__ void combine_block(const Combine<T>& cb, const cplx<T>* fresh, long bc_off, long tab_off,
+                                              long mode0, long mstride) {
+    cplx<T> X[FSM_MAX_IN][NB];
+    T tv[8][NB];
     FSM_UNROLL
     for (int i = 0; i < FSM_MAX_IN; ++i)
-        if (i < cb.n_in) X[1 + i] = cb.in[i][bc_off + mode];
-    T tv[8];
+        if (i < cb.n_in) {
+            FSM_UNROLL
+            for (int j = 0; j < NB; ++j) X[i][j] = cb.in[i][bc_off + mode0 + j * mstride];
+        }
     FSM_UNROLL
-    for (int i = 0; i < 8; ++i)
-        if (i < cb.n_tab) tv[i] = cb.tab[i][tab_off + mode];
+    for (int q = 0; q < 8; ++q)
+        if (q < cb.n_tab) {
+            FSM_UNROLL
+            for (int j = 0; j < NB; ++j) tv[q][j] = cb.tab[q][tab_off + mode0 + j * mstride];
+        }
     FSM_UNROLL
     for (int r = 0; r < FSM_MAX_OUT; ++r) {
         if (r < cb.n_out) {
-            cplx<T> s = mk<T>(T(0), T(0));
+            cplx<T> s[NB];
+            FSM_UNROLL
+            for (int j = 0; j < NB; ++j) s[j] = mk<T>(T(0), T(0));
             FSM_UNROLL
             for (int m = 0; m < FSM_MAX_IN + 1; ++m) {
                 const int ti = cb.ct[r][m];
                 if (ti != -2) {
-                    T coef = cb.ca[r][m];
                     FSM_UNROLL
-                    for (int q = 0; q < 8; ++q)
-                        if (ti == q) coef = fsm_fma(cb.cb[r][m], tv[q], coef);
-                    s.x = fsm_fma(coef, X[m].x, s.x);
-                    s.y = fsm_fma(coef, X[m].y, s.y);
+                    for (int j = 0; j < NB; ++j) {
+                        T coef = cb.ca[r][m];
+                        FSM_UNROLL
+                        for (int q = 0; q < 8; ++q)
+                            if (ti == q) coef = fsm_fma(cb.cb[r][m], tv[q][j], coef);
+                        const cplx<T> x = (m == 0) ? fresh[j] : X[(m == 0) ? 0 : m - 1][j];
+                        s[j].x = fsm_fma(coef, x.x, s[j].x);
+                        s[j].y = fsm_fma(coef, x.y, s[j].y);
+                    }
                 }
             }
-            cb.out[r][bc_off + mode] = s;
+            FSM_UNROLL
+            for (int j = 0; j < NB; ++j) cb.out[r][bc_off + mode0 + j * mstride] = s[j];
         }
     }
+}
+
+template <typename T>
+__device__ __forceinline__ void combine_mode(const Combine<T>& cb, cplx<T> fresh, long bc_off, long tab_off, long mode) {
+    combine_block<T, 1>(cb, &fresh, bc_off, tab_off, mode, 0);
 }
 
 template <typename T, class Cfg, int C>
@@ -590,47 +615,60 @@ __global__ void __launch_bounds__(kKL * Cfg::TL) k_pass_fx(Geom<T> g, const cplx
     // line coordinates
     int ky, kz = 0;
     if (g.ndim == 3) { ky = line / g.nh; kz = line % g.nh; } else { ky = line; }
-    FSM_UNROLL
-    for (int m = 0; m < EPT; ++m) {
-        const int p = tau + m * TL;
-        const long mode = (long)line * N + p;
-        cplx<T> f[C];
+    constexpr int NB = (EPT >= 4) ? 4 : EPT;
+    const long line_mode0 = (long)line * N;
+    static_for<0, EPT / NB>([&](auto mbc) {
+        constexpr int mb = decltype(mbc)::value * NB;
+        cplx<T> f[C][NB];
         FSM_UNROLL
-        for (int c = 0; c < C; ++c) f[c] = cscale(nhat[c][m], ep.nl_coef);
-        if constexpr (C == 3) {
-            if (ep.project) {
-                // result_i = (ik_i) lap^-1 sum_j (ik_j) c_j - c_i   (_navier_stokes.py:249-254), with the
-                // Hermitian projection of the composite symbol: a cross term is dropped when exactly one
-                // of its two axes sits on its Nyquist index.
-                const T d0 = g.dkraw[0][p], d1 = g.dkraw[1][ky], d2 = g.dkraw[2][kz];
-                const bool q0 = (p == g.n[0] / 2), q1 = (ky == g.n[1] / 2), q2 = (kz == g.n[2] / 2);
-                const T k2 = d0 * d0 + d1 * d1 + d2 * d2;
-                const T ik2 = (k2 == T(0)) ? T(0) : T(1) / k2;
-                const T dd[3] = {d0, d1, d2};
-                const bool qq[3] = {q0, q1, q2};
-                cplx<T> r[3];
-                FSM_UNROLL
-                for (int i = 0; i < 3; ++i) {
-                    cplx<T> s = mk<T>(T(0), T(0));
+        for (int j = 0; j < NB; ++j) {
+            const int p = tau + (mb + j) * TL;
+            FSM_UNROLL
+            for (int c = 0; c < C; ++c) f[c][j] = cscale(nhat[c][mb + j], ep.nl_coef);
+            if constexpr (C == 3) {
+                if (ep.project) {
+                    // result_i = (ik_i) lap^-1 sum_j (ik_j) c_j - c_i   (_navier_stokes.py:249-254), with the
+                    // Hermitian projection of the composite symbol: a cross term is dropped when exactly one
+                    // of its two axes sits on its Nyquist index.
+                    const T d0 = g.dkraw[0][p], d1 = g.dkraw[1][ky], d2 = g.dkraw[2][kz];
+                    const bool q0 = (p == g.n[0] / 2), q1 = (ky == g.n[1] / 2), q2 = (kz == g.n[2] / 2);
+                    const T k2 = d0 * d0 + d1 * d1 + d2 * d2;
+                    const T ik2 = (k2 == T(0)) ? T(0) : T(1) / k2;
+                    const T dd[3] = {d0, d1, d2};
+                    const bool qq[3] = {q0, q1, q2};
+                    cplx<T> r[3];
                     FSM_UNROLL
-                    for (int j = 0; j < 3; ++j) {
-                        const T w = (i == j || qq[i] == qq[j]) ? dd[i] * dd[j] * ik2 : T(0);
-                        s.x = fsm_fma(w, f[j].x, s.x);
-                        s.y = fsm_fma(w, f[j].y, s.y);
+                    for (int i = 0; i < 3; ++i) {
+                        cplx<T> s = mk<T>(T(0), T(0));
+                        FSM_UNROLL
+                        for (int jj = 0; jj < 3; ++jj) {
+                            const T w = (i == jj || qq[i] == qq[jj]) ? dd[i] * dd[jj] * ik2 : T(0);
+                            s.x = fsm_fma(w, f[jj][j].x, s.x);
+                            s.y = fsm_fma(w, f[jj][j].y, s.y);
+                        }
+                        r[i] = s - f[i][j];
                     }
-                    r[i] = s - f[i];
+                    FSM_UNROLL
+                    for (int i = 0; i < 3; ++i) f[i][j] = r[i];
                 }
-                FSM_UNROLL
-                for (int i = 0; i < 3; ++i) f[i] = r[i];
             }
         }
-        FSM_UNROLL
-        for (int c = 0; c < C; ++c) {
-            if (ep.source) f[c] = f[c] + ep.source[(long)c * g.nmodes + mode];
-            if (ep.dc_out && mode == 0 && c == 0) { ep.dc_out[b] = f[c].x; f[c] = mk<T>(T(0), T(0)); }
-            combine_mode<T>(cb, f[c], (b * C + c) * g.nmodes, c * cb.tab_cstride, mode);
+        if (ep.source) {
+            FSM_UNROLL
+            for (int c = 0; c < C; ++c) {
+                FSM_UNROLL
+                for (int j = 0; j < NB; ++j)
+                    f[c][j] = f[c][j] + ep.source[(long)c * g.nmodes + line_mode0 + tau + (mb + j) * TL];
+            }
         }
-    }
+        if (ep.dc_out && line == 0 && tau == 0 && mb == 0) {
+            ep.dc_out[b] = f[0][0].x;
+            f[0][0] = mk<T>(T(0), T(0));
+        }
+        FSM_UNROLL
+        for (int c = 0; c < C; ++c)
+            combine_block<T, NB>(cb, f[c], (b * C + c) * g.nmodes, c * cb.tab_cstride, line_mode0 + tau + mb * TL, TL);
+    });
 }
 
 // Combine without a nonlinear term (ETDRK0) or point-wise fix-ups: one thread per mode.

@@ -624,10 +624,17 @@ int fsm_plan_create(fsm_plan** out, const fsm_desc* d) {
     }
     int chunk = d->chunk;
     if (chunk <= 0) {
+        // enough samples per launch to give the smallest pass (FX) several waves of CTAs on 148 SMs,
+        // bounded by an 8 GiB budget for the per-chunk intermediates; then balance the chunks.
+        const long fx_ctas = (p->nmodes / p->n[0] + kKL - 1) / kKL;
+        chunk = (int)((148L * 8 + fx_ctas - 1) / fx_ctas);
         const size_t per = w1_per + w2_per + w3_per + w2b_per;
-        const size_t budget = (size_t)48 << 20;
-        chunk = (int)(budget / (per ? per : 1));
+        const size_t budget = (size_t)8 << 30;
+        if ((size_t)chunk * per > budget) chunk = (int)(budget / (per ? per : 1));
         if (chunk < 1) chunk = 1;
+        if (chunk > p->B) chunk = p->B;
+        const int nch = (p->B + chunk - 1) / chunk;
+        chunk = (p->B + nch - 1) / nch;
     }
     if (chunk > p->B) chunk = p->B;
     p->chunk = chunk;

@@ -61,6 +61,8 @@ class FourierMesh:
         else:
             self.mesh_info = [tuple(m) for m in mesh]
         self.device = torch.device(device) if device is not None else torch.device("cpu")
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.dtype = dtype if dtype is not None else torch.get_default_dtype()
         if self.dtype.is_complex:
             self.dtype = torch.float32 if self.dtype == torch.complex64 else torch.float64

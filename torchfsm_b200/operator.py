@@ -57,6 +57,16 @@ def _expand_table(t: torch.Tensor, shape) -> torch.Tensor:
     return t.expand(t.shape[0], *shape)
 
 
+def _same_device(a: torch.device, b: torch.device) -> bool:
+    if a.type != b.type:
+        return False
+    if a.type != "cuda":
+        return True
+    ia = a.index if a.index is not None else torch.cuda.current_device()
+    ib = b.index if b.index is not None else torch.cuda.current_device()
+    return ia == ib
+
+
 class FusedStepper:
     """What ``_build_integrator`` installs: a plan of the CUDA library plus the buffers it needs.
 
@@ -421,7 +431,7 @@ class OperatorLike:
         for i in range(mesh.n_dim):
             assert value.shape[i + 2] == mesh.mesh_info[i][2], \
                 f"Expect to have {mesh.mesh_info[i][2]} points in dim {i} but got {value.shape[i + 2]}"
-        assert value.device == mesh.device, \
+        assert _same_device(value.device, mesh.device), \
             "The device of mesh {} and the device of value {} are not the same".format(mesh.device, value.device)
         assert self._value_mesh_check_func(len(value.shape) - 2, mesh.n_dim), \
             "Value and mesh do not match the requirement"
