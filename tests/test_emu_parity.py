@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from golden_util import golden_names, load_golden, rel_l2
-from product_util import build_emulator, product_from_golden
+from product_util import build_emulator, product_from_golden, product_operator
 
 TOL = {"f32": 1e-5, "f64": 1e-12}
 SUPPORTED = [n for n in golden_names() if "1d" not in n]
@@ -108,3 +108,23 @@ def test_unsupported_requests_fail_loudly():
         fsm.ImplicitSource(lambda x: x ** 2)
     with pytest.raises(ValueError):
         fsm.VorticityConvection().integrate(u, mesh=[(0, 1, 32), (0, 1, 32)], dt=0.1, step=1)
+
+
+@pytest.mark.parametrize("rate", [1.0, 0.5])
+def test_ns2d_other_dealiasing_rates_vs_oracle(rate):
+    """Without de-aliasing the Nyquist lines take part (self-mirrored lines of the Z-line path)."""
+    import torchfsm_b200 as fsm
+    from oracle import OracleOperator
+    n0, n1 = 32, 16
+    mesh_info = [(0, 2 * np.pi, n0), (0, 2 * np.pi, n1)]
+    g = torch.Generator().manual_seed(3)
+    u0 = torch.randn(2, 1, n0, n1, generator=g, dtype=torch.float64)
+    terms = [("vorticity_convection", -1, {}), ("laplacian", 1 / 50, {})]
+    ora = OracleOperator(terms, de_aliasing_rate=rate).register_mesh(mesh_info, 1, dtype="float64")
+    ora.set_integrator("ETDRK2")
+    want = ora.integrate(u0.numpy(), dt=0.01, step=3)
+    op = product_operator(terms)
+    op.set_de_aliasing_rate(rate)
+    op.set_integrator(fsm.ETDRKIntegrator.ETDRK2)
+    got = op.integrate(u0, mesh=mesh_info, dt=0.01, step=3)
+    assert rel_l2(got.numpy(), want) <= 1e-12

@@ -39,11 +39,11 @@ template <typename T, int N, int PROG>
 static int launch_ix_p(const IxArgs<T>& a, cudaStream_t s) {
     using Cfg = typename CfgFor<N>::type;
     auto kern = k_pass_ix<T, Cfg, PROG>;
-    const size_t smem = Smem<Cfg, T>::bytes(kKL);
+    const size_t smem = Smem<Cfg, T>::bytes(2 * kKL);
     if (int e = set_smem(kern, smem)) return e;
     dim3 grid((a.n_t + kKL - 1) / kKL, a.n_outer, a.nbc), block(kKL * Cfg::TL);
     FSM_LAUNCH(kern, grid, block, smem, s, a.g, a.state, a.w1, a.state_bstride, a.w1_fstride, kKL, a.in_t_stride,
-               a.in_o_stride, a.out_o_stride, a.out_e_stride, a.n_t);
+               a.in_o_stride, a.out_o_stride, a.out_e_stride, a.n_t, a.symtab);
     return check_launch();
 }
 template <typename T, int N>
@@ -60,7 +60,7 @@ template <typename T, int N, int DIR>
 static int launch_mid_d(const MidArgs<T>& a, cudaStream_t s) {
     using Cfg = typename CfgFor<N>::type;
     auto kern = k_pass_mid<T, Cfg, DIR>;
-    const size_t smem = Smem<Cfg, T>::bytes(kKL);
+    const size_t smem = Smem<Cfg, T>::bytes(2 * kKL);
     if (int e = set_smem(kern, smem)) return e;
     dim3 grid((a.n_t + kKL - 1) / kKL, a.n_outer, a.nb), block(kKL * Cfg::TL);
     FSM_LAUNCH(kern, grid, block, smem, s, a.g, a.in, a.out, a.in_fstride, a.out_fstride, a.nfi, a.spec, kKL,

@@ -17,7 +17,12 @@
 
 namespace fsm {
 
-constexpr int kKL = 8;  // thread-lines per CTA in every line pass
+#ifndef FSM_KL
+#define FSM_KL 8
+#endif
+// ask ptxas for at least 512 resident threads per SM (register cap 128)
+#define FSM_MINB(nt) (((nt) >= 512) ? 1 : (512 / (nt)))
+constexpr int kKL = FSM_KL;  // thread-lines per CTA in every line pass
 
 enum Prog : int {
     PROG_NONE = 0,
@@ -65,6 +70,16 @@ __device__ __forceinline__ void fsm_sincospi(double x, double* s, double* c) {
 #endif
 }
 
+// -1/x: fp32 uses the hardware reciprocal (<= 1 ulp), fp64 the exact division
+__device__ __forceinline__ float neg_recip(float x) {
+#ifdef FSM_EMU
+    return -1.0f / x;
+#else
+    return -__frcp_rn(x);
+#endif
+}
+__device__ __forceinline__ double neg_recip(double x) { return -1.0 / x; }
+
 template <class Cfg, typename T>
 __device__ __forceinline__ void make_twiddles(cplx<T>* tw) {
     if constexpr (Cfg::R1 > 1) {
@@ -97,15 +112,15 @@ struct Smem {
 
 // Rotated ("transposed") store of K line buffers that hold natural-order results:
 //   dst[e * e_stride + t]  for e < n_e, t < K (t = line slot, fastest)
-template <class Cfg, typename T>
-__device__ __forceinline__ void rotated_store(const cplx<T>* bufs, int k_valid, cplx<T>* dst, long e_stride) {
+template <class Cfg, typename T, int SIGN = 1>
+__device__ __forceinline__ void rotated_store(const cplx<T>* bufs, int k_lo, int k_hi, cplx<T>* dst, long e_stride) {
     constexpr int K = kKL, NT = kKL * Cfg::TL, N = Cfg::N;
     static_assert((N * K) % NT == 0, "store loop must divide evenly");
     const int t = threadIdx.x % K;
     const int e0 = threadIdx.x / K;
     const cplx<T>* src = bufs + t * Cfg::LINE_PITCH + e0;
-    cplx<T>* d = dst + (long)e0 * e_stride + t;
-    if (t < k_valid) {
+    cplx<T>* d = dst + (long)e0 * e_stride + SIGN * t;
+    if (t >= k_lo && t < k_hi) {
         FSM_UNROLL
         for (int j = 0; j < (N * K) / NT; ++j) d[(long)j * (NT / K) * e_stride] = src[j * (NT / K)];
     }
@@ -127,10 +142,10 @@ struct IxFields {
 };
 
 template <typename T, class Cfg, int PROG>
-__global__ void __launch_bounds__(kKL * Cfg::TL) k_pass_ix(Geom<T> g, const cplx<T>* __restrict__ state, cplx<T>* __restrict__ w1,
+__global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass_ix(Geom<T> g, const cplx<T>* __restrict__ state, cplx<T>* __restrict__ w1,
                                                   long state_bstride /*per (b,c)*/, long w1_fstride, int K,
                                                   long in_t_stride, long in_o_stride, long out_o_stride,
-                                                  long out_e_stride, int n_t) {
+                                                  long out_e_stride, int n_t, const cplx<T>* __restrict__ symtab) {
     constexpr int N = Cfg::N, EPT = Cfg::EPT, TL = Cfg::TL;
     constexpr int NF = IxFields<PROG>::NF;
     FSM_DYN_SMEM(smem_raw);
@@ -156,6 +171,68 @@ __global__ void __launch_bounds__(kKL * Cfg::TL) k_pass_ix(Geom<T> g, const cplx
 
     cplx<T> u[EPT];
     const cplx<T>* src = state + bc * state_bstride + (long)t * in_t_stride + (long)o * in_o_stride;
+    LineSync<TL> sync{1 + lt};
+    cplx<T>* mybuf = bufs + lt * Cfg::LINE_PITCH;
+
+    if constexpr (PROG == PROG_NS2D) {
+        // "Z-lines": the two real fields of a pair ride in ONE complex line, Z = A + iB, so the last-axis
+        // pass needs no pairing work. For the stored line +ky:  Z+ = IFFTx[(S_A + i S_B) w_hat(kx, ky)];
+        // for the mirrored line -ky: w_hat(kx,-ky) = conj(w_hat(-kx, ky)), S(kx,-ky).  Pairs:
+        //   Z1 = u_x + i d_x w,   Z2 = u_y + i d_y w,   psi = -w/lap, u_x = d_y psi, u_y = -d_x psi
+        // W1 layout: [pair][x][ky' < n1] with the -ky line stored at ky' = n1 - ky.
+        const int n1 = g.n[1];
+        const bool self_conj = (t == 0) || (2 * t == n1);   // line equals its own mirror: project, store once
+        // symtab[j][ky][kx] (j = 0, 1): composite symbols S_j = S_A + i S_B of pair j on the +ky line with the
+        // dealiasing mask and the 1/N of the inverse transform folded in; on the mirrored line
+        // S_1(kx,-ky) = conj(S_1(kx,ky)) and S_2(kx,-ky) = -conj(S_2(kx,ky)).
+        const cplx<T>* sym_line = symtab + (long)t * in_t_stride;
+        static_for<0, 4>([&](auto sc) {
+            constexpr int sidx = decltype(sc)::value;        // 0: Z1+, 1: Z2+, 2: Z1-, 3: Z2-
+            constexpr bool minus = sidx >= 2;
+            if constexpr (sidx == 0 || sidx == 2) {
+                FSM_UNROLL
+                for (int m = 0; m < EPT; ++m) {
+                    const int p = tau + m * TL;
+                    const bool kept = line_kept && (iabs(signed_mode<N>(p)) <= g.kmax[0]);
+                    cplx<T> a = mk<T>(T(0), T(0));
+                    if (kept) {
+                        if (self_conj) a = cscale(src[p] + cconj(src[(N - p) & (N - 1)]), T(0.5));
+                        else a = minus ? cconj(src[(N - p) & (N - 1)]) : src[p];
+                    }
+                    u[m] = a;
+                }
+            }
+            cplx<T> v[EPT];
+            FSM_UNROLL
+            for (int m = 0; m < EPT; ++m) {
+                const int p = tau + m * TL;
+                cplx<T> sy = line_kept ? sym_line[(sidx & 1) * g.nmodes + p] : mk<T>(T(0), T(0));
+                if constexpr (sidx == 2) sy = cconj(sy);
+                if constexpr (sidx == 3) sy = mk<T>(-sy.x, sy.y);
+                v[m] = cmul(u[m], sy);
+            }
+            // ping-pong line buffers: one block barrier per transform, the rotated stores of transform s
+            // overlap the butterflies of transform s+1
+            cplx<T>* pbufs = bufs + (sidx & 1) * kKL * Cfg::LINE_PITCH;
+            cplx<T>* pbuf = pbufs + lt * Cfg::LINE_PITCH;
+            line_fft<Cfg, +1, T>(v, pbuf, tw, tau, sync);
+            sync();
+            FSM_UNROLL
+            for (int m = 0; m < EPT; ++m) pbuf[tau + m * TL] = v[m];
+            __syncthreads();
+            cplx<T>* base = w1 + (bc * 2 + (sidx & 1)) * w1_fstride;
+            if constexpr (!minus) {
+                rotated_store<Cfg, T, 1>(pbufs, 0, k_valid, base + t0, out_e_stride);
+            } else {
+                // skip lines that are their own mirror (ky = 0 and, without dealiasing, the Nyquist line)
+                const int lo = (t0 == 0) ? 1 : 0;
+                const int hi = (2 * (t0 + k_valid - 1) == n1) ? k_valid - 1 : k_valid;
+                rotated_store<Cfg, T, -1>(pbufs, lo, hi, base + (n1 - t0), out_e_stride);
+            }
+        });
+        return;
+    }
+
     FSM_UNROLL
     for (int m = 0; m < EPT; ++m) {
         const int p = tau + m * TL;
@@ -163,8 +240,6 @@ __global__ void __launch_bounds__(kKL * Cfg::TL) k_pass_ix(Geom<T> g, const cplx
         if (PROG != PROG_C2R) kept = kept && (iabs(signed_mode<N>(p)) <= g.kmax[0]);
         u[m] = kept ? cscale(src[p], g.inv_ntot) : mk<T>(T(0), T(0));
     }
-    LineSync<TL> sync{1 + lt};
-    cplx<T>* mybuf = bufs + lt * Cfg::LINE_PITCH;
 
     static_for<0, NF>([&](auto fc) {
         constexpr int f = decltype(fc)::value;
@@ -172,29 +247,18 @@ __global__ void __launch_bounds__(kKL * Cfg::TL) k_pass_ix(Geom<T> g, const cplx
         FSM_UNROLL
         for (int m = 0; m < EPT; ++m) {
             const int p = tau + m * TL;
-            if constexpr (PROG == PROG_NS2D) {
-                const T dkx = g.dk[0][p];
-                const T dkxraw = g.dkraw[0][p];
-                // lap = (i dkxraw)^2 + (i dkyraw)^2 (mesh.py:406-426); psi = -w * where(lap==0, 1, 1/lap)
-                const T lap = -(dkxraw * dkxraw) - (dkyraw * dkyraw);
-                const T ninv = (lap == T(0)) ? T(-1) : T(-1) / lap;
-                if constexpr (f == 0) v[m] = cmul_i(u[m], dky * ninv);          // u_x = d_y psi
-                else if constexpr (f == 1) v[m] = cmul_i(u[m], -dkx * ninv);    // u_y = -d_x psi
-                else if constexpr (f == 2) v[m] = cmul_i(u[m], dkx);            // d_x w
-                else v[m] = cmul_i(u[m], dky);                                  // d_y w
-            } else {
-                if constexpr (f == 0) v[m] = u[m];
-                else v[m] = cmul_i(u[m], g.dk[0][p]);                           // d_x
-            }
+            if constexpr (f == 0) v[m] = u[m];
+            else v[m] = cmul_i(u[m], g.dk[0][p]);                               // d_x
         }
-        line_fft<Cfg, +1, T>(v, mybuf, tw, tau, sync);
+        cplx<T>* pbufs = bufs + (f & 1) * kKL * Cfg::LINE_PITCH;
+        cplx<T>* pbuf = pbufs + lt * Cfg::LINE_PITCH;
+        line_fft<Cfg, +1, T>(v, pbuf, tw, tau, sync);
         sync();
         FSM_UNROLL
-        for (int m = 0; m < EPT; ++m) mybuf[tau + m * TL] = v[m];
+        for (int m = 0; m < EPT; ++m) pbuf[tau + m * TL] = v[m];
         __syncthreads();
         cplx<T>* dst = w1 + (bc * NF + f) * w1_fstride + (long)o * out_o_stride + t0;
-        rotated_store<Cfg, T>(bufs, k_valid, dst, out_e_stride);
-        __syncthreads();
+        rotated_store<Cfg, T>(pbufs, 0, k_valid, dst, out_e_stride);
     });
 }
 
@@ -210,7 +274,7 @@ struct MidSpec {
 };
 
 template <typename T, class Cfg, int DIR>
-__global__ void __launch_bounds__(kKL * Cfg::TL) k_pass_mid(Geom<T> g, const cplx<T>* __restrict__ in, cplx<T>* __restrict__ out,
+__global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass_mid(Geom<T> g, const cplx<T>* __restrict__ in, cplx<T>* __restrict__ out,
                                                    long in_fstride, long out_fstride, int nfi, MidSpec spec, int K,
                                                    long in_t_stride, long in_o_stride, long out_o_stride,
                                                    long out_e_stride, int n_t) {
@@ -240,14 +304,15 @@ __global__ void __launch_bounds__(kKL * Cfg::TL) k_pass_mid(Geom<T> g, const cpl
             if (spec.deriv[j]) x = cmul_i(x, g.dk[1][p]);
             v[m] = x;
         }
-        line_fft<Cfg, DIR, T>(v, mybuf, tw, tau, sync);
+        cplx<T>* pbufs = bufs + (j & 1) * kKL * Cfg::LINE_PITCH;
+        cplx<T>* pbuf = pbufs + lt * Cfg::LINE_PITCH;
+        line_fft<Cfg, DIR, T>(v, pbuf, tw, tau, sync);
         sync();
         FSM_UNROLL
-        for (int m = 0; m < EPT; ++m) mybuf[tau + m * TL] = v[m];
+        for (int m = 0; m < EPT; ++m) pbuf[tau + m * TL] = v[m];
         __syncthreads();
         cplx<T>* dst = out + (b * spec.nfo + j) * out_fstride + (long)o * out_o_stride + t0;
-        rotated_store<Cfg, T>(bufs, k_valid, dst, out_e_stride);
-        __syncthreads();
+        rotated_store<Cfg, T>(pbufs, 0, k_valid, dst, out_e_stride);
     }
 }
 
@@ -261,7 +326,7 @@ __global__ void __launch_bounds__(kKL * Cfg::TL) k_pass_mid(Geom<T> g, const cpl
 template <int PROG, int NDIM>
 struct PhysTraits;
 // NFI = input fields per sample, NOUT = output fields per sample, RPT = rows per thread-line
-template <> struct PhysTraits<PROG_NS2D, 2> { static constexpr int NFI = 4, NOUT = 1, RPT = 2; };
+template <> struct PhysTraits<PROG_NS2D, 2> { static constexpr int NFI = 2, NOUT = 1, RPT = 2; };
 template <> struct PhysTraits<PROG_KS, 2> { static constexpr int NFI = 2, NOUT = 1, RPT = 2; };
 template <> struct PhysTraits<PROG_KS, 3> { static constexpr int NFI = 3, NOUT = 1, RPT = 2; };
 template <> struct PhysTraits<PROG_CONV, 2> { static constexpr int NFI = 4, NOUT = 2, RPT = 1; };
@@ -288,7 +353,7 @@ __device__ __forceinline__ cplx<T> pair_load(const cplx<T>* a, const cplx<T>* b,
 }
 
 template <typename T, class Cfg, int PROG, int NDIM>
-__global__ void __launch_bounds__(kKL * Cfg::TL) k_pass_phys(Geom<T> g, const cplx<T>* __restrict__ win, cplx<T>* __restrict__ wout,
+__global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass_phys(Geom<T> g, const cplx<T>* __restrict__ win, cplx<T>* __restrict__ wout,
                                                     const T* __restrict__ phys_in, T* __restrict__ phys_out,
                                                     long win_fstride, long wout_fstride, int K /*rows per CTA*/,
                                                     long in_t_stride, long in_o_stride, long out_o_stride,
@@ -332,11 +397,22 @@ __global__ void __launch_bounds__(kKL * Cfg::TL) k_pass_phys(Geom<T> g, const cp
             line_fft<Cfg, +1, T>(v, mybuf, tw, tau, sync);
         };
         if constexpr (PROG == PROG_NS2D) {
-            // fields: 0 u_x, 1 u_y, 2 d_x w, 3 d_y w  ->  u_x d_x w + u_y d_y w
-            inverse_pair(0, 2, false, false);
+            // Z-lines written by IX: field 0 = u_x + i d_x w, field 1 = u_y + i d_y w (full complex rows)
+            auto inverse_z = [&](int f) {
+                const cplx<T>* z = wb + f * win_fstride + roff;
+                FSM_UNROLL
+                for (int m = 0; m < EPT; ++m) {
+                    const int p = tau + m * TL;
+                    const bool kept = row_ok && (p <= kmaxl || p >= N - kmaxl);
+                    v[m] = kept ? z[p] : mk<T>(T(0), T(0));
+                }
+                sync();
+                line_fft<Cfg, +1, T>(v, mybuf, tw, tau, sync);
+            };
+            inverse_z(0);
             FSM_UNROLL
             for (int m = 0; m < EPT; ++m) acc[0][m] = v[m].x * v[m].y;
-            inverse_pair(1, 3, false, false);
+            inverse_z(1);
             FSM_UNROLL
             for (int m = 0; m < EPT; ++m) acc[0][m] += v[m].x * v[m].y;
         } else if constexpr (PROG == PROG_KS && NDIM == 2) {
@@ -588,7 +664,7 @@ __device__ __forceinline__ void combine_mode(const Combine<T>& cb, cplx<T> fresh
 }
 
 template <typename T, class Cfg, int C>
-__global__ void __launch_bounds__(kKL * Cfg::TL) k_pass_fx(Geom<T> g, const cplx<T>* __restrict__ win, long win_fstride,
+__global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass_fx(Geom<T> g, const cplx<T>* __restrict__ win, long win_fstride,
                                                   Combine<T> cb, FxEpilogue<T> ep, int nlines, int b0) {
     constexpr int N = Cfg::N, EPT = Cfg::EPT, TL = Cfg::TL;
     FSM_DYN_SMEM(smem_raw);

@@ -386,15 +386,17 @@ int run_stage(const fsm_plan* p, const Buffers<T>& bf, const Stage& s, cudaStrea
         IxArgs<T> a;
         a.g = g; a.state = stage_in + (long)b0 * p->C * p->nmodes; a.w1 = bf.w1;
         a.state_bstride = p->nmodes; a.nbc = nb * p->C;
+        a.symtab = static_cast<const cplx<T>*>(p->d.sym_tab);
         PhysArgs<T> ph;
         ph.g = g; ph.wout = bf.w2; ph.phys_in = nullptr; ph.phys_out = nullptr; ph.nb = nb;
         if (p->ndim == 2) {
-            a.w1_fstride = (long)p->n[0] * p->ph;
-            a.in_t_stride = p->n[0]; a.in_o_stride = 0; a.out_o_stride = 0; a.out_e_stride = p->ph;
+            const int w1_pitch = (p->kprog == PROG_NS2D) ? p->n[1] : p->ph;   // NS2D: full complex Z-lines
+            a.w1_fstride = (long)p->n[0] * w1_pitch;
+            a.in_t_stride = p->n[0]; a.in_o_stride = 0; a.out_o_stride = 0; a.out_e_stride = w1_pitch;
             a.n_t = (p->d.kmax[1] + 1 < p->nh) ? p->d.kmax[1] + 1 : p->nh; a.n_outer = 1;
             { ProfScope ps(p, PASS_IX, st); if (int e = tx->ix(p->kprog, a, st)) return fail(e, "IX launch failed"); }
             ph.win = bf.w1; ph.win_fstride = a.w1_fstride; ph.wout_fstride = p->nmodes;
-            ph.in_t_stride = p->ph; ph.in_o_stride = 0; ph.out_o_stride = 0; ph.out_e_stride = p->n[0];
+            ph.in_t_stride = w1_pitch; ph.in_o_stride = 0; ph.out_o_stride = 0; ph.out_e_stride = p->n[0];
             ph.n_t = p->n[0]; ph.n_outer = 1;
         } else {
             const long plane = (long)p->n[0] * p->n[1];
@@ -490,7 +492,7 @@ int do_c2r(fsm_plan* p, const void* u_hat, void* u, void* ws, cudaStream_t st) {
         const int nf = (int)((nfields - f0 < (long)p->cap_fields) ? nfields - f0 : (long)p->cap_fields);
         IxArgs<T> a;
         a.g = g; a.state = static_cast<const cplx<T>*>(u_hat) + f0 * p->nmodes; a.w1 = bf.w1;
-        a.state_bstride = p->nmodes; a.nbc = nf;
+        a.state_bstride = p->nmodes; a.nbc = nf; a.symtab = nullptr;
         PhysArgs<T> ph;
         ph.g = g; ph.wout = nullptr; ph.phys_in = nullptr; ph.phys_out = static_cast<T*>(u) + f0 * p->ntot;
         ph.wout_fstride = 0; ph.out_o_stride = 0; ph.out_e_stride = 0; ph.nb = nf;
@@ -586,6 +588,7 @@ int fsm_plan_create(fsm_plan** out, const fsm_desc* d) {
             p->kprog = PROG_KS; p->nf_ix = 2; p->nfi = (p->ndim == 2) ? 2 : 3; p->nout = 1; break;
         case FSM_PROG_NS2D_VORT:
             if (p->C != 1 || p->ndim != 2) { delete p; return fail(-EINVAL, "vorticity convection needs a 2-D scalar field"); }
+            if (!d->sym_tab) { delete p; return fail(-EINVAL, "vorticity convection needs the composite symbol table (sym_tab)"); }
             p->kprog = PROG_NS2D; p->nf_ix = 4; p->nfi = 4; p->nout = 1; break;
         case FSM_PROG_NS3D:
             if (p->C != 3 || p->ndim != 3) { delete p; return fail(-EINVAL, "NS pressure convection needs a 3-D, 3-channel field"); }
@@ -614,7 +617,8 @@ int fsm_plan_create(fsm_plan** out, const fsm_desc* d) {
     const long plane = (long)p->n[0] * p->n[1];
     size_t w1_per, w2_per, w3_per = 0, w2b_per = 0;
     if (p->ndim == 2) {
-        w1_per = (size_t)p->C * p->nf_ix * p->n[0] * p->ph * esz;
+        w1_per = (p->kprog == PROG_NS2D) ? (size_t)2 * p->n[0] * p->n[1] * esz
+                                         : (size_t)p->C * p->nf_ix * p->n[0] * p->ph * esz;
         w2_per = (size_t)p->nout * p->nmodes * esz;
     } else {
         w1_per = (size_t)p->C * p->nf_ix * p->nh * plane * esz;
@@ -656,11 +660,25 @@ int fsm_plan_create(fsm_plan** out, const fsm_desc* d) {
     p->off_w2b = off; off = align_up(off + w2b_per * chunk, 256);
     p->off_dc = off; off = align_up(off + (size_t)p->B * (p->f64 ? 8 : 4), 256);
     p->ws_bytes = off;
-    // generic transforms process this many independent fields per launch
-    size_t cap = (size_t)chunk * p->C * p->nf_ix;
-    if ((size_t)chunk * p->nout < cap) cap = (size_t)chunk * p->nout;
-    if (p->ndim == 3 && (size_t)chunk * p->nfi < cap) cap = (size_t)chunk * p->nfi;
-    p->cap_fields = cap < 1 ? 1 : cap;
+    // generic transforms (r2c / c2r) process this many independent fields per launch: bounded by what
+    // each intermediate buffer can hold when every field takes one plain slot
+    {
+        size_t cap;
+        if (p->ndim == 2) {
+            cap = (w1_per * chunk) / ((size_t)p->n[0] * p->ph * esz);
+            const size_t c2 = (w2_per * chunk) / ((size_t)p->nmodes * esz);
+            if (c2 < cap) cap = c2;
+        } else {
+            cap = (w1_per * chunk) / ((size_t)p->nh * plane * esz);
+            const size_t c3 = (w3_per * chunk) / ((size_t)plane * p->ph * esz);
+            const size_t c2 = (w2_per * chunk) / ((size_t)p->nh * plane * esz);
+            const size_t c2b = (w2b_per * chunk) / ((size_t)p->nmodes * esz);
+            if (c3 < cap) cap = c3;
+            if (c2 < cap) cap = c2;
+            if (c2b < cap) cap = c2b;
+        }
+        p->cap_fields = cap < 1 ? 1 : cap;
+    }
     // bookkeeping for benchmarks (SURVEY.md §8d transform-pass model)
     {
         const int nchunks = (p->B + chunk - 1) / chunk;
