@@ -85,10 +85,6 @@ typedef struct fsm_desc {
     const void* tab_lin;      /* L itself (RK4 and fsm_rhs)   operator/_base.py:339-357              */
     const void* source_hat;   /* optional constant source spectrum, complex [C][modes], coefficient
                                  folded in (operator/_base.py:994-1015)                              */
-    const void* sym_tab;      /* FSM_PROG_NS2D_VORT only: complex [2][modes], the composite symbols of the two
-                                 paired fields  S_1 = S(u_x) + i S(d_x w),  S_2 = S(u_y) + i S(d_y w)  with
-                                 S(u_x) = -grad_y/lap, S(u_y) = grad_x/lap (_navier_stokes.py:41-45), times the
-                                 dealiasing mask (mesh.py:443-461) and 1/(n0*n1) of the inverse transform     */
 } fsm_desc;
 
 /* replaces: OperatorLike._build_integrator (operator/_base.py:441-526) */

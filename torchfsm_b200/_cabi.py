@@ -27,7 +27,7 @@ class FsmDesc(ctypes.Structure):
         ("ks_ext_count", ctypes.c_int32), ("reserved", ctypes.c_int32),
         ("dk", ctypes.c_void_p * 3), ("dkraw", ctypes.c_void_p * 3),
         ("tab_exp", ctypes.c_void_p), ("tab_half_exp", ctypes.c_void_p), ("tab_coef", ctypes.c_void_p * 6),
-        ("tab_lin", ctypes.c_void_p), ("source_hat", ctypes.c_void_p), ("sym_tab", ctypes.c_void_p),
+        ("tab_lin", ctypes.c_void_p), ("source_hat", ctypes.c_void_p),
     ]
 
 

@@ -43,7 +43,7 @@ static int launch_ix_p(const IxArgs<T>& a, cudaStream_t s) {
     if (int e = set_smem(kern, smem)) return e;
     dim3 grid((a.n_t + kKL - 1) / kKL, a.n_outer, a.nbc), block(kKL * Cfg::TL);
     FSM_LAUNCH(kern, grid, block, smem, s, a.g, a.state, a.w1, a.state_bstride, a.w1_fstride, kKL, a.in_t_stride,
-               a.in_o_stride, a.out_o_stride, a.out_e_stride, a.n_t, a.symtab);
+               a.in_o_stride, a.out_o_stride, a.out_e_stride, a.n_t);
     return check_launch();
 }
 template <typename T, int N>

@@ -12,7 +12,6 @@ struct IxArgs {
     cplx<T>* w1;
     long state_bstride, w1_fstride, in_t_stride, in_o_stride, out_o_stride, out_e_stride;
     int n_t, n_outer, nbc;
-    const cplx<T>* symtab;
 };
 template <typename T>
 struct MidArgs {

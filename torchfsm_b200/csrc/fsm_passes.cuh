@@ -145,7 +145,7 @@ template <typename T, class Cfg, int PROG>
 __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass_ix(Geom<T> g, const cplx<T>* __restrict__ state, cplx<T>* __restrict__ w1,
                                                   long state_bstride /*per (b,c)*/, long w1_fstride, int K,
                                                   long in_t_stride, long in_o_stride, long out_o_stride,
-                                                  long out_e_stride, int n_t, const cplx<T>* __restrict__ symtab) {
+                                                  long out_e_stride, int n_t) {
     constexpr int N = Cfg::N, EPT = Cfg::EPT, TL = Cfg::TL;
     constexpr int NF = IxFields<PROG>::NF;
     FSM_DYN_SMEM(smem_raw);
@@ -175,59 +175,77 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
     cplx<T>* mybuf = bufs + lt * Cfg::LINE_PITCH;
 
     if constexpr (PROG == PROG_NS2D) {
-        // "Z-lines": the two real fields of a pair ride in ONE complex line, Z = A + iB, so the last-axis
-        // pass needs no pairing work. For the stored line +ky:  Z+ = IFFTx[(S_A + i S_B) w_hat(kx, ky)];
-        // for the mirrored line -ky: w_hat(kx,-ky) = conj(w_hat(-kx, ky)), S(kx,-ky).  Pairs:
-        //   Z1 = u_x + i d_x w,   Z2 = u_y + i d_y w,   psi = -w/lap, u_x = d_y psi, u_y = -d_x psi
-        // W1 layout: [pair][x][ky' < n1] with the -ky line stored at ky' = n1 - ky.
+        // "Z-lines": the two real fields of a pair ride in ONE complex line Z = f_a + i f_b, so the last-axis
+        // pass needs no pairing work. Pairs: Z1 = u_x + i d_x w, Z2 = u_y + i d_y w with psi = -w/lap,
+        // u_x = d_y psi, u_y = -d_x psi (_navier_stokes.py:41-45). With the four plain x-transforms
+        //   A = T[kx w], B = T[i ky ninv w], C = T[w], D = T[i kx ninv w]      (ninv = -1/lap, T = IFFT_x)
+        // the stored +ky line and its mirror -ky (w_hat(kx,-ky) = conj(w_hat(-kx,ky))) are
+        //   Z1+ = B - A, Z1- = conj(A + B), Z2+ = -ky C - D, Z2- = conj(-ky C + D),
+        // formed while the data crosses shared memory for the rotated store.
+        // W1 layout: [pair][x][ky' < n1], the -ky line stored at ky' = n1 - ky.
         const int n1 = g.n[1];
-        const bool self_conj = (t == 0) || (2 * t == n1);   // line equals its own mirror: project, store once
-        // symtab[j][ky][kx] (j = 0, 1): composite symbols S_j = S_A + i S_B of pair j on the +ky line with the
-        // dealiasing mask and the 1/N of the inverse transform folded in; on the mirrored line
-        // S_1(kx,-ky) = conj(S_1(kx,ky)) and S_2(kx,-ky) = -conj(S_2(kx,ky)).
-        const cplx<T>* sym_line = symtab + (long)t * in_t_stride;
-        static_for<0, 4>([&](auto sc) {
-            constexpr int sidx = decltype(sc)::value;        // 0: Z1+, 1: Z2+, 2: Z1-, 3: Z2-
-            constexpr bool minus = sidx >= 2;
-            if constexpr (sidx == 0 || sidx == 2) {
-                FSM_UNROLL
-                for (int m = 0; m < EPT; ++m) {
-                    const int p = tau + m * TL;
-                    const bool kept = line_kept && (iabs(signed_mode<N>(p)) <= g.kmax[0]);
-                    cplx<T> a = mk<T>(T(0), T(0));
-                    if (kept) {
-                        if (self_conj) a = cscale(src[p] + cconj(src[(N - p) & (N - 1)]), T(0.5));
-                        else a = minus ? cconj(src[(N - p) & (N - 1)]) : src[p];
-                    }
-                    u[m] = a;
-                }
-            }
+        FSM_UNROLL
+        for (int m = 0; m < EPT; ++m) {
+            const int p = tau + m * TL;
+            const bool kept = line_kept && (iabs(signed_mode<N>(p)) <= g.kmax[0]);
+            u[m] = kept ? cscale(src[p], g.inv_ntot) : mk<T>(T(0), T(0));
+        }
+        static_for<0, 4>([&](auto fc) {
+            constexpr int f = decltype(fc)::value;
             cplx<T> v[EPT];
             FSM_UNROLL
             for (int m = 0; m < EPT; ++m) {
                 const int p = tau + m * TL;
-                cplx<T> sy = line_kept ? sym_line[(sidx & 1) * g.nmodes + p] : mk<T>(T(0), T(0));
-                if constexpr (sidx == 2) sy = cconj(sy);
-                if constexpr (sidx == 3) sy = mk<T>(-sy.x, sy.y);
-                v[m] = cmul(u[m], sy);
+                if constexpr (f == 2) {
+                    v[m] = u[m];
+                } else {
+                    const T dkx = g.dk[0][p];
+                    if constexpr (f == 0) {
+                        v[m] = cscale(u[m], dkx);
+                    } else {
+                        const T dkxraw = g.dkraw[0][p];
+                        // lap = (i dkxraw)^2 + (i dkyraw)^2 (mesh.py:406-426); psi = -w * where(lap==0, 1, 1/lap)
+                        const T lap = -(dkxraw * dkxraw) - (dkyraw * dkyraw);
+                        const T ninv = (lap == T(0)) ? T(-1) : neg_recip(lap);
+                        v[m] = cmul_i(u[m], (f == 1 ? dky : dkx) * ninv);
+                    }
+                }
             }
-            // ping-pong line buffers: one block barrier per transform, the rotated stores of transform s
-            // overlap the butterflies of transform s+1
-            cplx<T>* pbufs = bufs + (sidx & 1) * kKL * Cfg::LINE_PITCH;
+            cplx<T>* pbufs = bufs + (f & 1) * kKL * Cfg::LINE_PITCH;
             cplx<T>* pbuf = pbufs + lt * Cfg::LINE_PITCH;
             line_fft<Cfg, +1, T>(v, pbuf, tw, tau, sync);
             sync();
             FSM_UNROLL
             for (int m = 0; m < EPT; ++m) pbuf[tau + m * TL] = v[m];
-            __syncthreads();
-            cplx<T>* base = w1 + (bc * 2 + (sidx & 1)) * w1_fstride;
-            if constexpr (!minus) {
-                rotated_store<Cfg, T, 1>(pbufs, 0, k_valid, base + t0, out_e_stride);
-            } else {
-                // skip lines that are their own mirror (ky = 0 and, without dealiasing, the Nyquist line)
-                const int lo = (t0 == 0) ? 1 : 0;
-                const int hi = (2 * (t0 + k_valid - 1) == n1) ? k_valid - 1 : k_valid;
-                rotated_store<Cfg, T, -1>(pbufs, lo, hi, base + (n1 - t0), out_e_stride);
+            if constexpr (f & 1) {
+                __syncthreads();
+                constexpr int pair = f >> 1;
+                const int ts = threadIdx.x % kKL, e0 = threadIdx.x / kKL;
+                const int tg = t0 + ts;
+                const bool valid = ts < k_valid;
+                const bool selfc = (tg == 0) || (2 * tg == n1);
+                const T dky_s = valid ? g.dk[1][tg] : T(0);
+                const cplx<T>* s0 = bufs + ts * Cfg::LINE_PITCH + e0;
+                const cplx<T>* s1 = s0 + kKL * Cfg::LINE_PITCH;
+                cplx<T>* dp = w1 + (bc * 2 + pair) * w1_fstride + (long)e0 * out_e_stride + tg;
+                cplx<T>* dm = w1 + (bc * 2 + pair) * w1_fstride + (long)e0 * out_e_stride + (n1 - tg);
+                if (valid) {
+                    FSM_UNROLL
+                    for (int j = 0; j < EPT; ++j) {
+                        const cplx<T> a = s0[j * TL], b = s1[j * TL];
+                        cplx<T> zp, zm;
+                        if constexpr (pair == 0) {
+                            zp = selfc ? mk<T>(b.x, -a.y) : b - a;
+                            zm = mk<T>(a.x + b.x, -(a.y + b.y));
+                        } else {
+                            zp = selfc ? mk<T>(-b.x, -dky_s * a.y) : mk<T>(-dky_s * a.x - b.x, -dky_s * a.y - b.y);
+                            zm = mk<T>(dky_s * a.x - b.x, b.y - dky_s * a.y);
+                        }
+                        dp[(long)j * TL * out_e_stride] = zp;
+                        if (!selfc) dm[(long)j * TL * out_e_stride] = zm;
+                    }
+                }
+                if constexpr (f == 1) __syncthreads();
             }
         });
         return;

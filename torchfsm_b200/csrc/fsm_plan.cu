@@ -386,7 +386,6 @@ int run_stage(const fsm_plan* p, const Buffers<T>& bf, const Stage& s, cudaStrea
         IxArgs<T> a;
         a.g = g; a.state = stage_in + (long)b0 * p->C * p->nmodes; a.w1 = bf.w1;
         a.state_bstride = p->nmodes; a.nbc = nb * p->C;
-        a.symtab = static_cast<const cplx<T>*>(p->d.sym_tab);
         PhysArgs<T> ph;
         ph.g = g; ph.wout = bf.w2; ph.phys_in = nullptr; ph.phys_out = nullptr; ph.nb = nb;
         if (p->ndim == 2) {
@@ -492,7 +491,7 @@ int do_c2r(fsm_plan* p, const void* u_hat, void* u, void* ws, cudaStream_t st) {
         const int nf = (int)((nfields - f0 < (long)p->cap_fields) ? nfields - f0 : (long)p->cap_fields);
         IxArgs<T> a;
         a.g = g; a.state = static_cast<const cplx<T>*>(u_hat) + f0 * p->nmodes; a.w1 = bf.w1;
-        a.state_bstride = p->nmodes; a.nbc = nf; a.symtab = nullptr;
+        a.state_bstride = p->nmodes; a.nbc = nf;
         PhysArgs<T> ph;
         ph.g = g; ph.wout = nullptr; ph.phys_in = nullptr; ph.phys_out = static_cast<T*>(u) + f0 * p->ntot;
         ph.wout_fstride = 0; ph.out_o_stride = 0; ph.out_e_stride = 0; ph.nb = nf;
@@ -588,7 +587,6 @@ int fsm_plan_create(fsm_plan** out, const fsm_desc* d) {
             p->kprog = PROG_KS; p->nf_ix = 2; p->nfi = (p->ndim == 2) ? 2 : 3; p->nout = 1; break;
         case FSM_PROG_NS2D_VORT:
             if (p->C != 1 || p->ndim != 2) { delete p; return fail(-EINVAL, "vorticity convection needs a 2-D scalar field"); }
-            if (!d->sym_tab) { delete p; return fail(-EINVAL, "vorticity convection needs the composite symbol table (sym_tab)"); }
             p->kprog = PROG_NS2D; p->nf_ix = 4; p->nfi = 4; p->nout = 1; break;
         case FSM_PROG_NS3D:
             if (p->C != 3 || p->ndim != 3) { delete p; return fail(-EINVAL, "NS pressure convection needs a 3-D, 3-channel field"); }

@@ -164,10 +164,6 @@ class FusedStepper:
             self.source_rot = _rot_half(s, self.shape)
             self._keep.append(self.source_rot)
             desc.source_hat = self.source_rot.data_ptr()
-        if program == _cabi.PROG_NS2D_VORT:
-            self.sym_rot = self._ns2d_symbols(f_mesh, kmax)
-            self._keep.append(self.sym_rot)
-            desc.sym_tab = self.sym_rot.data_ptr()
         self.rot_tables = rot
         self._desc = desc
         plan = ctypes.c_void_p()
@@ -177,30 +173,6 @@ class FusedStepper:
         ws = lib.fsm_workspace_bytes(plan)
         self.workspace = torch.empty(max(ws, 16), dtype=torch.uint8, device=self.device)
         self.ws_bytes = ws
-
-    def _ns2d_symbols(self, f_mesh, kmax):
-        """Composite symbols of the vorticity-convection core (_navier_stokes.py:41-45) for the two paired
-        fields Z1 = u_x + i d_x w, Z2 = u_y + i d_y w, with the low-pass mask (mesh.py:443-461) and the
-        1/N of ifftn folded in; first-derivative symbols are Hermitian-projected (Nyquist entry zero)."""
-        dk, _ = f_mesh.wavenumber_tables()
-        n0, n1 = self.shape
-        gx = (1j * dk[0]).reshape(1, n0, 1).to(self.cdtype)
-        gy = (1j * dk[1]).reshape(1, 1, n1).to(self.cdtype)
-        lap = f_mesh.laplacian()[0]                                   # (1, n0, n1)
-        inv_lap = torch.where(lap == 0, 1.0, 1 / lap)                 # mesh.py:413-419
-        psi = -inv_lap                                                # psi_hat = -w_hat / lap
-        s_ux, s_uy = gy * psi, -gx * psi
-        s_wx, s_wy = gx.expand(1, n0, n1), gy.expand(1, n0, n1)
-        mask = torch.ones((1, n0, n1), dtype=self.rdtype, device=self.device)
-        for i, n in enumerate((n0, n1)):
-            idx = torch.arange(n, device=self.device)
-            m = torch.where(idx <= n // 2, idx, n - idx)
-            shape = [1, 1, 1]
-            shape[i + 1] = n
-            mask = mask * (m <= kmax[i]).to(self.rdtype).reshape(shape)
-        scale = mask / float(n0 * n1)
-        sym = torch.cat([(s_ux + 1j * s_wx) * scale, (s_uy + 1j * s_wy) * scale], dim=0).to(self.cdtype)
-        return _rot_half(sym, self.shape)
 
     # ---- plumbing ---------------------------------------------------------------------------
     def __del__(self):
