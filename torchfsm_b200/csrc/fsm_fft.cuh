@@ -150,14 +150,15 @@ struct LineSync {
     }
 };
 
-// v[m] holds x[tau + m*TL] on entry and X[tau + m*TL] on exit. `buf` is this line's
-// shared-memory buffer (Cfg::LINE_PITCH complex); `tw` the forward twiddle tables.
-// The caller must make sure every thread of the line is done with `buf` before calling.
+// ---- building blocks -----------------------------------------------------------------------
+// line_fft_head: all stages but the last. On exit the input of the last stage sits in `buf`
+// (padded layout); the caller synchronises before the last stage reads it.
 template <class Cfg, int DIR, typename T>
-__device__ __forceinline__ void line_fft(cplx<T>* v, cplx<T>* buf, const cplx<T>* tw, int tau,
-                                         const LineSync<Cfg::TL>& sync) {
+__device__ __forceinline__ void line_fft_head(cplx<T>* v, cplx<T>* buf, const cplx<T>* tw, int tau,
+                                              const LineSync<Cfg::TL>& sync) {
     constexpr int N = Cfg::N, EPT = Cfg::EPT, TL = Cfg::TL;
-    constexpr int R0 = Cfg::R0, R1 = Cfg::R1, R2 = Cfg::R2;
+    constexpr int R0 = Cfg::R0, R1 = Cfg::R1;
+    static_assert(Cfg::NST >= 2, "head/last split needs at least two stages");
     // ---- stage 0: Ns = 1, no twiddles
     static_for<0, EPT / R0>([&](auto qc) {
         constexpr int q = decltype(qc)::value;
@@ -167,23 +168,15 @@ __device__ __forceinline__ void line_fft(cplx<T>* v, cplx<T>* buf, const cplx<T>
             a[t] = v[q + t * (EPT / R0)];
         });
         Dft<R0, DIR, T>::run(a);
-        if constexpr (Cfg::NST == 1) {
-            static_for<0, R0>([&](auto tc) {
-                constexpr int t = decltype(tc)::value;
-                v[q + t * (EPT / R0)] = a[t];
-            });
-        } else {
-            const int w = tau + q * TL;
-            static_for<0, R0>([&](auto tc) {
-                constexpr int t = decltype(tc)::value;
-                buf[Cfg::pad(w * R0 + t)] = a[t];
-            });
-        }
+        const int w = tau + q * TL;
+        static_for<0, R0>([&](auto tc) {
+            constexpr int t = decltype(tc)::value;
+            buf[Cfg::pad(w * R0 + t)] = a[t];
+        });
     });
-    if constexpr (Cfg::NST == 1) return;
-    sync();
-    // ---- stage 1: Ns = R0
-    {
+    if constexpr (Cfg::NST == 3) {
+        sync();
+        // ---- stage 1: Ns = R0 (middle stage)
         constexpr int Ns = R0;
         static_for<0, EPT / R1>([&](auto qc) {
             constexpr int q = decltype(qc)::value;
@@ -193,8 +186,7 @@ __device__ __forceinline__ void line_fft(cplx<T>* v, cplx<T>* buf, const cplx<T>
                 v[q * R1 + t] = buf[Cfg::pad(w + t * (N / R1))];
             });
         });
-        if constexpr (Cfg::NST == 3) sync();  // everyone has read before anyone overwrites
-        cplx<T> out[EPT];
+        sync();  // everyone has read before anyone overwrites
         static_for<0, EPT / R1>([&](auto qc) {
             constexpr int q = decltype(qc)::value;
             const int w = tau + q * TL;
@@ -207,48 +199,57 @@ __device__ __forceinline__ void line_fft(cplx<T>* v, cplx<T>* buf, const cplx<T>
                 a[t] = (DIR < 0) ? cmul(v[q * R1 + t], wv) : cmulc(v[q * R1 + t], wv);
             });
             Dft<R1, DIR, T>::run(a);
-            if constexpr (Cfg::NST == 2) {
-                static_for<0, R1>([&](auto tc) {
-                    constexpr int t = decltype(tc)::value;
-                    out[q + t * (EPT / R1)] = a[t];
-                });
-            } else {
-                const int base = (w / Ns) * Ns * R1 + j;
-                static_for<0, R1>([&](auto tc) {
-                    constexpr int t = decltype(tc)::value;
-                    buf[Cfg::pad(base + t * Ns)] = a[t];
-                });
-            }
+            const int base = (w / Ns) * Ns * R1 + j;
+            static_for<0, R1>([&](auto tc) {
+                constexpr int t = decltype(tc)::value;
+                buf[Cfg::pad(base + t * Ns)] = a[t];
+            });
         });
-        if constexpr (Cfg::NST == 2) {
-            static_for<0, EPT>([&](auto mc) {
-                constexpr int m = decltype(mc)::value;
-                v[m] = out[m];
-            });
-            return;
-        }
     }
-    if constexpr (Cfg::NST == 3) {
+}
+
+// Last stage for work item w (0 <= w < N/RL): a[t] = X[w + t * N/RL], t < RL.
+template <class Cfg>
+struct LastStage {
+    static constexpr int RL = (Cfg::NST == 3) ? Cfg::R2 : Cfg::R1;
+    static constexpr int NS = Cfg::N / RL;   // stride between the outputs of one work item
+};
+template <class Cfg, int DIR, typename T>
+__device__ __forceinline__ void fft_last_item(const cplx<T>* buf, const cplx<T>* tw, int w, cplx<T>* a) {
+    constexpr int RL = LastStage<Cfg>::RL, NS = LastStage<Cfg>::NS;
+    const cplx<T>* twl = (Cfg::NST == 3) ? tw + Cfg::TW1 : tw;
+    // NST == 2: Ns = R0 = NS and j = w; NST == 3: Ns = R0*R1 = NS and j = w
+    a[0] = buf[Cfg::pad(w)];
+    static_for<1, RL>([&](auto tc) {
+        constexpr int t = decltype(tc)::value;
+        const cplx<T> x = buf[Cfg::pad(w + t * NS)];
+        const cplx<T> wv = twl[(t - 1) * NS + w];
+        a[t] = (DIR < 0) ? cmul(x, wv) : cmulc(x, wv);
+    });
+    Dft<RL, DIR, T>::run(a);
+}
+
+// v[m] holds x[tau + m*TL] on entry and X[tau + m*TL] on exit. `buf` is this line's
+// shared-memory buffer (Cfg::LINE_PITCH complex); `tw` the forward twiddle tables.
+// The caller must make sure every thread of the line is done with `buf` before calling.
+template <class Cfg, int DIR, typename T>
+__device__ __forceinline__ void line_fft(cplx<T>* v, cplx<T>* buf, const cplx<T>* tw, int tau,
+                                         const LineSync<Cfg::TL>& sync) {
+    constexpr int EPT = Cfg::EPT, TL = Cfg::TL;
+    if constexpr (Cfg::NST == 1) {
+        Dft<Cfg::R0, DIR, T>::run(v);
+    } else {
+        constexpr int RL = LastStage<Cfg>::RL;
+        line_fft_head<Cfg, DIR, T>(v, buf, tw, tau, sync);
         sync();
-        // ---- stage 2: Ns = R0*R1, last
-        constexpr int Ns = R0 * R1;
-        const cplx<T>* tw2 = tw + Cfg::TW1;
         cplx<T> out[EPT];
-        static_for<0, EPT / R2>([&](auto qc) {
+        static_for<0, EPT / RL>([&](auto qc) {
             constexpr int q = decltype(qc)::value;
-            const int w = tau + q * TL;  // w < N/R2 == Ns
-            cplx<T> a[R2];
-            a[0] = buf[Cfg::pad(w)];
-            static_for<1, R2>([&](auto tc) {
+            cplx<T> a[RL];
+            fft_last_item<Cfg, DIR, T>(buf, tw, tau + q * TL, a);
+            static_for<0, RL>([&](auto tc) {
                 constexpr int t = decltype(tc)::value;
-                const cplx<T> x = buf[Cfg::pad(w + t * (N / R2))];
-                const cplx<T> wv = tw2[(t - 1) * Ns + w];
-                a[t] = (DIR < 0) ? cmul(x, wv) : cmulc(x, wv);
-            });
-            Dft<R2, DIR, T>::run(a);
-            static_for<0, R2>([&](auto tc) {
-                constexpr int t = decltype(tc)::value;
-                out[q + t * (EPT / R2)] = a[t];
+                out[q + t * (EPT / RL)] = a[t];
             });
         });
         static_for<0, EPT>([&](auto mc) {

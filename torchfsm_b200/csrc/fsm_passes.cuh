@@ -126,6 +126,28 @@ __device__ __forceinline__ void rotated_store(const cplx<T>* bufs, int k_lo, int
     }
 }
 
+// Rotated last stage: once line_fft_head has run on every line of the CTA (and a block barrier has
+// passed), thread (t = tid % K, widx = tid / K) finishes the work items w = widx + q*TL of line t and
+// hands each output X_t[e] to emit(e, value). Consecutive lanes hold consecutive lines, so a store to
+// dst[e * stride + t] is coalesced and the natural-order staging round trip through shared memory
+// disappears.
+template <class Cfg, int DIR, typename T, class F>
+__device__ __forceinline__ void rotated_last_stage(const cplx<T>* bufs, const cplx<T>* tw, F&& emit) {
+    constexpr int RL = LastStage<Cfg>::RL, NS = LastStage<Cfg>::NS;
+    const int t = threadIdx.x % kKL, widx = threadIdx.x / kKL;
+    const cplx<T>* buf = bufs + t * Cfg::LINE_PITCH;
+    static_for<0, Cfg::EPT / RL>([&](auto qc) {
+        constexpr int q = decltype(qc)::value;
+        const int w = widx + q * Cfg::TL;
+        cplx<T> a[RL];
+        fft_last_item<Cfg, DIR, T>(buf, tw, w, a);
+        static_for<0, RL>([&](auto tc) {
+            constexpr int tp = decltype(tc)::value;
+            emit(w + tp * NS, a[tp]);
+        });
+    });
+}
+
 // ------------------------------------------------------------------------------------------
 // Pass IX: inverse transform along x of symbol-multiplied spectra (dealias mask, 1/N scale and
 // the x-derivative / stream-function symbols are applied while loading).
@@ -212,39 +234,45 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
                 }
             }
             cplx<T>* pbufs = bufs + (f & 1) * kKL * Cfg::LINE_PITCH;
-            cplx<T>* pbuf = pbufs + lt * Cfg::LINE_PITCH;
-            line_fft<Cfg, +1, T>(v, pbuf, tw, tau, sync);
-            sync();
-            FSM_UNROLL
-            for (int m = 0; m < EPT; ++m) pbuf[tau + m * TL] = v[m];
+            line_fft_head<Cfg, +1, T>(v, pbufs + lt * Cfg::LINE_PITCH, tw, tau, sync);
             if constexpr (f & 1) {
                 __syncthreads();
+                // last stage of both members of the pair in the rotated distribution, combine, store
                 constexpr int pair = f >> 1;
-                const int ts = threadIdx.x % kKL, e0 = threadIdx.x / kKL;
+                constexpr int RL = LastStage<Cfg>::RL, NS = LastStage<Cfg>::NS;
+                const int ts = threadIdx.x % kKL, widx = threadIdx.x / kKL;
                 const int tg = t0 + ts;
                 const bool valid = ts < k_valid;
                 const bool selfc = (tg == 0) || (2 * tg == n1);
                 const T dky_s = valid ? g.dk[1][tg] : T(0);
-                const cplx<T>* s0 = bufs + ts * Cfg::LINE_PITCH + e0;
+                const cplx<T>* s0 = bufs + ts * Cfg::LINE_PITCH;
                 const cplx<T>* s1 = s0 + kKL * Cfg::LINE_PITCH;
-                cplx<T>* dp = w1 + (bc * 2 + pair) * w1_fstride + (long)e0 * out_e_stride + tg;
-                cplx<T>* dm = w1 + (bc * 2 + pair) * w1_fstride + (long)e0 * out_e_stride + (n1 - tg);
-                if (valid) {
-                    FSM_UNROLL
-                    for (int j = 0; j < EPT; ++j) {
-                        const cplx<T> a = s0[j * TL], b = s1[j * TL];
-                        cplx<T> zp, zm;
-                        if constexpr (pair == 0) {
-                            zp = selfc ? mk<T>(b.x, -a.y) : b - a;
-                            zm = mk<T>(a.x + b.x, -(a.y + b.y));
-                        } else {
-                            zp = selfc ? mk<T>(-b.x, -dky_s * a.y) : mk<T>(-dky_s * a.x - b.x, -dky_s * a.y - b.y);
-                            zm = mk<T>(dky_s * a.x - b.x, b.y - dky_s * a.y);
-                        }
-                        dp[(long)j * TL * out_e_stride] = zp;
-                        if (!selfc) dm[(long)j * TL * out_e_stride] = zm;
+                cplx<T>* dp = w1 + (bc * 2 + pair) * w1_fstride + tg;
+                cplx<T>* dm = w1 + (bc * 2 + pair) * w1_fstride + (n1 - tg);
+                static_for<0, EPT / RL>([&](auto qc) {
+                    constexpr int q = decltype(qc)::value;
+                    const int w = widx + q * TL;
+                    cplx<T> a[RL], b[RL];
+                    fft_last_item<Cfg, +1, T>(s0, tw, w, a);
+                    fft_last_item<Cfg, +1, T>(s1, tw, w, b);
+                    if (valid) {
+                        static_for<0, RL>([&](auto tc) {
+                            constexpr int tp = decltype(tc)::value;
+                            const long off = (long)(w + tp * NS) * out_e_stride;
+                            cplx<T> zp, zm;
+                            if constexpr (pair == 0) {
+                                zp = selfc ? mk<T>(b[tp].x, -a[tp].y) : b[tp] - a[tp];
+                                zm = mk<T>(a[tp].x + b[tp].x, -(a[tp].y + b[tp].y));
+                            } else {
+                                zp = selfc ? mk<T>(-b[tp].x, -dky_s * a[tp].y)
+                                           : mk<T>(-dky_s * a[tp].x - b[tp].x, -dky_s * a[tp].y - b[tp].y);
+                                zm = mk<T>(dky_s * a[tp].x - b[tp].x, b[tp].y - dky_s * a[tp].y);
+                            }
+                            dp[off] = zp;
+                            if (!selfc) dm[off] = zm;
+                        });
                     }
-                }
+                });
                 if constexpr (f == 1) __syncthreads();
             }
         });
@@ -269,14 +297,13 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
             else v[m] = cmul_i(u[m], g.dk[0][p]);                               // d_x
         }
         cplx<T>* pbufs = bufs + (f & 1) * kKL * Cfg::LINE_PITCH;
-        cplx<T>* pbuf = pbufs + lt * Cfg::LINE_PITCH;
-        line_fft<Cfg, +1, T>(v, pbuf, tw, tau, sync);
-        sync();
-        FSM_UNROLL
-        for (int m = 0; m < EPT; ++m) pbuf[tau + m * TL] = v[m];
+        line_fft_head<Cfg, +1, T>(v, pbufs + lt * Cfg::LINE_PITCH, tw, tau, sync);
         __syncthreads();
-        cplx<T>* dst = w1 + (bc * NF + f) * w1_fstride + (long)o * out_o_stride + t0;
-        rotated_store<Cfg, T>(pbufs, 0, k_valid, dst, out_e_stride);
+        cplx<T>* dst = w1 + (bc * NF + f) * w1_fstride + (long)o * out_o_stride + t0 + threadIdx.x % kKL;
+        const bool valid = (int)(threadIdx.x % kKL) < k_valid;
+        rotated_last_stage<Cfg, +1, T>(pbufs, tw, [&](int e, cplx<T> val) {
+            if (valid) dst[(long)e * out_e_stride] = val;
+        });
     });
 }
 
@@ -323,14 +350,13 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
             v[m] = x;
         }
         cplx<T>* pbufs = bufs + (j & 1) * kKL * Cfg::LINE_PITCH;
-        cplx<T>* pbuf = pbufs + lt * Cfg::LINE_PITCH;
-        line_fft<Cfg, DIR, T>(v, pbuf, tw, tau, sync);
-        sync();
-        FSM_UNROLL
-        for (int m = 0; m < EPT; ++m) pbuf[tau + m * TL] = v[m];
+        line_fft_head<Cfg, DIR, T>(v, pbufs + lt * Cfg::LINE_PITCH, tw, tau, sync);
         __syncthreads();
-        cplx<T>* dst = out + (b * spec.nfo + j) * out_fstride + (long)o * out_o_stride + t0;
-        rotated_store<Cfg, T>(pbufs, 0, k_valid, dst, out_e_stride);
+        cplx<T>* dst = out + (b * spec.nfo + j) * out_fstride + (long)o * out_o_stride + t0 + threadIdx.x % kKL;
+        const bool valid = (int)(threadIdx.x % kKL) < k_valid;
+        rotated_last_stage<Cfg, DIR, T>(pbufs, tw, [&](int e, cplx<T> val) {
+            if (valid) dst[(long)e * out_e_stride] = val;
+        });
     }
 }
 
