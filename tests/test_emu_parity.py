@@ -12,7 +12,7 @@ from golden_util import golden_names, load_golden, rel_l2
 from product_util import build_emulator, product_from_golden, product_operator
 
 TOL = {"f32": 1e-5, "f64": 1e-12}
-SUPPORTED = [n for n in golden_names() if "1d" not in n]
+SUPPORTED = golden_names()
 
 
 @pytest.fixture(scope="module", autouse=True)

@@ -10,7 +10,7 @@ from product_util import product_from_golden, product_operator
 
 pytestmark = pytest.mark.gpu
 TOL = {"f32": 1e-5, "f64": 1e-12}
-SUPPORTED = [n for n in golden_names() if "1d" not in n]
+SUPPORTED = golden_names()
 
 
 @pytest.fixture(scope="module", autouse=True)

@@ -126,16 +126,41 @@ static int launch_fx(int C, const FxArgs<T>& a, cudaStream_t s) {
     return -ENOSYS;
 }
 
+template <typename T, int N>
+static int launch_step1d(const Step1dArgs<T>& a, cudaStream_t s) {
+    using Cfg = typename CfgFor<N>::type;
+    auto kern = k_step1d<T, Cfg>;
+    const size_t smem = Smem<Cfg, T>::bytes(1);
+    if (int e = set_smem(kern, smem)) return e;
+    FSM_LAUNCH(kern, dim3(a.nb), dim3(Cfg::TL), smem, s, a.g, a.sl, a.ep, a.n_steps);
+    return check_launch();
+}
+template <typename T, int N>
+static int launch_line1d(int mode, const void* in, void* out, long nfields, cudaStream_t s) {
+    using Cfg = typename CfgFor<N>::type;
+    const size_t smem = Smem<Cfg, T>::bytes(1);
+    if (mode == MODE1D_R2C) {
+        auto kern = k_line1d<T, Cfg, MODE1D_R2C>;
+        FSM_LAUNCH(kern, dim3((unsigned)nfields), dim3(Cfg::TL), smem, s, in, out);
+    } else {
+        auto kern = k_line1d<T, Cfg, MODE1D_C2R>;
+        FSM_LAUNCH(kern, dim3((unsigned)nfields), dim3(Cfg::TL), smem, s, in, out);
+    }
+    return check_launch();
+}
+
 #define FSM_CAT2(a, b) a##b
 #define FSM_CAT(a, b) FSM_CAT2(a, b)
 const LaunchTable<float>* FSM_CAT(table_f32_, FSM_N)() {
     static const LaunchTable<float> t = {FSM_N, launch_ix<float, FSM_N>, launch_mid<float, FSM_N>,
-                                         launch_phys<float, FSM_N>, launch_fx<float, FSM_N>};
+                                         launch_phys<float, FSM_N>, launch_fx<float, FSM_N>,
+                                         launch_step1d<float, FSM_N>, launch_line1d<float, FSM_N>};
     return &t;
 }
 const LaunchTable<double>* FSM_CAT(table_f64_, FSM_N)() {
     static const LaunchTable<double> t = {FSM_N, launch_ix<double, FSM_N>, launch_mid<double, FSM_N>,
-                                          launch_phys<double, FSM_N>, launch_fx<double, FSM_N>};
+                                          launch_phys<double, FSM_N>, launch_fx<double, FSM_N>,
+                                          launch_step1d<double, FSM_N>, launch_line1d<double, FSM_N>};
     return &t;
 }
 

@@ -42,6 +42,14 @@ struct FxArgs {
     int nlines, b0, nb;
 };
 
+template <typename T>
+struct Step1dArgs {
+    Geom<T> g;
+    StageList<T> sl;
+    FxEpilogue<T> ep;
+    int n_steps, nb;
+};
+
 // One table per supported line length; entries return 0 or a negative errno.
 template <typename T>
 struct LaunchTable {
@@ -50,6 +58,8 @@ struct LaunchTable {
     int (*mid)(int dir, const MidArgs<T>&, cudaStream_t);
     int (*phys)(int prog, int ndim, const PhysArgs<T>&, cudaStream_t);
     int (*fx)(int C, const FxArgs<T>&, cudaStream_t);
+    int (*step1d)(const Step1dArgs<T>&, cudaStream_t);
+    int (*line1d)(int mode, const void* in, void* out, long nfields, cudaStream_t);
 };
 
 template <typename T>

@@ -791,6 +791,109 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
     });
 }
 
+// ------------------------------------------------------------------------------------------
+// 1-D grids: the whole time loop of one sample runs inside ONE kernel launch (one CTA per sample,
+// state and stage arrays stay in L1/L2; the path is latency-bound).
+//   per stage: Z = u_hat + i (i k u_hat) (dealiased, mirrored) -> inverse FFT -> (u, u_x) -> u u_x
+//              -> forward FFT -> N_hat(k <= N/2) -> combine
+// Also provides the plain 1-D transforms (MODE_R2C / MODE_C2R).
+// ------------------------------------------------------------------------------------------
+#define FSM_MAX_STAGES 4
+template <typename T>
+struct StageList {
+    int n_stages;
+    const cplx<T>* input[FSM_MAX_STAGES];
+    Combine<T> cb[FSM_MAX_STAGES];
+};
+
+template <typename T, class Cfg>
+__global__ void __launch_bounds__(Cfg::TL) k_step1d(Geom<T> g, StageList<T> sl, FxEpilogue<T> ep, int n_steps) {
+    constexpr int N = Cfg::N, EPT = Cfg::EPT, TL = Cfg::TL;
+    FSM_DYN_SMEM(smem_raw);
+    cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);
+    cplx<T>* buf = tw + Smem<Cfg, T>::TWPAD;
+    make_twiddles<Cfg, T>(tw);
+    const int tau = threadIdx.x;
+    const long b = blockIdx.x;
+    const long boff = b * g.nmodes;
+    const int kmax = g.kmax[0];
+    const T* dk = g.dk[0];
+    LineSync<TL> sync{1};
+    for (int step = 0; step < n_steps; ++step) {
+        for (int si = 0; si < sl.n_stages; ++si) {
+            const cplx<T>* in = sl.input[si] + boff;
+            cplx<T> v[EPT];
+            FSM_UNROLL
+            for (int m = 0; m < EPT; ++m) {
+                const int p = tau + m * TL;
+                const int k = (p <= N / 2) ? p : N - p;
+                cplx<T> A = mk<T>(T(0), T(0));
+                if (k <= kmax) A = cscale(in[k], g.inv_ntot);
+                cplx<T> Bq = cmul_i(A, dk[k]);
+                if (k == 0 || k == N / 2) { A.y = T(0); Bq.y = T(0); }
+                if (p > N / 2) { A.y = -A.y; Bq.y = -Bq.y; }
+                v[m] = mk<T>(A.x - Bq.y, A.y + Bq.x);
+            }
+            line_fft<Cfg, +1, T>(v, buf, tw, tau, sync);
+            FSM_UNROLL
+            for (int m = 0; m < EPT; ++m) v[m] = mk<T>(v[m].x * v[m].y, T(0));
+            sync();
+            line_fft<Cfg, -1, T>(v, buf, tw, tau, sync);
+            FSM_UNROLL
+            for (int m = 0; m < EPT; ++m) {
+                const int p = tau + m * TL;
+                if (p <= N / 2) {
+                    cplx<T> f = cscale(v[m], ep.nl_coef);
+                    if (ep.source) f = f + ep.source[p];
+                    combine_mode<T>(sl.cb[si], f, boff, 0, p);
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+enum { MODE1D_R2C = 0, MODE1D_C2R = 1 };
+template <typename T, class Cfg, int MODE>
+__global__ void __launch_bounds__(Cfg::TL) k_line1d(const void* __restrict__ in_v, void* __restrict__ out_v) {
+    constexpr int N = Cfg::N, EPT = Cfg::EPT, TL = Cfg::TL, NH = N / 2 + 1;
+    FSM_DYN_SMEM(smem_raw);
+    cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);
+    cplx<T>* buf = tw + Smem<Cfg, T>::TWPAD;
+    make_twiddles<Cfg, T>(tw);
+    const int tau = threadIdx.x;
+    const long f = blockIdx.x;
+    LineSync<TL> sync{1};
+    cplx<T> v[EPT];
+    if constexpr (MODE == MODE1D_R2C) {
+        const T* in = static_cast<const T*>(in_v) + f * N;
+        cplx<T>* out = static_cast<cplx<T>*>(out_v) + f * NH;
+        FSM_UNROLL
+        for (int m = 0; m < EPT; ++m) v[m] = mk<T>(in[tau + m * TL], T(0));
+        line_fft<Cfg, -1, T>(v, buf, tw, tau, sync);
+        FSM_UNROLL
+        for (int m = 0; m < EPT; ++m) {
+            const int p = tau + m * TL;
+            if (p <= N / 2) out[p] = v[m];
+        }
+    } else {
+        const cplx<T>* in = static_cast<const cplx<T>*>(in_v) + f * NH;
+        T* out = static_cast<T*>(out_v) + f * N;
+        FSM_UNROLL
+        for (int m = 0; m < EPT; ++m) {
+            const int p = tau + m * TL;
+            const int k = (p <= N / 2) ? p : N - p;
+            cplx<T> A = cscale(in[k], T(1) / T(N));
+            if (k == 0 || k == N / 2) A.y = T(0);
+            if (p > N / 2) A.y = -A.y;
+            v[m] = A;
+        }
+        line_fft<Cfg, +1, T>(v, buf, tw, tau, sync);
+        FSM_UNROLL
+        for (int m = 0; m < EPT; ++m) out[tau + m * TL] = v[m].x;
+    }
+}
+
 // Combine without a nonlinear term (ETDRK0) or point-wise fix-ups: one thread per mode.
 template <typename T>
 __global__ void k_combine_only(Combine<T> cb, long nmodes, int C, long total /*B*C*nmodes*/) {

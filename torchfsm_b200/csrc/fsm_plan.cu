@@ -428,9 +428,35 @@ int run_stage(const fsm_plan* p, const Buffers<T>& bf, const Stage& s, cudaStrea
     return 0;
 }
 
+// 1-D: every stage of every step inside one launch (one CTA per sample)
+template <typename T>
+int run_1d(const fsm_plan* p, const Buffers<T>& bf, const Stage* stages, int n_stages, int n_steps, cudaStream_t st) {
+    Step1dArgs<T> a;
+    memset(&a.sl, 0, sizeof(a.sl));
+    a.g = make_geom<T>(p, false);
+    a.sl.n_stages = n_stages;
+    for (int i = 0; i < n_stages; ++i) {
+        a.sl.input[i] = bf.arr[stages[i].input];
+        if (int e = make_combine<T>(p, stages[i], bf.arr, true, &a.sl.cb[i])) return e;
+    }
+    a.ep.nl_coef = (T)p->d.nl_coef;
+    a.ep.source = static_cast<const cplx<T>*>(p->d.source_hat);
+    a.ep.dc_out = nullptr;
+    a.ep.project = 0;
+    a.n_steps = n_steps;
+    a.nb = p->B;
+    const LaunchTable<T>* tx = launch_table<T>(p->n[0]);
+    if (int e = tx->step1d(a, st)) return fail(e, "1-D step launch failed");
+    return 0;
+}
+
 template <typename T>
 int do_step(fsm_plan* p, void* u_hat, void* ws, int n_steps, cudaStream_t st) {
     Buffers<T> bf = carve<T>(p, u_hat, ws, nullptr);
+    if (p->ndim == 1 && p->prog != FSM_PROG_LINEAR) {
+        if (p->stages.size() > FSM_MAX_STAGES) return fail(-ENOSYS, "too many stages for the 1-D kernel");
+        return run_1d<T>(p, bf, p->stages.data(), (int)p->stages.size(), n_steps, st);
+    }
     for (int i = 0; i < n_steps; ++i)
         for (const Stage& s : p->stages)
             if (int e = run_stage<T>(p, bf, s, st)) return e;
@@ -440,11 +466,17 @@ int do_step(fsm_plan* p, void* u_hat, void* ws, int n_steps, cudaStream_t st) {
 template <typename T>
 int do_rhs(fsm_plan* p, const void* u_hat, void* out, void* ws, cudaStream_t st) {
     Buffers<T> bf = carve<T>(p, const_cast<void*>(u_hat), ws, out);
+    if (p->ndim == 1 && p->prog != FSM_PROG_LINEAR) return run_1d<T>(p, bf, &p->rhs_stage, 1, 1, st);
     return run_stage<T>(p, bf, p->rhs_stage, st);
 }
 
 template <typename T>
 int do_r2c(fsm_plan* p, const void* u, void* u_hat, void* ws, cudaStream_t st) {
+    if (p->ndim == 1) {
+        if (int e = launch_table<T>(p->n[0])->line1d(MODE1D_R2C, u, u_hat, (long)p->B * p->C, st))
+            return fail(e, "1-D R2C launch failed");
+        return 0;
+    }
     Buffers<T> bf = carve<T>(p, u_hat, ws, nullptr);
     const Geom<T> g = make_geom<T>(p, true);
     const LaunchTable<T>* tl = launch_table<T>(p->n[p->ndim - 1]);
@@ -482,6 +514,11 @@ int do_r2c(fsm_plan* p, const void* u, void* u_hat, void* ws, cudaStream_t st) {
 
 template <typename T>
 int do_c2r(fsm_plan* p, const void* u_hat, void* u, void* ws, cudaStream_t st) {
+    if (p->ndim == 1) {
+        if (int e = launch_table<T>(p->n[0])->line1d(MODE1D_C2R, u_hat, u, (long)p->B * p->C, st))
+            return fail(e, "1-D C2R launch failed");
+        return 0;
+    }
     Buffers<T> bf = carve<T>(p, const_cast<void*>(u_hat), ws, nullptr);
     const Geom<T> g = make_geom<T>(p, true);
     const LaunchTable<T>* tx = launch_table<T>(p->n[0]);
@@ -548,7 +585,7 @@ int fsm_plan_create(fsm_plan** out, const fsm_desc* d) {
     if (!out || !d) return fail(-EINVAL, "null argument");
     if (d->struct_size != (int32_t)sizeof(fsm_desc))
         return fail(-EINVAL, "fsm_desc size mismatch: caller %d, library %d", d->struct_size, (int)sizeof(fsm_desc));
-    if (d->ndim < 2 || d->ndim > 3) return fail(-ENOSYS, "ndim=%d: only 2-D and 3-D grids are supported by this build", d->ndim);
+    if (d->ndim < 1 || d->ndim > 3) return fail(-EINVAL, "ndim=%d: grids must be 1-D, 2-D or 3-D", d->ndim);
     if (d->dtype != FSM_F32 && d->dtype != FSM_F64) return fail(-EINVAL, "bad dtype %d", d->dtype);
     if (d->batch < 1 || d->channels < 1) return fail(-EINVAL, "batch and channels must be positive");
     fsm_plan* p = new fsm_plan();
@@ -584,6 +621,7 @@ int fsm_plan_create(fsm_plan** out, const fsm_desc* d) {
             p->kprog = PROG_CONV; p->nf_ix = 2; p->nfi = (p->ndim == 2) ? 4 : 9; p->nout = p->C; break;
         case FSM_PROG_KS:
             if (p->C != 1) { delete p; return fail(-EINVAL, "KS convection needs one channel"); }
+            if (p->ndim == 1) { delete p; return fail(-ENOSYS, "KS convection on 1-D grids is not supported by the fused CUDA path"); }
             p->kprog = PROG_KS; p->nf_ix = 2; p->nfi = (p->ndim == 2) ? 2 : 3; p->nout = 1; break;
         case FSM_PROG_NS2D_VORT:
             if (p->C != 1 || p->ndim != 2) { delete p; return fail(-EINVAL, "vorticity convection needs a 2-D scalar field"); }
@@ -613,8 +651,10 @@ int fsm_plan_create(fsm_plan** out, const fsm_desc* d) {
     // chunking: keep the per-chunk intermediates of 2-D runs inside the 126 MB L2
     const size_t esz = p->f64 ? 16 : 8;
     const long plane = (long)p->n[0] * p->n[1];
-    size_t w1_per, w2_per, w3_per = 0, w2b_per = 0;
-    if (p->ndim == 2) {
+    size_t w1_per = 0, w2_per = 0, w3_per = 0, w2b_per = 0;
+    if (p->ndim == 1) {
+        // the 1-D kernels keep everything on chip: no intermediates
+    } else if (p->ndim == 2) {
         w1_per = (p->kprog == PROG_NS2D) ? (size_t)2 * p->n[0] * p->n[1] * esz
                                          : (size_t)p->C * p->nf_ix * p->n[0] * p->ph * esz;
         w2_per = (size_t)p->nout * p->nmodes * esz;
@@ -628,8 +668,8 @@ int fsm_plan_create(fsm_plan** out, const fsm_desc* d) {
     if (chunk <= 0) {
         // enough samples per launch to give the smallest pass (FX) several waves of CTAs on 148 SMs,
         // bounded by an 8 GiB budget for the per-chunk intermediates; then balance the chunks.
-        const long fx_ctas = (p->nmodes / p->n[0] + kKL - 1) / kKL;
-        chunk = (int)((148L * 8 + fx_ctas - 1) / fx_ctas);
+        const long fx_ctas = (p->ndim == 1) ? 1 : (p->nmodes / p->n[0] + kKL - 1) / kKL;
+        chunk = (p->ndim == 1) ? p->B : (int)((148L * 8 + fx_ctas - 1) / fx_ctas);
         const size_t per = w1_per + w2_per + w3_per + w2b_per;
         const size_t budget = (size_t)8 << 30;
         if ((size_t)chunk * per > budget) chunk = (int)(budget / (per ? per : 1));
@@ -662,7 +702,9 @@ int fsm_plan_create(fsm_plan** out, const fsm_desc* d) {
     // each intermediate buffer can hold when every field takes one plain slot
     {
         size_t cap;
-        if (p->ndim == 2) {
+        if (p->ndim == 1) {
+            cap = (size_t)p->B * p->C;
+        } else if (p->ndim == 2) {
             cap = (w1_per * chunk) / ((size_t)p->n[0] * p->ph * esz);
             const size_t c2 = (w2_per * chunk) / ((size_t)p->nmodes * esz);
             if (c2 < cap) cap = c2;
@@ -685,6 +727,8 @@ int fsm_plan_create(fsm_plan** out, const fsm_desc* d) {
         for (const Stage& s : p->stages) {
             if (p->prog == FSM_PROG_LINEAR) {
                 launches += 1;
+            } else if (p->ndim == 1) {
+                launches = 1;   // the whole time loop is one launch
             } else {
                 launches += (int64_t)nchunks * (p->ndim == 2 ? 3 : 5) + ((p->prog == FSM_PROG_KS && d->ks_remove_mean) ? 1 : 0);
                 const int cnf = p->C * p->nf_ix;
