@@ -216,9 +216,20 @@ def run_b200(args):
         gbs = v["algo_bytes_per_step"] * prof_steps / (v["ms"] * 1e-3) / 1e9
         passes[k] = {"ms_per_step": v["ms"] / prof_steps, "launches_per_step": v["launches"] / prof_steps,
                      "algo_gb_per_step": v["algo_bytes_per_step"] / 1e9, "achieved_gbs": gbs, "frac": gbs / peak}
+    # DRAM traffic per launch of the dominant kernel from the committed ncu --set full capture (same chunk)
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
+        if info["chunk"] == 64:
+            traffic = tj["kernels"]["k_pass_" + dom.lower()]["dram_bytes_per_launch"]
+    except Exception:
+        traffic = None
     step_gbs = info["algo_bytes_per_step"] / (ms_step * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "k_pass_" + dom.lower(), "achieved": passes[dom]["achieved_gbs"], "peak": peak,
-                "unit": "GB/s", "frac": passes[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": passes[dom]["frac"], "traffic": traffic,
+                "traffic_source": "profiles/r1_ncu_traffic.json (ncu --set full, dram read+write bytes per launch)",
+                "algo_bytes_per_launch": passes[dom]["algo_gb_per_step"] * 1e9 / passes[dom]["launches_per_step"],
+                "peak_source": peak_src,
                 "passes": passes,
                 "whole_step": {"algo_gb_per_step": info["algo_bytes_per_step"] / 1e9, "achieved_gbs": step_gbs,
                                "frac": step_gbs / peak}}

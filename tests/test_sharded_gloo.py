@@ -1,0 +1,67 @@
+"""Multi-process path on CPU (gloo, world_size 2): the ensemble shards over ranks with no data-path
+collective; every rank integrates its shard through the same plugin layer + C ABI (host-emulator build)
+and the gathered result equals the single-process reference answer."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, name, lib_path, out_q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    from golden_util import load_golden, rel_l2
+    from product_util import product_from_golden
+    from torchfsm_b200 import _cabi
+    _cabi.use_library(lib_path)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = load_golden(name)
+        spec = g["spec"]
+        op, mesh, u0 = product_from_golden(g, "cpu")
+        per = u0.shape[0] // world
+        shard = u0[rank * per:(rank + 1) * per].contiguous()
+        uT = op.integrate(shard, mesh=mesh, dt=spec["dt"], step=spec["steps"])
+        gathered = [torch.empty_like(uT) for _ in range(world)]
+        dist.all_gather(gathered, uT)
+        # device-style timing reduction used by bench.py: max over ranks
+        t = torch.tensor([float(rank + 1)])
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            full = torch.cat(gathered, dim=0)
+            out_q.put((rel_l2(full.numpy(), g["uT"]), float(t.item())))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name", ["c3_ns2d_32_etdrk2_f64", "c4_burgers3d_16_f64"])
+def test_ensemble_shards_over_two_ranks(name):
+    from product_util import build_emulator
+    lib_path = build_emulator()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, name, lib_path, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    err, tmax = q.get(timeout=5)
+    assert err <= 1e-12 and tmax == 2.0
