@@ -85,6 +85,9 @@ typedef struct fsm_desc {
     const void* tab_lin;      /* L itself (RK4 and fsm_rhs)   operator/_base.py:339-357              */
     const void* source_hat;   /* optional constant source spectrum, complex [C][modes], coefficient
                                  folded in (operator/_base.py:994-1015)                              */
+    int32_t slab_rank;        /* slab decomposition of ONE 3-D grid over slab_nranks GPUs (0 / 1 = off):  */
+    int32_t slab_nranks;      /* spectral state and tables hold the local ky slab [n1/P][n2/2+1][n0],
+                                 physical fields the local x slab [n0/P][n1][n2]; see fsm_slab_phase      */
 } fsm_desc;
 
 /* replaces: OperatorLike._build_integrator (operator/_base.py:441-526) */
@@ -115,6 +118,21 @@ int fsm_full_to_half(fsm_plan* plan, const void* full_hat, void* u_hat, void* st
  * (transform-pass model), modes per field, chunk size */
 int fsm_plan_info(const fsm_plan* plan, int64_t* launches_per_step, int64_t* algo_bytes_per_step,
                   int64_t* modes_per_field, int32_t* chunk);
+
+/* Slab-decomposed evaluation (single large 3-D grids): the library runs the local passes of
+ * one phase; the caller performs the all-to-all between phases (torch.distributed all_to_all_single over
+ * NCCL/NVLink, equal splits) on the exchange buffers, which the kernels read and write directly in
+ * rank-blocked layouts (no pack/unpack pass).
+ *   op FSM_SLAB_STEP / FSM_SLAB_RHS, stage s:  phase 0: state -> x-transform -> send          [all-to-all]
+ *                                              phase 1: recv -> y, z, product, z, y -> send    [all-to-all]
+ *                                              phase 2: recv -> x-transform + integrator combine
+ *   op FSM_SLAB_R2C: phase 1 (aux = local physical slab -> send), phase 2 (recv -> u_hat)
+ *   op FSM_SLAB_C2R: phase 0 (u_hat -> send), phase 1 (recv -> aux = local physical slab)
+ * fsm_slab_info returns the complex-element counts of the two exchanges for an op and the stage count. */
+enum fsm_slab_op { FSM_SLAB_STEP = 0, FSM_SLAB_RHS = 1, FSM_SLAB_R2C = 2, FSM_SLAB_C2R = 3 };
+int fsm_slab_phase(fsm_plan* plan, int op, int stage, int phase, void* u_hat, void* aux, void* workspace,
+                   size_t ws_bytes, void* send, void* recv, void* stream);
+int fsm_slab_info(const fsm_plan* plan, int op, int64_t* exch1_elems, int64_t* exch2_elems, int32_t* n_stages);
 
 /* per-pass device timing for benchmarks: when enabled every pass launch is bracketed by CUDA
  * events on the caller's stream. fsm_profile_read waits for the recorded events, returns summed

@@ -28,11 +28,12 @@ class FsmDesc(ctypes.Structure):
         ("dk", ctypes.c_void_p * 3), ("dkraw", ctypes.c_void_p * 3),
         ("tab_exp", ctypes.c_void_p), ("tab_half_exp", ctypes.c_void_p), ("tab_coef", ctypes.c_void_p * 6),
         ("tab_lin", ctypes.c_void_p), ("source_hat", ctypes.c_void_p),
+        ("slab_rank", ctypes.c_int32), ("slab_nranks", ctypes.c_int32),
     ]
 
 
 EXPORTS = ["fsm_plan_create", "fsm_plan_destroy", "fsm_workspace_bytes", "fsm_step", "fsm_rhs", "fsm_r2c",
-           "fsm_c2r", "fsm_half_to_full", "fsm_full_to_half", "fsm_plan_info", "fsm_profile_enable", "fsm_profile_read", "fsm_last_error",
+           "fsm_c2r", "fsm_half_to_full", "fsm_full_to_half", "fsm_plan_info", "fsm_slab_phase", "fsm_slab_info", "fsm_profile_enable", "fsm_profile_read", "fsm_last_error",
            "fsm_abi_version", "fsm_backend"]
 
 _lib = None
@@ -61,6 +62,10 @@ def _declare(lib):
     lib.fsm_full_to_half.restype = i32
     lib.fsm_plan_info.argtypes = [vp, i64p, i64p, i64p, ctypes.POINTER(ctypes.c_int32)]
     lib.fsm_plan_info.restype = i32
+    lib.fsm_slab_phase.argtypes = [vp, i32, i32, i32, vp, vp, vp, sz, vp, vp, vp]
+    lib.fsm_slab_phase.restype = i32
+    lib.fsm_slab_info.argtypes = [vp, i32, i64p, i64p, ctypes.POINTER(ctypes.c_int32)]
+    lib.fsm_slab_info.restype = i32
     lib.fsm_profile_enable.argtypes = [vp, i32]
     lib.fsm_profile_enable.restype = i32
     lib.fsm_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), i64p, i64p]

@@ -19,6 +19,12 @@ template <> struct CfgFor<256> { using type = FftCfg<256, 16, 16, 16>; };
 template <> struct CfgFor<512> { using type = FftCfg<512, 16, 16, 16, 2>; };
 template <> struct CfgFor<1024> { using type = FftCfg<1024, 16, 16, 16, 4>; };
 
+// the last-axis pass may use its own decomposition (FSM_PHYS32: 32*32 on one warp per line)
+template <int N> struct CfgPhys { using type = typename CfgFor<N>::type; };
+#ifdef FSM_PHYS32
+template <> struct CfgPhys<1024> { using type = FftCfg<1024, 32, 32, 32>; };
+#endif
+
 
 #ifndef FSM_EMU
 template <class K>
@@ -43,7 +49,7 @@ static int launch_ix_p(const IxArgs<T>& a, cudaStream_t s) {
     if (int e = set_smem(kern, smem)) return e;
     dim3 grid((a.n_t + kKL - 1) / kKL, a.n_outer, a.nbc), block(kKL * Cfg::TL);
     FSM_LAUNCH(kern, grid, block, smem, s, a.g, a.state, a.w1, a.state_bstride, a.w1_fstride, kKL, a.in_t_stride,
-               a.in_o_stride, a.out_o_stride, a.out_e_stride, a.n_t);
+               a.in_o_stride, a.out_o_stride, a.out_e_stride, a.n_t, a.eb);
     return check_launch();
 }
 template <typename T, int N>
@@ -64,7 +70,7 @@ static int launch_mid_d(const MidArgs<T>& a, cudaStream_t s) {
     if (int e = set_smem(kern, smem)) return e;
     dim3 grid((a.n_t + kKL - 1) / kKL, a.n_outer, a.nb), block(kKL * Cfg::TL);
     FSM_LAUNCH(kern, grid, block, smem, s, a.g, a.in, a.out, a.in_fstride, a.out_fstride, a.nfi, a.spec, kKL,
-               a.in_t_stride, a.in_o_stride, a.out_o_stride, a.out_e_stride, a.n_t);
+               a.in_t_stride, a.in_o_stride, a.out_o_stride, a.out_e_stride, a.n_t, a.ib, a.eb);
     return check_launch();
 }
 template <typename T, int N>
@@ -74,7 +80,7 @@ static int launch_mid(int dir, const MidArgs<T>& a, cudaStream_t s) {
 
 template <typename T, int N, int PROG, int NDIM>
 static int launch_phys_p(const PhysArgs<T>& a, cudaStream_t s) {
-    using Cfg = typename CfgFor<N>::type;
+    using Cfg = typename CfgPhys<N>::type;
     using PT = PhysTraits<PROG, NDIM>;
     constexpr int NFW = (PT::NOUT * PT::RPT + 1) / 2;
     auto kern = k_pass_phys<T, Cfg, PROG, NDIM>;
@@ -110,7 +116,8 @@ static int launch_fx_c(const FxArgs<T>& a, cudaStream_t s) {
     const size_t smem = Smem<Cfg, T>::bytes(kKL);
     if (int e = set_smem(kern, smem)) return e;
     dim3 grid((a.nlines + kKL - 1) / kKL, 1, a.nb), block(kKL * Cfg::TL);
-    FSM_LAUNCH(kern, grid, block, smem, s, a.g, a.win, a.win_fstride, a.cb, a.ep, a.nlines, a.b0);
+    FSM_LAUNCH(kern, grid, block, smem, s, a.g, a.win, a.win_fstride, a.cb, a.ep, a.nlines, a.b0, a.ib,
+               a.line_stride ? a.line_stride : (long)Cfg::N);
     return check_launch();
 }
 template <typename T, int N>

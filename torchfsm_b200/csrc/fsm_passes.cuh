@@ -43,9 +43,20 @@ struct Geom {
     int kmax[3];   // dealiasing: keep |m_i| <= kmax[i]
     long nmodes;   // complex modes per field in the rot-half layout
     T inv_ntot;    // 1 / (n0*n1*n2)
+    int ky0;       // slab decomposition: first global ky of the local spectral slab (0 on one GPU)
     const T* dk[3];     // 2*pi*f_i(m), Nyquist entry zeroed (Hermitian projection of i*k)
     const T* dkraw[3];  // 2*pi*f_i(m) as the reference computes it (Nyquist kept, negative)
 };
+
+// Rank-blocked index (slab decomposition): index i lives in block i >> shift (block stride `stride`
+// elements) at position i & mask inside it. One GPU: shift = 30, i.e. a single block.
+struct Blk {
+    int shift;
+    long stride;
+};
+__device__ __forceinline__ long blk_off(int i, const Blk& b, long elem_stride) {
+    return (long)(i >> b.shift) * b.stride + (long)(i & ((1 << b.shift) - 1)) * elem_stride;
+}
 
 template <int N>
 __device__ __forceinline__ int signed_mode(int p) { return (p <= N / 2) ? p : p - N; }
@@ -167,7 +178,7 @@ template <typename T, class Cfg, int PROG>
 __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass_ix(Geom<T> g, const cplx<T>* __restrict__ state, cplx<T>* __restrict__ w1,
                                                   long state_bstride /*per (b,c)*/, long w1_fstride, int K,
                                                   long in_t_stride, long in_o_stride, long out_o_stride,
-                                                  long out_e_stride, int n_t) {
+                                                  long out_e_stride, int n_t, Blk eb) {
     constexpr int N = Cfg::N, EPT = Cfg::EPT, TL = Cfg::TL;
     constexpr int NF = IxFields<PROG>::NF;
     FSM_DYN_SMEM(smem_raw);
@@ -182,14 +193,15 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
     const int t = t0 + lt;  // ky index of this thread-line
     const int k_valid = (K < n_t - t0) ? K : (n_t - t0);
     // dealias test on the line coordinates
-    const int my = signed_mode_rt(t < n_t ? t : 0, g.n[1]);
+    const int tglob = (t < n_t ? t : 0) + g.ky0;   // global ky of this line
+    const int my = signed_mode_rt(tglob, g.n[1]);
     bool line_kept = (t < n_t);
     if (PROG != PROG_C2R) {
         line_kept = line_kept && (iabs(my) <= g.kmax[1]);
         if (g.ndim == 3) line_kept = line_kept && (o <= g.kmax[2]);
     }
-    const T dky = (t < n_t) ? g.dk[1][t] : T(0);
-    const T dkyraw = (t < n_t) ? g.dkraw[1][t] : T(0);
+    const T dky = (t < n_t) ? g.dk[1][tglob] : T(0);
+    const T dkyraw = (t < n_t) ? g.dkraw[1][tglob] : T(0);
 
     cplx<T> u[EPT];
     const cplx<T>* src = state + bc * state_bstride + (long)t * in_t_stride + (long)o * in_o_stride;
@@ -302,7 +314,7 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
         cplx<T>* dst = w1 + (bc * NF + f) * w1_fstride + (long)o * out_o_stride + t0 + threadIdx.x % kKL;
         const bool valid = (int)(threadIdx.x % kKL) < k_valid;
         rotated_last_stage<Cfg, +1, T>(pbufs, tw, [&](int e, cplx<T> val) {
-            if (valid) dst[(long)e * out_e_stride] = val;
+            if (valid) dst[blk_off(e, eb, out_e_stride)] = val;
         });
     });
 }
@@ -322,7 +334,7 @@ template <typename T, class Cfg, int DIR>
 __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass_mid(Geom<T> g, const cplx<T>* __restrict__ in, cplx<T>* __restrict__ out,
                                                    long in_fstride, long out_fstride, int nfi, MidSpec spec, int K,
                                                    long in_t_stride, long in_o_stride, long out_o_stride,
-                                                   long out_e_stride, int n_t) {
+                                                   long out_e_stride, int n_t, Blk ib, Blk eb) {
     constexpr int N = Cfg::N, EPT = Cfg::EPT, TL = Cfg::TL;
     FSM_DYN_SMEM(smem_raw);
     cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);
@@ -345,7 +357,7 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
             const int p = tau + m * TL;
             bool kept = line_ok;
             if (DIR > 0) kept = kept && (iabs(signed_mode<N>(p)) <= g.kmax[1]);
-            cplx<T> x = kept ? src[p] : mk<T>(T(0), T(0));
+            cplx<T> x = kept ? src[blk_off(p, ib, 1)] : mk<T>(T(0), T(0));
             if (spec.deriv[j]) x = cmul_i(x, g.dk[1][p]);
             v[m] = x;
         }
@@ -355,7 +367,7 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
         cplx<T>* dst = out + (b * spec.nfo + j) * out_fstride + (long)o * out_o_stride + t0 + threadIdx.x % kKL;
         const bool valid = (int)(threadIdx.x % kKL) < k_valid;
         rotated_last_stage<Cfg, DIR, T>(pbufs, tw, [&](int e, cplx<T> val) {
-            if (valid) dst[(long)e * out_e_stride] = val;
+            if (valid) dst[blk_off(e, eb, out_e_stride)] = val;
         });
     }
 }
@@ -709,7 +721,7 @@ __device__ __forceinline__ void combine_mode(const Combine<T>& cb, cplx<T> fresh
 
 template <typename T, class Cfg, int C>
 __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass_fx(Geom<T> g, const cplx<T>* __restrict__ win, long win_fstride,
-                                                  Combine<T> cb, FxEpilogue<T> ep, int nlines, int b0) {
+                                                  Combine<T> cb, FxEpilogue<T> ep, int nlines, int b0, Blk ib, long line_stride) {
     constexpr int N = Cfg::N, EPT = Cfg::EPT, TL = Cfg::TL;
     FSM_DYN_SMEM(smem_raw);
     cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);
@@ -726,15 +738,15 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
     cplx<T> nhat[C][EPT];
     static_for<0, C>([&](auto cc) {
         constexpr int c = decltype(cc)::value;
-        const cplx<T>* src = win + (bl * C + c) * win_fstride + (long)line * N;
+        const cplx<T>* src = win + (bl * C + c) * win_fstride + (long)line * line_stride;
         FSM_UNROLL
-        for (int m = 0; m < EPT; ++m) nhat[c][m] = src[tau + m * TL];
+        for (int m = 0; m < EPT; ++m) nhat[c][m] = src[blk_off(tau + m * TL, ib, 1)];
         if (c > 0) sync();
         line_fft<Cfg, -1, T>(nhat[c], mybuf, tw, tau, sync);
     });
     // line coordinates
     int ky, kz = 0;
-    if (g.ndim == 3) { ky = line / g.nh; kz = line % g.nh; } else { ky = line; }
+    if (g.ndim == 3) { ky = line / g.nh + g.ky0; kz = line % g.nh; } else { ky = line; }
     constexpr int NB = (EPT >= 4) ? 4 : EPT;
     const long line_mode0 = (long)line * N;
     static_for<0, EPT / NB>([&](auto mbc) {
@@ -781,7 +793,7 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
                     f[c][j] = f[c][j] + ep.source[(long)c * g.nmodes + line_mode0 + tau + (mb + j) * TL];
             }
         }
-        if (ep.dc_out && line == 0 && tau == 0 && mb == 0) {
+        if (ep.dc_out && line == 0 && g.ky0 == 0 && tau == 0 && mb == 0) {
             ep.dc_out[b] = f[0][0].x;
             f[0][0] = mk<T>(T(0), T(0));
         }

@@ -179,6 +179,7 @@ struct fsm_plan {
     long nmodes, ntot;
     int chunk;
     int nf_ix, nfi, nout;  // fields: IX per channel, PHYS inputs per sample, PHYS outputs per sample
+    int P = 1, rank = 0, kyl = 0, nxl = 0, nkz1 = 0;  // slab decomposition (P > 1): local ky / x extents, kept kz planes
     std::vector<Stage> stages;
     Stage rhs_stage;
     // workspace (offsets in bytes)
@@ -232,6 +233,7 @@ Geom<T> make_geom(const fsm_plan* p, bool nomask) {
         g.dk[i] = static_cast<const T*>(p->d.dk[i]);
         g.dkraw[i] = static_cast<const T*>(p->d.dkraw[i]);
     }
+    g.ky0 = (p->P > 1) ? p->rank * p->kyl : 0;
     g.nh = p->nh;
     g.ph = p->ph;
     g.nmodes = p->nmodes;
@@ -564,6 +566,140 @@ int do_c2r(fsm_plan* p, const void* u_hat, void* u, void* ws, cudaStream_t st) {
     return 0;
 }
 
+int ilog2(int x) { int s = 0; while ((1 << s) < x) ++s; return s; }
+
+// ---------------------------------------------------------------------------------------------
+// Slab decomposition: local passes of one phase (see include/fsm_b200.h, fsm_slab_phase)
+//   exchange 1 (inverse side)  [dst rank q][field][kz < nkz][x_local][ky_local]
+//   exchange 2 (forward side)  [dst rank q][field][ky_local][kz < nh][x_local]
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+int slab_ix(const fsm_plan* p, const Geom<T>& g, int kprog, const cplx<T>* state, cplx<T>* send, int nfields_in, int nf,
+            int nkz, cudaStream_t st) {
+    const LaunchTable<T>* tx = launch_table<T>(p->n[0]);
+    IxArgs<T> a;
+    a.g = g; a.state = state; a.w1 = send; a.state_bstride = p->nmodes; a.nbc = nfields_in;
+    a.w1_fstride = (long)nkz * p->nxl * p->kyl;
+    a.in_t_stride = (long)p->nh * p->n[0]; a.in_o_stride = p->n[0];
+    a.out_o_stride = (long)p->nxl * p->kyl; a.out_e_stride = p->kyl;
+    a.n_t = p->kyl; a.n_outer = nkz;
+    a.eb.shift = ilog2(p->nxl); a.eb.stride = (long)nfields_in * nf * a.w1_fstride;
+    ProfScope ps(p, PASS_IX, st);
+    if (int e = tx->ix(kprog, a, st)) return fail(e, "slab IX launch failed");
+    return 0;
+}
+
+template <typename T>
+int slab_mid_inverse(const fsm_plan* p, const Geom<T>& g, const cplx<T>* recv, cplx<T>* w3, int nfi_in, const MidSpec& spec,
+                     int nkz, int nb, cudaStream_t st) {
+    const LaunchTable<T>* ty = launch_table<T>(p->n[1]);
+    MidArgs<T> m;
+    m.g = g; m.in = recv; m.out = w3;
+    m.in_fstride = (long)nkz * p->nxl * p->kyl; m.out_fstride = (long)p->nxl * p->n[1] * p->ph;
+    m.in_t_stride = (long)p->nxl * p->kyl; m.in_o_stride = p->kyl;
+    m.out_o_stride = (long)p->n[1] * p->ph; m.out_e_stride = p->ph;
+    m.nfi = nfi_in; m.n_t = nkz; m.n_outer = p->nxl; m.nb = nb; m.spec = spec;
+    m.ib.shift = ilog2(p->kyl); m.ib.stride = (long)nb * nfi_in * m.in_fstride;
+    ProfScope ps(p, PASS_MID, st);
+    if (int e = ty->mid(+1, m, st)) return fail(e, "slab MID inverse launch failed");
+    return 0;
+}
+
+template <typename T>
+int slab_mid_forward(const fsm_plan* p, const Geom<T>& g, const cplx<T>* w2a, cplx<T>* send, int nf, int nb, cudaStream_t st) {
+    const LaunchTable<T>* ty = launch_table<T>(p->n[1]);
+    MidArgs<T> m;
+    m.g = g; m.in = w2a; m.out = send;
+    m.in_fstride = (long)p->nh * p->nxl * p->n[1]; m.out_fstride = (long)p->kyl * p->nh * p->nxl;
+    m.in_t_stride = p->n[1]; m.in_o_stride = (long)p->nxl * p->n[1];
+    m.out_o_stride = p->nxl; m.out_e_stride = (long)p->nh * p->nxl;
+    m.nfi = nf; m.n_t = p->nxl; m.n_outer = p->nh; m.nb = nb; m.spec = mid_spec_identity(nf);
+    m.eb.shift = ilog2(p->kyl); m.eb.stride = (long)nb * nf * m.out_fstride;
+    ProfScope ps(p, PASS_MID, st);
+    if (int e = ty->mid(-1, m, st)) return fail(e, "slab MID forward launch failed");
+    return 0;
+}
+
+template <typename T>
+int slab_phys(const fsm_plan* p, const Geom<T>& g, int kprog, const cplx<T>* w3, cplx<T>* w2a, const T* phys_in, T* phys_out,
+              int nb, cudaStream_t st) {
+    const LaunchTable<T>* tl = launch_table<T>(p->n[2]);
+    PhysArgs<T> ph;
+    ph.g = g; ph.win = w3; ph.wout = w2a; ph.phys_in = phys_in; ph.phys_out = phys_out; ph.nb = nb;
+    ph.win_fstride = (long)p->nxl * p->n[1] * p->ph; ph.wout_fstride = (long)p->nh * p->nxl * p->n[1];
+    ph.in_t_stride = p->ph; ph.in_o_stride = (long)p->n[1] * p->ph;
+    ph.out_o_stride = p->n[1]; ph.out_e_stride = (long)p->nxl * p->n[1];
+    ph.n_t = p->n[1]; ph.n_outer = p->nxl;
+    ProfScope ps(p, PASS_PHYS, st);
+    if (int e = tl->phys(kprog, 3, ph, st)) return fail(e, "slab PHYS launch failed");
+    return 0;
+}
+
+template <typename T>
+int slab_fx(const fsm_plan* p, const Geom<T>& g, const cplx<T>* recv, int C, int nb, const Combine<T>& cb, const FxEpilogue<T>& ep,
+            cudaStream_t st) {
+    const LaunchTable<T>* tx = launch_table<T>(p->n[0]);
+    FxArgs<T> f;
+    f.g = g; f.win = recv; f.win_fstride = (long)p->kyl * p->nh * p->nxl; f.cb = cb; f.ep = ep;
+    f.nlines = p->kyl * p->nh; f.b0 = 0; f.nb = nb;
+    f.ib.shift = ilog2(p->nxl); f.ib.stride = (long)nb * C * f.win_fstride;
+    f.line_stride = p->nxl;
+    ProfScope ps(p, PASS_FX, st);
+    if (int e = tx->fx(C, f, st)) return fail(e, "slab FX launch failed");
+    return 0;
+}
+
+template <typename T>
+int do_slab_phase(fsm_plan* p, int op, int stage, int phase, void* u_hat, void* aux, void* ws, void* send, void* recv,
+                  cudaStream_t st) {
+    Buffers<T> bf = carve<T>(p, u_hat, ws, (op == FSM_SLAB_RHS) ? aux : nullptr);
+    cplx<T>* snd = static_cast<cplx<T>*>(send);
+    const cplx<T>* rcv = static_cast<const cplx<T>*>(recv);
+    if (op == FSM_SLAB_STEP || op == FSM_SLAB_RHS) {
+        if (p->prog == FSM_PROG_LINEAR) return fail(-EINVAL, "linear operators have no slab phases; call fsm_step");
+        const Stage& s = (op == FSM_SLAB_RHS) ? p->rhs_stage : p->stages[stage];
+        const Geom<T> g = make_geom<T>(p, false);
+        if (phase == 0) return slab_ix<T>(p, g, p->kprog, bf.arr[s.input], snd, p->B * p->C, p->nf_ix, p->nkz1, st);
+        if (phase == 1) {
+            if (int e = slab_mid_inverse<T>(p, g, rcv, bf.w3, p->C * p->nf_ix, mid_spec_inverse(p), p->nkz1, p->B, st)) return e;
+            if (int e = slab_phys<T>(p, g, p->kprog, bf.w3, bf.w2, nullptr, nullptr, p->B, st)) return e;
+            return slab_mid_forward<T>(p, g, bf.w2, snd, p->nout, p->B, st);
+        }
+        Combine<T> cb;
+        if (int e = make_combine<T>(p, s, bf.arr, true, &cb)) return e;
+        FxEpilogue<T> ep;
+        ep.nl_coef = (T)p->d.nl_coef;
+        ep.source = static_cast<const cplx<T>*>(p->d.source_hat);
+        ep.dc_out = nullptr;
+        ep.project = (p->prog == FSM_PROG_NS3D) ? 1 : 0;
+        return slab_fx<T>(p, g, rcv, p->C, p->B, cb, ep, st);
+    }
+    const Geom<T> g = make_geom<T>(p, true);
+    const int nf = p->B * p->C;
+    if (op == FSM_SLAB_R2C) {
+        if (phase == 1) {
+            if (int e = slab_phys<T>(p, g, PROG_R2C, nullptr, bf.w2, static_cast<const T*>(aux), nullptr, nf, st)) return e;
+            return slab_mid_forward<T>(p, g, bf.w2, snd, 1, nf, st);
+        }
+        Stage s;
+        s.input = ARR_U; s.n_in = 0; s.n_out = 1; s.out[0] = ARR_U;
+        s.c[0][0] = scal(1.0);
+        Combine<T> cb;
+        fsm_plan tmp = *p;
+        tmp.d.tab_channels = 1;
+        if (int e = make_combine<T>(&tmp, s, bf.arr, true, &cb)) return e;
+        FxEpilogue<T> ep;
+        ep.nl_coef = T(1); ep.source = nullptr; ep.dc_out = nullptr; ep.project = 0;
+        return slab_fx<T>(p, g, rcv, 1, nf, cb, ep, st);
+    }
+    if (op == FSM_SLAB_C2R) {
+        if (phase == 0) return slab_ix<T>(p, g, PROG_C2R, static_cast<const cplx<T>*>(u_hat), snd, nf, 1, p->nh, st);
+        if (int e = slab_mid_inverse<T>(p, g, rcv, bf.w3, 1, mid_spec_identity(1), p->nh, nf, st)) return e;
+        return slab_phys<T>(p, g, PROG_C2R, bf.w3, nullptr, nullptr, static_cast<T*>(aux), nf, st);
+    }
+    return fail(-EINVAL, "unknown slab op %d", op);
+}
+
 }  // namespace
 
 // =============================================================================================
@@ -613,6 +749,17 @@ int fsm_plan_create(fsm_plan** out, const fsm_desc* d) {
     p->nh = nlast / 2 + 1;
     p->ph = (p->nh + 7) / 8 * 8;
     p->nmodes = (long)p->nh * (p->ntot / nlast);
+    if (d->slab_nranks > 1) {
+        const int P = d->slab_nranks;
+        if (p->ndim != 3) { delete p; return fail(-EINVAL, "slab decomposition needs a 3-D grid"); }
+        if (!is_pow2(P) || p->n[0] % P || p->n[1] % P || d->slab_rank < 0 || d->slab_rank >= P) {
+            delete p;
+            return fail(-EINVAL, "slab decomposition: %d ranks must be a power of two dividing n0=%d and n1=%d", P, p->n[0], p->n[1]);
+        }
+        p->P = P; p->rank = d->slab_rank; p->kyl = p->n[1] / P; p->nxl = p->n[0] / P;
+        p->nkz1 = (d->kmax[2] + 1 < p->nh) ? d->kmax[2] + 1 : p->nh;
+        p->nmodes = (long)p->kyl * p->nh * p->n[0];   // local spectral slab
+    }
     // program -> kernel program and field counts
     switch (p->prog) {
         case FSM_PROG_LINEAR: p->kprog = PROG_NONE; p->nf_ix = 1; p->nfi = 1; p->nout = 1; break;
@@ -633,6 +780,10 @@ int fsm_plan_create(fsm_plan** out, const fsm_desc* d) {
     }
     if (p->prog == FSM_PROG_LINEAR && d->integrator != FSM_INT_ETDRK0 && d->integrator != FSM_INT_RK4) {
         // a purely linear operator under an ETD scheme: the nonlinear term is identically zero
+    }
+    if (p->P > 1 && p->prog != FSM_PROG_CONVECTION && p->prog != FSM_PROG_NS3D && p->prog != FSM_PROG_LINEAR) {
+        delete p;
+        return fail(-ENOSYS, "slab decomposition supports the convection and Navier-Stokes programs only");
     }
     if (p->prog != FSM_PROG_LINEAR && d->integrator == FSM_INT_ETDRK0) {
         delete p;
@@ -659,10 +810,18 @@ int fsm_plan_create(fsm_plan** out, const fsm_desc* d) {
                                          : (size_t)p->C * p->nf_ix * p->n[0] * p->ph * esz;
         w2_per = (size_t)p->nout * p->nmodes * esz;
     } else {
-        w1_per = (size_t)p->C * p->nf_ix * p->nh * plane * esz;
-        w3_per = (size_t)p->nfi * plane * p->ph * esz;
-        w2_per = (size_t)p->nout * p->nh * plane * esz;
-        w2b_per = (size_t)p->nout * p->nmodes * esz;
+        if (p->P > 1) {   // the exchange buffers are the caller's; only the x-slab intermediates live here
+            const int nf3 = (p->nfi > p->C) ? p->nfi : p->C;
+            w1_per = 0;
+            w3_per = (size_t)nf3 * p->nxl * p->n[1] * p->ph * esz;
+            w2_per = (size_t)((p->nout > p->C) ? p->nout : p->C) * p->nh * p->nxl * p->n[1] * esz;
+            w2b_per = 0;
+        } else {
+            w1_per = (size_t)p->C * p->nf_ix * p->nh * plane * esz;
+            w3_per = (size_t)p->nfi * plane * p->ph * esz;
+            w2_per = (size_t)p->nout * p->nh * plane * esz;
+            w2b_per = (size_t)p->nout * p->nmodes * esz;
+        }
     }
     int chunk = d->chunk;
     if (chunk <= 0) {
@@ -672,13 +831,13 @@ int fsm_plan_create(fsm_plan** out, const fsm_desc* d) {
         const size_t per = w1_per + w2_per + w3_per + w2b_per;
         const size_t budget = (size_t)8 << 30;
         chunk = p->B;
-        if (per > 0 && (size_t)chunk * per > budget) chunk = (int)(budget / per);
+        if (per > 0 && (size_t)chunk * per > budget && p->P == 1) chunk = (int)(budget / per);
         if (chunk < 1) chunk = 1;
         if (chunk > p->B) chunk = p->B;
         const int nch = (p->B + chunk - 1) / chunk;
         chunk = (p->B + nch - 1) / nch;
     }
-    if (chunk > p->B) chunk = p->B;
+    if (chunk > p->B || p->P > 1) chunk = p->B;
     p->chunk = chunk;
     // workspace layout
     size_t off = 0;
@@ -708,6 +867,8 @@ int fsm_plan_create(fsm_plan** out, const fsm_desc* d) {
             cap = (w1_per * chunk) / ((size_t)p->n[0] * p->ph * esz);
             const size_t c2 = (w2_per * chunk) / ((size_t)p->nmodes * esz);
             if (c2 < cap) cap = c2;
+        } else if (p->P > 1) {
+            cap = (size_t)p->B * p->C;
         } else {
             cap = (w1_per * chunk) / ((size_t)p->nh * plane * esz);
             const size_t c3 = (w3_per * chunk) / ((size_t)plane * p->ph * esz);
@@ -768,6 +929,34 @@ int fsm_plan_info(const fsm_plan* plan, int64_t* launches_per_step, int64_t* alg
     return 0;
 }
 
+int fsm_slab_info(const fsm_plan* plan, int op, int64_t* exch1_elems, int64_t* exch2_elems, int32_t* n_stages) {
+    if (!plan || plan->P <= 1) return fail(-EINVAL, "plan has no slab decomposition");
+    const int64_t blk1 = (int64_t)plan->nxl * plan->kyl, blk2 = (int64_t)plan->kyl * plan->nh * plan->nxl;
+    int64_t e1, e2;
+    if (op == FSM_SLAB_STEP || op == FSM_SLAB_RHS) {
+        e1 = (int64_t)plan->P * plan->B * plan->C * plan->nf_ix * plan->nkz1 * blk1;
+        e2 = (int64_t)plan->P * plan->B * plan->nout * blk2;
+    } else {
+        e1 = (int64_t)plan->P * plan->B * plan->C * plan->nh * blk1;
+        e2 = (int64_t)plan->P * plan->B * plan->C * blk2;
+    }
+    if (exch1_elems) *exch1_elems = e1;
+    if (exch2_elems) *exch2_elems = e2;
+    if (n_stages) *n_stages = (int32_t)plan->stages.size();
+    return 0;
+}
+
+int fsm_slab_phase(fsm_plan* plan, int op, int stage, int phase, void* u_hat, void* aux, void* workspace, size_t ws_bytes,
+                   void* send, void* recv, void* stream) {
+    if (!plan || plan->P <= 1) return fail(-EINVAL, "plan has no slab decomposition");
+    if (!workspace || ws_bytes < plan->ws_bytes) return fail(-ENOMEM, "workspace too small");
+    if (op == FSM_SLAB_STEP && (stage < 0 || stage >= (int)plan->stages.size())) return fail(-EINVAL, "bad stage %d", stage);
+    if (phase < 0 || phase > 2) return fail(-EINVAL, "bad phase %d", phase);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return plan->f64 ? do_slab_phase<double>(plan, op, stage, phase, u_hat, aux, workspace, send, recv, st)
+                     : do_slab_phase<float>(plan, op, stage, phase, u_hat, aux, workspace, send, recv, st);
+}
+
 int fsm_profile_enable(fsm_plan* plan, int on) {
     if (!plan) return fail(-EINVAL, "null plan");
     plan->profile = on != 0;
@@ -803,6 +992,7 @@ int fsm_profile_read(fsm_plan* plan, double* ms, int64_t* launches, int64_t* alg
 int fsm_step(fsm_plan* plan, void* u_hat, void* workspace, size_t ws_bytes, int n_steps, void* stream) {
     FSM_CHECK_WS(plan, workspace, ws_bytes);
     if (!u_hat || n_steps < 0) return fail(-EINVAL, "bad argument");
+    if (plan->P > 1 && plan->prog != FSM_PROG_LINEAR) return fail(-EINVAL, "slab-decomposed plans are driven through fsm_slab_phase");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     return plan->f64 ? do_step<double>(plan, u_hat, workspace, n_steps, st) : do_step<float>(plan, u_hat, workspace, n_steps, st);
 }

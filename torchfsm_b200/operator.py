@@ -78,8 +78,11 @@ class FusedStepper:
     def __init__(self, f_mesh: FourierMesh, batch: int, n_channel: int, program: int, integrator: str, dt: float,
                  linear_coef: Optional[torch.Tensor], nl_coef: float, source_hat: Optional[torch.Tensor],
                  kmax: Sequence[int], ks_remove_mean: bool, integrator_cfg: dict, chunk: int = 0,
-                 tables: Optional[dict] = None):
+                 tables: Optional[dict] = None, slab=None):
         lib = _cabi.lib()
+        # slab = (rank, nranks, process_group): ONE 3-D grid decomposed over nranks GPUs
+        self.slab = slab
+        self.P, self.rank, self.group = (slab[1], slab[0], slab[2]) if slab else (1, 0, None)
         self.f_mesh, self.B, self.C, self.dt = f_mesh, batch, n_channel, dt
         self.shape = tuple(f_mesh.shape)
         self.n_dim = len(self.shape)
@@ -90,6 +93,14 @@ class FusedStepper:
         self.nmodes = nh
         for n in self.shape[:-1]:
             self.nmodes *= n
+        if self.P > 1:
+            if self.n_dim != 3 or self.shape[0] % self.P or self.shape[1] % self.P:
+                raise ValueError("slab decomposition needs a 3-D grid whose first two axes are divisible by the rank count")
+            self.kyl, self.nxl = self.shape[1] // self.P, self.shape[0] // self.P
+            self.nmodes //= self.P                        # local ky slab [n1/P][nh][n0]
+            self.local_shape = (self.nxl,) + self.shape[1:]   # local physical x slab
+        else:
+            self.local_shape = self.shape
         self.integrator = integrator
         self._keep = []  # tensors referenced by the plan descriptor
 
@@ -144,7 +155,7 @@ class FusedStepper:
             t = rot[k]
             if t.shape[0] != tab_channels:
                 t = t.expand(tab_channels, *t.shape[1:])
-            rot[k] = _rot_half(t, self.shape)
+            rot[k] = self._local_slab(_rot_half(t, self.shape))
             self._keep.append(rot[k])
         desc.tab_channels = tab_channels
         if "exp" in rot:
@@ -161,9 +172,11 @@ class FusedStepper:
             if s.shape[0] not in (1, n_channel):
                 raise ValueError("explicit source has an incompatible channel count")
             s = s.expand(n_channel, *self.shape).to(self.cdtype)
-            self.source_rot = _rot_half(s, self.shape)
+            self.source_rot = self._local_slab(_rot_half(s, self.shape))
             self._keep.append(self.source_rot)
             desc.source_hat = self.source_rot.data_ptr()
+        if self.P > 1:
+            desc.slab_rank, desc.slab_nranks = self.rank, self.P
         self.rot_tables = rot
         self._desc = desc
         plan = ctypes.c_void_p()
@@ -173,6 +186,44 @@ class FusedStepper:
         ws = lib.fsm_workspace_bytes(plan)
         self.workspace = torch.empty(max(ws, 16), dtype=torch.uint8, device=self.device)
         self.ws_bytes = ws
+        if self.P > 1:
+            self._slab_counts = {}
+            n1 = n2 = 0
+            for op in range(4):
+                a, b, c = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int32()
+                _cabi.check(lib.fsm_slab_info(plan, op, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)), "slab_info")
+                self._slab_counts[op] = (a.value, b.value)
+                self.n_stages = c.value
+                n1, n2 = max(n1, a.value), max(n2, b.value)
+            # exchange buffers: kernels write/read them directly in rank-blocked layouts
+            self._send = [torch.empty(n, dtype=self.cdtype, device=self.device) for n in (n1, n2)]
+            self._recv = [torch.empty(n, dtype=self.cdtype, device=self.device) for n in (n1, n2)]
+
+    def _local_slab(self, t):
+        """(X, n1, nh, n0) rot-half table -> contiguous local ky slab when the grid is slab-decomposed."""
+        if self.P == 1:
+            return t
+        return t[:, self.rank * self.kyl:(self.rank + 1) * self.kyl].contiguous()
+
+    # ---- slab-decomposed phases ---------------------------------------------------------------------
+    def _exchange(self, which, count):
+        import torch.distributed as dist
+        dist.all_to_all_single(self._recv[which][:count], self._send[which][:count], group=self.group)
+
+    def _slab_phase(self, op, stage, phase, u_hat, aux, which_send, which_recv):
+        snd = self._send[which_send].data_ptr() if which_send is not None else None
+        rcv = self._recv[which_recv].data_ptr() if which_recv is not None else None
+        _cabi.check(self._lib.fsm_slab_phase(self._plan, op, stage, phase, u_hat.data_ptr() if u_hat is not None else None,
+                                             aux.data_ptr() if aux is not None else None, self.workspace.data_ptr(),
+                                             self.ws_bytes, snd, rcv, self._stream()), "slab_phase")
+
+    def _slab_eval(self, op, stage, u_hat, aux=None):
+        c1, c2 = self._slab_counts[op]
+        self._slab_phase(op, stage, 0, u_hat, aux, 0, None)
+        self._exchange(0, c1)
+        self._slab_phase(op, stage, 1, u_hat, aux, 1, 0)
+        self._exchange(1, c2)
+        self._slab_phase(op, stage, 2, u_hat, aux, None, 1)
 
     # ---- plumbing ---------------------------------------------------------------------------
     def __del__(self):
@@ -211,23 +262,39 @@ class FusedStepper:
     def r2c(self, u: torch.Tensor) -> torch.Tensor:
         u = u.to(self.rdtype).contiguous()
         out = self.empty_half()
+        if self.P > 1:
+            _, c2 = self._slab_counts[2]
+            self._slab_phase(2, 0, 1, out, u, 1, None)
+            self._exchange(1, c2)
+            self._slab_phase(2, 0, 2, out, u, None, 1)
+            return out
         _cabi.check(self._lib.fsm_r2c(self._plan, u.data_ptr(), out.data_ptr(), self.workspace.data_ptr(),
                                       self.ws_bytes, self._stream()), "r2c")
         return out
 
     def c2r(self, u_hat: torch.Tensor) -> torch.Tensor:
-        out = torch.empty((self.B, self.C) + self.shape, dtype=self.rdtype, device=self.device)
+        out = torch.empty((self.B, self.C) + self.local_shape, dtype=self.rdtype, device=self.device)
+        if self.P > 1:
+            c1, _ = self._slab_counts[3]
+            self._slab_phase(3, 0, 0, u_hat, out, 0, None)
+            self._exchange(0, c1)
+            self._slab_phase(3, 0, 1, u_hat, out, None, 0)
+            return out
         _cabi.check(self._lib.fsm_c2r(self._plan, u_hat.data_ptr(), out.data_ptr(), self.workspace.data_ptr(),
                                       self.ws_bytes, self._stream()), "c2r")
         return out
 
     def half_to_full(self, u_hat: torch.Tensor) -> torch.Tensor:
+        if self.P > 1:
+            raise NotImplementedError("full-spectrum frames are not available for slab-decomposed grids")
         out = torch.empty((self.B, self.C) + self.shape, dtype=self.cdtype, device=self.device)
         _cabi.check(self._lib.fsm_half_to_full(self._plan, u_hat.data_ptr(), out.data_ptr(), self._stream()),
                     "half_to_full")
         return out
 
     def full_to_half(self, full_hat: torch.Tensor) -> torch.Tensor:
+        if self.P > 1:
+            raise NotImplementedError("full-spectrum input is not available for slab-decomposed grids")
         full_hat = full_hat.to(self.cdtype).contiguous()
         out = self.empty_half()
         _cabi.check(self._lib.fsm_full_to_half(self._plan, full_hat.data_ptr(), out.data_ptr(), self._stream()),
@@ -236,12 +303,20 @@ class FusedStepper:
 
     def step_half(self, u_hat: torch.Tensor, n_steps: int = 1) -> torch.Tensor:
         """Advance the rot-half state in place by ``n_steps``."""
+        if self.P > 1 and self.n_stages and self._desc.program != _cabi.PROG_LINEAR:
+            for _ in range(int(n_steps)):
+                for stage in range(self.n_stages):
+                    self._slab_eval(0, stage, u_hat)
+            return u_hat
         _cabi.check(self._lib.fsm_step(self._plan, u_hat.data_ptr(), self.workspace.data_ptr(), self.ws_bytes,
                                        int(n_steps), self._stream()), "step")
         return u_hat
 
     def rhs_half(self, u_hat: torch.Tensor) -> torch.Tensor:
         out = self.empty_half()
+        if self.P > 1 and self._desc.program != _cabi.PROG_LINEAR:
+            self._slab_eval(1, 0, u_hat, out)
+            return out
         _cabi.check(self._lib.fsm_rhs(self._plan, u_hat.data_ptr(), out.data_ptr(), self.workspace.data_ptr(),
                                       self.ws_bytes, self._stream()), "rhs")
         return out
@@ -270,6 +345,7 @@ class OperatorLike:
         self._state_dict = {"f_mesh": None, "n_channel": None, "linear_coef": None, "integrator": None}
         self._lowered = None
         self._chunk = 0
+        self._slab = None
 
     # ---- algebra (operator/_base.py:170-206, 826-850) ------------------------------------------
     def _new(self, terms):
@@ -334,6 +410,16 @@ class OperatorLike:
         self._de_aliasing_rate = de_aliasing_rate
         self._state_dict["integrator"] = None
         self._lowered = None
+
+    def set_slab_decomposition(self, group=None, rank: Optional[int] = None, nranks: Optional[int] = None):
+        """Decompose ONE 3-D grid over the ranks of a torch.distributed process group:
+        ``integrate`` / ``__call__`` then take and return the local physical x-slab
+        ``(B, C, n0/P, n1, n2)`` of the rank; the two transposes per evaluation are all-to-alls."""
+        import torch.distributed as dist
+        self._slab = (dist.get_rank(group) if rank is None else rank,
+                      dist.get_world_size(group) if nranks is None else nranks, group)
+        self._state_dict["integrator"] = None
+        self._rhs_stepper = None
 
     def set_chunk(self, chunk: int):
         """Samples per pass launch (0 = library default); a tuning knob of the CUDA path."""
@@ -429,8 +515,11 @@ class OperatorLike:
         assert len(value.shape) == mesh.n_dim + 2, \
             f"the value shape {tuple(value.shape)} is not compatible with mesh dim {mesh.n_dim}"
         for i in range(mesh.n_dim):
-            assert value.shape[i + 2] == mesh.mesh_info[i][2], \
-                f"Expect to have {mesh.mesh_info[i][2]} points in dim {i} but got {value.shape[i + 2]}"
+            expect = mesh.mesh_info[i][2]
+            if i == 0 and getattr(self, "_slab", None) is not None:
+                expect //= self._slab[1]                     # local x-slab of a slab-decomposed grid
+            assert value.shape[i + 2] == expect, \
+                f"Expect to have {expect} points in dim {i} but got {value.shape[i + 2]}"
         assert _same_device(value.device, mesh.device), \
             "The device of mesh {} and the device of value {} are not the same".format(mesh.device, value.device)
         assert self._value_mesh_check_func(len(value.shape) - 2, mesh.n_dim), \
@@ -451,7 +540,7 @@ class OperatorLike:
         try:
             st = FusedStepper(sd["f_mesh"], batch, sd["n_channel"], lo["program"], name, dt, sd["linear_coef"],
                               lo["nl_coef"], lo["source_hat"], lo["kmax"], lo["ks_remove_mean"], cfg,
-                              chunk=self._chunk, tables=tables)
+                              chunk=self._chunk, tables=tables, slab=self._slab)
         except torch.cuda.OutOfMemoryError as e:
             raise RuntimeError(os.linesep.join([
                 "Cuda out of memory when building the integrator.",
