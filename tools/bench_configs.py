@@ -40,6 +40,17 @@ def timed(st, u_hat, steps, warmup=2, one_call=False):
     return e0.elapsed_time(e1) / steps
 
 
+def pass_breakdown(st, u_hat, steps=2):
+    st.profile(True)
+    st.step_half(u_hat, steps)
+    torch.cuda.synchronize()
+    prof = st.profile_read()
+    st.profile(False)
+    return {k: {"ms_per_step": round(v["ms"] / steps, 3), "launches_per_step": v["launches"] / steps,
+                "algo_gbs": round(v["algo_bytes_per_step"] * steps / max(v["ms"], 1e-9) / 1e6, 1)}
+            for k, v in prof.items() if v["launches"]}
+
+
 def report(name, st, ms, extra=None):
     info = st.info()
     gbs = info["algo_bytes_per_step"] / (ms * 1e-3) / 1e9
@@ -77,7 +88,8 @@ def c2(steps):
     st = op._state_dict["integrator"]
     u_hat = st.r2c(u0)
     ms = timed(st, u_hat, steps)
-    report("C2 ks2d 256^2 B=256 SETDRK4", st, ms, {"finite": bool(torch.isfinite(u_hat.real).all())})
+    report("C2 ks2d 256^2 B=256 SETDRK4", st, ms, {"finite": bool(torch.isfinite(u_hat.real).all()),
+                                                    "passes": pass_breakdown(st, u_hat)})
 
 
 def c4(steps):
@@ -94,7 +106,8 @@ def c4(steps):
     u_hat = st.r2c(u)
     del u
     ms = timed(st, u_hat, steps, warmup=1)
-    report("C4 burgers3d 256^3 B=8 C=3 SETDRK4", st, ms, {"finite": bool(torch.isfinite(u_hat.real).all())})
+    report("C4 burgers3d 256^3 B=8 C=3 SETDRK4", st, ms, {"finite": bool(torch.isfinite(u_hat.real).all()),
+                                                           "passes": pass_breakdown(st, u_hat, 1)})
 
 
 def c5(steps):
@@ -112,7 +125,8 @@ def c5(steps):
     u_hat = st.r2c(u)
     del u
     ms = timed(st, u_hat, steps, warmup=1)
-    report("C5 ns3d 512^3 B=1 C=3 SETDRK4 (single GPU)", st, ms, {"finite": bool(torch.isfinite(u_hat.real).all())})
+    report("C5 ns3d 512^3 B=1 C=3 SETDRK4 (single GPU)", st, ms, {"finite": bool(torch.isfinite(u_hat.real).all()),
+                                                                   "passes": pass_breakdown(st, u_hat, 1)})
 
 
 if __name__ == "__main__":

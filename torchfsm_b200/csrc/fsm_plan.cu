@@ -357,6 +357,12 @@ int run_forward_tail(const fsm_plan* p, const Buffers<T>& bf, const Geom<T>& g, 
     FxArgs<T> f;
     f.g = g; f.win = fx_in; f.win_fstride = p->nmodes; f.cb = cb; f.ep = ep;
     f.nlines = (int)(p->nmodes / p->n[0]); f.b0 = b0; f.nb = nb;
+    // independent channels (no projection, no per-channel table or source): run them as separate
+    // single-channel fields -> no three-channel register tile, C times the parallelism
+    if (C > 1 && !ep.project && !ep.source && !ep.dc_out && cb.tab_cstride == 0) {
+        f.b0 = b0 * C; f.nb = nb * C;
+        C = 1;
+    }
     { ProfScope ps(p, PASS_FX, st); if (int e = tx->fx(C, f, st)) return fail(e, "FX launch failed (channels=%d, n0=%d)", C, p->n[0]); }
     return 0;
 }
