@@ -126,12 +126,15 @@ int fsm_plan_info(const fsm_plan* plan, int64_t* launches_per_step, int64_t* alg
  *   op FSM_SLAB_STEP / FSM_SLAB_RHS, stage s:  phase 0: state -> x-transform -> send          [all-to-all]
  *                                              phase 1: recv -> y, z, product, z, y -> send    [all-to-all]
  *                                              phase 2: recv -> x-transform + integrator combine
+ * The local x range can be split into nsub sub-slabs (power of two): the exchange buffers are then laid out
+ * [sub-slab][rank][...], phase 0 and 2 cover all sub-slabs, phase 1 runs sub-slab `sub`, so the all-to-all of
+ * one sub-slab overlaps the local chain of another (caller-side streams/events).
  *   op FSM_SLAB_R2C: phase 1 (aux = local physical slab -> send), phase 2 (recv -> u_hat)
  *   op FSM_SLAB_C2R: phase 0 (u_hat -> send), phase 1 (recv -> aux = local physical slab)
  * fsm_slab_info returns the complex-element counts of the two exchanges for an op and the stage count. */
 enum fsm_slab_op { FSM_SLAB_STEP = 0, FSM_SLAB_RHS = 1, FSM_SLAB_R2C = 2, FSM_SLAB_C2R = 3 };
-int fsm_slab_phase(fsm_plan* plan, int op, int stage, int phase, void* u_hat, void* aux, void* workspace,
-                   size_t ws_bytes, void* send, void* recv, void* stream);
+int fsm_slab_phase(fsm_plan* plan, int op, int stage, int phase, int sub, int nsub, void* u_hat, void* aux,
+                   void* workspace, size_t ws_bytes, void* send, void* recv, void* stream);
 int fsm_slab_info(const fsm_plan* plan, int op, int64_t* exch1_elems, int64_t* exch2_elems, int32_t* n_stages);
 
 /* per-pass device timing for benchmarks: when enabled every pass launch is bracketed by CUDA

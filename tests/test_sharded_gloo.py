@@ -67,7 +67,7 @@ def test_ensemble_shards_over_two_ranks(name):
     assert err <= 1e-12 and tmax == 2.0
 
 
-def _slab_worker(rank, world, port, name, lib_path, out_q):
+def _slab_worker(rank, world, port, name, lib_path, out_q, nsub=0):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     from golden_util import load_golden, rel_l2
     from product_util import product_from_golden
@@ -78,7 +78,7 @@ def _slab_worker(rank, world, port, name, lib_path, out_q):
         g = load_golden(name)
         spec = g["spec"]
         op, mesh, u0 = product_from_golden(g, "cpu")
-        op.set_slab_decomposition()
+        op.set_slab_decomposition(nsub=nsub)
         nxl = u0.shape[2] // world
         local = u0[:, :, rank * nxl:(rank + 1) * nxl].contiguous()       # this rank's physical x-slab
         uT = op.integrate(local, mesh=mesh, dt=spec["dt"], step=spec["steps"])
@@ -95,10 +95,10 @@ def _slab_worker(rank, world, port, name, lib_path, out_q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name,world", [("c5_ns3d_16_setdrk4_f64", 2), ("c4_burgers3d_16_f64", 2),
-                                        ("c5_ns3d_32x16x8_etdrk2_f64", 2), ("burgers3d_8x16x32_rk4_f64", 2),
-                                        ("c5_ns3d_32x16x8_etdrk2_f32", 4)])
-def test_slab_decomposed_grid_matches_reference(name, world):
+@pytest.mark.parametrize("name,world,nsub", [("c5_ns3d_16_setdrk4_f64", 2, 1), ("c4_burgers3d_16_f64", 2, 2),
+                                             ("c5_ns3d_32x16x8_etdrk2_f64", 2, 4), ("burgers3d_8x16x32_rk4_f64", 2, 0),
+                                             ("c5_ns3d_32x16x8_etdrk2_f32", 4, 2)])
+def test_slab_decomposed_grid_matches_reference(name, world, nsub):
     """ONE 3-D grid split into x-slabs (physical) / ky-slabs (spectral) over the ranks; the transposes are
     all_to_all_single (gloo here, NCCL on GPUs); results equal the reference's single-device answer."""
     from product_util import build_emulator
@@ -106,7 +106,7 @@ def test_slab_decomposed_grid_matches_reference(name, world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_slab_worker, args=(r, world, port, name, lib_path, q)) for r in range(world)]
+    procs = [ctx.Process(target=_slab_worker, args=(r, world, port, name, lib_path, q, nsub)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:

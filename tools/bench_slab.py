@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--integrator", default="SETDRK4")
+    ap.add_argument("--nsub", type=int, default=0, help="sub-slabs for exchange/compute overlap (0 = default)")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -70,7 +71,7 @@ def main():
     op.set_integrator(getattr(fsm.SETDRKIntegrator, a.integrator) if a.integrator.startswith("S")
                       else getattr(fsm.ETDRKIntegrator, a.integrator))
     if world > 1:
-        op.set_slab_decomposition()
+        op.set_slab_decomposition(nsub=a.nsub)
     t0 = time.perf_counter()
     op.integrate(u, mesh=mesh, dt=0.0025, step=1)
     torch.cuda.synchronize()
@@ -117,7 +118,7 @@ def main():
         info = st.info()
         print(json.dumps({"config": f"C5 ns3d {n}^3 B=1 C=3 {a.integrator} slab x{world}", "n_gpus": world,
                           "ms_per_step": float(ms.item()), "steps_per_sec": 1e3 / float(ms.item()), "steps": a.steps,
-                          "finite": finite, "setup_s": setup_s, "all_to_all": a2a, "parity_rel_l2_16cubed_fp32": parity,
+                          "finite": finite, "setup_s": setup_s, "nsub": getattr(st, "nsub", 1), "all_to_all": a2a, "parity_rel_l2_16cubed_fp32": parity,
                           "algo_gb_per_step_global": info["algo_bytes_per_step"] / 1e9}), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -62,7 +62,7 @@ def _declare(lib):
     lib.fsm_full_to_half.restype = i32
     lib.fsm_plan_info.argtypes = [vp, i64p, i64p, i64p, ctypes.POINTER(ctypes.c_int32)]
     lib.fsm_plan_info.restype = i32
-    lib.fsm_slab_phase.argtypes = [vp, i32, i32, i32, vp, vp, vp, sz, vp, vp, vp]
+    lib.fsm_slab_phase.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, vp, sz, vp, vp, vp]
     lib.fsm_slab_phase.restype = i32
     lib.fsm_slab_info.argtypes = [vp, i32, i64p, i64p, ctypes.POINTER(ctypes.c_int32)]
     lib.fsm_slab_info.restype = i32

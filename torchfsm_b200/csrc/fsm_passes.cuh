@@ -51,11 +51,15 @@ struct Geom {
 // Rank-blocked index (slab decomposition): index i lives in block i >> shift (block stride `stride`
 // elements) at position i & mask inside it. One GPU: shift = 30, i.e. a single block.
 struct Blk {
-    int shift;
+    int shift;      // rank block:     i >> shift
     long stride;
+    int shift2;     // sub-slab block: (i & mask) >> shift2   (30 = none)
+    long stride2;
 };
 __device__ __forceinline__ long blk_off(int i, const Blk& b, long elem_stride) {
-    return (long)(i >> b.shift) * b.stride + (long)(i & ((1 << b.shift) - 1)) * elem_stride;
+    const int r = i & ((1 << b.shift) - 1);
+    const int lo = (b.shift2 < b.shift) ? b.shift2 : b.shift;
+    return (long)(i >> b.shift) * b.stride + (long)(r >> b.shift2) * b.stride2 + (long)(r & ((1 << lo) - 1)) * elem_stride;
 }
 
 template <int N>

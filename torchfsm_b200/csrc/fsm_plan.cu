@@ -579,17 +579,21 @@ int ilog2(int x) { int s = 0; while ((1 << s) < x) ++s; return s; }
 //   exchange 1 (inverse side)  [dst rank q][field][kz < nkz][x_local][ky_local]
 //   exchange 2 (forward side)  [dst rank q][field][ky_local][kz < nh][x_local]
 // ---------------------------------------------------------------------------------------------
+// `nsub` sub-slabs split the local x range so the exchange of one sub-slab can overlap the local chain of
+// another: exchange buffers are laid out [sub-slab h][rank q][field][...], each h a contiguous all-to-all.
 template <typename T>
 int slab_ix(const fsm_plan* p, const Geom<T>& g, int kprog, const cplx<T>* state, cplx<T>* send, int nfields_in, int nf,
-            int nkz, cudaStream_t st) {
+            int nkz, int nsub, cudaStream_t st) {
     const LaunchTable<T>* tx = launch_table<T>(p->n[0]);
+    const int nxh = p->nxl / nsub;
     IxArgs<T> a;
     a.g = g; a.state = state; a.w1 = send; a.state_bstride = p->nmodes; a.nbc = nfields_in;
-    a.w1_fstride = (long)nkz * p->nxl * p->kyl;
+    a.w1_fstride = (long)nkz * nxh * p->kyl;
     a.in_t_stride = (long)p->nh * p->n[0]; a.in_o_stride = p->n[0];
-    a.out_o_stride = (long)p->nxl * p->kyl; a.out_e_stride = p->kyl;
+    a.out_o_stride = (long)nxh * p->kyl; a.out_e_stride = p->kyl;
     a.n_t = p->kyl; a.n_outer = nkz;
     a.eb.shift = ilog2(p->nxl); a.eb.stride = (long)nfields_in * nf * a.w1_fstride;
+    a.eb.shift2 = ilog2(nxh); a.eb.stride2 = (long)p->P * a.eb.stride;
     ProfScope ps(p, PASS_IX, st);
     if (int e = tx->ix(kprog, a, st)) return fail(e, "slab IX launch failed");
     return 0;
@@ -597,30 +601,37 @@ int slab_ix(const fsm_plan* p, const Geom<T>& g, int kprog, const cplx<T>* state
 
 template <typename T>
 int slab_mid_inverse(const fsm_plan* p, const Geom<T>& g, const cplx<T>* recv, cplx<T>* w3, int nfi_in, const MidSpec& spec,
-                     int nkz, int nb, cudaStream_t st) {
+                     int nkz, int nb, int sub, int nsub, cudaStream_t st) {
     const LaunchTable<T>* ty = launch_table<T>(p->n[1]);
+    const int nxh = p->nxl / nsub;
     MidArgs<T> m;
-    m.g = g; m.in = recv; m.out = w3;
-    m.in_fstride = (long)nkz * p->nxl * p->kyl; m.out_fstride = (long)p->nxl * p->n[1] * p->ph;
-    m.in_t_stride = (long)p->nxl * p->kyl; m.in_o_stride = p->kyl;
+    m.g = g;
+    m.in_fstride = (long)nkz * nxh * p->kyl; m.out_fstride = (long)p->nxl * p->n[1] * p->ph;
+    m.in_t_stride = (long)nxh * p->kyl; m.in_o_stride = p->kyl;
     m.out_o_stride = (long)p->n[1] * p->ph; m.out_e_stride = p->ph;
-    m.nfi = nfi_in; m.n_t = nkz; m.n_outer = p->nxl; m.nb = nb; m.spec = spec;
+    m.nfi = nfi_in; m.n_t = nkz; m.n_outer = nxh; m.nb = nb; m.spec = spec;
     m.ib.shift = ilog2(p->kyl); m.ib.stride = (long)nb * nfi_in * m.in_fstride;
+    m.in = recv + (long)sub * p->P * m.ib.stride;
+    m.out = w3 + (long)sub * nxh * m.out_o_stride;
     ProfScope ps(p, PASS_MID, st);
     if (int e = ty->mid(+1, m, st)) return fail(e, "slab MID inverse launch failed");
     return 0;
 }
 
 template <typename T>
-int slab_mid_forward(const fsm_plan* p, const Geom<T>& g, const cplx<T>* w2a, cplx<T>* send, int nf, int nb, cudaStream_t st) {
+int slab_mid_forward(const fsm_plan* p, const Geom<T>& g, const cplx<T>* w2a, cplx<T>* send, int nf, int nb, int sub, int nsub,
+                     cudaStream_t st) {
     const LaunchTable<T>* ty = launch_table<T>(p->n[1]);
+    const int nxh = p->nxl / nsub;
     MidArgs<T> m;
-    m.g = g; m.in = w2a; m.out = send;
-    m.in_fstride = (long)p->nh * p->nxl * p->n[1]; m.out_fstride = (long)p->kyl * p->nh * p->nxl;
+    m.g = g;
+    m.in_fstride = (long)p->nh * p->nxl * p->n[1]; m.out_fstride = (long)p->kyl * p->nh * nxh;
     m.in_t_stride = p->n[1]; m.in_o_stride = (long)p->nxl * p->n[1];
-    m.out_o_stride = p->nxl; m.out_e_stride = (long)p->nh * p->nxl;
-    m.nfi = nf; m.n_t = p->nxl; m.n_outer = p->nh; m.nb = nb; m.spec = mid_spec_identity(nf);
+    m.out_o_stride = nxh; m.out_e_stride = (long)p->nh * nxh;
+    m.nfi = nf; m.n_t = nxh; m.n_outer = p->nh; m.nb = nb; m.spec = mid_spec_identity(nf);
     m.eb.shift = ilog2(p->kyl); m.eb.stride = (long)nb * nf * m.out_fstride;
+    m.in = w2a + (long)sub * nxh * m.in_t_stride;
+    m.out = send + (long)sub * p->P * m.eb.stride;
     ProfScope ps(p, PASS_MID, st);
     if (int e = ty->mid(-1, m, st)) return fail(e, "slab MID forward launch failed");
     return 0;
@@ -628,14 +639,17 @@ int slab_mid_forward(const fsm_plan* p, const Geom<T>& g, const cplx<T>* w2a, cp
 
 template <typename T>
 int slab_phys(const fsm_plan* p, const Geom<T>& g, int kprog, const cplx<T>* w3, cplx<T>* w2a, const T* phys_in, T* phys_out,
-              int nb, cudaStream_t st) {
+              int nb, int sub, int nsub, cudaStream_t st) {
     const LaunchTable<T>* tl = launch_table<T>(p->n[2]);
+    const int nxh = p->nxl / nsub;
     PhysArgs<T> ph;
-    ph.g = g; ph.win = w3; ph.wout = w2a; ph.phys_in = phys_in; ph.phys_out = phys_out; ph.nb = nb;
+    ph.g = g; ph.phys_in = phys_in; ph.phys_out = phys_out; ph.nb = nb;
     ph.win_fstride = (long)p->nxl * p->n[1] * p->ph; ph.wout_fstride = (long)p->nh * p->nxl * p->n[1];
     ph.in_t_stride = p->ph; ph.in_o_stride = (long)p->n[1] * p->ph;
     ph.out_o_stride = p->n[1]; ph.out_e_stride = (long)p->nxl * p->n[1];
-    ph.n_t = p->n[1]; ph.n_outer = p->nxl;
+    ph.n_t = p->n[1]; ph.n_outer = nxh;
+    ph.win = w3 ? w3 + (long)sub * nxh * ph.in_o_stride : nullptr;
+    ph.wout = w2a ? w2a + (long)sub * nxh * ph.out_o_stride : nullptr;
     ProfScope ps(p, PASS_PHYS, st);
     if (int e = tl->phys(kprog, 3, ph, st)) return fail(e, "slab PHYS launch failed");
     return 0;
@@ -643,21 +657,23 @@ int slab_phys(const fsm_plan* p, const Geom<T>& g, int kprog, const cplx<T>* w3,
 
 template <typename T>
 int slab_fx(const fsm_plan* p, const Geom<T>& g, const cplx<T>* recv, int C, int nb, const Combine<T>& cb, const FxEpilogue<T>& ep,
-            cudaStream_t st) {
+            int nsub, cudaStream_t st) {
     const LaunchTable<T>* tx = launch_table<T>(p->n[0]);
+    const int nxh = p->nxl / nsub;
     FxArgs<T> f;
-    f.g = g; f.win = recv; f.win_fstride = (long)p->kyl * p->nh * p->nxl; f.cb = cb; f.ep = ep;
+    f.g = g; f.win = recv; f.win_fstride = (long)p->kyl * p->nh * nxh; f.cb = cb; f.ep = ep;
     f.nlines = p->kyl * p->nh; f.b0 = 0; f.nb = nb;
     f.ib.shift = ilog2(p->nxl); f.ib.stride = (long)nb * C * f.win_fstride;
-    f.line_stride = p->nxl;
+    f.ib.shift2 = ilog2(nxh); f.ib.stride2 = (long)p->P * f.ib.stride;
+    f.line_stride = nxh;
     ProfScope ps(p, PASS_FX, st);
     if (int e = tx->fx(C, f, st)) return fail(e, "slab FX launch failed");
     return 0;
 }
 
 template <typename T>
-int do_slab_phase(fsm_plan* p, int op, int stage, int phase, void* u_hat, void* aux, void* ws, void* send, void* recv,
-                  cudaStream_t st) {
+int do_slab_phase(fsm_plan* p, int op, int stage, int phase, int sub, int nsub, void* u_hat, void* aux, void* ws, void* send,
+                  void* recv, cudaStream_t st) {
     Buffers<T> bf = carve<T>(p, u_hat, ws, (op == FSM_SLAB_RHS) ? aux : nullptr);
     cplx<T>* snd = static_cast<cplx<T>*>(send);
     const cplx<T>* rcv = static_cast<const cplx<T>*>(recv);
@@ -665,11 +681,11 @@ int do_slab_phase(fsm_plan* p, int op, int stage, int phase, void* u_hat, void* 
         if (p->prog == FSM_PROG_LINEAR) return fail(-EINVAL, "linear operators have no slab phases; call fsm_step");
         const Stage& s = (op == FSM_SLAB_RHS) ? p->rhs_stage : p->stages[stage];
         const Geom<T> g = make_geom<T>(p, false);
-        if (phase == 0) return slab_ix<T>(p, g, p->kprog, bf.arr[s.input], snd, p->B * p->C, p->nf_ix, p->nkz1, st);
+        if (phase == 0) return slab_ix<T>(p, g, p->kprog, bf.arr[s.input], snd, p->B * p->C, p->nf_ix, p->nkz1, nsub, st);
         if (phase == 1) {
-            if (int e = slab_mid_inverse<T>(p, g, rcv, bf.w3, p->C * p->nf_ix, mid_spec_inverse(p), p->nkz1, p->B, st)) return e;
-            if (int e = slab_phys<T>(p, g, p->kprog, bf.w3, bf.w2, nullptr, nullptr, p->B, st)) return e;
-            return slab_mid_forward<T>(p, g, bf.w2, snd, p->nout, p->B, st);
+            if (int e = slab_mid_inverse<T>(p, g, rcv, bf.w3, p->C * p->nf_ix, mid_spec_inverse(p), p->nkz1, p->B, sub, nsub, st)) return e;
+            if (int e = slab_phys<T>(p, g, p->kprog, bf.w3, bf.w2, nullptr, nullptr, p->B, sub, nsub, st)) return e;
+            return slab_mid_forward<T>(p, g, bf.w2, snd, p->nout, p->B, sub, nsub, st);
         }
         Combine<T> cb;
         if (int e = make_combine<T>(p, s, bf.arr, true, &cb)) return e;
@@ -678,14 +694,15 @@ int do_slab_phase(fsm_plan* p, int op, int stage, int phase, void* u_hat, void* 
         ep.source = static_cast<const cplx<T>*>(p->d.source_hat);
         ep.dc_out = nullptr;
         ep.project = (p->prog == FSM_PROG_NS3D) ? 1 : 0;
-        return slab_fx<T>(p, g, rcv, p->C, p->B, cb, ep, st);
+        return slab_fx<T>(p, g, rcv, p->C, p->B, cb, ep, nsub, st);
     }
+    if (nsub != 1) return fail(-EINVAL, "the plain transforms run with one sub-slab");
     const Geom<T> g = make_geom<T>(p, true);
     const int nf = p->B * p->C;
     if (op == FSM_SLAB_R2C) {
         if (phase == 1) {
-            if (int e = slab_phys<T>(p, g, PROG_R2C, nullptr, bf.w2, static_cast<const T*>(aux), nullptr, nf, st)) return e;
-            return slab_mid_forward<T>(p, g, bf.w2, snd, 1, nf, st);
+            if (int e = slab_phys<T>(p, g, PROG_R2C, nullptr, bf.w2, static_cast<const T*>(aux), nullptr, nf, 0, 1, st)) return e;
+            return slab_mid_forward<T>(p, g, bf.w2, snd, 1, nf, 0, 1, st);
         }
         Stage s;
         s.input = ARR_U; s.n_in = 0; s.n_out = 1; s.out[0] = ARR_U;
@@ -696,12 +713,12 @@ int do_slab_phase(fsm_plan* p, int op, int stage, int phase, void* u_hat, void* 
         if (int e = make_combine<T>(&tmp, s, bf.arr, true, &cb)) return e;
         FxEpilogue<T> ep;
         ep.nl_coef = T(1); ep.source = nullptr; ep.dc_out = nullptr; ep.project = 0;
-        return slab_fx<T>(p, g, rcv, 1, nf, cb, ep, st);
+        return slab_fx<T>(p, g, rcv, 1, nf, cb, ep, 1, st);
     }
     if (op == FSM_SLAB_C2R) {
-        if (phase == 0) return slab_ix<T>(p, g, PROG_C2R, static_cast<const cplx<T>*>(u_hat), snd, nf, 1, p->nh, st);
-        if (int e = slab_mid_inverse<T>(p, g, rcv, bf.w3, 1, mid_spec_identity(1), p->nh, nf, st)) return e;
-        return slab_phys<T>(p, g, PROG_C2R, bf.w3, nullptr, nullptr, static_cast<T*>(aux), nf, st);
+        if (phase == 0) return slab_ix<T>(p, g, PROG_C2R, static_cast<const cplx<T>*>(u_hat), snd, nf, 1, p->nh, 1, st);
+        if (int e = slab_mid_inverse<T>(p, g, rcv, bf.w3, 1, mid_spec_identity(1), p->nh, nf, 0, 1, st)) return e;
+        return slab_phys<T>(p, g, PROG_C2R, bf.w3, nullptr, nullptr, static_cast<T*>(aux), nf, 0, 1, st);
     }
     return fail(-EINVAL, "unknown slab op %d", op);
 }
@@ -952,15 +969,17 @@ int fsm_slab_info(const fsm_plan* plan, int op, int64_t* exch1_elems, int64_t* e
     return 0;
 }
 
-int fsm_slab_phase(fsm_plan* plan, int op, int stage, int phase, void* u_hat, void* aux, void* workspace, size_t ws_bytes,
-                   void* send, void* recv, void* stream) {
+int fsm_slab_phase(fsm_plan* plan, int op, int stage, int phase, int sub, int nsub, void* u_hat, void* aux, void* workspace,
+                   size_t ws_bytes, void* send, void* recv, void* stream) {
     if (!plan || plan->P <= 1) return fail(-EINVAL, "plan has no slab decomposition");
     if (!workspace || ws_bytes < plan->ws_bytes) return fail(-ENOMEM, "workspace too small");
     if (op == FSM_SLAB_STEP && (stage < 0 || stage >= (int)plan->stages.size())) return fail(-EINVAL, "bad stage %d", stage);
     if (phase < 0 || phase > 2) return fail(-EINVAL, "bad phase %d", phase);
+    if (nsub < 1 || (nsub & (nsub - 1)) || plan->nxl % nsub || sub < 0 || sub >= nsub)
+        return fail(-EINVAL, "bad sub-slab %d of %d (local x extent %d)", sub, nsub, plan->nxl);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    return plan->f64 ? do_slab_phase<double>(plan, op, stage, phase, u_hat, aux, workspace, send, recv, st)
-                     : do_slab_phase<float>(plan, op, stage, phase, u_hat, aux, workspace, send, recv, st);
+    return plan->f64 ? do_slab_phase<double>(plan, op, stage, phase, sub, nsub, u_hat, aux, workspace, send, recv, st)
+                     : do_slab_phase<float>(plan, op, stage, phase, sub, nsub, u_hat, aux, workspace, send, recv, st);
 }
 
 int fsm_profile_enable(fsm_plan* plan, int on) {

@@ -198,6 +198,13 @@ class FusedStepper:
             # exchange buffers: kernels write/read them directly in rank-blocked layouts
             self._send = [torch.empty(n, dtype=self.cdtype, device=self.device) for n in (n1, n2)]
             self._recv = [torch.empty(n, dtype=self.cdtype, device=self.device) for n in (n1, n2)]
+            nsub = int(slab[3]) if len(slab) > 3 and slab[3] else int(os.environ.get("FSM_SLAB_SUB", "0"))
+            if nsub <= 0:
+                nsub = 2 if self.nxl >= 16 else 1
+            while nsub > 1 and self.nxl % nsub:
+                nsub //= 2
+            self.nsub = max(1, nsub)
+            self._comm_stream = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
 
     def _local_slab(self, t):
         """(X, n1, nh, n0) rot-half table -> contiguous local ky slab when the grid is slab-decomposed."""
@@ -206,24 +213,51 @@ class FusedStepper:
         return t[:, self.rank * self.kyl:(self.rank + 1) * self.kyl].contiguous()
 
     # ---- slab-decomposed phases ---------------------------------------------------------------------
-    def _exchange(self, which, count):
+    def _exchange(self, which, count, offset=0, async_op=False):
         import torch.distributed as dist
-        dist.all_to_all_single(self._recv[which][:count], self._send[which][:count], group=self.group)
+        return dist.all_to_all_single(self._recv[which][offset:offset + count], self._send[which][offset:offset + count],
+                                      group=self.group, async_op=async_op)
 
-    def _slab_phase(self, op, stage, phase, u_hat, aux, which_send, which_recv):
+    def _slab_phase(self, op, stage, phase, u_hat, aux, which_send, which_recv, sub=0, nsub=1):
         snd = self._send[which_send].data_ptr() if which_send is not None else None
         rcv = self._recv[which_recv].data_ptr() if which_recv is not None else None
-        _cabi.check(self._lib.fsm_slab_phase(self._plan, op, stage, phase, u_hat.data_ptr() if u_hat is not None else None,
+        _cabi.check(self._lib.fsm_slab_phase(self._plan, op, stage, phase, sub, nsub,
+                                             u_hat.data_ptr() if u_hat is not None else None,
                                              aux.data_ptr() if aux is not None else None, self.workspace.data_ptr(),
                                              self.ws_bytes, snd, rcv, self._stream()), "slab_phase")
 
     def _slab_eval(self, op, stage, u_hat, aux=None):
+        """One nonlinear evaluation + stage combine on a slab-decomposed grid. With nsub > 1 sub-slabs the
+        all-to-all of sub-slab h+1 (side stream) overlaps the local y/z chain of sub-slab h."""
         c1, c2 = self._slab_counts[op]
-        self._slab_phase(op, stage, 0, u_hat, aux, 0, None)
-        self._exchange(0, c1)
-        self._slab_phase(op, stage, 1, u_hat, aux, 1, 0)
-        self._exchange(1, c2)
-        self._slab_phase(op, stage, 2, u_hat, aux, None, 1)
+        H = self.nsub
+        h1, h2 = c1 // H, c2 // H
+        self._slab_phase(op, stage, 0, u_hat, aux, 0, None, 0, H)
+        if H == 1 or self.device.type != "cuda":
+            for h in range(H):
+                self._exchange(0, h1, h * h1)
+                self._slab_phase(op, stage, 1, u_hat, aux, 1, 0, h, H)
+                self._exchange(1, h2, h * h2)
+        else:
+            cur = torch.cuda.current_stream(self.device)
+            comm = self._comm_stream
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            with torch.cuda.stream(comm):
+                comm.wait_event(ev)
+                works1 = [self._exchange(0, h1, h * h1, async_op=True) for h in range(H)]
+            works2 = []
+            for h in range(H):
+                works1[h].wait()                         # the compute stream waits for this sub-slab only
+                self._slab_phase(op, stage, 1, u_hat, aux, 1, 0, h, H)
+                evc = torch.cuda.Event()
+                evc.record(cur)
+                with torch.cuda.stream(comm):
+                    comm.wait_event(evc)
+                    works2.append(self._exchange(1, h2, h * h2, async_op=True))
+            for w in works2:
+                w.wait()
+        self._slab_phase(op, stage, 2, u_hat, aux, None, 1, 0, H)
 
     # ---- plumbing ---------------------------------------------------------------------------
     def __del__(self):
@@ -411,13 +445,15 @@ class OperatorLike:
         self._state_dict["integrator"] = None
         self._lowered = None
 
-    def set_slab_decomposition(self, group=None, rank: Optional[int] = None, nranks: Optional[int] = None):
+    def set_slab_decomposition(self, group=None, rank: Optional[int] = None, nranks: Optional[int] = None,
+                               nsub: int = 0):
         """Decompose ONE 3-D grid over the ranks of a torch.distributed process group:
         ``integrate`` / ``__call__`` then take and return the local physical x-slab
-        ``(B, C, n0/P, n1, n2)`` of the rank; the two transposes per evaluation are all-to-alls."""
+        ``(B, C, n0/P, n1, n2)`` of the rank; the two transposes per evaluation are all-to-alls. ``nsub``
+        sub-slabs (0 = choose) pipeline the exchange of one part with the local work on another."""
         import torch.distributed as dist
         self._slab = (dist.get_rank(group) if rank is None else rank,
-                      dist.get_world_size(group) if nranks is None else nranks, group)
+                      dist.get_world_size(group) if nranks is None else nranks, group, nsub)
         self._state_dict["integrator"] = None
         self._rhs_stepper = None
 
