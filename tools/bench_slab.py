@@ -39,7 +39,11 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        opts = None
+        if os.environ.get("FSM_NCCL_HIGH_PRIORITY", "1") == "1":
+            # the local passes occupy every SM; a high-priority NCCL stream lets the exchange's CTAs in
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
 
     # ---- parity of the NCCL slab path on a golden fixture (16^3, fp32, SETDRK4)
     parity = None
