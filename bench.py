@@ -181,16 +181,16 @@ def run_b200(args):
         return float(t.item())
 
     # ---------------- device-resident throughput
-    for _ in range(args.warmup):
-        st.step_half(u_hat, 1)
+    # one fsm_step call advances all K steps (the FX of a stage is fused with the IX of the next one,
+    # also across step boundaries); the state (269 MB) and scratch exceed the L2, so no flush is needed
+    st.step_half(u_hat, args.warmup)
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        st.step_half(u_hat, 1)
+    st.step_half(u_hat, args.steps)
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -202,8 +202,7 @@ def run_b200(args):
     # ---------------- per-pass timing for the roofline entry (same state, right after the timed region)
     st.profile(True)
     prof_steps = max(3, min(10, args.steps))
-    for _ in range(prof_steps):
-        st.step_half(u_hat, 1)
+    st.step_half(u_hat, prof_steps)
     torch.cuda.synchronize()
     prof = st.profile_read()
     st.profile(False)

@@ -138,6 +138,21 @@ static int launch_fx(int C, const FxArgs<T>& a, cudaStream_t s) {
 }
 
 template <typename T, int N>
+static int launch_fxix_ns2d(const FxIxArgs<T>& a, cudaStream_t s) {
+    using Cfg = typename CfgFor<N>::type;
+    if constexpr (Cfg::NST < 2) {
+        return -ENOSYS;
+    } else {
+        auto kern = k_pass_fxix_ns2d<T, Cfg>;
+        const size_t smem = Smem<Cfg, T>::bytes(2 * kKL);
+        if (int e = set_smem(kern, smem)) return e;
+        dim3 grid((a.fx.nlines + kKL - 1) / kKL, 1, a.fx.nb), block(kKL * Cfg::TL);
+        FSM_LAUNCH(kern, grid, block, smem, s, a.fx.g, a.fx.win, a.fx.win_fstride, a.fx.cb, a.fx.ep, a.fx.nlines, a.fx.b0,
+                   a.w1, a.w1_fstride, a.out_e_stride, a.n_keep, a.do_ix);
+        return check_launch();
+    }
+}
+template <typename T, int N>
 static int launch_step1d(const Step1dArgs<T>& a, cudaStream_t s) {
     using Cfg = typename CfgFor<N>::type;
     auto kern = k_step1d<T, Cfg>;
@@ -164,13 +179,13 @@ static int launch_line1d(int mode, const void* in, void* out, long nfields, cuda
 #define FSM_CAT(a, b) FSM_CAT2(a, b)
 const LaunchTable<float>* FSM_CAT(table_f32_, FSM_N)() {
     static const LaunchTable<float> t = {FSM_N, launch_ix<float, FSM_N>, launch_mid<float, FSM_N>,
-                                         launch_phys<float, FSM_N>, launch_fx<float, FSM_N>,
+                                         launch_phys<float, FSM_N>, launch_fx<float, FSM_N>, launch_fxix_ns2d<float, FSM_N>,
                                          launch_step1d<float, FSM_N>, launch_line1d<float, FSM_N>};
     return &t;
 }
 const LaunchTable<double>* FSM_CAT(table_f64_, FSM_N)() {
     static const LaunchTable<double> t = {FSM_N, launch_ix<double, FSM_N>, launch_mid<double, FSM_N>,
-                                          launch_phys<double, FSM_N>, launch_fx<double, FSM_N>,
+                                          launch_phys<double, FSM_N>, launch_fx<double, FSM_N>, launch_fxix_ns2d<double, FSM_N>,
                                           launch_step1d<double, FSM_N>, launch_line1d<double, FSM_N>};
     return &t;
 }

@@ -649,18 +649,25 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
 // ------------------------------------------------------------------------------------------
 #define FSM_MAX_IN 3
 #define FSM_MAX_OUT 3
+#define FSM_MAX_TAB 4
 template <typename T>
 struct Combine {
     int n_in, n_out, n_tab;
     int use_fresh;                 // 0: no nonlinear term (pure linear step)
     const cplx<T>* in[FSM_MAX_IN];
     cplx<T>* out[FSM_MAX_OUT];
-    const T* tab[8];               // real tables [tab_channels][nmodes]
+    const T* tab[FSM_MAX_TAB];     // real tables [tab_channels][nmodes]
     long tab_cstride;              // 0 if one table serves every channel
-    // out[r] = sum_m (ca[r][m] + cb[r][m] * tab[ct[r][m]]) * X_m,  X_0 = fresh N, X_{1+i} = in[i]
-    int ct[FSM_MAX_OUT][FSM_MAX_IN + 1];   // table index, -1 = scalar only, -2 = term absent
-    T ca[FSM_MAX_OUT][FSM_MAX_IN + 1];
-    T cb[FSM_MAX_OUT][FSM_MAX_IN + 1];
+    // row[r] = sum_m (ca + cb * tab[ct] + cb2 * tab[ct2])[r][m] * X_m,  X_0 = fresh N, X_{1+i} = in[i].
+    // Rows 0..n_out-1 are stored to out[r]; row FSM_MAX_OUT (if has_next) is the next stage state, handed
+    // in registers to the fused inverse transforms and never stored.
+    int has_next;
+    int any_ct2;                                // some coefficient uses a second table
+    int ct[FSM_MAX_OUT + 1][FSM_MAX_IN + 1];    // table index, -1 = scalar only, -2 = term absent
+    int ct2[FSM_MAX_OUT + 1][FSM_MAX_IN + 1];   // optional second table, -1 = none
+    T ca[FSM_MAX_OUT + 1][FSM_MAX_IN + 1];
+    T cb[FSM_MAX_OUT + 1][FSM_MAX_IN + 1];
+    T cb2[FSM_MAX_OUT + 1][FSM_MAX_IN + 1];
 };
 
 template <typename T>
@@ -675,9 +682,9 @@ struct FxEpilogue {
 // before the first store so the memory system sees them all in flight.
 template <typename T, int NB>
 __device__ __forceinline__ void combine_block(const Combine<T>& cb, const cplx<T>* fresh, long bc_off, long tab_off,
-                                              long mode0, long mstride) {
+                                              long mode0, long mstride, cplx<T>* next = nullptr, bool store = true) {
     cplx<T> X[FSM_MAX_IN][NB];
-    T tv[8][NB];
+    T tv[FSM_MAX_TAB][NB];
     FSM_UNROLL
     for (int i = 0; i < FSM_MAX_IN; ++i)
         if (i < cb.n_in) {
@@ -685,14 +692,15 @@ __device__ __forceinline__ void combine_block(const Combine<T>& cb, const cplx<T
             for (int j = 0; j < NB; ++j) X[i][j] = cb.in[i][bc_off + mode0 + j * mstride];
         }
     FSM_UNROLL
-    for (int q = 0; q < 8; ++q)
+    for (int q = 0; q < FSM_MAX_TAB; ++q)
         if (q < cb.n_tab) {
             FSM_UNROLL
             for (int j = 0; j < NB; ++j) tv[q][j] = cb.tab[q][tab_off + mode0 + j * mstride];
         }
     FSM_UNROLL
-    for (int r = 0; r < FSM_MAX_OUT; ++r) {
-        if (r < cb.n_out) {
+    for (int r = 0; r < FSM_MAX_OUT + 1; ++r) {
+        const bool is_next = (r == FSM_MAX_OUT);
+        if (is_next ? (cb.has_next && next != nullptr) : (r < cb.n_out)) {
             cplx<T> s[NB];
             FSM_UNROLL
             for (int j = 0; j < NB; ++j) s[j] = mk<T>(T(0), T(0));
@@ -700,20 +708,31 @@ __device__ __forceinline__ void combine_block(const Combine<T>& cb, const cplx<T
             for (int m = 0; m < FSM_MAX_IN + 1; ++m) {
                 const int ti = cb.ct[r][m];
                 if (ti != -2) {
+                    const int ti2 = cb.ct2[r][m];
                     FSM_UNROLL
                     for (int j = 0; j < NB; ++j) {
                         T coef = cb.ca[r][m];
                         FSM_UNROLL
-                        for (int q = 0; q < 8; ++q)
+                        for (int q = 0; q < FSM_MAX_TAB; ++q)
                             if (ti == q) coef = fsm_fma(cb.cb[r][m], tv[q][j], coef);
+                        if (cb.any_ct2) {
+                            FSM_UNROLL
+                            for (int q = 0; q < FSM_MAX_TAB; ++q)
+                                if (ti2 == q) coef = fsm_fma(cb.cb2[r][m], tv[q][j], coef);
+                        }
                         const cplx<T> x = (m == 0) ? fresh[j] : X[(m == 0) ? 0 : m - 1][j];
                         s[j].x = fsm_fma(coef, x.x, s[j].x);
                         s[j].y = fsm_fma(coef, x.y, s[j].y);
                     }
                 }
             }
-            FSM_UNROLL
-            for (int j = 0; j < NB; ++j) cb.out[r][bc_off + mode0 + j * mstride] = s[j];
+            if (is_next) {
+                FSM_UNROLL
+                for (int j = 0; j < NB; ++j) next[j] = s[j];
+            } else if (store) {
+                FSM_UNROLL
+                for (int j = 0; j < NB; ++j) cb.out[r][bc_off + mode0 + j * mstride] = s[j];
+            }
         }
     }
 }
@@ -908,6 +927,132 @@ __global__ void __launch_bounds__(Cfg::TL) k_line1d(const void* __restrict__ in_
         FSM_UNROLL
         for (int m = 0; m < EPT; ++m) out[tau + m * TL] = v[m].x;
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// Pass FXIX (2-D vorticity program): FX of stage s fused with IX of stage s+1 on the same ky line.
+// The combine hands the next stage state over in registers (Combine::has_next), so that state is never
+// written to or read from HBM; lines beyond the dealiasing cut only do the FX half.
+// ------------------------------------------------------------------------------------------
+template <typename T, class Cfg>
+__global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL))
+k_pass_fxix_ns2d(Geom<T> g, const cplx<T>* __restrict__ win, long win_fstride, Combine<T> cb, FxEpilogue<T> ep, int nlines,
+                 int b0, cplx<T>* __restrict__ w1, long w1_fstride, long out_e_stride, int n_keep, int do_ix) {
+    constexpr int N = Cfg::N, EPT = Cfg::EPT, TL = Cfg::TL;
+    FSM_DYN_SMEM(smem_raw);
+    cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);
+    cplx<T>* bufs = tw + Smem<Cfg, T>::TWPAD;
+    make_twiddles<Cfg, T>(tw);
+    const int lt = threadIdx.x / TL, tau = threadIdx.x % TL;
+    const int t0 = blockIdx.x * kKL;
+    const int line = t0 + lt;
+    const bool line_ok = line < nlines;
+    const long bl = blockIdx.z;
+    const long b = b0 + bl;
+    LineSync<TL> sync{1 + lt};
+    cplx<T> u[EPT];
+    // ---- FX half: forward x-transform of the nonlinear term, epilogue, combine
+    {
+        const cplx<T>* src = win + bl * win_fstride + (long)(line_ok ? line : 0) * N;
+        FSM_UNROLL
+        for (int m = 0; m < EPT; ++m) u[m] = line_ok ? src[tau + m * TL] : mk<T>(T(0), T(0));
+        line_fft<Cfg, -1, T>(u, bufs + lt * Cfg::LINE_PITCH, tw, tau, sync);
+        constexpr int NB = (EPT >= 4) ? 4 : EPT;
+        const long line_mode0 = (long)(line_ok ? line : 0) * N;
+        static_for<0, EPT / NB>([&](auto mbc) {
+            constexpr int mb = decltype(mbc)::value * NB;
+            cplx<T> f[NB], nx[NB];
+            FSM_UNROLL
+            for (int j = 0; j < NB; ++j) {
+                f[j] = cscale(u[mb + j], ep.nl_coef);
+                nx[j] = mk<T>(T(0), T(0));
+            }
+            if (ep.source) {
+                FSM_UNROLL
+                for (int j = 0; j < NB; ++j) f[j] = f[j] + ep.source[line_mode0 + tau + (mb + j) * TL];
+            }
+            if (line_ok)
+                combine_block<T, NB>(cb, f, b * g.nmodes, 0, line_mode0 + tau + mb * TL, TL, nx, true);
+            FSM_UNROLL
+            for (int j = 0; j < NB; ++j) u[mb + j] = nx[j];
+        });
+    }
+    if (!do_ix || t0 >= n_keep) return;   // block-uniform
+    // ---- IX half (see k_pass_ix, PROG_NS2D): four plain transforms, paired Z-lines formed at store time
+    const int k_valid = (kKL < n_keep - t0) ? kKL : (n_keep - t0);
+    const bool line_kept = line < n_keep;
+    const int n1 = g.n[1];
+    const T dky = line_kept ? g.dk[1][line] : T(0);
+    const T dkyraw = line_kept ? g.dkraw[1][line] : T(0);
+    FSM_UNROLL
+    for (int m = 0; m < EPT; ++m) {
+        const int p = tau + m * TL;
+        const bool kept = line_kept && (iabs(signed_mode<N>(p)) <= g.kmax[0]);
+        u[m] = kept ? cscale(u[m], g.inv_ntot) : mk<T>(T(0), T(0));
+    }
+    __syncthreads();   // every line is done with its forward-transform buffer
+    static_for<0, 4>([&](auto fc) {
+        constexpr int f = decltype(fc)::value;
+        cplx<T> v[EPT];
+        FSM_UNROLL
+        for (int m = 0; m < EPT; ++m) {
+            const int p = tau + m * TL;
+            if constexpr (f == 2) {
+                v[m] = u[m];
+            } else {
+                const T dkx = g.dk[0][p];
+                if constexpr (f == 0) {
+                    v[m] = cscale(u[m], dkx);
+                } else {
+                    const T dkxraw = g.dkraw[0][p];
+                    const T lap = -(dkxraw * dkxraw) - (dkyraw * dkyraw);
+                    const T ninv = (lap == T(0)) ? T(-1) : neg_recip(lap);
+                    v[m] = cmul_i(u[m], (f == 1 ? dky : dkx) * ninv);
+                }
+            }
+        }
+        cplx<T>* pbufs = bufs + (f & 1) * kKL * Cfg::LINE_PITCH;
+        line_fft_head<Cfg, +1, T>(v, pbufs + lt * Cfg::LINE_PITCH, tw, tau, sync);
+        if constexpr (f & 1) {
+            __syncthreads();
+            constexpr int pair = f >> 1;
+            constexpr int RL = LastStage<Cfg>::RL, NS = LastStage<Cfg>::NS;
+            const int ts = threadIdx.x % kKL, widx = threadIdx.x / kKL;
+            const int tg = t0 + ts;
+            const bool valid = ts < k_valid;
+            const bool selfc = (tg == 0) || (2 * tg == n1);
+            const T dky_s = valid ? g.dk[1][tg] : T(0);
+            const cplx<T>* s0 = bufs + ts * Cfg::LINE_PITCH;
+            const cplx<T>* s1 = s0 + kKL * Cfg::LINE_PITCH;
+            cplx<T>* dp = w1 + (bl * 2 + pair) * w1_fstride + tg;
+            cplx<T>* dm = w1 + (bl * 2 + pair) * w1_fstride + (n1 - tg);
+            static_for<0, EPT / RL>([&](auto qc) {
+                constexpr int q = decltype(qc)::value;
+                const int w = widx + q * TL;
+                cplx<T> a[RL], bb[RL];
+                fft_last_item<Cfg, +1, T>(s0, tw, w, a);
+                fft_last_item<Cfg, +1, T>(s1, tw, w, bb);
+                if (valid) {
+                    static_for<0, RL>([&](auto tc) {
+                        constexpr int tp = decltype(tc)::value;
+                        const long off = (long)(w + tp * NS) * out_e_stride;
+                        cplx<T> zp, zm;
+                        if constexpr (pair == 0) {
+                            zp = selfc ? mk<T>(bb[tp].x, -a[tp].y) : bb[tp] - a[tp];
+                            zm = mk<T>(a[tp].x + bb[tp].x, -(a[tp].y + bb[tp].y));
+                        } else {
+                            zp = selfc ? mk<T>(-bb[tp].x, -dky_s * a[tp].y)
+                                       : mk<T>(-dky_s * a[tp].x - bb[tp].x, -dky_s * a[tp].y - bb[tp].y);
+                            zm = mk<T>(dky_s * a[tp].x - bb[tp].x, bb[tp].y - dky_s * a[tp].y);
+                        }
+                        dp[off] = zp;
+                        if (!selfc) dm[off] = zm;
+                    });
+                }
+            });
+            if constexpr (f == 1) __syncthreads();
+        }
+    });
 }
 
 // Combine without a nonlinear term (ETDRK0) or point-wise fix-ups: one thread per mode.
