@@ -128,3 +128,17 @@ def test_ns2d_other_dealiasing_rates_vs_oracle(rate):
     op.set_integrator(fsm.ETDRKIntegrator.ETDRK2)
     got = op.integrate(u0, mesh=mesh_info, dt=0.01, step=3)
     assert rel_l2(got.numpy(), want) <= 1e-12
+
+
+def test_linear_solve_matches_closed_form():
+    """LinearOperator.solve (operator/_base.py:217-262): (nu lap - 1) x = b has x_hat = b_hat / (-(nu k^2) - 1)."""
+    import torchfsm_b200 as fsm
+    n, nu = 32, 0.3
+    mesh_info = [(0, 2 * np.pi, n), (0, 2 * np.pi, n)]
+    ax = torch.arange(n, dtype=torch.float64) * (2 * np.pi / n)
+    x, y = torch.meshgrid(ax, ax, indexing="ij")
+    b = (torch.sin(3 * x) * torch.cos(2 * y) + 0.5 * torch.cos(x))[None, None]
+    op = nu * fsm.Laplacian() - fsm.ImplicitSource()
+    got = op.solve(b, mesh=mesh_info)
+    want = torch.sin(3 * x) * torch.cos(2 * y) / (-nu * 13 - 1) + 0.5 * torch.cos(x) / (-nu - 1)
+    assert float((got[0, 0] - want).abs().max()) < 1e-13

@@ -61,6 +61,7 @@ template <typename T, int N>
 static int launch_ix(int prog, const IxArgs<T>& a, cudaStream_t s) {
     switch (prog) {
         case PROG_NS2D: return launch_ix_p<T, N, PROG_NS2D>(a, s);
+        case PROG_KS2D: return launch_ix_p<T, N, PROG_KS2D>(a, s);
         case PROG_C2R: return launch_ix_p<T, N, PROG_C2R>(a, s);
         case PROG_CONV: case PROG_KS: case PROG_NS3D: return launch_ix_p<T, N, PROG_CONV>(a, s);
         default: return -ENOSYS;
@@ -104,6 +105,7 @@ static int launch_phys(int prog, int ndim, const PhysArgs<T>& a, cudaStream_t s)
     if (ndim == 2) {
         if (prog == PROG_NS2D) return launch_phys_p<T, N, PROG_NS2D, 2>(a, s);
         if (prog == PROG_KS) return launch_phys_p<T, N, PROG_KS, 2>(a, s);
+        if (prog == PROG_KS2D) return launch_phys_p<T, N, PROG_KS2D, 2>(a, s);
         if (prog == PROG_CONV) return launch_phys_p<T, N, PROG_CONV, 2>(a, s);
     } else if (ndim == 3) {
         if (prog == PROG_KS) return launch_phys_p<T, N, PROG_KS, 3>(a, s);

@@ -32,6 +32,7 @@ enum Prog : int {
     PROG_NS3D = 4,     // conv + pressure projection, 3-D   (dedicated/_navier_stokes.py:241-254)
     PROG_C2R = 5,      // plain inverse transform to physical space (mesh.py:487-491, .real)
     PROG_R2C = 6,      // plain forward transform of a real field   (mesh.py:481-485)
+    PROG_KS2D = 7,     // 2-D KS with paired Z-lines (kernel-side variant of PROG_KS)
 };
 
 template <typename T>
@@ -176,6 +177,7 @@ __device__ __forceinline__ void rotated_last_stage(const cplx<T>* bufs, const cp
 template <int PROG>
 struct IxFields {
     static constexpr int NF = (PROG == PROG_NS2D) ? 4 : ((PROG == PROG_C2R) ? 1 : 2);
+    static constexpr int NPAIR = (PROG == PROG_NS2D) ? 2 : 1;   // Z-line programs (NS2D, KS2D)
 };
 
 template <typename T, class Cfg, int PROG>
@@ -212,7 +214,7 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
     LineSync<TL> sync{1 + lt};
     cplx<T>* mybuf = bufs + lt * Cfg::LINE_PITCH;
 
-    if constexpr (PROG == PROG_NS2D) {
+    if constexpr (PROG == PROG_NS2D || PROG == PROG_KS2D) {
         // "Z-lines": the two real fields of a pair ride in ONE complex line Z = f_a + i f_b, so the last-axis
         // pass needs no pairing work. Pairs: Z1 = u_x + i d_x w, Z2 = u_y + i d_y w with psi = -w/lap,
         // u_x = d_y psi, u_y = -d_x psi (_navier_stokes.py:41-45). With the four plain x-transforms
@@ -221,20 +223,26 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
         //   Z1+ = B - A, Z1- = conj(A + B), Z2+ = -ky C - D, Z2- = conj(-ky C + D),
         // formed while the data crosses shared memory for the rotated store.
         // W1 layout: [pair][x][ky' < n1], the -ky line stored at ky' = n1 - ky.
+        // KS2D (1/2 |grad phi|^2): one pair Z = phi_x + i phi_y from A = T[kx phi], C = T[phi]:
+        //   Z+ = i A - ky C,  Z- = conj(i A + ky C).
         const int n1 = g.n[1];
+        constexpr int NPAIR = IxFields<PROG>::NPAIR;
         FSM_UNROLL
         for (int m = 0; m < EPT; ++m) {
             const int p = tau + m * TL;
             const bool kept = line_kept && (iabs(signed_mode<N>(p)) <= g.kmax[0]);
             u[m] = kept ? cscale(src[p], g.inv_ntot) : mk<T>(T(0), T(0));
         }
-        static_for<0, 4>([&](auto fc) {
+        static_for<0, 2 * NPAIR>([&](auto fc) {
             constexpr int f = decltype(fc)::value;
             cplx<T> v[EPT];
             FSM_UNROLL
             for (int m = 0; m < EPT; ++m) {
                 const int p = tau + m * TL;
-                if constexpr (f == 2) {
+                if constexpr (PROG == PROG_KS2D) {
+                    if constexpr (f == 0) v[m] = cscale(u[m], g.dk[0][p]);
+                    else v[m] = u[m];
+                } else if constexpr (f == 2) {
                     v[m] = u[m];
                 } else {
                     const T dkx = g.dk[0][p];
@@ -263,8 +271,8 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
                 const T dky_s = valid ? g.dk[1][tg] : T(0);
                 const cplx<T>* s0 = bufs + ts * Cfg::LINE_PITCH;
                 const cplx<T>* s1 = s0 + kKL * Cfg::LINE_PITCH;
-                cplx<T>* dp = w1 + (bc * 2 + pair) * w1_fstride + tg;
-                cplx<T>* dm = w1 + (bc * 2 + pair) * w1_fstride + (n1 - tg);
+                cplx<T>* dp = w1 + (bc * NPAIR + pair) * w1_fstride + tg;
+                cplx<T>* dm = w1 + (bc * NPAIR + pair) * w1_fstride + (n1 - tg);
                 static_for<0, EPT / RL>([&](auto qc) {
                     constexpr int q = decltype(qc)::value;
                     const int w = widx + q * TL;
@@ -276,7 +284,11 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
                             constexpr int tp = decltype(tc)::value;
                             const long off = (long)(w + tp * NS) * out_e_stride;
                             cplx<T> zp, zm;
-                            if constexpr (pair == 0) {
+                            if constexpr (PROG == PROG_KS2D) {      // a = A = T[kx phi], b = C = T[phi]
+                                zp = selfc ? mk<T>(-a[tp].y, -dky_s * b[tp].y)
+                                           : mk<T>(-a[tp].y - dky_s * b[tp].x, a[tp].x - dky_s * b[tp].y);
+                                zm = mk<T>(dky_s * b[tp].x - a[tp].y, -(a[tp].x + dky_s * b[tp].y));
+                            } else if constexpr (pair == 0) {
                                 zp = selfc ? mk<T>(b[tp].x, -a[tp].y) : b[tp] - a[tp];
                                 zm = mk<T>(a[tp].x + b[tp].x, -(a[tp].y + b[tp].y));
                             } else {
@@ -289,7 +301,7 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
                         });
                     }
                 });
-                if constexpr (f == 1) __syncthreads();
+                if constexpr (f == 1 && NPAIR == 2) __syncthreads();
             }
         });
         return;
@@ -388,6 +400,7 @@ struct PhysTraits;
 // NFI = input fields per sample, NOUT = output fields per sample, RPT = rows per thread-line
 template <> struct PhysTraits<PROG_NS2D, 2> { static constexpr int NFI = 2, NOUT = 1, RPT = 2; };
 template <> struct PhysTraits<PROG_KS, 2> { static constexpr int NFI = 2, NOUT = 1, RPT = 2; };
+template <> struct PhysTraits<PROG_KS2D, 2> { static constexpr int NFI = 1, NOUT = 1, RPT = 2; };
 template <> struct PhysTraits<PROG_KS, 3> { static constexpr int NFI = 3, NOUT = 1, RPT = 2; };
 template <> struct PhysTraits<PROG_CONV, 2> { static constexpr int NFI = 4, NOUT = 2, RPT = 1; };
 template <> struct PhysTraits<PROG_CONV, 3> { static constexpr int NFI = 9, NOUT = 3, RPT = 2; };
@@ -456,8 +469,9 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
             sync();
             line_fft<Cfg, +1, T>(v, mybuf, tw, tau, sync);
         };
-        if constexpr (PROG == PROG_NS2D) {
-            // Z-lines written by IX: field 0 = u_x + i d_x w, field 1 = u_y + i d_y w (full complex rows)
+        if constexpr (PROG == PROG_NS2D || PROG == PROG_KS2D) {
+            // Z-lines written by IX: NS2D field 0 = u_x + i d_x w, field 1 = u_y + i d_y w; KS2D field 0 =
+            // phi_x + i phi_y (full complex rows)
             auto inverse_z = [&](int f) {
                 const cplx<T>* z = wb + f * win_fstride + roff;
                 FSM_UNROLL
@@ -470,11 +484,16 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
                 line_fft<Cfg, +1, T>(v, mybuf, tw, tau, sync);
             };
             inverse_z(0);
-            FSM_UNROLL
-            for (int m = 0; m < EPT; ++m) acc[0][m] = v[m].x * v[m].y;
-            inverse_z(1);
-            FSM_UNROLL
-            for (int m = 0; m < EPT; ++m) acc[0][m] += v[m].x * v[m].y;
+            if constexpr (PROG == PROG_KS2D) {
+                FSM_UNROLL
+                for (int m = 0; m < EPT; ++m) acc[0][m] = T(0.5) * (v[m].x * v[m].x + v[m].y * v[m].y);
+            } else {
+                FSM_UNROLL
+                for (int m = 0; m < EPT; ++m) acc[0][m] = v[m].x * v[m].y;
+                inverse_z(1);
+                FSM_UNROLL
+                for (int m = 0; m < EPT; ++m) acc[0][m] += v[m].x * v[m].y;
+            }
         } else if constexpr (PROG == PROG_KS && NDIM == 2) {
             // fields: 0 phi (x-transformed), 1 d_x phi  ->  1/2 (phi_x^2 + phi_y^2)
             inverse_pair(1, 0, false, true);

@@ -441,7 +441,8 @@ int run_stage(const fsm_plan* p, const Buffers<T>& bf, const Stage& s, cudaStrea
         PhysArgs<T> ph;
         ph.g = g; ph.wout = bf.w2; ph.phys_in = nullptr; ph.phys_out = nullptr; ph.nb = nb;
         if (p->ndim == 2) {
-            const int w1_pitch = (p->kprog == PROG_NS2D) ? p->n[1] : p->ph;   // NS2D: full complex Z-lines
+            const bool zlines = (p->kprog == PROG_NS2D || p->kprog == PROG_KS2D);
+            const int w1_pitch = zlines ? p->n[1] : p->ph;   // Z-line programs: full complex rows
             a.w1_fstride = (long)p->n[0] * w1_pitch;
             a.in_t_stride = p->n[0]; a.in_o_stride = 0; a.out_o_stride = 0; a.out_e_stride = w1_pitch;
             a.n_t = (p->d.kmax[1] + 1 < p->nh) ? p->d.kmax[1] + 1 : p->nh; a.n_outer = 1;
@@ -882,7 +883,7 @@ int fsm_plan_create(fsm_plan** out, const fsm_desc* d) {
         case FSM_PROG_KS:
             if (p->C != 1) { delete p; return fail(-EINVAL, "KS convection needs one channel"); }
             if (p->ndim == 1) { delete p; return fail(-ENOSYS, "KS convection on 1-D grids is not supported by the fused CUDA path"); }
-            p->kprog = PROG_KS; p->nf_ix = 2; p->nfi = (p->ndim == 2) ? 2 : 3; p->nout = 1; break;
+            p->kprog = (p->ndim == 2) ? PROG_KS2D : PROG_KS; p->nf_ix = 2; p->nfi = (p->ndim == 2) ? 2 : 3; p->nout = 1; break;
         case FSM_PROG_NS2D_VORT:
             if (p->C != 1 || p->ndim != 2) { delete p; return fail(-EINVAL, "vorticity convection needs a 2-D scalar field"); }
             p->kprog = PROG_NS2D; p->nf_ix = 4; p->nfi = 4; p->nout = 1; break;
@@ -922,7 +923,7 @@ int fsm_plan_create(fsm_plan** out, const fsm_desc* d) {
     if (p->ndim == 1) {
         // the 1-D kernels keep everything on chip: no intermediates
     } else if (p->ndim == 2) {
-        w1_per = (p->kprog == PROG_NS2D) ? (size_t)2 * p->n[0] * p->n[1] * esz
+        w1_per = (p->kprog == PROG_NS2D || p->kprog == PROG_KS2D) ? (size_t)2 * p->n[0] * p->n[1] * esz
                                          : (size_t)p->C * p->nf_ix * p->n[0] * p->ph * esz;
         w2_per = (size_t)p->nout * p->nmodes * esz;
     } else {

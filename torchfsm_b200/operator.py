@@ -665,6 +665,33 @@ class Operator(OperatorLike):
     pass
 
 
+def _solve(self, b: Optional[torch.Tensor] = None, b_fft: Optional[torch.Tensor] = None, mesh=None,
+           n_channel: Optional[int] = None, return_in_fourier: bool = False):
+    """Solve the linear equation ``A x = b`` (mirror of ``_InverseSolveMixin.solve``, operator/_base.py:217-262):
+    ``x_hat = b_hat * where(L == 0, 1, 1/L)``. Runs on the CUDA library: r2c, one table multiply, c2r."""
+    if not self.is_linear:
+        raise NotImplementedError("solve is only defined for linear operators")
+    value = b if b is not None else b_fft
+    if value is None:
+        raise ValueError("Either b or b_fft should be given")
+    if mesh is None:
+        assert self._state_dict["f_mesh"] is not None, "Mesh and n_channel should be given when calling solve"
+        mesh = self._state_dict["f_mesh"]
+    f_mesh, c = self._pre_check(b, b_fft, mesh)
+    n_channel = c if n_channel is None else n_channel
+    self.register_mesh(f_mesh, n_channel)
+    L = self._state_dict["linear_coef"]
+    inv = torch.where(L == 0, 1.0, 1 / L)                                   # operator/_base.py:250-255
+    st = FusedStepper(f_mesh, value.shape[0], n_channel, _cabi.PROG_LINEAR, "ETDRK0", 1.0, None, 0.0, None,
+                      [n // 2 for n in f_mesh.shape], True, {}, tables={"exp": inv})
+    x_hat = st.r2c(b) if b_fft is None else st.full_to_half(b_fft)
+    st.step_half(x_hat, 1)
+    return st.half_to_full(x_hat) if return_in_fourier else st.c2r(x_hat)
+
+
+OperatorLike.solve = _solve
+
+
 class LinearOperator(OperatorLike):
     pass
 
