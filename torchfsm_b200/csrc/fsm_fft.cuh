@@ -32,6 +32,79 @@ template <typename T> FSM_HD __forceinline__ cplx<T> cconj(cplx<T> a) { return m
 // multiply by i*s (s real)
 template <typename T> FSM_HD __forceinline__ cplx<T> cmul_i(cplx<T> a, T s) { return mk<T>(-a.y * s, a.x * s); }
 
+// ------------------------------------------------------------------------------------
+// Blackwell packed fp32 pairs: add/mul/fma.rn.f32x2 (SASS FADD2 / FMUL2 / FFMA2) work on a 64-bit
+// register pair, i.e. on one complex number; ptxas folds the half-swap, per-half sign flips and scalar
+// broadcasts into operand modifiers. The passes are issue-bound, so a complex add is 1 instruction
+// instead of 2, a complex multiply 2 instead of 4, a twiddled radix-2 butterfly 4 instead of 8.
+// ------------------------------------------------------------------------------------
+#if defined(__CUDACC__) && !defined(FSM_EMU) && !defined(FSM_NO_F32X2)
+#define FSM_PACKED 1
+typedef unsigned long long fsm_u64;
+__device__ __forceinline__ fsm_u64 pk(float lo, float hi) { fsm_u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ fsm_u64 pk(cplx<float> a) { return pk(a.x, a.y); }
+__device__ __forceinline__ cplx<float> upk(fsm_u64 v) { cplx<float> r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
+__device__ __forceinline__ fsm_u64 add2(fsm_u64 a, fsm_u64 b) { fsm_u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ fsm_u64 sub2(fsm_u64 a, fsm_u64 b) { fsm_u64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ fsm_u64 mul2(fsm_u64 a, fsm_u64 b) { fsm_u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ fsm_u64 fma2(fsm_u64 a, fsm_u64 b, fsm_u64 c) { fsm_u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+// non-template overloads win over the generic templates for cplx<float>
+__device__ __forceinline__ cplx<float> operator+(cplx<float> a, cplx<float> b) { return upk(add2(pk(a), pk(b))); }
+__device__ __forceinline__ cplx<float> operator-(cplx<float> a, cplx<float> b) { return upk(sub2(pk(a), pk(b))); }
+__device__ __forceinline__ cplx<float> cmul(cplx<float> a, cplx<float> b) {
+    return upk(fma2(pk(a.y, a.x), pk(-b.y, b.y), mul2(pk(a), pk(b.x, b.x))));
+}
+__device__ __forceinline__ cplx<float> cmulc(cplx<float> a, cplx<float> b) {
+    return upk(fma2(pk(a.y, a.x), pk(b.y, -b.y), mul2(pk(a), pk(b.x, b.x))));
+}
+__device__ __forceinline__ cplx<float> cscale(cplx<float> a, float s) { return upk(mul2(pk(a), pk(s, s))); }
+__device__ __forceinline__ cplx<float> cmul_i(cplx<float> a, float s) { return upk(mul2(pk(a.y, a.x), pk(-s, s))); }
+#endif
+
+// Radix-2 combine  p = e + W o,  m = e - W o  for W = (c, s) given at compile time.
+template <typename T>
+struct Bfly {
+    static FSM_HD __forceinline__ void plain(cplx<T> e, cplx<T> o, cplx<T>& p, cplx<T>& m) { p = e + o; m = e - o; }
+    template <int D>  // W = (0, D)
+    static FSM_HD __forceinline__ void rot(cplx<T> e, cplx<T> o, cplx<T>& p, cplx<T>& m) {
+        const cplx<T> t = mk<T>(-T(D) * o.y, T(D) * o.x);
+        p = e + t; m = e - t;
+    }
+    static FSM_HD __forceinline__ void gen(cplx<T> e, cplx<T> o, T c, T s, cplx<T>& p, cplx<T>& m) {
+        const cplx<T> t = mk<T>(c * o.x - s * o.y, c * o.y + s * o.x);
+        p = e + t; m = e - t;
+    }
+};
+#ifdef FSM_PACKED
+template <>
+struct Bfly<float> {
+    static __device__ __forceinline__ void plain(cplx<float> e, cplx<float> o, cplx<float>& p, cplx<float>& m) {
+        p = upk(add2(pk(e), pk(o))); m = upk(sub2(pk(e), pk(o)));
+    }
+    template <int D>
+    static __device__ __forceinline__ void rot(cplx<float> e, cplx<float> o, cplx<float>& p, cplx<float>& m) {
+        const fsm_u64 so = pk(o.y, o.x), ee = pk(e);
+        p = upk(fma2(so, pk(-float(D), float(D)), ee));
+        m = upk(fma2(so, pk(float(D), -float(D)), ee));
+    }
+    static __device__ __forceinline__ void gen(cplx<float> e, cplx<float> o, float c, float s, cplx<float>& p, cplx<float>& m) {
+        const fsm_u64 so = pk(o.y, o.x), oo = pk(o), ee = pk(e);
+        p = upk(fma2(so, pk(-s, s), fma2(oo, pk(c, c), ee)));
+        m = upk(fma2(so, pk(s, -s), fma2(oo, pk(-c, -c), ee)));
+    }
+};
+#endif
+
+// acc + coef * x (real coefficient)
+template <typename T> FSM_HD __forceinline__ cplx<T> cfma_s(T coef, cplx<T> x, cplx<T> acc) {
+    return mk<T>(coef * x.x + acc.x, coef * x.y + acc.y);
+}
+#ifdef FSM_PACKED
+__device__ __forceinline__ cplx<float> cfma_s(float coef, cplx<float> x, cplx<float> acc) {
+    return upk(fma2(pk(coef, coef), pk(x), pk(acc)));
+}
+#endif
+
 // compile-time loop with a constexpr index
 template <int I, int E, class F>
 FSM_HD __forceinline__ void static_for(F&& f) {
@@ -80,33 +153,25 @@ struct Dft {
         static_for<0, R / 2>([&](auto kc) {
             constexpr int k = decltype(kc)::value;
             constexpr int j = k * (32 / R);  // W_R^k = W_32^j, 0 <= j < 16
-            cplx<T> t;
             if constexpr (j == 0) {
-                t = o[k];
+                Bfly<T>::plain(e[k], o[k], a[k], a[k + R / 2]);
             } else if constexpr (j == 8) {  // W = (0, DIR)
-                t = mk<T>(-T(DIR) * o[k].y, T(DIR) * o[k].x);
-            } else if constexpr (j == 4) {  // W = h (1, DIR)
-                constexpr T h = T(0.70710678118654752440);
-                t = mk<T>(h * (o[k].x - T(DIR) * o[k].y), h * (o[k].y + T(DIR) * o[k].x));
-            } else if constexpr (j == 12) {  // W = h (-1, DIR)
-                constexpr T h = T(0.70710678118654752440);
-                t = mk<T>(-h * (o[k].x + T(DIR) * o[k].y), h * (T(DIR) * o[k].x - o[k].y));
+                Bfly<T>::template rot<DIR>(e[k], o[k], a[k], a[k + R / 2]);
             } else {
                 constexpr T c = T(cos32(j));
                 constexpr T s = T(DIR) * T(sin32(j));
-                t = mk<T>(c * o[k].x - s * o[k].y, c * o[k].y + s * o[k].x);
+                Bfly<T>::gen(e[k], o[k], c, s, a[k], a[k + R / 2]);
             }
-            a[k] = e[k] + t;
-            a[k + R / 2] = e[k] - t;
         });
     }
 };
 template <int DIR, typename T>
 struct Dft<2, DIR, T> {
     static FSM_HD __forceinline__ void run(cplx<T>* a) {
-        cplx<T> t = a[0];
-        a[0] = t + a[1];
-        a[1] = t - a[1];
+        cplx<T> p, m;
+        Bfly<T>::plain(a[0], a[1], p, m);
+        a[0] = p;
+        a[1] = m;
     }
 };
 template <int DIR, typename T>

@@ -740,8 +740,7 @@ __device__ __forceinline__ void combine_block(const Combine<T>& cb, const cplx<T
                                 if (ti2 == q) coef = fsm_fma(cb.cb2[r][m], tv[q][j], coef);
                         }
                         const cplx<T> x = (m == 0) ? fresh[j] : X[(m == 0) ? 0 : m - 1][j];
-                        s[j].x = fsm_fma(coef, x.x, s[j].x);
-                        s[j].y = fsm_fma(coef, x.y, s[j].y);
+                        s[j] = cfma_s(coef, x, s[j]);
                     }
                 }
             }
