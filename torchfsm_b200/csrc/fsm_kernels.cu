@@ -16,8 +16,17 @@ template <> struct CfgFor<32> { using type = FftCfg<32, 8, 8, 4>; };
 template <> struct CfgFor<64> { using type = FftCfg<64, 8, 8, 8>; };
 template <> struct CfgFor<128> { using type = FftCfg<128, 16, 16, 8>; };
 template <> struct CfgFor<256> { using type = FftCfg<256, 16, 16, 16>; };
-template <> struct CfgFor<512> { using type = FftCfg<512, 16, 16, 16, 2>; };
-template <> struct CfgFor<1024> { using type = FftCfg<1024, 16, 16, 16, 4>; };
+#ifndef FSM_C512_R1
+#define FSM_C512_R1 8    // measured on C5: (16,8,4) 38.1 ms/step, (16,16,2) 39.0
+#define FSM_C512_R2 4
+#endif
+template <> struct CfgFor<512> { using type = FftCfg<512, 16, 16, FSM_C512_R1, FSM_C512_R2>; };
+#ifndef FSM_C1024_R0   // tuning hooks: -DFSM_C1024_R0=.. -DFSM_C1024_R1=.. -DFSM_C1024_R2=.. (EPT stays 16)
+#define FSM_C1024_R0 16   // measured on C3: (16,8,8) 2.10 ms/step, (16,16,4) 2.17, (8,16,8) 2.19, (8,8,16) 2.23, (4,16,16) 2.28
+#define FSM_C1024_R1 8
+#define FSM_C1024_R2 8
+#endif
+template <> struct CfgFor<1024> { using type = FftCfg<1024, 16, FSM_C1024_R0, FSM_C1024_R1, FSM_C1024_R2>; };
 
 // Pass-specific decompositions. The 3-D last-axis pass carries three accumulators of u.grad(u) plus the
 // working line, and the 3-channel FX pass three spectra (NS pressure projection couples the channels):

@@ -21,7 +21,10 @@ namespace fsm {
 #define FSM_KL 8
 #endif
 // ask ptxas for at least 512 resident threads per SM (register cap 128)
-#define FSM_MINB(nt) (((nt) >= 512) ? 1 : (512 / (nt)))
+#ifndef FSM_TARGET_THREADS
+#define FSM_TARGET_THREADS 512
+#endif
+#define FSM_MINB(nt) (((nt) >= FSM_TARGET_THREADS) ? 1 : (FSM_TARGET_THREADS / (nt)))
 constexpr int kKL = FSM_KL;  // thread-lines per CTA in every line pass
 
 enum Prog : int {
@@ -407,22 +410,35 @@ template <> struct PhysTraits<PROG_CONV, 3> { static constexpr int NFI = 9, NOUT
 template <int NDIM> struct PhysTraits<PROG_C2R, NDIM> { static constexpr int NFI = 1, NOUT = 0, RPT = 2; };
 template <int NDIM> struct PhysTraits<PROG_R2C, NDIM> { static constexpr int NFI = 0, NOUT = 1, RPT = 2; };
 
-// Build Z(p) = A + iB from half-lines (k <= kmax kept; DC/Nyquist imaginary parts dropped as a C2R does).
-template <typename T, int N>
-__device__ __forceinline__ cplx<T> pair_load(const cplx<T>* a, const cplx<T>* b, bool da, bool db, const T* dk, int p,
-                                             int kmax, bool row_ok) {
-    const int k = (p <= N / 2) ? p : N - p;
-    cplx<T> A = mk<T>(T(0), T(0)), B = mk<T>(T(0), T(0));
-    if (row_ok && k <= kmax) {
-        if (a) A = a[k];
-        if (b) B = b[k];
-        const T d = dk[k];
-        if (da) A = cmul_i(A, d);
-        if (db) B = cmul_i(B, d);
-        if (k == 0 || k == N / 2) { A.y = T(0); B.y = T(0); }
-        if (p > N / 2) { A.y = -A.y; B.y = -B.y; }
-    }
-    return mk<T>(A.x - B.y, A.y + B.x);
+// Build the paired line Z(p) = A(p) + i B(p), p = tau + m*TL, from two half-lines (k <= kmax kept; the
+// imaginary parts of the DC / Nyquist entries are dropped as a C2R transform does). The first half of a
+// thread's elements is read directly (p < N/2), the second half mirrored and conjugated (k = N - p), so the
+// index and conjugation selects are resolved at compile time; only tau == 0 touches p = 0 and p = N/2.
+template <typename T, class Cfg>
+__device__ __forceinline__ void pair_fill(cplx<T>* v, const cplx<T>* a, const cplx<T>* b, bool da, bool db, const T* dk,
+                                          int tau, int kmax, bool row_ok) {
+    constexpr int N = Cfg::N, EPT = Cfg::EPT, TL = Cfg::TL;
+    static_for<0, EPT>([&](auto mc) {
+        constexpr int m = decltype(mc)::value;
+        constexpr bool mirrored = (2 * m * TL >= N);          // p >= N/2 for every tau (p == N/2 only if tau == 0)
+        const int p = tau + m * TL;
+        const int k = mirrored ? N - p : p;
+        cplx<T> A = mk<T>(T(0), T(0)), B = mk<T>(T(0), T(0));
+        if (row_ok && k <= kmax) {
+            if (a) A = a[k];
+            if (b) B = b[k];
+            if (da || db) {
+                const T d = dk[k];
+                if (da) A = cmul_i(A, d);
+                if (db) B = cmul_i(B, d);
+            }
+            if constexpr (m == 0 || 2 * m * TL == N) {
+                if (tau == 0) { A.y = T(0); B.y = T(0); }       // k == 0 or k == N/2
+            }
+            if constexpr (mirrored) { A.y = -A.y; B.y = -B.y; }
+        }
+        v[m] = mk<T>(A.x - B.y, A.y + B.x);
+    });
 }
 
 template <typename T, class Cfg, int PROG, int NDIM>
@@ -464,8 +480,7 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
         auto inverse_pair = [&](int fa, int fb, bool da, bool db) {
             const cplx<T>* pa = (fa >= 0) ? wb + fa * win_fstride + roff : nullptr;
             const cplx<T>* pb = (fb >= 0) ? wb + fb * win_fstride + roff : nullptr;
-            FSM_UNROLL
-            for (int m = 0; m < EPT; ++m) v[m] = pair_load<T, N>(pa, pb, da, db, dkl, tau + m * TL, kmaxl, row_ok);
+            pair_fill<T, Cfg>(v, pa, pb, da, db, dkl, tau, kmaxl, row_ok);
             sync();
             line_fft<Cfg, +1, T>(v, mybuf, tw, tau, sync);
         };
