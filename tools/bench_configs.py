@@ -41,6 +41,12 @@ def timed(st, u_hat, steps, warmup=2, one_call=False):
 
 
 def pass_breakdown(st, u_hat, steps=2):
+    if os.environ.get("FSM_NCU_WINDOW"):          # ncu --profile-from-start off: profile exactly one step
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        st.step_half(u_hat, 1)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     st.profile(True)
     st.step_half(u_hat, steps)
     torch.cuda.synchronize()

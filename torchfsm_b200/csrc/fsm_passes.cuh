@@ -368,18 +368,26 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
     const bool line_ok = t < n_t;
     LineSync<TL> sync{1 + lt};
     cplx<T>* mybuf = bufs + lt * Cfg::LINE_PITCH;
-    for (int j = 0; j < spec.nfo; ++j) {
+    // the line of output field j+1 is loaded (registers) before field j is transformed and stored, so its
+    // latency hides behind the butterflies, the block barrier and the rotated stores of field j
+    auto load_line = [&](int j, cplx<T>* raw) {
         const cplx<T>* src = in + (b * nfi + spec.src[j]) * in_fstride + (long)t * in_t_stride + (long)o * in_o_stride;
-        cplx<T> v[EPT];
         FSM_UNROLL
         for (int m = 0; m < EPT; ++m) {
             const int p = tau + m * TL;
             bool kept = line_ok;
             if (DIR > 0) kept = kept && (iabs(signed_mode<N>(p)) <= g.kmax[1]);
-            cplx<T> x = kept ? src[blk_off(p, ib, 1)] : mk<T>(T(0), T(0));
-            if (spec.deriv[j]) x = cmul_i(x, g.dk[1][p]);
-            v[m] = x;
+            raw[m] = kept ? src[blk_off(p, ib, 1)] : mk<T>(T(0), T(0));
         }
+    };
+    cplx<T> raw[EPT];
+    load_line(0, raw);
+    for (int j = 0; j < spec.nfo; ++j) {
+        cplx<T> v[EPT];
+        const bool deriv = spec.deriv[j] != 0;
+        FSM_UNROLL
+        for (int m = 0; m < EPT; ++m) v[m] = deriv ? cmul_i(raw[m], g.dk[1][tau + m * TL]) : raw[m];
+        if (j + 1 < spec.nfo) load_line(j + 1, raw);
         cplx<T>* pbufs = bufs + (j & 1) * kKL * Cfg::LINE_PITCH;
         line_fft_head<Cfg, DIR, T>(v, pbufs + lt * Cfg::LINE_PITCH, tw, tau, sync);
         __syncthreads();
@@ -415,30 +423,47 @@ template <int NDIM> struct PhysTraits<PROG_R2C, NDIM> { static constexpr int NFI
 // thread's elements is read directly (p < N/2), the second half mirrored and conjugated (k = N - p), so the
 // index and conjugation selects are resolved at compile time; only tau == 0 touches p = 0 and p = N/2.
 template <typename T, class Cfg>
-__device__ __forceinline__ void pair_fill(cplx<T>* v, const cplx<T>* a, const cplx<T>* b, bool da, bool db, const T* dk,
-                                          int tau, int kmax, bool row_ok) {
+__device__ __forceinline__ void pair_load_raw(cplx<T>* A, cplx<T>* B, const cplx<T>* a, const cplx<T>* b, int tau, int kmax,
+                                              bool row_ok) {
+    constexpr int N = Cfg::N, EPT = Cfg::EPT, TL = Cfg::TL;
+    static_for<0, EPT>([&](auto mc) {
+        constexpr int m = decltype(mc)::value;
+        constexpr bool mirrored = (2 * m * TL >= N);
+        const int p = tau + m * TL;
+        const int k = mirrored ? N - p : p;
+        const bool kept = row_ok && k <= kmax;
+        A[m] = (kept && a) ? a[k] : mk<T>(T(0), T(0));
+        B[m] = (kept && b) ? b[k] : mk<T>(T(0), T(0));
+    });
+}
+template <typename T, class Cfg>
+__device__ __forceinline__ void pair_combine(cplx<T>* v, const cplx<T>* Ar, const cplx<T>* Br, bool da, bool db, const T* dk,
+                                             int tau, int kmax) {
     constexpr int N = Cfg::N, EPT = Cfg::EPT, TL = Cfg::TL;
     static_for<0, EPT>([&](auto mc) {
         constexpr int m = decltype(mc)::value;
         constexpr bool mirrored = (2 * m * TL >= N);          // p >= N/2 for every tau (p == N/2 only if tau == 0)
         const int p = tau + m * TL;
         const int k = mirrored ? N - p : p;
-        cplx<T> A = mk<T>(T(0), T(0)), B = mk<T>(T(0), T(0));
-        if (row_ok && k <= kmax) {
-            if (a) A = a[k];
-            if (b) B = b[k];
-            if (da || db) {
-                const T d = dk[k];
-                if (da) A = cmul_i(A, d);
-                if (db) B = cmul_i(B, d);
-            }
-            if constexpr (m == 0 || 2 * m * TL == N) {
-                if (tau == 0) { A.y = T(0); B.y = T(0); }       // k == 0 or k == N/2
-            }
-            if constexpr (mirrored) { A.y = -A.y; B.y = -B.y; }
+        cplx<T> A = Ar[m], B = Br[m];
+        if (da || db) {
+            const T d = (k <= kmax) ? dk[k] : T(0);
+            if (da) A = cmul_i(A, d);
+            if (db) B = cmul_i(B, d);
         }
+        if constexpr (m == 0 || 2 * m * TL == N) {
+            if (tau == 0) { A.y = T(0); B.y = T(0); }           // k == 0 or k == N/2
+        }
+        if constexpr (mirrored) { A.y = -A.y; B.y = -B.y; }
         v[m] = mk<T>(A.x - B.y, A.y + B.x);
     });
+}
+template <typename T, class Cfg>
+__device__ __forceinline__ void pair_fill(cplx<T>* v, const cplx<T>* a, const cplx<T>* b, bool da, bool db, const T* dk,
+                                          int tau, int kmax, bool row_ok) {
+    cplx<T> A[Cfg::EPT], B[Cfg::EPT];
+    pair_load_raw<T, Cfg>(A, B, a, b, tau, kmax, row_ok);
+    pair_combine<T, Cfg>(v, A, B, da, db, dk, tau, kmax);
 }
 
 template <typename T, class Cfg, int PROG, int NDIM>
@@ -469,6 +494,8 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
     const cplx<T>* wb = win + b * NFI * win_fstride + (long)o * in_o_stride;
 
     T keep2[EPT];   // CONV3D: third component of row 0 waits for row 1
+    cplx<T> rawA[(PROG == PROG_CONV && NDIM == 3) ? EPT : 1], rawB[(PROG == PROG_CONV && NDIM == 3) ? EPT : 1];
+    (void)rawA; (void)rawB;
     T acc[(NOUT > 0 ? NOUT : 1)][EPT];
     (void)keep2;
     static_for<0, RPT>([&](auto rc) {
@@ -535,24 +562,41 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
             FSM_UNROLL
             for (int m = 0; m < EPT; ++m) { acc[0][m] += u1[m] * v[m].x; acc[1][m] += u1[m] * v[m].y; }
         } else if constexpr (PROG == PROG_CONV && NDIM == 3) {
-            // fields: c = u_c (0..2), 3+c = d_x u_c, 6+c = d_y u_c ; d_z applied here.
-            // direction j: (d_j u_2, u_j) then (d_j u_0, d_j u_1)
+            // fields: c = u_c (0..2), 3+c = d_x u_c, 6+c = d_y u_c ; d_z applied here. Six paired transforms per
+            // row: for direction j  (d_j u_2, u_j)  then  (d_j u_0, d_j u_1). The half-lines of transform i+1
+            // are loaded (registers) before transform i runs, so the load latency hides behind the butterflies.
+            constexpr int FA[6] = {5, 3, 8, 6, 2, 0}, FB[6] = {0, 4, 1, 7, 2, 1};
+            constexpr bool DA[6] = {false, false, false, false, true, true}, DB[6] = {false, false, false, false, false, true};
             T uj[EPT];
-            static_for<0, 3>([&](auto jc) {
-                constexpr int j = decltype(jc)::value;
-                constexpr int base = (j == 0) ? 3 : ((j == 1) ? 6 : 0);
-                constexpr bool dz = (j == 2);
-                inverse_pair(base + 2, j, dz, false);
-                FSM_UNROLL
-                for (int m = 0; m < EPT; ++m) {
-                    uj[m] = v[m].y;
-                    acc[2][m] = (j == 0) ? uj[m] * v[m].x : acc[2][m] + uj[m] * v[m].x;
+            if constexpr (r == 0) pair_load_raw<T, Cfg>(rawA, rawB, wb + FA[0] * win_fstride + roff, wb + FB[0] * win_fstride + roff,
+                                                        tau, kmaxl, row_ok);
+            static_for<0, 6>([&](auto ic) {
+                constexpr int i = decltype(ic)::value;
+                pair_combine<T, Cfg>(v, rawA, rawB, DA[i], DB[i], dkl, tau, kmaxl);
+                if constexpr (i + 1 < 6) {
+                    pair_load_raw<T, Cfg>(rawA, rawB, wb + FA[i + 1] * win_fstride + roff, wb + FB[i + 1] * win_fstride + roff,
+                                          tau, kmaxl, row_ok);
+                } else if constexpr (r + 1 < RPT) {
+                    const int row2 = row + 1;
+                    const long roff2 = (long)row2 * in_t_stride;
+                    pair_load_raw<T, Cfg>(rawA, rawB, wb + FA[0] * win_fstride + roff2, wb + FB[0] * win_fstride + roff2, tau,
+                                          kmaxl, row2 < n_t);
                 }
-                inverse_pair(base + 0, base + 1, dz, dz);
-                FSM_UNROLL
-                for (int m = 0; m < EPT; ++m) {
-                    acc[0][m] = (j == 0) ? uj[m] * v[m].x : acc[0][m] + uj[m] * v[m].x;
-                    acc[1][m] = (j == 0) ? uj[m] * v[m].y : acc[1][m] + uj[m] * v[m].y;
+                sync();
+                line_fft<Cfg, +1, T>(v, mybuf, tw, tau, sync);
+                constexpr int j = i / 2;
+                if constexpr ((i & 1) == 0) {
+                    FSM_UNROLL
+                    for (int m = 0; m < EPT; ++m) {
+                        uj[m] = v[m].y;
+                        acc[2][m] = (j == 0) ? uj[m] * v[m].x : acc[2][m] + uj[m] * v[m].x;
+                    }
+                } else {
+                    FSM_UNROLL
+                    for (int m = 0; m < EPT; ++m) {
+                        acc[0][m] = (j == 0) ? uj[m] * v[m].x : acc[0][m] + uj[m] * v[m].x;
+                        acc[1][m] = (j == 0) ? uj[m] * v[m].y : acc[1][m] + uj[m] * v[m].y;
+                    }
                 }
             });
         } else if constexpr (PROG == PROG_C2R) {
