@@ -758,23 +758,31 @@ struct FxEpilogue {
 
 // Evaluate the combine for NB modes (mode0 + j*mstride): every global load of the block is issued
 // before the first store so the memory system sees them all in flight.
+// Operands of NB modes (mode0 + j*mstride) of one combine: every global load is issued up front.
 template <typename T, int NB>
-__device__ __forceinline__ void combine_block(const Combine<T>& cb, const cplx<T>* fresh, long bc_off, long tab_off,
-                                              long mode0, long mstride, cplx<T>* next = nullptr, bool store = true) {
+struct CombineOperands {
     cplx<T> X[FSM_MAX_IN][NB];
     T tv[FSM_MAX_TAB][NB];
+};
+template <typename T, int NB>
+__device__ __forceinline__ void combine_load(const Combine<T>& cb, long bc_off, long tab_off, long mode0, long mstride,
+                                             CombineOperands<T, NB>& op) {
     FSM_UNROLL
     for (int i = 0; i < FSM_MAX_IN; ++i)
         if (i < cb.n_in) {
             FSM_UNROLL
-            for (int j = 0; j < NB; ++j) X[i][j] = cb.in[i][bc_off + mode0 + j * mstride];
+            for (int j = 0; j < NB; ++j) op.X[i][j] = cb.in[i][bc_off + mode0 + j * mstride];
         }
     FSM_UNROLL
     for (int q = 0; q < FSM_MAX_TAB; ++q)
         if (q < cb.n_tab) {
             FSM_UNROLL
-            for (int j = 0; j < NB; ++j) tv[q][j] = cb.tab[q][tab_off + mode0 + j * mstride];
+            for (int j = 0; j < NB; ++j) op.tv[q][j] = cb.tab[q][tab_off + mode0 + j * mstride];
         }
+}
+template <typename T, int NB>
+__device__ __forceinline__ void combine_apply(const Combine<T>& cb, const cplx<T>* fresh, const CombineOperands<T, NB>& op,
+                                              long bc_off, long mode0, long mstride, cplx<T>* next = nullptr) {
     FSM_UNROLL
     for (int r = 0; r < FSM_MAX_OUT + 1; ++r) {
         const bool is_next = (r == FSM_MAX_OUT);
@@ -792,13 +800,13 @@ __device__ __forceinline__ void combine_block(const Combine<T>& cb, const cplx<T
                         T coef = cb.ca[r][m];
                         FSM_UNROLL
                         for (int q = 0; q < FSM_MAX_TAB; ++q)
-                            if (ti == q) coef = fsm_fma(cb.cb[r][m], tv[q][j], coef);
+                            if (ti == q) coef = fsm_fma(cb.cb[r][m], op.tv[q][j], coef);
                         if (cb.any_ct2) {
                             FSM_UNROLL
                             for (int q = 0; q < FSM_MAX_TAB; ++q)
-                                if (ti2 == q) coef = fsm_fma(cb.cb2[r][m], tv[q][j], coef);
+                                if (ti2 == q) coef = fsm_fma(cb.cb2[r][m], op.tv[q][j], coef);
                         }
-                        const cplx<T> x = (m == 0) ? fresh[j] : X[(m == 0) ? 0 : m - 1][j];
+                        const cplx<T> x = (m == 0) ? fresh[j] : op.X[(m == 0) ? 0 : m - 1][j];
                         s[j] = cfma_s(coef, x, s[j]);
                     }
                 }
@@ -806,12 +814,20 @@ __device__ __forceinline__ void combine_block(const Combine<T>& cb, const cplx<T
             if (is_next) {
                 FSM_UNROLL
                 for (int j = 0; j < NB; ++j) next[j] = s[j];
-            } else if (store) {
+            } else {
                 FSM_UNROLL
                 for (int j = 0; j < NB; ++j) cb.out[r][bc_off + mode0 + j * mstride] = s[j];
             }
         }
     }
+}
+template <typename T, int NB>
+__device__ __forceinline__ void combine_block(const Combine<T>& cb, const cplx<T>* fresh, long bc_off, long tab_off,
+                                              long mode0, long mstride, cplx<T>* next = nullptr, bool store = true) {
+    (void)store;
+    CombineOperands<T, NB> op;
+    combine_load<T, NB>(cb, bc_off, tab_off, mode0, mstride, op);
+    combine_apply<T, NB>(cb, fresh, op, bc_off, mode0, mstride, next);
 }
 
 template <typename T>
@@ -835,6 +851,15 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
     if (line >= nlines) return;
     LineSync<TL> sync{1 + lt};
     cplx<T>* mybuf = bufs + lt * Cfg::LINE_PITCH;
+    constexpr int NB = (EPT >= 4) ? 4 : EPT;
+    const long line_mode0 = (long)line * N;
+    // single-channel lines: the operands of the first combine block are requested before the transform runs and
+    // every later block is requested while the previous one is being combined (software pipeline)
+    // (measured: at N = 1024 the extra operand registers spill and cost more than the hidden latency, so the
+    // pipeline is used for lines up to 512 points only)
+    constexpr bool kPipe = (C == 1) && (N <= 512);
+    CombineOperands<T, NB> opq[2];   // dead (optimised away) when !kPipe
+    if constexpr (kPipe) combine_load<T, NB>(cb, b * g.nmodes, 0, line_mode0 + tau, TL, opq[0]);
     cplx<T> nhat[C][EPT];
     static_for<0, C>([&](auto cc) {
         constexpr int c = decltype(cc)::value;
@@ -847,10 +872,11 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
     // line coordinates
     int ky, kz = 0;
     if (g.ndim == 3) { ky = line / g.nh + g.ky0; kz = line % g.nh; } else { ky = line; }
-    constexpr int NB = (EPT >= 4) ? 4 : EPT;
-    const long line_mode0 = (long)line * N;
     static_for<0, EPT / NB>([&](auto mbc) {
         constexpr int mb = decltype(mbc)::value * NB;
+        constexpr int cur = decltype(mbc)::value & 1;
+        if constexpr (kPipe && mb + NB < EPT)
+            combine_load<T, NB>(cb, b * g.nmodes, 0, line_mode0 + tau + (mb + NB) * TL, TL, opq[cur ^ 1]);
         cplx<T> f[C][NB];
         FSM_UNROLL
         for (int j = 0; j < NB; ++j) {
@@ -897,9 +923,13 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
             ep.dc_out[b] = f[0][0].x;
             f[0][0] = mk<T>(T(0), T(0));
         }
-        FSM_UNROLL
-        for (int c = 0; c < C; ++c)
-            combine_block<T, NB>(cb, f[c], (b * C + c) * g.nmodes, c * cb.tab_cstride, line_mode0 + tau + mb * TL, TL);
+        if constexpr (kPipe) {
+            combine_apply<T, NB>(cb, f[0], opq[cur], b * g.nmodes, line_mode0 + tau + mb * TL, TL);
+        } else {
+            FSM_UNROLL
+            for (int c = 0; c < C; ++c)
+                combine_block<T, NB>(cb, f[c], (b * C + c) * g.nmodes, c * cb.tab_cstride, line_mode0 + tau + mb * TL, TL);
+        }
     });
 }
 
