@@ -230,11 +230,14 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
         //   Z+ = i A - ky C,  Z- = conj(i A + ky C).
         const int n1 = g.n[1];
         constexpr int NPAIR = IxFields<PROG>::NPAIR;
+        // the x wavenumbers of this thread's elements are loaded once, together with the line itself
+        T dkxr[EPT];
         FSM_UNROLL
         for (int m = 0; m < EPT; ++m) {
             const int p = tau + m * TL;
             const bool kept = line_kept && (iabs(signed_mode<N>(p)) <= g.kmax[0]);
             u[m] = kept ? cscale(src[p], g.inv_ntot) : mk<T>(T(0), T(0));
+            dkxr[m] = g.dkraw[0][p];
         }
         static_for<0, 2 * NPAIR>([&](auto fc) {
             constexpr int f = decltype(fc)::value;
@@ -242,17 +245,19 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
             FSM_UNROLL
             for (int m = 0; m < EPT; ++m) {
                 const int p = tau + m * TL;
+                // first-derivative symbol: zero on the Nyquist index (Hermitian projection), else the raw value
+                const T dkx_h = (2 * p == N) ? T(0) : dkxr[m];
                 if constexpr (PROG == PROG_KS2D) {
-                    if constexpr (f == 0) v[m] = cscale(u[m], g.dk[0][p]);
+                    if constexpr (f == 0) v[m] = cscale(u[m], dkx_h);
                     else v[m] = u[m];
                 } else if constexpr (f == 2) {
                     v[m] = u[m];
                 } else {
-                    const T dkx = g.dk[0][p];
+                    const T dkx = dkx_h;
                     if constexpr (f == 0) {
                         v[m] = cscale(u[m], dkx);
                     } else {
-                        const T dkxraw = g.dkraw[0][p];
+                        const T dkxraw = dkxr[m];
                         // lap = (i dkxraw)^2 + (i dkyraw)^2 (mesh.py:406-426); psi = -w * where(lap==0, 1, 1/lap)
                         const T lap = -(dkxraw * dkxraw) - (dkyraw * dkyraw);
                         const T ninv = (lap == T(0)) ? T(-1) : neg_recip(lap);
