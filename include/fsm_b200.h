@@ -74,8 +74,8 @@ typedef struct fsm_desc {
     int32_t chunk;            /* samples processed per pass launch; 0 = choose automatically         */
     double dt;                /* time step (RK4 only uses it; ETD tables already contain it)         */
     double nl_coef;           /* scalar coefficient of the convective nonlinear term                 */
-    double ks_ext_sum;        /* multi-GPU KS: sum of zero modes of the OTHER ranks (0 if single)    */
-    int32_t ks_ext_count;     /* multi-GPU KS: number of samples on the other ranks                  */
+    double ks_ext_sum;        /* reserved (0)                                                         */
+    int32_t ks_ext_count;     /* reserved (0)                                                         */
     int32_t reserved;
     const void* dk[3];        /* per-axis 2*pi*f(m), Nyquist entry zeroed (length n[i])  mesh.py:399-404 */
     const void* dkraw[3];     /* per-axis 2*pi*f(m) as the reference has it (length n[i])           */
@@ -136,6 +136,13 @@ enum fsm_slab_op { FSM_SLAB_STEP = 0, FSM_SLAB_RHS = 1, FSM_SLAB_R2C = 2, FSM_SL
 int fsm_slab_phase(fsm_plan* plan, int op, int stage, int phase, int sub, int nsub, void* u_hat, void* aux,
                    void* workspace, size_t ws_bytes, void* send, void* recv, void* stream);
 int fsm_slab_info(const fsm_plan* plan, int op, int64_t* exch1_elems, int64_t* exch2_elems, int32_t* n_stages);
+
+/* KS ensembles sharded over ranks: the batch mean of _ks_convection.py:34-36 spans every rank, but it only
+ * touches the k=0 bin, which never feeds back. With a log attached, every nonlinear evaluation appends the
+ * LOCAL sum of the per-sample zero modes (plan dtype, `capacity` entries, device memory owned by the caller;
+ * a new call resets the position). One all-reduce of the log after the run gives the exact zero-mode correction
+ * (torchfsm_b200.FusedStepper.ks_allreduce_correction) - no collective inside the step. */
+int fsm_ks_log(fsm_plan* plan, void* log, int64_t capacity);
 
 /* per-pass device timing for benchmarks: when enabled every pass launch is bracketed by CUDA
  * events on the caller's stream. fsm_profile_read waits for the recorded events, returns summed

@@ -115,3 +115,43 @@ def test_slab_decomposed_grid_matches_reference(name, world, nsub):
     e_step, e_rhs, e_rt = q.get(timeout=5)
     tol = 1e-12 if name.endswith("f64") else 1e-5
     assert e_step <= tol * (1 if name.endswith("f64") else 3) and e_rhs <= 10 * tol and e_rt <= tol
+
+
+def _ks_worker(rank, world, port, name, lib_path, out_q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    from golden_util import load_golden, rel_l2
+    from product_util import product_from_golden
+    from torchfsm_b200 import _cabi
+    _cabi.use_library(lib_path)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = load_golden(name)
+        spec = g["spec"]
+        op, mesh, u0 = product_from_golden(g, "cpu")
+        op.set_ensemble_group(dist.group.WORLD)
+        cut = u0.shape[0] - 1                                          # uneven shards when B = 3: 2 + 1 samples
+        lo, hi = (0, cut) if rank == 0 else (cut, u0.shape[0])
+        uT = op.integrate(u0[lo:hi].contiguous(), mesh=mesh, dt=spec["dt"], step=spec["steps"])
+        err = torch.tensor([rel_l2(uT.numpy(), g["uT"][lo:hi])], dtype=torch.float64)
+        dist.all_reduce(err, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            out_q.put(float(err.item()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name", ["c2_ks2d_32_f64", "ks3d_16_f64"])
+def test_ks_ensemble_mean_spans_ranks(name):
+    """KS batch mean across ranks: local means + one all-reduce of the zero-mode log."""
+    from product_util import build_emulator
+    lib_path = build_emulator()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ks_worker, args=(r, 2, port, name, lib_path, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) <= 1e-12

@@ -1181,13 +1181,14 @@ __global__ void k_combine_only(Combine<T> cb, long nmodes, int C, long total /*B
 // KS: N_hat_b(0) = coef * (S_b - mean_b S_b). The FX pass stored coef*S_b in dc[b] and combined a zero.
 // This kernel adds the missing contribution (coefficient of the fresh term at mode 0) to every output.
 template <typename T>
-__global__ void k_ks_dc_fix(Combine<T> cb, const T* dc, int B, long nmodes, T ext_sum, int ext_count) {
+__global__ void k_ks_dc_fix(Combine<T> cb, const T* dc, int B, long nmodes, T* log_slot) {
     FSM_DYN_SMEM(smem_raw);
     T* s_mean = reinterpret_cast<T*>(smem_raw);
     if (threadIdx.x == 0) {
-        T s = ext_sum;
+        T s = T(0);
         for (int b = 0; b < B; ++b) s += dc[b];
-        s_mean[0] = s / T(B + ext_count);
+        s_mean[0] = s / T(B);
+        if (log_slot) *log_slot = s;   // local sum of this evaluation (multi-rank zero-mode correction)
     }
     __syncthreads();
     for (int b = threadIdx.x; b < B; b += blockDim.x) {

@@ -206,6 +206,9 @@ struct fsm_plan {
     long nmodes, ntot;
     int chunk;
     int nf_ix, nfi, nout;  // fields: IX per channel, PHYS inputs per sample, PHYS outputs per sample
+    void* ks_log = nullptr;      // optional device log of the per-evaluation local KS zero-mode sums
+    long ks_log_cap = 0;
+    mutable long ks_log_pos = 0;
     int P = 1, rank = 0, kyl = 0, nxl = 0, nkz1 = 0;  // slab decomposition (P > 1): local ky / x extents, kept kz planes
     std::vector<Stage> stages;
     std::vector<Stage> fused_stages;   // non-empty: FX of a stage is fused with IX of the next one
@@ -475,8 +478,9 @@ int run_stage(const fsm_plan* p, const Buffers<T>& bf, const Stage& s, cudaStrea
     }
     if (ep.dc_out) {
         auto kern = k_ks_dc_fix<T>;
-        FSM_LAUNCH(kern, dim3(1), dim3(128), sizeof(T) * 2, st, cb, (const T*)bf.dc, p->B, p->nmodes,
-                   (T)p->d.ks_ext_sum, (int)p->d.ks_ext_count);
+        T* slot = nullptr;
+        if (p->ks_log && p->ks_log_pos < p->ks_log_cap) slot = static_cast<T*>(p->ks_log) + p->ks_log_pos++;
+        FSM_LAUNCH(kern, dim3(1), dim3(128), sizeof(T) * 2, st, cb, (const T*)bf.dc, p->B, p->nmodes, slot);
     }
     return 0;
 }
@@ -1075,6 +1079,14 @@ int fsm_slab_phase(fsm_plan* plan, int op, int stage, int phase, int sub, int ns
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     return plan->f64 ? do_slab_phase<double>(plan, op, stage, phase, sub, nsub, u_hat, aux, workspace, send, recv, st)
                      : do_slab_phase<float>(plan, op, stage, phase, sub, nsub, u_hat, aux, workspace, send, recv, st);
+}
+
+int fsm_ks_log(fsm_plan* plan, void* log, int64_t capacity) {
+    if (!plan) return fail(-EINVAL, "null plan");
+    plan->ks_log = log;
+    plan->ks_log_cap = log ? capacity : 0;
+    plan->ks_log_pos = 0;
+    return 0;
 }
 
 int fsm_profile_enable(fsm_plan* plan, int on) {

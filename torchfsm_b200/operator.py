@@ -337,6 +337,9 @@ class FusedStepper:
 
     def step_half(self, u_hat: torch.Tensor, n_steps: int = 1) -> torch.Tensor:
         """Advance the rot-half state in place by ``n_steps``."""
+        if getattr(self, "ks_group", None) is not None and self._desc.program == _cabi.PROG_KS \
+                and self._desc.ks_remove_mean and int(n_steps) > 0:
+            return self._step_half_ks_sharded(u_hat, int(n_steps))
         if self.P > 1 and self.n_stages and self._desc.program != _cabi.PROG_LINEAR:
             for _ in range(int(n_steps)):
                 for stage in range(self.n_stages):
@@ -344,6 +347,46 @@ class FusedStepper:
             return u_hat
         _cabi.check(self._lib.fsm_step(self._plan, u_hat.data_ptr(), self.workspace.data_ptr(), self.ws_bytes,
                                        int(n_steps), self._stream()), "step")
+        return u_hat
+
+    _KS_FINAL_WEIGHTS = {"ETDRK1": [("coef_1", 1.0)], "SETDRK1": [("coef_1", 1.0)],
+                         "ETDRK2": [("coef_1", 1.0, "coef_2", -1.0), ("coef_2", 1.0)],
+                         "SETDRK2": [("coef_1", 1.0, "coef_2", -1.0), ("coef_2", 1.0)],
+                         "SETDRK3": [("coef_3", 1.0), ("coef_4", 1.0), ("coef_5", 1.0)],
+                         "SETDRK4": [("coef_4", 1.0), ("coef_5", 2.0), ("coef_5", 2.0), ("coef_6", 1.0)]}
+
+    def _step_half_ks_sharded(self, u_hat: torch.Tensor, n_steps: int) -> torch.Tensor:
+        """KS ensemble sharded over the ranks of ``ks_group``: the batch mean of _ks_convection.py:34-36 spans
+        all ranks but only touches the k=0 bin, which never feeds back. Every rank steps with its local mean
+        while the library logs the per-evaluation local zero-mode sums; ONE all-reduce of that log afterwards
+        gives the exact correction of the zero mode (no collective inside the step)."""
+        import torch.distributed as dist
+        if self.integrator not in self._KS_FINAL_WEIGHTS:
+            raise NotImplementedError(f"sharded KS ensembles are not supported with the {self.integrator} integrator")
+        spec = self._KS_FINAL_WEIGHTS[self.integrator]
+        n_stage = len(spec)
+        log = torch.zeros(n_steps * n_stage, dtype=self.rdtype, device=self.device)
+        _cabi.check(self._lib.fsm_ks_log(self._plan, log.data_ptr(), log.numel()), "ks_log")
+        try:
+            _cabi.check(self._lib.fsm_step(self._plan, u_hat.data_ptr(), self.workspace.data_ptr(), self.ws_bytes,
+                                           n_steps, self._stream()), "step")
+        finally:
+            _cabi.check(self._lib.fsm_ks_log(self._plan, None, 0), "ks_log")
+        glob = torch.cat([log, torch.tensor([float(self.B)], dtype=self.rdtype, device=self.device)])
+        dist.all_reduce(glob, group=self.ks_group)
+        delta = (log / self.B - glob[:-1] / glob[-1]).reshape(n_steps, n_stage)     # local mean - global mean
+        tab0 = {k: v.reshape(v.shape[0], -1)[0, 0] for k, v in self.rot_tables.items()}
+        w = []
+        for term in spec:
+            x = tab0[term[0]] * term[1]
+            if len(term) == 4:
+                x = x + tab0[term[2]] * term[3]
+            w.append(x)
+        w = torch.stack(w)
+        e0 = tab0["exp"]
+        powers = e0 ** torch.arange(n_steps - 1, -1, -1, device=self.device, dtype=self.rdtype)
+        corr = (powers[:, None] * w[None, :] * delta).sum()
+        u_hat[:, 0, 0] += corr
         return u_hat
 
     def rhs_half(self, u_hat: torch.Tensor) -> torch.Tensor:
@@ -456,6 +499,14 @@ class OperatorLike:
                       dist.get_world_size(group) if nranks is None else nranks, group, nsub)
         self._state_dict["integrator"] = None
         self._rhs_stepper = None
+
+    def set_ensemble_group(self, group):
+        """The batch is sharded over the ranks of ``group`` (one process per GPU). Samples are independent
+        except for KSConvection(remove_mean=True), whose mean spans every rank; see
+        ``FusedStepper._step_half_ks_sharded``."""
+        self._ensemble_group = group
+        if self._state_dict.get("integrator") is not None:
+            self._state_dict["integrator"].ks_group = group
 
     def set_chunk(self, chunk: int):
         """Samples per pass launch (0 = library default); a tuning knob of the CUDA path."""
@@ -582,6 +633,7 @@ class OperatorLike:
                 "Cuda out of memory when building the integrator.",
                 "Original error message: {}".format(str(e)),
                 "Please try to use a smaller mesh or a low-order integrator."]))
+        st.ks_group = getattr(self, "_ensemble_group", None)
         if rhs_only:
             self._rhs_stepper = st
         else:
