@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-DEFAULT_LIB = os.path.join(_HERE, "libfsm_b200.so")
+# FSM_B200_LIB: kernel-tuning hook, points at another CUDA build of the same ABI (tools/ only)
+DEFAULT_LIB = os.environ.get("FSM_B200_LIB") or os.path.join(_HERE, "libfsm_b200.so")
 
 FSM_F32, FSM_F64 = 0, 1
 PROG_LINEAR, PROG_CONVECTION, PROG_KS, PROG_NS2D_VORT, PROG_NS3D = range(5)

@@ -56,6 +56,7 @@ template <typename T> static inline T __ldg(const T* p) { return *p; }
 static inline float fsm_fma(float a, float b, float c) { return std::fma(a, b, c); }
 static inline double fsm_fma(double a, double b, double c) { return std::fma(a, b, c); }
 #define FSM_HD
+#define FSM_PIN(ptr) (void)0
 #define FSM_CUDA_CHECK_LAUNCH() 0
 
 #else
@@ -71,4 +72,7 @@ static inline double fsm_fma(double a, double b, double c) { return std::fma(a, 
 static __device__ __forceinline__ float fsm_fma(float a, float b, float c) { return fmaf(a, b, c); }
 static __device__ __forceinline__ double fsm_fma(double a, double b, double c) { return fma(a, b, c); }
 #define FSM_HD __host__ __device__
+// Materialise a base pointer in a register pair here and now. Without it the compiler sinks the 64-bit
+// address arithmetic (strides are runtime longs) into every predicated element access.
+#define FSM_PIN(ptr) asm volatile("" : "+l"(ptr))
 #endif

@@ -192,6 +192,11 @@ struct FftCfg {
     static constexpr int PADSHIFT = (R0_ >= 32) ? 5 : 4;
     // padded index inside a line buffer
     static FSM_HD constexpr int pad(int i) { return i + (i >> PADSHIFT); }
+    // pad(a + c) == pad(a) + pad(c) when the low PADSHIFT bits cannot carry. Every buffer index of the
+    // stages is (thread part) + (compile-time part); where the split is exact the thread part is padded
+    // once and the compile-time part becomes the immediate offset of the LDS/STS.
+    static constexpr int PADG = 1 << PADSHIFT;
+    static constexpr int TLG = (N_ / EPT_ < PADG) ? N_ / EPT_ : PADG;   // granularity of tau's low bits
     // complex elements per line buffer, rounded so that LINE_PITCH % 16 == 2: eight lines
     // read "column-wise" by consecutive lanes (transposed stores) hit distinct banks.
     static constexpr int RAWLEN = N_ + (N_ >> PADSHIFT) + 1;
@@ -243,19 +248,27 @@ __device__ __forceinline__ void line_fft_head(cplx<T>* v, cplx<T>* buf, const cp
         sync();
         // ---- stage 1: Ns = R0 (middle stage)
         constexpr int Ns = R0;
+        constexpr bool kAffLd = ((N / R1) % Cfg::TLG == 0);
+        const cplx<T>* ldb = buf + Cfg::pad(tau);
         static_for<0, EPT / R1>([&](auto qc) {
             constexpr int q = decltype(qc)::value;
             const int w = tau + q * TL;
             static_for<0, R1>([&](auto tc) {
                 constexpr int t = decltype(tc)::value;
-                v[q * R1 + t] = buf[Cfg::pad(w + t * (N / R1))];
+                if constexpr (kAffLd) v[q * R1 + t] = ldb[Cfg::pad(q * TL + t * (N / R1))];
+                else v[q * R1 + t] = buf[Cfg::pad(w + t * (N / R1))];
             });
         });
         sync();  // everyone has read before anyone overwrites
+        // w = tau + q*TL: with TL a multiple of Ns the twiddle row j and the output base split the same way
+        constexpr bool kAffSt = (TL % Ns == 0) && (Cfg::PADG % Ns == 0) && ((Ns * R1) % Cfg::PADG == 0) &&
+                                ((TL * R1) % Cfg::PADG == 0);
+        const int jt = tau & (Ns - 1);
+        cplx<T>* stb = buf + Cfg::pad((tau / Ns) * Ns * R1 + jt);
         static_for<0, EPT / R1>([&](auto qc) {
             constexpr int q = decltype(qc)::value;
             const int w = tau + q * TL;
-            const int j = w & (Ns - 1);
+            const int j = kAffSt ? jt : (w & (Ns - 1));
             cplx<T> a[R1];
             a[0] = v[q * R1];
             static_for<1, R1>([&](auto tc) {
@@ -267,7 +280,8 @@ __device__ __forceinline__ void line_fft_head(cplx<T>* v, cplx<T>* buf, const cp
             const int base = (w / Ns) * Ns * R1 + j;
             static_for<0, R1>([&](auto tc) {
                 constexpr int t = decltype(tc)::value;
-                buf[Cfg::pad(base + t * Ns)] = a[t];
+                if constexpr (kAffSt) stb[Cfg::pad(q * TL * R1 + t * Ns)] = a[t];
+                else buf[Cfg::pad(base + t * Ns)] = a[t];
             });
         });
     }
@@ -279,16 +293,23 @@ struct LastStage {
     static constexpr int RL = (Cfg::NST == 3) ? Cfg::R2 : Cfg::R1;
     static constexpr int NS = Cfg::N / RL;   // stride between the outputs of one work item
 };
-template <class Cfg, int DIR, typename T>
-__device__ __forceinline__ void fft_last_item(const cplx<T>* buf, const cplx<T>* tw, int w, cplx<T>* a) {
+// The work item is w = wt + WC with WC known at compile time (a multiple of TL).
+template <class Cfg, int DIR, typename T, int WC = 0>
+__device__ __forceinline__ void fft_last_item(const cplx<T>* buf, const cplx<T>* tw, int wt, cplx<T>* a) {
     constexpr int RL = LastStage<Cfg>::RL, NS = LastStage<Cfg>::NS;
-    const cplx<T>* twl = (Cfg::NST == 3) ? tw + Cfg::TW1 : tw;
+    const cplx<T>* twl = ((Cfg::NST == 3) ? tw + Cfg::TW1 : tw) + wt;
     // NST == 2: Ns = R0 = NS and j = w; NST == 3: Ns = R0*R1 = NS and j = w
-    a[0] = buf[Cfg::pad(w)];
+    constexpr bool kAff = (WC % Cfg::TLG == 0) && (NS % Cfg::TLG == 0);
+    const int w = wt + WC;
+    const cplx<T>* ldb = buf + Cfg::pad(wt);
+    if constexpr (kAff) a[0] = ldb[Cfg::pad(WC)];
+    else a[0] = buf[Cfg::pad(w)];
     static_for<1, RL>([&](auto tc) {
         constexpr int t = decltype(tc)::value;
-        const cplx<T> x = buf[Cfg::pad(w + t * NS)];
-        const cplx<T> wv = twl[(t - 1) * NS + w];
+        cplx<T> x;
+        if constexpr (kAff) x = ldb[Cfg::pad(WC + t * NS)];
+        else x = buf[Cfg::pad(w + t * NS)];
+        const cplx<T> wv = twl[(t - 1) * NS + WC];
         a[t] = (DIR < 0) ? cmul(x, wv) : cmulc(x, wv);
     });
     Dft<RL, DIR, T>::run(a);
@@ -311,7 +332,7 @@ __device__ __forceinline__ void line_fft(cplx<T>* v, cplx<T>* buf, const cplx<T>
         static_for<0, EPT / RL>([&](auto qc) {
             constexpr int q = decltype(qc)::value;
             cplx<T> a[RL];
-            fft_last_item<Cfg, DIR, T>(buf, tw, tau + q * TL, a);
+            fft_last_item<Cfg, DIR, T, q * TL>(buf, tw, tau, a);
             static_for<0, RL>([&](auto tc) {
                 constexpr int t = decltype(tc)::value;
                 out[q + t * (EPT / RL)] = a[t];

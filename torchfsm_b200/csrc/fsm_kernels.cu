@@ -1,6 +1,8 @@
 // Kernel instantiations for ONE line length: compile with -DFSM_N=<N> (8..1024).
 #include "fsm_launch.h"
 #include <cerrno>
+#include <mutex>
+#include <vector>
 
 #ifndef FSM_N
 #error "compile with -DFSM_N=<line length>"
@@ -50,7 +52,17 @@ static inline int set_smem(K kern, size_t bytes) {
     return 0;
 }
 static inline int check_launch() { return cudaGetLastError() == cudaSuccess ? 0 : -EIO; }
+// CTAs of this kernel resident on the whole GPU at once = the L2 prefetch distance (Geom::pf_wave)
+template <class K>
+static inline int resident_ctas(K kern, int block, size_t smem) {
+    int per_sm = 0, dev = 0, sms = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, smem) != cudaSuccess) return 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    return per_sm * sms;
+}
 #else
+template <class K> static inline int resident_ctas(K, int, size_t) { return 0; }
 template <class K> static inline int set_smem(K, size_t) { return 0; }
 static inline int check_launch() { return 0; }
 #endif
@@ -62,7 +74,10 @@ static int launch_ix_p(const IxArgs<T>& a, cudaStream_t s) {
     const size_t smem = Smem<Cfg, T>::bytes(2 * kKL);
     if (int e = set_smem(kern, smem)) return e;
     dim3 grid((a.n_t + kKL - 1) / kKL, a.n_outer, a.nbc), block(kKL * Cfg::TL);
-    FSM_LAUNCH(kern, grid, block, smem, s, a.g, a.state, a.w1, a.state_bstride, a.w1_fstride, kKL, a.in_t_stride,
+    static const int wave = resident_ctas(kern, kKL * Cfg::TL, smem);
+    Geom<T> g = a.g;
+    g.pf_wave = wave;
+    FSM_LAUNCH(kern, grid, block, smem, s, g, a.state, a.w1, a.state_bstride, a.w1_fstride, kKL, a.in_t_stride,
                a.in_o_stride, a.out_o_stride, a.out_e_stride, a.n_t, a.eb);
     return check_launch();
 }
@@ -103,7 +118,10 @@ static int launch_phys_p(const PhysArgs<T>& a, cudaStream_t s) {
     const size_t smem = Smem<Cfg, T>::bytes(kKL * (1 + (NFW > 0 ? NFW : 0)));
     if (int e = set_smem(kern, smem)) return e;
     dim3 grid((a.n_t + K - 1) / K, a.n_outer, a.nb), block(kKL * Cfg::TL);
-    FSM_LAUNCH(kern, grid, block, smem, s, a.g, a.win, a.wout, a.phys_in, a.phys_out, a.win_fstride, a.wout_fstride, K,
+    static const int wave = resident_ctas(kern, kKL * Cfg::TL, smem);
+    Geom<T> g = a.g;
+    g.pf_wave = wave;
+    FSM_LAUNCH(kern, grid, block, smem, s, g, a.win, a.wout, a.phys_in, a.phys_out, a.win_fstride, a.wout_fstride, K,
                a.in_t_stride, a.in_o_stride, a.out_o_stride, a.out_e_stride, a.n_t, 1);
     return check_launch();
 }
@@ -137,7 +155,10 @@ static int launch_fx_c(const FxArgs<T>& a, cudaStream_t s) {
     const size_t smem = Smem<Cfg, T>::bytes(KF);
     if (int e = set_smem(kern, smem)) return e;
     dim3 grid((a.nlines + KF - 1) / KF, 1, a.nb), block(KF * Cfg::TL);
-    FSM_LAUNCH(kern, grid, block, smem, s, a.g, a.win, a.win_fstride, a.cb, a.ep, a.nlines, a.b0, a.ib,
+    static const int wave = resident_ctas(kern, KF * Cfg::TL, smem);
+    Geom<T> g = a.g;
+    g.pf_wave = wave;
+    FSM_LAUNCH(kern, grid, block, smem, s, g, a.win, a.win_fstride, a.cb, a.ep, a.nlines, a.b0, a.ib,
                a.line_stride ? a.line_stride : (long)Cfg::N);
     return check_launch();
 }
@@ -191,18 +212,54 @@ static int launch_line1d(int mode, const void* in, void* out, long nfields, cuda
     return check_launch();
 }
 
+// ---- static twiddle tables -------------------------------------------------------------------
+#ifndef FSM_EMU
+template <typename T, class Cfg>
+static int fill_table() {
+    if constexpr (Cfg::TW_TOTAL > 0) {
+        std::vector<cplx<T>> host(Cfg::TW_TOTAL);
+        fill_twiddles<Cfg, T>(host.data());
+        if (cudaMemcpyToSymbol(g_twiddles<T, Cfg>, host.data(), sizeof(cplx<T>) * Cfg::TW_TOTAL) != cudaSuccess) return -EIO;
+    }
+    return 0;
+}
+template <typename T, int N>
+static int prepare_tables() {
+    static std::mutex mu;
+    static bool done[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -EIO;
+    std::lock_guard<std::mutex> lk(mu);
+    if (done[dev]) return 0;
+    if (int e = fill_table<T, typename CfgFor<N>::type>()) return e;
+    if constexpr (!std::is_same<typename CfgPhys<N, 3>::type, typename CfgFor<N>::type>::value) {
+        if (int e = fill_table<T, typename CfgPhys<N, 3>::type>()) return e;
+    }
+    if constexpr (!std::is_same<typename CfgFx<N, 3>::type, typename CfgFor<N>::type>::value &&
+                  !std::is_same<typename CfgFx<N, 3>::type, typename CfgPhys<N, 3>::type>::value) {
+        if (int e = fill_table<T, typename CfgFx<N, 3>::type>()) return e;
+    }
+    done[dev] = true;
+    return 0;
+}
+#else
+template <typename T, int N> static int prepare_tables() { return 0; }
+#endif
+
 #define FSM_CAT2(a, b) a##b
 #define FSM_CAT(a, b) FSM_CAT2(a, b)
 const LaunchTable<float>* FSM_CAT(table_f32_, FSM_N)() {
     static const LaunchTable<float> t = {FSM_N, launch_ix<float, FSM_N>, launch_mid<float, FSM_N>,
                                          launch_phys<float, FSM_N>, launch_fx<float, FSM_N>, launch_fxix_ns2d<float, FSM_N>,
-                                         launch_step1d<float, FSM_N>, launch_line1d<float, FSM_N>};
+                                         launch_step1d<float, FSM_N>, launch_line1d<float, FSM_N>,
+                                         prepare_tables<float, FSM_N>};
     return &t;
 }
 const LaunchTable<double>* FSM_CAT(table_f64_, FSM_N)() {
     static const LaunchTable<double> t = {FSM_N, launch_ix<double, FSM_N>, launch_mid<double, FSM_N>,
                                           launch_phys<double, FSM_N>, launch_fx<double, FSM_N>, launch_fxix_ns2d<double, FSM_N>,
-                                          launch_step1d<double, FSM_N>, launch_line1d<double, FSM_N>};
+                                          launch_step1d<double, FSM_N>, launch_line1d<double, FSM_N>,
+                                          prepare_tables<double, FSM_N>};
     return &t;
 }
 

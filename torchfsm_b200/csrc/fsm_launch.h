@@ -73,6 +73,7 @@ struct LaunchTable {
     int (*fxix_ns2d)(const FxIxArgs<T>&, cudaStream_t);
     int (*step1d)(const Step1dArgs<T>&, cudaStream_t);
     int (*line1d)(int mode, const void* in, void* out, long nfields, cudaStream_t);
+    int (*prepare)();   // once per device: fill the static twiddle tables of this line length (synchronous)
 };
 
 template <typename T>

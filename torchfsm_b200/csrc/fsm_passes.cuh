@@ -48,6 +48,8 @@ struct Geom {
     long nmodes;   // complex modes per field in the rot-half layout
     T inv_ntot;    // 1 / (n0*n1*n2)
     int ky0;       // slab decomposition: first global ky of the local spectral slab (0 on one GPU)
+    int pf;        // L2 prefetch switches (PF_* bits)
+    int pf_wave;   // CTAs resident on the whole GPU for this launch = prefetch distance in CTAs
     const T* dk[3];     // 2*pi*f_i(m), Nyquist entry zeroed (Hermitian projection of i*k)
     const T* dkraw[3];  // 2*pi*f_i(m) as the reference computes it (Nyquist kept, negative)
 };
@@ -66,12 +68,52 @@ __device__ __forceinline__ long blk_off(int i, const Blk& b, long elem_stride) {
     return (long)(i >> b.shift) * b.stride + (long)(r >> b.shift2) * b.stride2 + (long)(r & ((1 << lo) - 1)) * elem_stride;
 }
 
+// ------------------------------------------------------------------------------------------
+// L2 prefetch. Every pass is latency bound on its first loads (16 warps per SM leave nothing to switch
+// to), so a CTA asks the L2 for data ahead of time with cp.async.bulk.prefetch.L2: no registers, no
+// shared memory, nothing to wait on. Two uses: (1) its OWN later operands (FX combine rows) while its
+// transform runs; (2) the input lines of the CTA that will occupy this slot one wave later
+// (linear block id + pf_wave), so that CTA's first loads hit the L2 instead of HBM.
+// ------------------------------------------------------------------------------------------
+enum : int { PF_IX = 1, PF_PHYS = 2, PF_FX_OPS = 4, PF_FX_WIN = 8, PF_MID = 16, PF_TW_EARLY = 32 };
+
+__device__ __forceinline__ void l2_prefetch(const void* p, long bytes) {
+#ifndef FSM_EMU
+    const unsigned long long a = reinterpret_cast<unsigned long long>(p);
+    const unsigned long long lo = a & ~15ull, hi = (a + (unsigned long long)bytes + 15ull) & ~15ull;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(lo), "r"((unsigned)(hi - lo)) : "memory");
+#else
+    (void)p; (void)bytes;
+#endif
+}
+// the kept part of one spectral line of n points: modes [0, kmax] and [n - kmax, n)
+template <typename T>
+__device__ __forceinline__ void l2_prefetch_line(const cplx<T>* line, int n, int kmax) {
+    if (2 * kmax + 1 >= n) {
+        l2_prefetch(line, (long)n * sizeof(cplx<T>));
+    } else {
+        l2_prefetch(line, (long)(kmax + 1) * sizeof(cplx<T>));
+        l2_prefetch(line + (n - kmax), (long)kmax * sizeof(cplx<T>));
+    }
+}
+// block coordinates of the CTA `wave` positions further in launch order (x fastest); false past the end
+__device__ __forceinline__ bool next_wave_block(int wave, int& x, int& y, int& z) {
+    const unsigned gx = gridDim.x, gy = gridDim.y, gz = gridDim.z;   // launch grids stay far below 2^31 CTAs
+    const unsigned lin = blockIdx.x + gx * (blockIdx.y + gy * blockIdx.z) + (unsigned)wave;
+    if (wave <= 0 || lin >= gx * gy * gz) return false;
+    const unsigned r = lin / gx;
+    x = (int)(lin - r * gx);
+    z = (int)(r / gy);
+    y = (int)(r - (unsigned)z * gy);
+    return true;
+}
+
 template <int N>
 __device__ __forceinline__ int signed_mode(int p) { return (p <= N / 2) ? p : p - N; }
 __device__ __forceinline__ int signed_mode_rt(int p, int n) { return (p <= n / 2) ? p : p - n; }
 __device__ __forceinline__ int iabs(int a) { return a < 0 ? -a : a; }
 
-// Stage twiddles are generated once per CTA with sincospi (no global table, no allocation).
+// sin/cos of pi*x (emulator build of the stage twiddles; the CUDA build reads a static table)
 __device__ __forceinline__ void fsm_sincospi(float x, float* s, float* c) {
 #ifdef FSM_EMU
     *s = (float)std::sin(3.14159265358979323846 * (double)x);
@@ -99,8 +141,34 @@ __device__ __forceinline__ float neg_recip(float x) {
 }
 __device__ __forceinline__ double neg_recip(double x) { return -1.0 / x; }
 
-template <class Cfg, typename T>
-__device__ __forceinline__ void make_twiddles(cplx<T>* tw) {
+#ifndef FSM_TW_CPASYNC
+#define FSM_TW_CPASYNC 1
+#endif
+#ifndef FSM_EMU
+// Stage twiddles of one FFT configuration: static device memory, filled once per device by the launch layer
+// (LaunchTable::prepare, called from fsm_plan_create); every CTA copies them into shared memory.
+template <typename T, class Cfg>
+__device__ cplx<T> g_twiddles[Cfg::TW_TOTAL + 2];
+#endif
+
+// twiddles_begin starts the copy into shared memory (cp.async: no registers, nothing waited for) so that the
+// caller can put its own first global loads in flight; twiddles_ready waits for the copy and publishes it to
+// the CTA. The first use of a twiddle is after stage 0 of the first transform.
+template <class Cfg, typename T, bool ASYNC = true>
+__device__ __forceinline__ void twiddles_begin(cplx<T>* tw) {
+#ifndef FSM_EMU
+    if constexpr (Cfg::TW_TOTAL > 0) {
+#pragma unroll 1
+        for (int i = threadIdx.x; i < Cfg::TW_TOTAL; i += blockDim.x) {
+            if constexpr (ASYNC && FSM_TW_CPASYNC) {
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(tw + i);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst), "l"(&g_twiddles<T, Cfg>[i]), "n"(sizeof(cplx<T>)) : "memory");
+            } else {
+                tw[i] = g_twiddles<T, Cfg>[i];
+            }
+        }
+    }
+#else
     if constexpr (Cfg::R1 > 1) {
         constexpr int Ns = Cfg::R0;
         for (int i = threadIdx.x; i < Cfg::TW1; i += blockDim.x) {
@@ -119,7 +187,18 @@ __device__ __forceinline__ void make_twiddles(cplx<T>* tw) {
             tw[Cfg::TW1 + i] = mk<T>(c, s);
         }
     }
+#endif
+}
+__device__ __forceinline__ void twiddles_ready() {
+#ifndef FSM_EMU
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
     __syncthreads();
+}
+template <class Cfg, typename T>
+__device__ __forceinline__ void make_twiddles(cplx<T>* tw) {
+    twiddles_begin<Cfg, T>(tw);
+    twiddles_ready();
 }
 
 // Shared-memory carve-up used by every pass: [twiddles][NBUF line buffers]
@@ -159,7 +238,7 @@ __device__ __forceinline__ void rotated_last_stage(const cplx<T>* bufs, const cp
         constexpr int q = decltype(qc)::value;
         const int w = widx + q * Cfg::TL;
         cplx<T> a[RL];
-        fft_last_item<Cfg, DIR, T>(buf, tw, w, a);
+        fft_last_item<Cfg, DIR, T, q * Cfg::TL>(buf, tw, widx, a);
         static_for<0, RL>([&](auto tc) {
             constexpr int tp = decltype(tc)::value;
             emit(w + tp * NS, a[tp]);
@@ -193,9 +272,24 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
     FSM_DYN_SMEM(smem_raw);
     cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);
     cplx<T>* bufs = tw + Smem<Cfg, T>::TWPAD;
-    make_twiddles<Cfg, T>(tw);
-
     const int lt = threadIdx.x / TL, tau = threadIdx.x % TL;
+    if ((g.pf & PF_IX) && tau == 0) {
+        int x2, o2, z2;
+        if (next_wave_block(g.pf_wave, x2, o2, z2)) {
+            const int t2 = x2 * K + lt;
+            bool want = t2 < n_t;
+            if (want && PROG != PROG_C2R) {
+                want = iabs(signed_mode_rt(t2 + g.ky0, g.n[1])) <= g.kmax[1];
+                if (g.ndim == 3) want = want && (o2 <= g.kmax[2]);
+            }
+            if (want)
+                l2_prefetch_line<T>(state + (long)z2 * state_bstride + (long)t2 * in_t_stride + (long)o2 * in_o_stride, N,
+                                    PROG == PROG_C2R ? N : g.kmax[0]);
+        }
+    }
+    twiddles_begin<Cfg, T>(tw);
+    if (g.pf & PF_TW_EARLY) twiddles_ready();
+
     const int t0 = blockIdx.x * K;
     const int o = blockIdx.y;
     const long bc = blockIdx.z;
@@ -213,7 +307,8 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
     const T dkyraw = (t < n_t) ? g.dkraw[1][tglob] : T(0);
 
     cplx<T> u[EPT];
-    const cplx<T>* src = state + bc * state_bstride + (long)t * in_t_stride + (long)o * in_o_stride;
+    const cplx<T>* src = state + bc * state_bstride + (long)(t < n_t ? t : 0) * in_t_stride + (long)o * in_o_stride + tau;
+    FSM_PIN(src);
     LineSync<TL> sync{1 + lt};
     cplx<T>* mybuf = bufs + lt * Cfg::LINE_PITCH;
 
@@ -232,13 +327,18 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
         constexpr int NPAIR = IxFields<PROG>::NPAIR;
         // the x wavenumbers of this thread's elements are loaded once, together with the line itself
         T dkxr[EPT];
+        const T* dkx_t = g.dkraw[0] + tau;
+        FSM_PIN(dkx_t);
         FSM_UNROLL
         for (int m = 0; m < EPT; ++m) {
             const int p = tau + m * TL;
             const bool kept = line_kept && (iabs(signed_mode<N>(p)) <= g.kmax[0]);
-            u[m] = kept ? cscale(src[p], g.inv_ntot) : mk<T>(T(0), T(0));
-            dkxr[m] = g.dkraw[0][p];
+            u[m] = kept ? src[m * TL] : mk<T>(T(0), T(0));
+            dkxr[m] = dkx_t[m * TL];
         }
+        twiddles_ready();   // the line is in flight; now wait for the twiddle copy
+        FSM_UNROLL
+        for (int m = 0; m < EPT; ++m) u[m] = cscale(u[m], g.inv_ntot);
         static_for<0, 2 * NPAIR>([&](auto fc) {
             constexpr int f = decltype(fc)::value;
             cplx<T> v[EPT];
@@ -281,16 +381,18 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
                 const cplx<T>* s1 = s0 + kKL * Cfg::LINE_PITCH;
                 cplx<T>* dp = w1 + (bc * NPAIR + pair) * w1_fstride + tg;
                 cplx<T>* dm = w1 + (bc * NPAIR + pair) * w1_fstride + (n1 - tg);
+                FSM_PIN(dp);
+                FSM_PIN(dm);
                 static_for<0, EPT / RL>([&](auto qc) {
                     constexpr int q = decltype(qc)::value;
                     const int w = widx + q * TL;
                     cplx<T> a[RL], b[RL];
-                    fft_last_item<Cfg, +1, T>(s0, tw, w, a);
-                    fft_last_item<Cfg, +1, T>(s1, tw, w, b);
+                    fft_last_item<Cfg, +1, T, q * TL>(s0, tw, widx, a);
+                    fft_last_item<Cfg, +1, T, q * TL>(s1, tw, widx, b);
                     if (valid) {
                         static_for<0, RL>([&](auto tc) {
                             constexpr int tp = decltype(tc)::value;
-                            const long off = (long)(w + tp * NS) * out_e_stride;
+                            const int off = (w + tp * NS) * (int)out_e_stride;   // inside one field: fits 32 bits
                             cplx<T> zp, zm;
                             if constexpr (PROG == PROG_KS2D) {      // a = A = T[kx phi], b = C = T[phi]
                                 zp = selfc ? mk<T>(-a[tp].y, -dky_s * b[tp].y)
@@ -320,8 +422,11 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
         const int p = tau + m * TL;
         bool kept = line_kept;
         if (PROG != PROG_C2R) kept = kept && (iabs(signed_mode<N>(p)) <= g.kmax[0]);
-        u[m] = kept ? cscale(src[p], g.inv_ntot) : mk<T>(T(0), T(0));
+        u[m] = kept ? src[m * TL] : mk<T>(T(0), T(0));
     }
+    twiddles_ready();
+    FSM_UNROLL
+    for (int m = 0; m < EPT; ++m) u[m] = cscale(u[m], g.inv_ntot);
 
     static_for<0, NF>([&](auto fc) {
         constexpr int f = decltype(fc)::value;
@@ -337,9 +442,16 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
         __syncthreads();
         cplx<T>* dst = w1 + (bc * NF + f) * w1_fstride + (long)o * out_o_stride + t0 + threadIdx.x % kKL;
         const bool valid = (int)(threadIdx.x % kKL) < k_valid;
-        rotated_last_stage<Cfg, +1, T>(pbufs, tw, [&](int e, cplx<T> val) {
-            if (valid) dst[blk_off(e, eb, out_e_stride)] = val;
-        });
+        if (eb.shift >= 30) {   // one GPU: plain strided store, 32-bit index inside the field
+            const int es = (int)out_e_stride;
+            rotated_last_stage<Cfg, +1, T>(pbufs, tw, [&](int e, cplx<T> val) {
+                if (valid) dst[e * es] = val;
+            });
+        } else {
+            rotated_last_stage<Cfg, +1, T>(pbufs, tw, [&](int e, cplx<T> val) {
+                if (valid) dst[blk_off(e, eb, out_e_stride)] = val;
+            });
+        }
     });
 }
 
@@ -363,7 +475,8 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
     FSM_DYN_SMEM(smem_raw);
     cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);
     cplx<T>* bufs = tw + Smem<Cfg, T>::TWPAD;
-    make_twiddles<Cfg, T>(tw);
+    twiddles_begin<Cfg, T, false>(tw);   // measured (C4/C5): the y pass is 7 % faster with the plain copy than with cp.async
+    if (g.pf & PF_TW_EARLY) twiddles_ready();
     const int lt = threadIdx.x / TL, tau = threadIdx.x % TL;
     const int t0 = blockIdx.x * K;
     const int o = blockIdx.y;
@@ -375,6 +488,7 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
     cplx<T>* mybuf = bufs + lt * Cfg::LINE_PITCH;
     // the line of output field j+1 is loaded (registers) before field j is transformed and stored, so its
     // latency hides behind the butterflies, the block barrier and the rotated stores of field j
+    const bool one_block = ib.shift >= 30;
     auto load_line = [&](int j, cplx<T>* raw) {
         const cplx<T>* src = in + (b * nfi + spec.src[j]) * in_fstride + (long)t * in_t_stride + (long)o * in_o_stride;
         FSM_UNROLL
@@ -382,11 +496,12 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
             const int p = tau + m * TL;
             bool kept = line_ok;
             if (DIR > 0) kept = kept && (iabs(signed_mode<N>(p)) <= g.kmax[1]);
-            raw[m] = kept ? src[blk_off(p, ib, 1)] : mk<T>(T(0), T(0));
+            raw[m] = kept ? src[one_block ? (long)p : blk_off(p, ib, 1)] : mk<T>(T(0), T(0));
         }
     };
     cplx<T> raw[EPT];
     load_line(0, raw);
+    twiddles_ready();
     for (int j = 0; j < spec.nfo; ++j) {
         cplx<T> v[EPT];
         const bool deriv = spec.deriv[j] != 0;
@@ -398,9 +513,16 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
         __syncthreads();
         cplx<T>* dst = out + (b * spec.nfo + j) * out_fstride + (long)o * out_o_stride + t0 + threadIdx.x % kKL;
         const bool valid = (int)(threadIdx.x % kKL) < k_valid;
-        rotated_last_stage<Cfg, DIR, T>(pbufs, tw, [&](int e, cplx<T> val) {
-            if (valid) dst[blk_off(e, eb, out_e_stride)] = val;
-        });
+        if (eb.shift >= 30) {
+            const int es = (int)out_e_stride;
+            rotated_last_stage<Cfg, DIR, T>(pbufs, tw, [&](int e, cplx<T> val) {
+                if (valid) dst[e * es] = val;
+            });
+        } else {
+            rotated_last_stage<Cfg, DIR, T>(pbufs, tw, [&](int e, cplx<T> val) {
+                if (valid) dst[blk_off(e, eb, out_e_stride)] = val;
+            });
+        }
     }
 }
 
@@ -411,6 +533,9 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
 // The nonlinear product is formed in registers between the two.
 //   rows: 2-D x;  3-D (x, y) with y the line-minor index. Output rotated.
 // ------------------------------------------------------------------------------------------
+#ifndef FSM_PHYS_PARK
+#define FSM_PHYS_PARK 1
+#endif
 template <int PROG, int NDIM>
 struct PhysTraits;
 // NFI = input fields per sample, NOUT = output fields per sample, RPT = rows per thread-line
@@ -484,13 +609,34 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
     FSM_DYN_SMEM(smem_raw);
     cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);
     cplx<T>* bufs = tw + Smem<Cfg, T>::TWPAD;
-    make_twiddles<Cfg, T>(tw);
     const int NL = K / RPT;  // thread-lines per CTA
     const int lt = threadIdx.x / TL, tau = threadIdx.x % TL;
+    const int kmaxl = (PROG == PROG_C2R) ? N / 2 : g.kmax[NDIM - 1];
+    if constexpr (PROG == PROG_NS2D || PROG == PROG_KS2D) {
+        if ((g.pf & PF_PHYS) && tau == 0) {
+            int x2, o2, z2;
+            if (next_wave_block(g.pf_wave, x2, o2, z2)) {
+                const cplx<T>* wb2 = win + (long)z2 * NFI * win_fstride + (long)o2 * in_o_stride;
+                FSM_UNROLL
+                for (int r = 0; r < RPT; ++r) {
+                    const int row2 = x2 * K + lt * RPT + r;
+                    if (row2 < n_t) {
+                        FSM_UNROLL
+                        for (int f = 0; f < NFI; ++f) l2_prefetch_line<T>(wb2 + f * win_fstride + (long)row2 * in_t_stride, N, kmaxl);
+                    }
+                }
+            }
+        }
+    }
+    twiddles_begin<Cfg, T>(tw);
+    if (g.pf & PF_TW_EARLY) twiddles_ready();
+    bool tw_pending = true;   // resolved at compile time: the code below is straight-line
+    auto tw_ready_once = [&]() {
+        if (tw_pending) { twiddles_ready(); tw_pending = false; }
+    };
     const int t0 = blockIdx.x * K;
     const int o = blockIdx.y;
     const long b = blockIdx.z;
-    const int kmaxl = (PROG == PROG_C2R) ? N / 2 : g.kmax[NDIM - 1];
     const T* dkl = g.dk[NDIM - 1];
     LineSync<TL> sync{1 + lt};
     // smem: NL fft buffers, then NL*NFW staging lines
@@ -513,6 +659,7 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
             const cplx<T>* pa = (fa >= 0) ? wb + fa * win_fstride + roff : nullptr;
             const cplx<T>* pb = (fb >= 0) ? wb + fb * win_fstride + roff : nullptr;
             pair_fill<T, Cfg>(v, pa, pb, da, db, dkl, tau, kmaxl, row_ok);
+            tw_ready_once();
             sync();
             line_fft<Cfg, +1, T>(v, mybuf, tw, tau, sync);
         };
@@ -527,6 +674,7 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
                     const bool kept = row_ok && (p <= kmaxl || p >= N - kmaxl);
                     v[m] = kept ? z[p] : mk<T>(T(0), T(0));
                 }
+                tw_ready_once();
                 sync();
                 line_fft<Cfg, +1, T>(v, mybuf, tw, tau, sync);
             };
@@ -575,6 +723,7 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
             T uj[EPT];
             if constexpr (r == 0) pair_load_raw<T, Cfg>(rawA, rawB, wb + FA[0] * win_fstride + roff, wb + FB[0] * win_fstride + roff,
                                                         tau, kmaxl, row_ok);
+            tw_ready_once();
             static_for<0, 6>([&](auto ic) {
                 constexpr int i = decltype(ic)::value;
                 pair_combine<T, Cfg>(v, rawA, rawB, DA[i], DB[i], dkl, tau, kmaxl);
@@ -610,16 +759,24 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
             const T* prow = phys_in + (b * (long)n_t * gridDim.y + ((long)o * n_t + row)) * N;
             FSM_UNROLL
             for (int m = 0; m < EPT; ++m) acc[0][m] = row_ok ? prow[tau + m * TL] : T(0);
+            tw_ready_once();
         }
 
         // ---- forward side: pack real results pairwise into complex lines and transform
         if constexpr (NOUT == 1) {
+            // the product of row 0 waits for row 1: with 16 elements per thread it is parked in this thread-line's
+            // (still unused) staging line instead of 16 registers, which the two inverse transforms of row 1 need
+            constexpr bool kPark = (EPT >= 16) && FSM_PHYS_PARK;
+            T* park = reinterpret_cast<T*>(stage);
             if constexpr (r == 0) {
                 FSM_UNROLL
-                for (int m = 0; m < EPT; ++m) keep2[m] = acc[0][m];
+                for (int m = 0; m < EPT; ++m) {
+                    if constexpr (kPark) park[tau + m * TL] = acc[0][m];
+                    else keep2[m] = acc[0][m];
+                }
             } else {
                 FSM_UNROLL
-                for (int m = 0; m < EPT; ++m) v[m] = mk<T>(keep2[m], acc[0][m]);
+                for (int m = 0; m < EPT; ++m) v[m] = mk<T>(kPark ? park[tau + m * TL] : keep2[m], acc[0][m]);
                 sync();
                 line_fft<Cfg, -1, T>(v, mybuf, tw, tau, sync);
                 FSM_UNROLL
@@ -670,6 +827,7 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
             if (p > N / 2) { A.y = -A.y; B.y = -B.y; }
             v[m] = mk<T>(A.x - B.y, A.y + B.x);
         }
+        tw_ready_once();
         line_fft<Cfg, +1, T>(v, mybuf, tw, tau, sync);
         T* prow = phys_out + (b * (long)n_t * gridDim.y + ((long)o * n_t + row)) * N;
         FSM_UNROLL
@@ -847,13 +1005,36 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
     FSM_DYN_SMEM(smem_raw);
     cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);
     cplx<T>* bufs = tw + Smem<Cfg, T>::TWPAD;
-    make_twiddles<Cfg, T>(tw);
     const int K = blockDim.x / TL;
     const int lt = threadIdx.x / TL, tau = threadIdx.x % TL;
     const int line = blockIdx.x * K + lt;
     const long bl = blockIdx.z;          // sample index inside the chunk (W buffers)
     const long b = b0 + bl;              // global sample index (state arrays)
-    if (line >= nlines) return;
+    if ((g.pf & (PF_FX_OPS | PF_FX_WIN)) && tau == 0) {
+        if (C == 1 && (g.pf & PF_FX_OPS) && line < nlines) {   // measured: hurts the 3-channel lines of C4/C5
+            // this line's combine operands: requested now, used after the transform
+            FSM_UNROLL
+            for (int c = 0; c < C; ++c) {
+                FSM_UNROLL
+                for (int i = 0; i < FSM_MAX_IN; ++i)
+                    if (i < cb.n_in) l2_prefetch(cb.in[i] + (b * C + c) * g.nmodes + (long)line * N, (long)N * sizeof(cplx<T>));
+                FSM_UNROLL
+                for (int q = 0; q < FSM_MAX_TAB; ++q)
+                    if (q < cb.n_tab) l2_prefetch(cb.tab[q] + c * cb.tab_cstride + (long)line * N, (long)N * sizeof(T));
+            }
+        }
+        int x2, y2, z2;
+        if ((g.pf & PF_FX_WIN) && ib.shift >= 30 && next_wave_block(g.pf_wave, x2, y2, z2)) {
+            const int line2 = x2 * K + lt;
+            if (line2 < nlines) {
+                FSM_UNROLL
+                for (int c = 0; c < C; ++c)
+                    l2_prefetch(win + ((long)z2 * C + c) * win_fstride + (long)line2 * line_stride, (long)N * sizeof(cplx<T>));
+            }
+        }
+    }
+    twiddles_begin<Cfg, T>(tw);
+    if (g.pf & PF_TW_EARLY) twiddles_ready();
     LineSync<TL> sync{1 + lt};
     cplx<T>* mybuf = bufs + lt * Cfg::LINE_PITCH;
     constexpr int NB = (EPT >= 4) ? 4 : EPT;
@@ -864,13 +1045,21 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
     // pipeline is used for lines up to 512 points only)
     constexpr bool kPipe = (C == 1) && (N <= 512);
     CombineOperands<T, NB> opq[2];   // dead (optimised away) when !kPipe
-    if constexpr (kPipe) combine_load<T, NB>(cb, b * g.nmodes, 0, line_mode0 + tau, TL, opq[0]);
+    if constexpr (kPipe) {
+        if (line < nlines) combine_load<T, NB>(cb, b * g.nmodes, 0, line_mode0 + tau, TL, opq[0]);
+    }
     cplx<T> nhat[C][EPT];
-    static_for<0, C>([&](auto cc) {
-        constexpr int c = decltype(cc)::value;
+    auto load_channel = [&](int c, cplx<T>* dst) {
         const cplx<T>* src = win + (bl * C + c) * win_fstride + (long)line * line_stride;
         FSM_UNROLL
-        for (int m = 0; m < EPT; ++m) nhat[c][m] = src[blk_off(tau + m * TL, ib, 1)];
+        for (int m = 0; m < EPT; ++m) dst[m] = src[(ib.shift >= 30) ? (long)(tau + m * TL) : blk_off(tau + m * TL, ib, 1)];
+    };
+    if (line < nlines) load_channel(0, nhat[0]);
+    twiddles_ready();      // first channel in flight while the twiddle copy lands
+    if (line >= nlines) return;
+    static_for<0, C>([&](auto cc) {
+        constexpr int c = decltype(cc)::value;
+        if constexpr (c > 0) load_channel(c, nhat[c]);
         if (c > 0) sync();
         line_fft<Cfg, -1, T>(nhat[c], mybuf, tw, tau, sync);
     });
@@ -1147,7 +1336,7 @@ k_pass_fxix_ns2d(Geom<T> g, const cplx<T>* __restrict__ win, long win_fstride, C
                 if (valid) {
                     static_for<0, RL>([&](auto tc) {
                         constexpr int tp = decltype(tc)::value;
-                        const long off = (long)(w + tp * NS) * out_e_stride;
+                        const int off = (w + tp * NS) * (int)out_e_stride;
                         cplx<T> zp, zm;
                         if constexpr (pair == 0) {
                             zp = selfc ? mk<T>(bb[tp].x, -a[tp].y) : bb[tp] - a[tp];

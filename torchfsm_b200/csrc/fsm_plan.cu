@@ -10,6 +10,10 @@
 #include <vector>
 #include <utility>
 
+#ifndef FSM_PF_DEFAULT
+#define FSM_PF_DEFAULT 5   // PF_IX | PF_FX_OPS (measured on C3: 1.908 -> 1.861 ms/step; PF_PHYS and PF_FX_WIN cost time)
+#endif
+
 namespace fsm {
 
 #define FSM_DECL_TABLE(N)                      \
@@ -206,6 +210,7 @@ struct fsm_plan {
     long nmodes, ntot;
     int chunk;
     int nf_ix, nfi, nout;  // fields: IX per channel, PHYS inputs per sample, PHYS outputs per sample
+    int pf = 0;                  // L2 prefetch switches (PF_* in fsm_passes.cuh)
     void* ks_log = nullptr;      // optional device log of the per-evaluation local KS zero-mode sums
     long ks_log_cap = 0;
     mutable long ks_log_pos = 0;
@@ -265,6 +270,8 @@ Geom<T> make_geom(const fsm_plan* p, bool nomask) {
         g.dkraw[i] = static_cast<const T*>(p->d.dkraw[i]);
     }
     g.ky0 = (p->P > 1) ? p->rank * p->kyl : 0;
+    g.pf = p->pf;
+    g.pf_wave = 0;
     g.nh = p->nh;
     g.ph = p->ph;
     g.nmodes = p->nmodes;
@@ -907,10 +914,16 @@ int fsm_plan_create(fsm_plan** out, const fsm_desc* d) {
         delete p;
         return fail(-EINVAL, "The ETDRK0 integrator only supports linear term");
     }
+    for (int i = 0; i < p->ndim; ++i) {
+        const int e = p->f64 ? launch_table<double>(p->n[i])->prepare() : launch_table<float>(p->n[i])->prepare();
+        if (e) { delete p; return fail(e, "could not initialise the twiddle tables"); }
+    }
     p->stages = build_stages(d->integrator, d->dt, d->tab_lin != nullptr);
     if (p->stages.empty()) { delete p; return fail(-ENOSYS, "unknown integrator %d", d->integrator); }
     // FX(stage s) + IX(stage s+1) fusion for the 2-D vorticity program: opt-in experiment (FSM_FUSE=1). Measured on
     // C3 it is 8 % slower than the two separate kernels (the halves serialise inside the one CTA an SM holds).
+    p->pf = FSM_PF_DEFAULT;
+    if (const char* e = getenv("FSM_PF")) p->pf = atoi(e);    // tuning hook
     if (p->kprog == PROG_NS2D && getenv("FSM_FUSE") && p->n[0] >= 16) p->fused_stages = build_stages_fused(d->integrator);
     // right-hand side L u + N(u)
     {
