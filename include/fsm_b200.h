@@ -119,6 +119,10 @@ int fsm_full_to_half(fsm_plan* plan, const void* full_hat, void* u_hat, void* st
 int fsm_plan_info(const fsm_plan* plan, int64_t* launches_per_step, int64_t* algo_bytes_per_step,
                   int64_t* modes_per_field, int32_t* chunk);
 
+/* introspection for tests: number of integrator stages; kinds[i] = index of the compile-time combine
+ * structure stage i runs with in the forward-x epilogue (-1 = generic data-driven path) */
+int fsm_stage_kinds(const fsm_plan* plan, int32_t* kinds, int32_t capacity);
+
 /* Slab-decomposed evaluation (single large 3-D grids): the library runs the local passes of
  * one phase; the caller performs the all-to-all between phases (torch.distributed all_to_all_single over
  * NCCL/NVLink, equal splits) on the exchange buffers, which the kernels read and write directly in

@@ -142,3 +142,24 @@ def test_linear_solve_matches_closed_form():
     got = op.solve(b, mesh=mesh_info)
     want = torch.sin(3 * x) * torch.cos(2 * y) / (-nu * 13 - 1) + 0.5 * torch.cos(x) / (-nu - 1)
     assert float((got[0, 0] - want).abs().max()) < 1e-13
+
+
+EXPECTED_KINDS = {"burgers1d_64_etdrk1_f64": [0], "burgers1d_64_etdrk2_f64": [1, 2], "burgers1d_64_setdrk1_f64": [0],
+                  "burgers1d_64_setdrk2_f64": [1, 2], "burgers1d_64_setdrk3_f64": [3, 5, 6],
+                  "c5_ns3d_16_setdrk4_f64": [3, 4, 5, 6], "c3_ns2d_32_etdrk2_f32": [1, 2], "c2_ks2d_32_f32": [3, 4, 5, 6],
+                  "ns2d_32_rk4_f64": [-1, -1, -1, -1]}
+
+
+@pytest.mark.parametrize("name", sorted(EXPECTED_KINDS))
+def test_etd_stages_use_compile_time_combine_shapes(name, monkeypatch):
+    """Every stage of the ETD integrators must hit a specialised combine; the generic path gives the same numbers."""
+    g = load_golden(name)
+    spec = g["spec"]
+    op, mesh, u0 = product_from_golden(g, "cpu")
+    uT = op.integrate(u0, mesh=mesh, dt=spec["dt"], step=spec["steps"])
+    assert op._state_dict["integrator"].stage_kinds() == EXPECTED_KINDS[name]
+    monkeypatch.setenv("FSM_GENERIC_COMBINE", "1")
+    op2, mesh2, _ = product_from_golden(g, "cpu")
+    uG = op2.integrate(u0, mesh=mesh2, dt=spec["dt"], step=spec["steps"])
+    assert all(k == -1 for k in op2._state_dict["integrator"].stage_kinds())
+    assert rel_l2(uT.numpy(), uG.numpy()) <= (1e-6 if name.endswith("f32") else 1e-14)

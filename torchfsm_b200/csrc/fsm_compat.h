@@ -74,5 +74,9 @@ static __device__ __forceinline__ double fsm_fma(double a, double b, double c) {
 #define FSM_HD __host__ __device__
 // Materialise a base pointer in a register pair here and now. Without it the compiler sinks the 64-bit
 // address arithmetic (strides are runtime longs) into every predicated element access.
-#define FSM_PIN(ptr) asm volatile("" : "+l"(ptr))
+#define FSM_PIN(ptr)                    \
+    do {                                \
+        asm volatile("" : "+l"(ptr));   \
+        __builtin_assume(__isGlobal(ptr)); /* keep LDG/STG: the asm hides the address space */ \
+    } while (0)
 #endif

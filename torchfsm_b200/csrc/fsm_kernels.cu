@@ -143,15 +143,11 @@ static int launch_phys(int prog, int ndim, const PhysArgs<T>& a, cudaStream_t s)
     return -ENOSYS;
 }
 
-#ifndef FSM_KL_FX
-#define FSM_KL_FX 4   // FX has no rotated store: fewer lines per CTA -> two CTAs per SM overlap their phases
-#endif
 template <typename T, int N, int C>
 static int launch_fx_c(const FxArgs<T>& a, cudaStream_t s) {
     using Cfg = typename CfgFx<N, C>::type;
     auto kern = k_pass_fx<T, Cfg, C>;
-    // measured: helps when a line already spans >= 32 threads (N >= 512); smaller lines keep the full tile
-    constexpr int KF = (Cfg::TL >= 32 && FSM_KL_FX < kKL) ? FSM_KL_FX : kKL;
+    constexpr int KF = kFxLines<Cfg>;
     const size_t smem = Smem<Cfg, T>::bytes(KF);
     if (int e = set_smem(kern, smem)) return e;
     dim3 grid((a.nlines + KF - 1) / KF, 1, a.nb), block(KF * Cfg::TL);

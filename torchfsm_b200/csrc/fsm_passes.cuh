@@ -26,6 +26,14 @@ namespace fsm {
 #endif
 #define FSM_MINB(nt) (((nt) >= FSM_TARGET_THREADS) ? 1 : (FSM_TARGET_THREADS / (nt)))
 constexpr int kKL = FSM_KL;  // thread-lines per CTA in every line pass
+#ifndef FSM_KL_FX
+#define FSM_KL_FX 4   // FX has no rotated store: fewer lines per CTA -> more CTAs per SM overlap their phases
+#endif
+#ifndef FSM_FX_MINB
+#define FSM_FX_MINB 3 // resident FX CTAs per SM the register allocation aims for (single-channel lines)
+#endif
+// measured: the smaller FX tile helps when a line already spans >= 32 threads (N >= 512)
+template <class Cfg> constexpr int kFxLines = (Cfg::TL >= 32 && FSM_KL_FX < kKL) ? FSM_KL_FX : kKL;
 
 enum Prog : int {
     PROG_NONE = 0,
@@ -75,7 +83,7 @@ __device__ __forceinline__ long blk_off(int i, const Blk& b, long elem_stride) {
 // transform runs; (2) the input lines of the CTA that will occupy this slot one wave later
 // (linear block id + pf_wave), so that CTA's first loads hit the L2 instead of HBM.
 // ------------------------------------------------------------------------------------------
-enum : int { PF_IX = 1, PF_PHYS = 2, PF_FX_OPS = 4, PF_FX_WIN = 8, PF_MID = 16, PF_TW_EARLY = 32 };
+enum : int { PF_IX = 1, PF_PHYS = 2, PF_FX_OPS = 4, PF_FX_WIN = 8, PF_MID = 16, PF_TW_EARLY = 32, PF_PHYS_SELF = 64 };
 
 __device__ __forceinline__ void l2_prefetch(const void* p, long bytes) {
 #ifndef FSM_EMU
@@ -613,6 +621,19 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
     const int lt = threadIdx.x / TL, tau = threadIdx.x % TL;
     const int kmaxl = (PROG == PROG_C2R) ? N / 2 : g.kmax[NDIM - 1];
     if constexpr (PROG == PROG_NS2D || PROG == PROG_KS2D) {
+        if ((g.pf & PF_PHYS_SELF) && tau == 0) {
+            // this thread-line's later rows: asked for now, read after the first transform(s)
+            const cplx<T>* wb1 = win + (long)blockIdx.z * NFI * win_fstride + (long)blockIdx.y * in_o_stride;
+            FSM_UNROLL
+            for (int r = 0; r < RPT; ++r) {
+                const int row1 = blockIdx.x * K + lt * RPT + r;
+                if (row1 < n_t) {
+                    FSM_UNROLL
+                    for (int f = 0; f < NFI; ++f)
+                        if (r + f > 0) l2_prefetch_line<T>(wb1 + f * win_fstride + (long)row1 * in_t_stride, N, kmaxl);
+                }
+            }
+        }
         if ((g.pf & PF_PHYS) && tau == 0) {
             int x2, o2, z2;
             if (next_wave_block(g.pf_wave, x2, o2, z2)) {
@@ -644,6 +665,12 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
     cplx<T>* stage = bufs + (NL + lt * (NFW > 0 ? NFW : 1)) * Cfg::LINE_PITCH;
     const cplx<T>* wb = win + b * NFI * win_fstride + (long)o * in_o_stride;
 
+    unsigned keepmask = 0;   // bit m: element p = tau + m*TL of a full complex row survives the dealiasing
+    FSM_UNROLL
+    for (int m = 0; m < EPT; ++m) {
+        const int p = tau + m * TL;
+        if (p <= kmaxl || p >= N - kmaxl) keepmask |= 1u << m;
+    }
     T keep2[EPT];   // CONV3D: third component of row 0 waits for row 1
     cplx<T> rawA[(PROG == PROG_CONV && NDIM == 3) ? EPT : 1], rawB[(PROG == PROG_CONV && NDIM == 3) ? EPT : 1];
     (void)rawA; (void)rawB;
@@ -667,13 +694,11 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
             // Z-lines written by IX: NS2D field 0 = u_x + i d_x w, field 1 = u_y + i d_y w; KS2D field 0 =
             // phi_x + i phi_y (full complex rows)
             auto inverse_z = [&](int f) {
-                const cplx<T>* z = wb + f * win_fstride + roff;
+                const cplx<T>* z = wb + f * win_fstride + (row_ok ? roff : 0) + tau;
+                FSM_PIN(z);
+                const unsigned km = row_ok ? keepmask : 0u;
                 FSM_UNROLL
-                for (int m = 0; m < EPT; ++m) {
-                    const int p = tau + m * TL;
-                    const bool kept = row_ok && (p <= kmaxl || p >= N - kmaxl);
-                    v[m] = kept ? z[p] : mk<T>(T(0), T(0));
-                }
+                for (int m = 0; m < EPT; ++m) v[m] = ((km >> m) & 1u) ? z[m * TL] : mk<T>(T(0), T(0));
                 tw_ready_once();
                 sync();
                 line_fft<Cfg, +1, T>(v, mybuf, tw, tau, sync);
@@ -767,16 +792,25 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
             // the product of row 0 waits for row 1: with 16 elements per thread it is parked in this thread-line's
             // (still unused) staging line instead of 16 registers, which the two inverse transforms of row 1 need
             constexpr bool kPark = (EPT >= 16) && FSM_PHYS_PARK;
-            T* park = reinterpret_cast<T*>(stage);
+            cplx<T>* park = stage;   // two values per 2*sizeof(T) slot
             if constexpr (r == 0) {
                 FSM_UNROLL
-                for (int m = 0; m < EPT; ++m) {
-                    if constexpr (kPark) park[tau + m * TL] = acc[0][m];
-                    else keep2[m] = acc[0][m];
+                for (int m = 0; m < EPT; m += 2) {
+                    if constexpr (kPark) park[tau + (m / 2) * TL] = mk<T>(acc[0][m], acc[0][m + 1]);
+                    else { keep2[m] = acc[0][m]; keep2[m + 1] = acc[0][m + 1]; }
                 }
             } else {
                 FSM_UNROLL
-                for (int m = 0; m < EPT; ++m) v[m] = mk<T>(kPark ? park[tau + m * TL] : keep2[m], acc[0][m]);
+                for (int m = 0; m < EPT; m += 2) {
+                    if constexpr (kPark) {
+                        const cplx<T> pk2 = park[tau + (m / 2) * TL];
+                        v[m] = mk<T>(pk2.x, acc[0][m]);
+                        v[m + 1] = mk<T>(pk2.y, acc[0][m + 1]);
+                    } else {
+                        v[m] = mk<T>(keep2[m], acc[0][m]);
+                        v[m + 1] = mk<T>(keep2[m + 1], acc[0][m + 1]);
+                    }
+                }
                 sync();
                 line_fft<Cfg, -1, T>(v, mybuf, tw, tau, sync);
                 FSM_UNROLL
@@ -842,14 +876,14 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
     if constexpr (NOUT > 0) {
         __syncthreads();
         // ---- split the packed spectra and store rotated: wout[f][k * out_e_stride + row]
-        const int nh = N / 2 + 1;
+        // Thread (l = tid % kKL, k0 = tid / kKL) handles line slot l and the modes k0 + it*TL < N/2 (compile-time
+        // trip count, constant strides); the kKL Nyquist modes k = N/2 are a tail for the first kKL threads.
         cplx<T>* ob = wout + b * NOUT * wout_fstride + (long)o * out_o_stride + t0;
+        FSM_PIN(ob);
         const cplx<T>* st0 = bufs + NL * Cfg::LINE_PITCH;
         constexpr int NLc = kKL;
-        const int total = NLc * nh;
-        for (int i = threadIdx.x; i < total; i += kKL * TL) {
-            const int l = i % NLc, k = i / NLc;
-            const int kn = (k == 0) ? 0 : N - k;
+        const int es = (int)out_e_stride;   // offsets inside one field fit 32 bits
+        auto emit = [&](int l, int k, int kn) {
             const cplx<T>* sl = st0 + l * NFW * Cfg::LINE_PITCH;
             auto split = [&](const cplx<T>* line, cplx<T>& s0, cplx<T>& s1) {
                 const cplx<T> zk = line[k], zn = line[kn];
@@ -857,28 +891,39 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
                 s1 = mk<T>(T(0.5) * (zk.y + zn.y), T(0.5) * (zn.x - zk.x));
             };
             cplx<T> s0, s1;
+            cplx<T>* dst = ob + k * es;
             if constexpr (NOUT == 1) {
                 split(sl, s0, s1);
                 const int row = l * 2;
-                if (t0 + row < n_t) ob[(long)k * out_e_stride + row] = s0;
-                if (t0 + row + 1 < n_t) ob[(long)k * out_e_stride + row + 1] = s1;
+                if (t0 + row < n_t) dst[row] = s0;
+                if (t0 + row + 1 < n_t) dst[row + 1] = s1;
             } else if constexpr (NOUT == 2) {
                 split(sl, s0, s1);
                 if (t0 + l < n_t) {
-                    ob[(long)k * out_e_stride + l] = s0;
-                    ob[wout_fstride + (long)k * out_e_stride + l] = s1;
+                    dst[l] = s0;
+                    dst[wout_fstride + l] = s1;
                 }
             } else {
                 const int row = l * 2;
                 const bool ok0 = t0 + row < n_t, ok1 = t0 + row + 1 < n_t;
                 split(sl, s0, s1);
-                if (ok0) { ob[(long)k * out_e_stride + row] = s0; ob[wout_fstride + (long)k * out_e_stride + row] = s1; }
+                if (ok0) { dst[row] = s0; dst[wout_fstride + row] = s1; }
                 split(sl + 2 * Cfg::LINE_PITCH, s0, s1);
-                if (ok1) { ob[(long)k * out_e_stride + row + 1] = s0; ob[wout_fstride + (long)k * out_e_stride + row + 1] = s1; }
+                if (ok1) { dst[row + 1] = s0; dst[wout_fstride + row + 1] = s1; }
                 split(sl + Cfg::LINE_PITCH, s0, s1);
-                if (ok0) ob[2 * wout_fstride + (long)k * out_e_stride + row] = s0;
-                if (ok1) ob[2 * wout_fstride + (long)k * out_e_stride + row + 1] = s1;
+                if (ok0) dst[2 * wout_fstride + row] = s0;
+                if (ok1) dst[2 * wout_fstride + row + 1] = s1;
             }
+        };
+        {
+            const int l = threadIdx.x % NLc, k0 = threadIdx.x / NLc;   // k0 < TL
+            static_for<0, EPT / 2>([&](auto itc) {
+                constexpr int it = decltype(itc)::value;
+                const int k = k0 + it * TL;
+                if constexpr (it == 0) emit(l, k, (k == 0) ? 0 : N - k);
+                else emit(l, k, N - k);
+            });
+            if (threadIdx.x < NLc) emit(threadIdx.x, N / 2, N / 2);
         }
     }
 }
@@ -903,6 +948,7 @@ struct Combine {
     // Rows 0..n_out-1 are stored to out[r]; row FSM_MAX_OUT (if has_next) is the next stage state, handed
     // in registers to the fused inverse transforms and never stored.
     int has_next;
+    int kind;                                   // index of the matching CombineShape (compile-time structure), -1 = generic
     int any_ct2;                                // some coefficient uses a second table
     int ct[FSM_MAX_OUT + 1][FSM_MAX_IN + 1];    // table index, -1 = scalar only, -2 = term absent
     int ct2[FSM_MAX_OUT + 1][FSM_MAX_IN + 1];   // optional second table, -1 = none
@@ -919,52 +965,133 @@ struct FxEpilogue {
     int project;                   // NS3D pressure projection
 };
 
-// Evaluate the combine for NB modes (mode0 + j*mstride): every global load of the block is issued
-// before the first store so the memory system sees them all in flight.
-// Operands of NB modes (mode0 + j*mstride) of one combine: every global load is issued up front.
+// ---- compile-time combine structures ---------------------------------------------------------------------
+// The stage programs of the ETD integrators (fsm_plan.cu: build_stages) come in a handful of shapes. Which
+// operand and which table slot feeds which output row is then known at compile time and the data-driven
+// selects of the generic path fold away; the numeric coefficients (ca, cb) stay run-time data. The host
+// (match_combine_shape) picks the shape; anything else (RK4, rhs, linear-only, fused) runs the generic path.
+// ct(r, m): table slot of the coefficient of operand m (0 = fresh nonlinear term, 1.. = in[m-1]) in output
+// row r; -1 = scalar only; -2 = term absent. Slots are numbered in order of appearance (make_combine).
+constexpr int kCombineShapes = 7;
+template <int KIND>
+struct CShape {   // generic: structure read from the Combine at run time
+    static constexpr int n_in = FSM_MAX_IN, n_out = FSM_MAX_OUT, n_tab = FSM_MAX_TAB;
+    static FSM_HD constexpr int ct(int, int) { return -2; }
+};
+#define FSM_CSHAPE(K, NIN, NOUT, NTAB, ...)                              \
+    template <>                                                          \
+    struct CShape<K> {                                                   \
+        static constexpr int n_in = NIN, n_out = NOUT, n_tab = NTAB;     \
+        static FSM_HD constexpr int ct(int r, int m) {                   \
+            constexpr int t[FSM_MAX_OUT][FSM_MAX_IN + 1] = __VA_ARGS__;  \
+            return t[r][m];                                              \
+        }                                                                \
+    }
+// u' = c1 N + E u                                               (ETDRK1 / SETDRK1)
+FSM_CSHAPE(0, 1, 1, 2, {{0, 1, -2, -2}, {-2, -2, -2, -2}, {-2, -2, -2, -2}});
+// a = c1 N + E u ; N0 = N                                       (ETDRK2 / SETDRK2 stage 1)
+FSM_CSHAPE(1, 1, 2, 2, {{0, 1, -2, -2}, {-1, -2, -2, -2}, {-2, -2, -2, -2}});
+// u' = c2 N + a - c2 N0                                         (ETDRK2 / SETDRK2 stage 2)
+FSM_CSHAPE(2, 2, 1, 1, {{0, -1, 0, -2}, {-2, -2, -2, -2}, {-2, -2, -2, -2}});
+// a = c1 N + E2 u ; N0 = N ; sum = c4 N + E u                   (SETDRK3 / SETDRK4 stage 1)
+FSM_CSHAPE(3, 1, 3, 4, {{0, 1, -2, -2}, {-1, -2, -2, -2}, {2, 3, -2, -2}});
+// b = c2 N + E2 u ; sum += 2 c5 N                               (SETDRK4 stage 2)
+FSM_CSHAPE(4, 2, 2, 3, {{0, 1, -2, -2}, {2, -2, -1, -2}, {-2, -2, -2, -2}});
+// c = 2 c3 N + E2 a - c3 N0 ; sum += 2 c5 N                     (SETDRK4 stage 3, SETDRK3 stage 2)
+FSM_CSHAPE(5, 3, 2, 3, {{0, 1, 0, -2}, {2, -2, -2, -1}, {-2, -2, -2, -2}});
+// u' = c6 N + sum                                               (last stage of SETDRK3 / SETDRK4)
+FSM_CSHAPE(6, 1, 1, 1, {{0, -1, -2, -2}, {-2, -2, -2, -2}, {-2, -2, -2, -2}});
+#undef FSM_CSHAPE
+
+// host and device: does this Combine have the structure of shape KIND?
+template <int KIND, typename T>
+FSM_HD inline bool combine_matches(const Combine<T>& cb) {
+    using S = CShape<KIND>;
+    if (cb.n_in != S::n_in || cb.n_out != S::n_out || cb.n_tab != S::n_tab || cb.has_next || cb.any_ct2 || !cb.use_fresh)
+        return false;
+    for (int r = 0; r < FSM_MAX_OUT; ++r)
+        for (int m = 0; m < FSM_MAX_IN + 1; ++m)
+            if (cb.ct[r][m] != S::ct(r, m)) return false;
+    return cb.ct[FSM_MAX_OUT][0] == -2 || !cb.has_next;
+}
+template <typename T>
+inline int match_combine_shape(const Combine<T>& cb) {
+    if (combine_matches<0>(cb)) return 0;
+    if (combine_matches<1>(cb)) return 1;
+    if (combine_matches<2>(cb)) return 2;
+    if (combine_matches<3>(cb)) return 3;
+    if (combine_matches<4>(cb)) return 4;
+    if (combine_matches<5>(cb)) return 5;
+    if (combine_matches<6>(cb)) return 6;
+    return -1;
+}
+// run f(integral_constant<int, KIND>) for the run-time kind (uniform across the grid)
+template <class F>
+__device__ __forceinline__ void with_combine_kind(int kind, F&& f) {
+    switch (kind) {
+        case 0: f(std::integral_constant<int, 0>{}); break;
+        case 1: f(std::integral_constant<int, 1>{}); break;
+        case 2: f(std::integral_constant<int, 2>{}); break;
+        case 3: f(std::integral_constant<int, 3>{}); break;
+        case 4: f(std::integral_constant<int, 4>{}); break;
+        case 5: f(std::integral_constant<int, 5>{}); break;
+        case 6: f(std::integral_constant<int, 6>{}); break;
+        default: f(std::integral_constant<int, -1>{}); break;
+    }
+}
+
+// Operands of NB modes (mode0 + j*mstride) of one combine: every global load is issued up front so the
+// memory system sees them all in flight.
 template <typename T, int NB>
 struct CombineOperands {
     cplx<T> X[FSM_MAX_IN][NB];
     T tv[FSM_MAX_TAB][NB];
 };
-template <typename T, int NB>
+template <typename T, int NB, int KIND = -1>
 __device__ __forceinline__ void combine_load(const Combine<T>& cb, long bc_off, long tab_off, long mode0, long mstride,
                                              CombineOperands<T, NB>& op) {
+    using S = CShape<KIND>;
     FSM_UNROLL
     for (int i = 0; i < FSM_MAX_IN; ++i)
-        if (i < cb.n_in) {
+        if ((KIND >= 0) ? (i < S::n_in) : (i < cb.n_in)) {
+            const cplx<T>* src = cb.in[i] + bc_off + mode0;
             FSM_UNROLL
-            for (int j = 0; j < NB; ++j) op.X[i][j] = cb.in[i][bc_off + mode0 + j * mstride];
+            for (int j = 0; j < NB; ++j) op.X[i][j] = src[j * mstride];
         }
     FSM_UNROLL
     for (int q = 0; q < FSM_MAX_TAB; ++q)
-        if (q < cb.n_tab) {
+        if ((KIND >= 0) ? (q < S::n_tab) : (q < cb.n_tab)) {
+            const T* src = cb.tab[q] + tab_off + mode0;
             FSM_UNROLL
-            for (int j = 0; j < NB; ++j) op.tv[q][j] = cb.tab[q][tab_off + mode0 + j * mstride];
+            for (int j = 0; j < NB; ++j) op.tv[q][j] = src[j * mstride];
         }
 }
-template <typename T, int NB>
+template <typename T, int NB, int KIND = -1>
 __device__ __forceinline__ void combine_apply(const Combine<T>& cb, const cplx<T>* fresh, const CombineOperands<T, NB>& op,
                                               long bc_off, long mode0, long mstride, cplx<T>* next = nullptr) {
+    using S = CShape<KIND>;
     FSM_UNROLL
     for (int r = 0; r < FSM_MAX_OUT + 1; ++r) {
         const bool is_next = (r == FSM_MAX_OUT);
-        if (is_next ? (cb.has_next && next != nullptr) : (r < cb.n_out)) {
+        bool row_on;
+        if constexpr (KIND >= 0) row_on = !is_next && r < S::n_out;
+        else row_on = is_next ? (cb.has_next && next != nullptr) : (r < cb.n_out);
+        if (row_on) {
             cplx<T> s[NB];
             FSM_UNROLL
             for (int j = 0; j < NB; ++j) s[j] = mk<T>(T(0), T(0));
             FSM_UNROLL
             for (int m = 0; m < FSM_MAX_IN + 1; ++m) {
-                const int ti = cb.ct[r][m];
+                const int ti = (KIND >= 0) ? S::ct(r < FSM_MAX_OUT ? r : 0, m) : cb.ct[r][m];
                 if (ti != -2) {
-                    const int ti2 = cb.ct2[r][m];
+                    const int ti2 = (KIND >= 0) ? -1 : cb.ct2[r][m];
                     FSM_UNROLL
                     for (int j = 0; j < NB; ++j) {
                         T coef = cb.ca[r][m];
                         FSM_UNROLL
                         for (int q = 0; q < FSM_MAX_TAB; ++q)
                             if (ti == q) coef = fsm_fma(cb.cb[r][m], op.tv[q][j], coef);
-                        if (cb.any_ct2) {
+                        if (KIND < 0 && cb.any_ct2) {
                             FSM_UNROLL
                             for (int q = 0; q < FSM_MAX_TAB; ++q)
                                 if (ti2 == q) coef = fsm_fma(cb.cb2[r][m], op.tv[q][j], coef);
@@ -978,19 +1105,20 @@ __device__ __forceinline__ void combine_apply(const Combine<T>& cb, const cplx<T
                 FSM_UNROLL
                 for (int j = 0; j < NB; ++j) next[j] = s[j];
             } else {
+                cplx<T>* dst = cb.out[r] + bc_off + mode0;
                 FSM_UNROLL
-                for (int j = 0; j < NB; ++j) cb.out[r][bc_off + mode0 + j * mstride] = s[j];
+                for (int j = 0; j < NB; ++j) dst[j * mstride] = s[j];
             }
         }
     }
 }
-template <typename T, int NB>
+template <typename T, int NB, int KIND = -1>
 __device__ __forceinline__ void combine_block(const Combine<T>& cb, const cplx<T>* fresh, long bc_off, long tab_off,
                                               long mode0, long mstride, cplx<T>* next = nullptr, bool store = true) {
     (void)store;
     CombineOperands<T, NB> op;
-    combine_load<T, NB>(cb, bc_off, tab_off, mode0, mstride, op);
-    combine_apply<T, NB>(cb, fresh, op, bc_off, mode0, mstride, next);
+    combine_load<T, NB, KIND>(cb, bc_off, tab_off, mode0, mstride, op);
+    combine_apply<T, NB, KIND>(cb, fresh, op, bc_off, mode0, mstride, next);
 }
 
 template <typename T>
@@ -999,7 +1127,8 @@ __device__ __forceinline__ void combine_mode(const Combine<T>& cb, cplx<T> fresh
 }
 
 template <typename T, class Cfg, int C>
-__global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass_fx(Geom<T> g, const cplx<T>* __restrict__ win, long win_fstride,
+__global__ void __launch_bounds__(kFxLines<Cfg> * Cfg::TL, (C == 1 && kFxLines<Cfg> < kKL) ? FSM_FX_MINB : FSM_MINB(kFxLines<Cfg> * Cfg::TL))
+k_pass_fx(Geom<T> g, const cplx<T>* __restrict__ win, long win_fstride,
                                                   Combine<T> cb, FxEpilogue<T> ep, int nlines, int b0, Blk ib, long line_stride) {
     constexpr int N = Cfg::N, EPT = Cfg::EPT, TL = Cfg::TL;
     FSM_DYN_SMEM(smem_raw);
@@ -1066,11 +1195,14 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
     // line coordinates
     int ky, kz = 0;
     if (g.ndim == 3) { ky = line / g.nh + g.ky0; kz = line % g.nh; } else { ky = line; }
+    // the epilogue is instantiated once per compile-time combine shape (and once generic); cb.kind is uniform
+    with_combine_kind(cb.kind, [&](auto kindc) {
+    constexpr int KIND = decltype(kindc)::value;
     static_for<0, EPT / NB>([&](auto mbc) {
         constexpr int mb = decltype(mbc)::value * NB;
         constexpr int cur = decltype(mbc)::value & 1;
         if constexpr (kPipe && mb + NB < EPT)
-            combine_load<T, NB>(cb, b * g.nmodes, 0, line_mode0 + tau + (mb + NB) * TL, TL, opq[cur ^ 1]);
+            combine_load<T, NB, KIND>(cb, b * g.nmodes, 0, line_mode0 + tau + (mb + NB) * TL, TL, opq[cur ^ 1]);
         cplx<T> f[C][NB];
         FSM_UNROLL
         for (int j = 0; j < NB; ++j) {
@@ -1118,12 +1250,13 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
             f[0][0] = mk<T>(T(0), T(0));
         }
         if constexpr (kPipe) {
-            combine_apply<T, NB>(cb, f[0], opq[cur], b * g.nmodes, line_mode0 + tau + mb * TL, TL);
+            combine_apply<T, NB, KIND>(cb, f[0], opq[cur], b * g.nmodes, line_mode0 + tau + mb * TL, TL);
         } else {
             FSM_UNROLL
             for (int c = 0; c < C; ++c)
-                combine_block<T, NB>(cb, f[c], (b * C + c) * g.nmodes, c * cb.tab_cstride, line_mode0 + tau + mb * TL, TL);
+                combine_block<T, NB, KIND>(cb, f[c], (b * C + c) * g.nmodes, c * cb.tab_cstride, line_mode0 + tau + mb * TL, TL);
         }
+    });
     });
 }
 

@@ -340,6 +340,7 @@ int make_combine(const fsm_plan* p, const Stage& s, cplx<T>* const* arr, bool fr
                 cb.ct2[r][m] = sl;
             }
         }
+    cb.kind = (getenv("FSM_GENERIC_COMBINE") != nullptr) ? -1 : match_combine_shape(cb);
     *out = cb;
     return 0;
 }
@@ -1062,6 +1063,25 @@ int fsm_plan_info(const fsm_plan* plan, int64_t* launches_per_step, int64_t* alg
     if (modes_per_field) *modes_per_field = plan->nmodes;
     if (chunk) *chunk = plan->chunk;
     return 0;
+}
+
+int fsm_stage_kinds(const fsm_plan* plan, int32_t* kinds, int32_t capacity) {
+    if (!plan) return fail(-EINVAL, "null plan");
+    const int n = (int)plan->stages.size();
+    for (int i = 0; i < n && i < capacity; ++i) {
+        int kind = -1;
+        if (plan->f64) {
+            cplx<double>* arr[ARR_COUNT] = {};
+            Combine<double> cb;
+            if (make_combine<double>(plan, plan->stages[i], arr, plan->prog != FSM_PROG_LINEAR, &cb) == 0) kind = cb.kind;
+        } else {
+            cplx<float>* arr[ARR_COUNT] = {};
+            Combine<float> cb;
+            if (make_combine<float>(plan, plan->stages[i], arr, plan->prog != FSM_PROG_LINEAR, &cb) == 0) kind = cb.kind;
+        }
+        if (kinds) kinds[i] = kind;
+    }
+    return n;
 }
 
 int fsm_slab_info(const fsm_plan* plan, int op, int64_t* exch1_elems, int64_t* exch2_elems, int32_t* n_stages) {

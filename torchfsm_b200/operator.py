@@ -280,6 +280,13 @@ class FusedStepper:
         return {"launches_per_step": a.value, "algo_bytes_per_step": b.value, "modes_per_field": c.value,
                 "chunk": d.value}
 
+    def stage_kinds(self):
+        """Per integrator stage: index of the compile-time combine structure used by the forward-x epilogue
+        (-1 = generic data-driven path)."""
+        buf = (ctypes.c_int32 * 8)()
+        n = self._lib.fsm_stage_kinds(self._plan, buf, 8)
+        return [int(buf[i]) for i in range(min(n, 8))]
+
     def profile(self, on: bool):
         _cabi.check(self._lib.fsm_profile_enable(self._plan, 1 if on else 0), "profile_enable")
 
