@@ -141,6 +141,15 @@ int fsm_slab_phase(fsm_plan* plan, int op, int stage, int phase, int sub, int ns
                    void* workspace, size_t ws_bytes, void* send, void* recv, void* stream);
 int fsm_slab_info(const fsm_plan* plan, int op, int64_t* exch1_elems, int64_t* exch2_elems, int32_t* n_stages);
 
+/* Direct exchange: register, for exchange 1 (spectral ky-slabs -> physical x-slabs, written by phase 0) or
+ * exchange 2 (x-slabs -> ky-slabs, written by phase 1), the receive buffer of EVERY rank as addressable from
+ * this process (CUDA: NVLink peer mappings, e.g. torch symmetric memory; emulator: shared host memory). The
+ * transform kernels then store straight into the destination ranks' buffers -- the transfer rides inside the
+ * kernel, no send buffer, no separate all-to-all. The caller separates writers and readers with a barrier
+ * across ranks on the stream (after phase 0 / phase 1, before the next phase reads). n = 0 or ptrs = NULL
+ * returns to the send-buffer path. Replaces the all_to_all a torch.distributed slab FFT would issue. */
+int fsm_slab_peers(fsm_plan* plan, int exchange, const void* const* ptrs, int32_t n);
+
 /* KS ensembles sharded over ranks: the batch mean of _ks_convection.py:34-36 spans every rank, but it only
  * touches the k=0 bin, which never feeds back. With a log attached, every nonlinear evaluation appends the
  * LOCAL sum of the per-sample zero modes (plan dtype, `capacity` entries, device memory owned by the caller;

@@ -71,3 +71,34 @@ def product_from_golden(g, device):
     mesh = fsm.MeshGrid([tuple(m) for m in spec["mesh"]], device=device, dtype=dtype)
     u0 = torch.from_numpy(g["u0"]).to(device)
     return op, mesh, u0
+
+
+class SharedFilePeers:
+    """Peer provider for the CPU tests of the direct slab exchange (torchfsm_b200/peer.py protocol): every
+    rank's receive buffer is a shared memory-mapped file that all (emulator) processes map, the barrier is
+    the gloo barrier. On GPUs the same role is played by torch symmetric memory."""
+
+    def __init__(self, rank, world, directory):
+        self.rank, self.world, self.dir = rank, world, directory
+        self._n = 0
+        self._keep = []
+
+    def alloc(self, numel, dtype, device):
+        import torch
+        import torch.distributed as dist
+        nbytes = int(numel) * torch.empty((), dtype=dtype).element_size()
+        idx, self._n = self._n, self._n + 1
+        path = lambda r: os.path.join(self.dir, f"recv{idx}_rank{r}.bin")   # noqa: E731
+        with open(path(self.rank), "wb") as f:
+            f.truncate(nbytes)
+        dist.barrier()
+        maps = [torch.from_file(path(r), shared=True, size=nbytes, dtype=torch.uint8) for r in range(self.world)]
+        self._keep.append([m.view(dtype) for m in maps])
+        return maps[self.rank].view(dtype), [m.data_ptr() for m in maps], idx
+
+    def remote(self, index, rank):
+        return self._keep[index][rank]
+
+    def barrier(self, index=0, channel=0):
+        import torch.distributed as dist
+        dist.barrier()

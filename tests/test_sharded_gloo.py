@@ -78,7 +78,11 @@ def _slab_worker(rank, world, port, name, lib_path, out_q, nsub=0):
         g = load_golden(name)
         spec = g["spec"]
         op, mesh, u0 = product_from_golden(g, "cpu")
-        op.set_slab_decomposition(nsub=nsub)
+        if nsub in ("store", "dma"):   # peer-visible receive buffers: kernels (store) or block copies (dma) fill them
+            from product_util import SharedFilePeers
+            op.set_slab_decomposition(exchange=nsub, peers=SharedFilePeers(rank, world, os.environ["FSM_TEST_PEER_DIR"]))
+        else:
+            op.set_slab_decomposition(nsub=nsub)
         nxl = u0.shape[2] // world
         local = u0[:, :, rank * nxl:(rank + 1) * nxl].contiguous()       # this rank's physical x-slab
         uT = op.integrate(local, mesh=mesh, dt=spec["dt"], step=spec["steps"])
@@ -97,12 +101,16 @@ def _slab_worker(rank, world, port, name, lib_path, out_q, nsub=0):
 
 @pytest.mark.parametrize("name,world,nsub", [("c5_ns3d_16_setdrk4_f64", 2, 1), ("c4_burgers3d_16_f64", 2, 2),
                                              ("c5_ns3d_32x16x8_etdrk2_f64", 2, 4), ("burgers3d_8x16x32_rk4_f64", 2, 0),
-                                             ("c5_ns3d_32x16x8_etdrk2_f32", 4, 2)])
-def test_slab_decomposed_grid_matches_reference(name, world, nsub):
+                                             ("c5_ns3d_32x16x8_etdrk2_f32", 4, 2),
+                                             ("c5_ns3d_16_setdrk4_f64", 2, "store"), ("c4_burgers3d_16_f64", 4, "store"),
+                                             ("c5_ns3d_32x16x8_etdrk2_f32", 4, "store"),
+                                             ("c5_ns3d_16_setdrk4_f64", 2, "dma"), ("c5_ns3d_32x16x8_etdrk2_f32", 4, "dma")])
+def test_slab_decomposed_grid_matches_reference(name, world, nsub, tmp_path, monkeypatch):
     """ONE 3-D grid split into x-slabs (physical) / ky-slabs (spectral) over the ranks; the transposes are
     all_to_all_single (gloo here, NCCL on GPUs); results equal the reference's single-device answer."""
     from product_util import build_emulator
     lib_path = build_emulator()
+    monkeypatch.setenv("FSM_TEST_PEER_DIR", str(tmp_path))
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()

@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--integrator", default="SETDRK4")
     ap.add_argument("--nsub", type=int, default=0, help="sub-slabs for exchange/compute overlap (0 = default)")
+    ap.add_argument("--modes", default="nccl", help="comma list of exchange paths to time: nccl, dma, store")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -45,7 +46,18 @@ def main():
             opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
         dist.init_process_group("nccl", device_id=dev, pg_options=opts)
 
-    # ---- parity of the NCCL slab path on a golden fixture (16^3, fp32, SETDRK4)
+    for mode in a.modes.split(","):
+        try:
+            run(a, mode.strip(), world, rank, dev)
+        except Exception as exc:   # report and go on to the next mode
+            if rank == 0:
+                print(json.dumps({"mode": mode, "n_gpus": world, "error": repr(exc)[:300]}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run(a, mode, world, rank, dev):
+    # ---- parity of the slab path on a golden fixture (16^3, fp32, SETDRK4)
     parity = None
     if world > 1:
         from golden_util import load_golden, rel_l2
@@ -53,7 +65,7 @@ def main():
         g = load_golden("c5_ns3d_16_setdrk4_f32")
         if g["u0"].shape[2] % world == 0 and g["u0"].shape[2] // world >= 2:
             op, mesh, u0 = product_from_golden(g, dev)
-            op.set_slab_decomposition()
+            op.set_slab_decomposition(exchange=mode)
             nxl = u0.shape[2] // world
             sl = slice(rank * nxl, (rank + 1) * nxl)
             uT = op.integrate(u0[:, :, sl].contiguous(), mesh=mesh, dt=g["spec"]["dt"], step=g["spec"]["steps"])
@@ -75,7 +87,7 @@ def main():
     op.set_integrator(getattr(fsm.SETDRKIntegrator, a.integrator) if a.integrator.startswith("S")
                       else getattr(fsm.ETDRKIntegrator, a.integrator))
     if world > 1:
-        op.set_slab_decomposition(nsub=a.nsub)
+        op.set_slab_decomposition(nsub=a.nsub, exchange=mode)
     t0 = time.perf_counter()
     op.integrate(u, mesh=mesh, dt=0.0025, step=1)
     torch.cuda.synchronize()
@@ -118,14 +130,16 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         a2a = {"send_bytes_per_gpu_per_step": bytes_per_step, "bare_exchange_ms_per_step": float(t.item()),
                "bare_exchange_gbs_per_gpu": bytes_per_step / (float(t.item()) * 1e-3) / 1e9}
+        if mode == "store":   # the "exchange" is only the barrier pair: the bytes moved inside the kernels
+            a2a = {"send_bytes_per_gpu_per_step": bytes_per_step, "barriers_ms_per_step": float(t.item())}
     if rank == 0:
         info = st.info()
-        print(json.dumps({"config": f"C5 ns3d {n}^3 B=1 C=3 {a.integrator} slab x{world}", "n_gpus": world,
+        print(json.dumps({"config": f"C5 ns3d {n}^3 B=1 C=3 {a.integrator} slab x{world}", "mode": mode, "n_gpus": world,
                           "ms_per_step": float(ms.item()), "steps_per_sec": 1e3 / float(ms.item()), "steps": a.steps,
                           "finite": finite, "setup_s": setup_s, "nsub": getattr(st, "nsub", 1), "all_to_all": a2a, "parity_rel_l2_16cubed_fp32": parity,
                           "algo_gb_per_step_global": info["algo_bytes_per_step"] / 1e9}), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    del st, op, u_hat
+    torch.cuda.empty_cache()
 
 
 if __name__ == "__main__":

@@ -34,7 +34,7 @@ class FsmDesc(ctypes.Structure):
 
 
 EXPORTS = ["fsm_plan_create", "fsm_plan_destroy", "fsm_workspace_bytes", "fsm_step", "fsm_rhs", "fsm_r2c",
-           "fsm_c2r", "fsm_half_to_full", "fsm_full_to_half", "fsm_plan_info", "fsm_stage_kinds", "fsm_slab_phase", "fsm_slab_info", "fsm_ks_log", "fsm_profile_enable", "fsm_profile_read", "fsm_last_error",
+           "fsm_c2r", "fsm_half_to_full", "fsm_full_to_half", "fsm_plan_info", "fsm_stage_kinds", "fsm_slab_phase", "fsm_slab_info", "fsm_slab_peers", "fsm_ks_log", "fsm_profile_enable", "fsm_profile_read", "fsm_last_error",
            "fsm_abi_version", "fsm_backend"]
 
 _lib = None
@@ -69,6 +69,8 @@ def _declare(lib):
     lib.fsm_slab_phase.restype = i32
     lib.fsm_slab_info.argtypes = [vp, i32, i64p, i64p, ctypes.POINTER(ctypes.c_int32)]
     lib.fsm_slab_info.restype = i32
+    lib.fsm_slab_peers.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_void_p), i32]
+    lib.fsm_slab_peers.restype = i32
     lib.fsm_ks_log.argtypes = [vp, vp, ctypes.c_int64]
     lib.fsm_ks_log.restype = i32
     lib.fsm_profile_enable.argtypes = [vp, i32]

@@ -78,7 +78,7 @@ static int launch_ix_p(const IxArgs<T>& a, cudaStream_t s) {
     Geom<T> g = a.g;
     g.pf_wave = wave;
     FSM_LAUNCH(kern, grid, block, smem, s, g, a.state, a.w1, a.state_bstride, a.w1_fstride, kKL, a.in_t_stride,
-               a.in_o_stride, a.out_o_stride, a.out_e_stride, a.n_t, a.eb);
+               a.in_o_stride, a.out_o_stride, a.out_e_stride, a.n_t, a.eb, a.pe);
     return check_launch();
 }
 template <typename T, int N>
@@ -100,7 +100,7 @@ static int launch_mid_d(const MidArgs<T>& a, cudaStream_t s) {
     if (int e = set_smem(kern, smem)) return e;
     dim3 grid((a.n_t + kKL - 1) / kKL, a.n_outer, a.nb), block(kKL * Cfg::TL);
     FSM_LAUNCH(kern, grid, block, smem, s, a.g, a.in, a.out, a.in_fstride, a.out_fstride, a.nfi, a.spec, kKL,
-               a.in_t_stride, a.in_o_stride, a.out_o_stride, a.out_e_stride, a.n_t, a.ib, a.eb);
+               a.in_t_stride, a.in_o_stride, a.out_o_stride, a.out_e_stride, a.n_t, a.ib, a.eb, a.pe);
     return check_launch();
 }
 template <typename T, int N>

@@ -13,6 +13,7 @@ struct IxArgs {
     long state_bstride, w1_fstride, in_t_stride, in_o_stride, out_o_stride, out_e_stride;
     int n_t, n_outer, nbc;
     Blk eb = {30, 0, 30, 0};
+    Peers pe = {{nullptr}, 0, 0};
 };
 template <typename T>
 struct MidArgs {
@@ -23,6 +24,7 @@ struct MidArgs {
     int nfi, n_t, n_outer, nb;
     MidSpec spec;
     Blk ib = {30, 0, 30, 0}, eb = {30, 0, 30, 0};
+    Peers pe = {{nullptr}, 0, 0};
 };
 template <typename T>
 struct PhysArgs {

@@ -70,6 +70,16 @@ struct Blk {
     int shift2;     // sub-slab block: (i & mask) >> shift2   (30 = none)
     long stride2;
 };
+// Direct exchange (slab decomposition): instead of a local send buffer the pass stores straight into the
+// receive buffers of the destination ranks (peer memory over NVLink; plain addresses in the emulator).
+// Element i of the exchanged axis belongs to rank i >> Blk::shift; that rank's buffer holds one block per
+// source rank, ours at self_off.
+#define FSM_MAX_PEERS 8
+struct Peers {
+    void* base[FSM_MAX_PEERS];
+    int n;            // 0: no direct exchange
+    long self_off;    // elements: (this rank) * Blk::stride
+};
 __device__ __forceinline__ long blk_off(int i, const Blk& b, long elem_stride) {
     const int r = i & ((1 << b.shift) - 1);
     const int lo = (b.shift2 < b.shift) ? b.shift2 : b.shift;
@@ -114,6 +124,12 @@ __device__ __forceinline__ bool next_wave_block(int wave, int& x, int& y, int& z
     z = (int)(r / gy);
     y = (int)(r - (unsigned)z * gy);
     return true;
+}
+
+template <typename T>
+__device__ __forceinline__ cplx<T>* peer_ptr(const Peers& pe, const Blk& b, int i, long off0, long elem_stride) {
+    const int r = i & ((1 << b.shift) - 1);
+    return static_cast<cplx<T>*>(pe.base[i >> b.shift]) + pe.self_off + off0 + (long)r * elem_stride;
 }
 
 template <int N>
@@ -274,7 +290,7 @@ template <typename T, class Cfg, int PROG>
 __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass_ix(Geom<T> g, const cplx<T>* __restrict__ state, cplx<T>* __restrict__ w1,
                                                   long state_bstride /*per (b,c)*/, long w1_fstride, int K,
                                                   long in_t_stride, long in_o_stride, long out_o_stride,
-                                                  long out_e_stride, int n_t, Blk eb) {
+                                                  long out_e_stride, int n_t, Blk eb, Peers pe) {
     constexpr int N = Cfg::N, EPT = Cfg::EPT, TL = Cfg::TL;
     constexpr int NF = IxFields<PROG>::NF;
     FSM_DYN_SMEM(smem_raw);
@@ -455,6 +471,11 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
             rotated_last_stage<Cfg, +1, T>(pbufs, tw, [&](int e, cplx<T> val) {
                 if (valid) dst[e * es] = val;
             });
+        } else if (pe.n > 0) {  // direct exchange: the x-slab owner's receive buffer
+            const long off0 = dst - w1;
+            rotated_last_stage<Cfg, +1, T>(pbufs, tw, [&](int e, cplx<T> val) {
+                if (valid) *peer_ptr<T>(pe, eb, e, off0, out_e_stride) = val;
+            });
         } else {
             rotated_last_stage<Cfg, +1, T>(pbufs, tw, [&](int e, cplx<T> val) {
                 if (valid) dst[blk_off(e, eb, out_e_stride)] = val;
@@ -478,7 +499,7 @@ template <typename T, class Cfg, int DIR>
 __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass_mid(Geom<T> g, const cplx<T>* __restrict__ in, cplx<T>* __restrict__ out,
                                                    long in_fstride, long out_fstride, int nfi, MidSpec spec, int K,
                                                    long in_t_stride, long in_o_stride, long out_o_stride,
-                                                   long out_e_stride, int n_t, Blk ib, Blk eb) {
+                                                   long out_e_stride, int n_t, Blk ib, Blk eb, Peers pe) {
     constexpr int N = Cfg::N, EPT = Cfg::EPT, TL = Cfg::TL;
     FSM_DYN_SMEM(smem_raw);
     cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);
@@ -497,14 +518,23 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
     // the line of output field j+1 is loaded (registers) before field j is transformed and stored, so its
     // latency hides behind the butterflies, the block barrier and the rotated stores of field j
     const bool one_block = ib.shift >= 30;
+    unsigned keepmask = 0;   // bit m: element p = tau + m*TL of an input line is read (dealiasing, valid line)
+    FSM_UNROLL
+    for (int m = 0; m < EPT; ++m) {
+        const int p = tau + m * TL;
+        if (line_ok && (DIR < 0 || iabs(signed_mode<N>(p)) <= g.kmax[1])) keepmask |= 1u << m;
+    }
     auto load_line = [&](int j, cplx<T>* raw) {
-        const cplx<T>* src = in + (b * nfi + spec.src[j]) * in_fstride + (long)t * in_t_stride + (long)o * in_o_stride;
-        FSM_UNROLL
-        for (int m = 0; m < EPT; ++m) {
-            const int p = tau + m * TL;
-            bool kept = line_ok;
-            if (DIR > 0) kept = kept && (iabs(signed_mode<N>(p)) <= g.kmax[1]);
-            raw[m] = kept ? src[one_block ? (long)p : blk_off(p, ib, 1)] : mk<T>(T(0), T(0));
+        const cplx<T>* src = in + (b * nfi + spec.src[j]) * in_fstride + (long)(line_ok ? t : 0) * in_t_stride + (long)o * in_o_stride;
+        if (one_block) {
+            src += tau;
+            FSM_PIN(src);
+            FSM_UNROLL
+            for (int m = 0; m < EPT; ++m) raw[m] = ((keepmask >> m) & 1u) ? src[m * TL] : mk<T>(T(0), T(0));
+        } else {
+            FSM_UNROLL
+            for (int m = 0; m < EPT; ++m)
+                raw[m] = ((keepmask >> m) & 1u) ? src[blk_off(tau + m * TL, ib, 1)] : mk<T>(T(0), T(0));
         }
     };
     cplx<T> raw[EPT];
@@ -525,6 +555,11 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
             const int es = (int)out_e_stride;
             rotated_last_stage<Cfg, DIR, T>(pbufs, tw, [&](int e, cplx<T> val) {
                 if (valid) dst[e * es] = val;
+            });
+        } else if (pe.n > 0) {  // direct exchange: the ky-slab owner's receive buffer
+            const long off0 = dst - out;
+            rotated_last_stage<Cfg, DIR, T>(pbufs, tw, [&](int e, cplx<T> val) {
+                if (valid) *peer_ptr<T>(pe, eb, e, off0, out_e_stride) = val;
             });
         } else {
             rotated_last_stage<Cfg, DIR, T>(pbufs, tw, [&](int e, cplx<T> val) {
@@ -564,14 +599,26 @@ template <typename T, class Cfg>
 __device__ __forceinline__ void pair_load_raw(cplx<T>* A, cplx<T>* B, const cplx<T>* a, const cplx<T>* b, int tau, int kmax,
                                               bool row_ok) {
     constexpr int N = Cfg::N, EPT = Cfg::EPT, TL = Cfg::TL;
+    // element m reads k = p (first half) or k = N - p (mirrored half): two base pointers per field, constant offsets
+    const bool ha = row_ok && a != nullptr, hb = row_ok && b != nullptr;
+    const cplx<T>* alo = (a ? a : b) + tau;
+    const cplx<T>* ahi = (a ? a : b) + (N - tau);
+    const cplx<T>* blo = (b ? b : a) + tau;
+    const cplx<T>* bhi = (b ? b : a) + (N - tau);
+    FSM_PIN(alo); FSM_PIN(ahi); FSM_PIN(blo); FSM_PIN(bhi);   // (never dereferenced for a row beyond the end)
     static_for<0, EPT>([&](auto mc) {
         constexpr int m = decltype(mc)::value;
         constexpr bool mirrored = (2 * m * TL >= N);
         const int p = tau + m * TL;
         const int k = mirrored ? N - p : p;
-        const bool kept = row_ok && k <= kmax;
-        A[m] = (kept && a) ? a[k] : mk<T>(T(0), T(0));
-        B[m] = (kept && b) ? b[k] : mk<T>(T(0), T(0));
+        const bool kept = k <= kmax;
+        if constexpr (mirrored) {
+            A[m] = (kept && ha) ? ahi[-m * TL] : mk<T>(T(0), T(0));
+            B[m] = (kept && hb) ? bhi[-m * TL] : mk<T>(T(0), T(0));
+        } else {
+            A[m] = (kept && ha) ? alo[m * TL] : mk<T>(T(0), T(0));
+            B[m] = (kept && hb) ? blo[m * TL] : mk<T>(T(0), T(0));
+        }
     });
 }
 template <typename T, class Cfg>

@@ -210,6 +210,8 @@ struct fsm_plan {
     long nmodes, ntot;
     int chunk;
     int nf_ix, nfi, nout;  // fields: IX per channel, PHYS inputs per sample, PHYS outputs per sample
+    void* peers[2][FSM_MAX_PEERS] = {};   // direct exchange: receive buffers of every rank (exchange 1, 2)
+    int n_peers[2] = {0, 0};
     int pf = 0;                  // L2 prefetch switches (PF_* in fsm_passes.cuh)
     void* ks_log = nullptr;      // optional device log of the per-evaluation local KS zero-mode sums
     long ks_log_cap = 0;
@@ -697,6 +699,12 @@ int slab_ix(const fsm_plan* p, const Geom<T>& g, int kprog, const cplx<T>* state
     a.n_t = p->kyl; a.n_outer = nkz;
     a.eb.shift = ilog2(p->nxl); a.eb.stride = (long)nfields_in * nf * a.w1_fstride;
     a.eb.shift2 = ilog2(nxh); a.eb.stride2 = (long)p->P * a.eb.stride;
+    if (p->n_peers[0] > 0) {
+        if (nsub != 1) return fail(-EINVAL, "the direct exchange runs with one sub-slab");
+        a.pe.n = p->n_peers[0];
+        for (int r = 0; r < a.pe.n; ++r) a.pe.base[r] = p->peers[0][r];
+        a.pe.self_off = (long)p->rank * a.eb.stride;
+    }
     ProfScope ps(p, PASS_IX, st);
     if (int e = tx->ix(kprog, a, st)) return fail(e, "slab IX launch failed");
     return 0;
@@ -735,6 +743,12 @@ int slab_mid_forward(const fsm_plan* p, const Geom<T>& g, const cplx<T>* w2a, cp
     m.eb.shift = ilog2(p->kyl); m.eb.stride = (long)nb * nf * m.out_fstride;
     m.in = w2a + (long)sub * nxh * m.in_t_stride;
     m.out = send + (long)sub * p->P * m.eb.stride;
+    if (p->n_peers[1] > 0) {
+        if (nsub != 1) return fail(-EINVAL, "the direct exchange runs with one sub-slab");
+        m.pe.n = p->n_peers[1];
+        for (int r = 0; r < m.pe.n; ++r) m.pe.base[r] = p->peers[1][r];
+        m.pe.self_off = (long)p->rank * m.eb.stride;
+    }
     ProfScope ps(p, PASS_MID, st);
     if (int e = ty->mid(-1, m, st)) return fail(e, "slab MID forward launch failed");
     return 0;
@@ -1062,6 +1076,19 @@ int fsm_plan_info(const fsm_plan* plan, int64_t* launches_per_step, int64_t* alg
     if (algo_bytes_per_step) *algo_bytes_per_step = plan->algo_bytes_per_step;
     if (modes_per_field) *modes_per_field = plan->nmodes;
     if (chunk) *chunk = plan->chunk;
+    return 0;
+}
+
+int fsm_slab_peers(fsm_plan* plan, int exchange, const void* const* ptrs, int32_t n) {
+    if (!plan || plan->P <= 1) return fail(-EINVAL, "plan has no slab decomposition");
+    if (exchange != 1 && exchange != 2) return fail(-EINVAL, "exchange must be 1 (inverse side) or 2 (forward side)");
+    if (!ptrs || n == 0) { plan->n_peers[exchange - 1] = 0; return 0; }
+    if (n != plan->P || n > FSM_MAX_PEERS) return fail(-EINVAL, "need one receive buffer per rank (%d), at most %d", plan->P, FSM_MAX_PEERS);
+    for (int r = 0; r < n; ++r) {
+        if (!ptrs[r]) return fail(-EINVAL, "null receive buffer for rank %d", r);
+        plan->peers[exchange - 1][r] = const_cast<void*>(ptrs[r]);
+    }
+    plan->n_peers[exchange - 1] = n;
     return 0;
 }
 

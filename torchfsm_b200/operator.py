@@ -67,6 +67,21 @@ def _same_device(a: torch.device, b: torch.device) -> bool:
     return ia == ib
 
 
+class _StreamWork:
+    """Completion handle of work queued on the (side) stream that was current at construction; ``wait()`` orders
+    the then-current stream after it, like the Work objects of torch.distributed."""
+
+    def __init__(self, device):
+        self._ev = None
+        if device.type == "cuda":
+            self._ev = torch.cuda.Event()
+            self._ev.record(torch.cuda.current_stream(device))
+
+    def wait(self):
+        if self._ev is not None:
+            torch.cuda.current_stream().wait_event(self._ev)
+
+
 class FusedStepper:
     """What ``_build_integrator`` installs: a plan of the CUDA library plus the buffers it needs.
 
@@ -196,9 +211,33 @@ class FusedStepper:
                 self.n_stages = c.value
                 n1, n2 = max(n1, a.value), max(n2, b.value)
             # exchange buffers: kernels write/read them directly in rank-blocked layouts
-            self._send = [torch.empty(n, dtype=self.cdtype, device=self.device) for n in (n1, n2)]
-            self._recv = [torch.empty(n, dtype=self.cdtype, device=self.device) for n in (n1, n2)]
+            self._peer = slab[4] if len(slab) > 4 else None
+            self._exch_mode = (slab[5] if len(slab) > 5 else None) or ("store" if self._peer is not None else "nccl")
+            if self._exch_mode != "nccl" and self._peer is None:
+                raise ValueError("the 'store' and 'dma' exchanges need a peer provider (torchfsm_b200.peer)")
+            if self._peer is not None:
+                self._recv, self._peer_idx = [], []
+                for which, n in enumerate((n1, n2)):
+                    t, ptrs, idx = self._peer.alloc(n, self.cdtype, self.device)
+                    self._peer_idx.append(idx)
+                    if len(ptrs) != self.P:
+                        raise ValueError("peer provider must return one address per rank")
+                    if self._exch_mode == "store":
+                        # the kernels store into the destination ranks' receive buffers themselves
+                        arr = (ctypes.c_void_p * self.P)(*[int(x) for x in ptrs])
+                        _cabi.check(lib.fsm_slab_peers(plan, which + 1, arr, self.P), "slab_peers")
+                    self._recv.append(t)
+                if self._exch_mode == "store":
+                    self._send = self._recv      # never written: the library ignores the send pointer in this mode
+                else:                            # "dma": local send buffers, blocks pushed by the copy engines
+                    self._send = [torch.empty(n, dtype=self.cdtype, device=self.device) for n in (n1, n2)]
+                    self._remote = [[self._peer.remote(self._peer_idx[which], r) for r in range(self.P)] for which in range(2)]
+            else:
+                self._send = [torch.empty(n, dtype=self.cdtype, device=self.device) for n in (n1, n2)]
+                self._recv = [torch.empty(n, dtype=self.cdtype, device=self.device) for n in (n1, n2)]
             nsub = int(slab[3]) if len(slab) > 3 and slab[3] else int(os.environ.get("FSM_SLAB_SUB", "0"))
+            if self._exch_mode == "store":
+                nsub = 1
             if nsub <= 0:
                 nsub = 2 if self.nxl >= 16 else 1
             while nsub > 1 and self.nxl % nsub:
@@ -215,6 +254,20 @@ class FusedStepper:
     # ---- slab-decomposed phases ---------------------------------------------------------------------
     def _exchange(self, which, count, offset=0, async_op=False):
         import torch.distributed as dist
+        if self._exch_mode == "store":      # the data already sits in the peers' buffers: separate writers and readers
+            self._peer.barrier(self._peer_idx[which])
+            return None
+        if self._exch_mode == "dma":
+            # block q of the send range goes to rank q's receive range, slot `rank`: P-1 peer copies on the copy
+            # engines (+ one local), then a device-side barrier; nothing here occupies an SM for long
+            blk = count // self.P
+            src = self._send[which]
+            for i in range(self.P):
+                q = (self.rank + i) % self.P                 # stagger the destinations across ranks
+                self._remote[which][q][offset + self.rank * blk: offset + (self.rank + 1) * blk].copy_(
+                    src[offset + q * blk: offset + (q + 1) * blk], non_blocking=True)
+            self._peer.barrier(self._peer_idx[which])
+            return _StreamWork(self.device) if async_op else None
         return dist.all_to_all_single(self._recv[which][offset:offset + count], self._send[which][offset:offset + count],
                                       group=self.group, async_op=async_op)
 
@@ -225,6 +278,12 @@ class FusedStepper:
                                              u_hat.data_ptr() if u_hat is not None else None,
                                              aux.data_ptr() if aux is not None else None, self.workspace.data_ptr(),
                                              self.ws_bytes, snd, rcv, self._stream()), "slab_phase")
+
+    def _slab_begin(self):
+        """Direct exchange: the previous operation's last reads of the receive buffers must be over on every rank
+        before this one's first remote stores."""
+        if self.P > 1 and self._peer is not None:
+            self._peer.barrier(self._peer_idx[0], channel=1)
 
     def _slab_eval(self, op, stage, u_hat, aux=None):
         """One nonlinear evaluation + stage combine on a slab-decomposed grid. With nsub > 1 sub-slabs the
@@ -305,6 +364,7 @@ class FusedStepper:
         out = self.empty_half()
         if self.P > 1:
             _, c2 = self._slab_counts[2]
+            self._slab_begin()
             self._slab_phase(2, 0, 1, out, u, 1, None)
             self._exchange(1, c2)
             self._slab_phase(2, 0, 2, out, u, None, 1)
@@ -317,6 +377,7 @@ class FusedStepper:
         out = torch.empty((self.B, self.C) + self.local_shape, dtype=self.rdtype, device=self.device)
         if self.P > 1:
             c1, _ = self._slab_counts[3]
+            self._slab_begin()
             self._slab_phase(3, 0, 0, u_hat, out, 0, None)
             self._exchange(0, c1)
             self._slab_phase(3, 0, 1, u_hat, out, None, 0)
@@ -348,6 +409,7 @@ class FusedStepper:
                 and self._desc.ks_remove_mean and int(n_steps) > 0:
             return self._step_half_ks_sharded(u_hat, int(n_steps))
         if self.P > 1 and self.n_stages and self._desc.program != _cabi.PROG_LINEAR:
+            self._slab_begin()
             for _ in range(int(n_steps)):
                 for stage in range(self.n_stages):
                     self._slab_eval(0, stage, u_hat)
@@ -399,6 +461,7 @@ class FusedStepper:
     def rhs_half(self, u_hat: torch.Tensor) -> torch.Tensor:
         out = self.empty_half()
         if self.P > 1 and self._desc.program != _cabi.PROG_LINEAR:
+            self._slab_begin()
             self._slab_eval(1, 0, u_hat, out)
             return out
         _cabi.check(self._lib.fsm_rhs(self._plan, u_hat.data_ptr(), out.data_ptr(), self.workspace.data_ptr(),
@@ -496,14 +559,29 @@ class OperatorLike:
         self._lowered = None
 
     def set_slab_decomposition(self, group=None, rank: Optional[int] = None, nranks: Optional[int] = None,
-                               nsub: int = 0):
+                               nsub: int = 0, exchange: str = "nccl", peers=None):
         """Decompose ONE 3-D grid over the ranks of a torch.distributed process group:
         ``integrate`` / ``__call__`` then take and return the local physical x-slab
-        ``(B, C, n0/P, n1, n2)`` of the rank; the two transposes per evaluation are all-to-alls. ``nsub``
-        sub-slabs (0 = choose) pipeline the exchange of one part with the local work on another."""
+        ``(B, C, n0/P, n1, n2)`` of the rank. The two transposes per evaluation run as ``exchange`` =
+
+        * ``"nccl"``: all-to-alls of rank-blocked send buffers;
+        * ``"dma"``: the same send buffers, each block pushed into its owner's receive buffer by the copy
+          engines (peer-to-peer copies over NVLink), so no SM is taken from the transforms;
+        * ``"store"``: no send buffer, the transform kernels store straight into the destination ranks'
+          receive buffers; an exchange is only a device-side barrier.
+
+        ``"dma"`` and ``"store"`` need peer-visible buffers: ``peers`` is a provider from ``torchfsm_b200.peer``
+        (default: torch symmetric memory). ``nsub`` sub-slabs (0 = choose) pipeline the exchange of one part
+        with the local work on another ("nccl", "dma")."""
         import torch.distributed as dist
+        if exchange not in ("nccl", "dma", "store"):
+            raise ValueError(f"unknown exchange {exchange!r}")
+        if exchange != "nccl" and peers is None:
+            from .peer import SymmetricMemoryPeers
+            peers = SymmetricMemoryPeers(group)
         self._slab = (dist.get_rank(group) if rank is None else rank,
-                      dist.get_world_size(group) if nranks is None else nranks, group, nsub)
+                      dist.get_world_size(group) if nranks is None else nranks, group, nsub,
+                      peers if exchange != "nccl" else None, exchange)
         self._state_dict["integrator"] = None
         self._rhs_stepper = None
 
