@@ -163,3 +163,38 @@ def test_etd_stages_use_compile_time_combine_shapes(name, monkeypatch):
     uG = op2.integrate(u0, mesh=mesh2, dt=spec["dt"], step=spec["steps"])
     assert all(k == -1 for k in op2._state_dict["integrator"].stage_kinds())
     assert rel_l2(uT.numpy(), uG.numpy()) <= (1e-6 if name.endswith("f32") else 1e-14)
+
+
+def test_recorders_real_frames_equal_the_spectrum_protocol():
+    """AutoRecorder / CPURecorder take physical frames from the C2R pass; a recorder that only speaks the reference
+    protocol (full-spectrum frames, ifftn at the end) must see the same trajectory."""
+    import torchfsm_b200 as fsm
+    from torchfsm_b200.traj_recorder import _TrajRecorder
+
+    class SpectrumOnly(_TrajRecorder):              # reference-style recorder: no record_real
+        def __init__(self, control):
+            super().__init__(control)
+            self.frames = []
+
+        def _record(self, step, frame):
+            assert frame.is_complex() and frame.shape[-1] == frame.shape[-2]      # full spectrum (B, C, n, n)
+            self.frames.append(frame.clone())
+
+        @property
+        def trajectory(self):
+            return torch.fft.ifftn(torch.stack(self.frames, dim=1), dim=(-1, -2)).real
+
+    g = load_golden("c3_ns2d_32_etdrk2_f64")
+    spec = g["spec"]
+    op, mesh, u0 = product_from_golden(g, "cpu")
+    ctl = fsm.IntervalController(interval=2, start=1)                                # steps 1, 3, 5
+    want = op.integrate(u0, mesh=mesh, dt=spec["dt"], step=5, trajectory_recorder=SpectrumOnly(ctl))
+    for cls in (fsm.AutoRecorder, fsm.CPURecorder):
+        rec = cls(ctl)
+        got = op.integrate(u0, dt=spec["dt"], step=5, trajectory_recorder=rec)
+        assert rec._real is True and got.shape == want.shape == (u0.shape[0], 3) + tuple(u0.shape[1:])
+        assert rel_l2(got.numpy(), want.numpy()) <= 1e-13
+    rec = fsm.AutoRecorder(ctl, include_initial_state=False)
+    spec_traj = op.integrate(u0, dt=spec["dt"], step=5, trajectory_recorder=rec, return_in_fourier=True)
+    assert rec._real is False and spec_traj.is_complex()
+    assert rel_l2(torch.fft.ifftn(spec_traj, dim=(-1, -2)).real.numpy(), want.numpy()) <= 1e-13

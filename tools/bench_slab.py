@@ -48,7 +48,10 @@ def main():
 
     for mode in a.modes.split(","):
         try:
-            run(a, mode.strip(), world, rank, dev)
+            mode = mode.strip()
+            if ":" in mode:                      # "dma:4" = exchange path : sub-slabs
+                mode, a.nsub = mode.split(":")[0], int(mode.split(":")[1])
+            run(a, mode, world, rank, dev)
         except Exception as exc:   # report and go on to the next mode
             if rank == 0:
                 print(json.dumps({"mode": mode, "n_gpus": world, "error": repr(exc)[:300]}), flush=True)

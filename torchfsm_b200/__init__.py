@@ -10,7 +10,7 @@ from .integrator import ETDRKIntegrator, SETDRKIntegrator, RKIntegrator  # noqa:
 from .operator import (Operator, LinearOperator, NonlinearOperator, Laplacian, Biharmonic,  # noqa: F401
                        SpatialDerivative, ImplicitSource, ExplicitSource, Convection, KSConvection,
                        VorticityConvection, NSPressureConvection, FusedStepper)
-from .traj_recorder import AutoRecorder, IntervalController  # noqa: F401
+from .traj_recorder import AutoRecorder, CPURecorder, IntervalController  # noqa: F401
 from . import pde, field  # noqa: F401
 
 __version__ = "0.1.0"

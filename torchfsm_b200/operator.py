@@ -754,9 +754,19 @@ class OperatorLike:
             else:
                 i = 0
                 control = getattr(trajectory_recorder, "control_func", None) if trajectory_recorder is not None else None
+                # recorders of this package take physical frames straight from the C2R pass; anything else gets
+                # the reference's full-spectrum frame (traj_recorder.py:46-55)
+                real_frames = (trajectory_recorder is not None and not return_in_fourier
+                               and getattr(trajectory_recorder, "accepts_real_frames", False))
+
+                def emit(k):
+                    if real_frames:
+                        trajectory_recorder.record_real(k, st.c2r(u_hat))
+                    else:
+                        trajectory_recorder.record(k, st.half_to_full(u_hat))
                 while i < step:
                     if trajectory_recorder is not None and (control is None or control(i)):
-                        trajectory_recorder.record(i, st.half_to_full(u_hat))
+                        emit(i)
                     # fuse the steps up to the next frame the recorder may want
                     j = i + 1
                     if control is not None or trajectory_recorder is None:
@@ -770,7 +780,8 @@ class OperatorLike:
             if bar is not None:
                 bar.close()
             if trajectory_recorder is not None:
-                trajectory_recorder.record(step, st.half_to_full(u_hat))
+                if control is None or control(step):
+                    emit(step)
                 trajectory_recorder.return_in_fourier = return_in_fourier
                 return trajectory_recorder.trajectory
             return st.half_to_full(u_hat) if return_in_fourier else st.c2r(u_hat)
