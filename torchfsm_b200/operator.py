@@ -238,8 +238,8 @@ class FusedStepper:
             nsub = int(slab[3]) if len(slab) > 3 and slab[3] else int(os.environ.get("FSM_SLAB_SUB", "0"))
             if self._exch_mode == "store":
                 nsub = 1
-            if nsub <= 0:
-                nsub = 2 if self.nxl >= 16 else 1
+            if nsub <= 0:       # measured on C5 (profiles/r1_slab_scaling_c5_v3.md): 2 sub-slabs at 8 ranks, 4 at 2 ranks (dma)
+                nsub = (4 if (self._exch_mode == "dma" and self.P <= 2 and self.nxl >= 32) else 2) if self.nxl >= 16 else 1
             while nsub > 1 and self.nxl % nsub:
                 nsub //= 2
             self.nsub = max(1, nsub)
