@@ -76,7 +76,8 @@ typedef struct fsm_desc {
     double nl_coef;           /* scalar coefficient of the convective nonlinear term                 */
     double ks_ext_sum;        /* reserved (0)                                                         */
     int32_t ks_ext_count;     /* reserved (0)                                                         */
-    int32_t reserved;
+    int32_t tab_complex;      /* 1: every coefficient table holds complex entries (2 reals per mode): odd-order
+                               * linear terms such as KdV's dispersion (_spatial_derivative.py:7-20). 1-D grids only */
     const void* dk[3];        /* per-axis 2*pi*f(m), Nyquist entry zeroed (length n[i])  mesh.py:399-404 */
     const void* dkraw[3];     /* per-axis 2*pi*f(m) as the reference has it (length n[i])           */
     const void* tab_exp;      /* exp(dt L)            _etdrk.py:21 / _uncached.py:30                 */

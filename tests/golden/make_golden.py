@@ -179,6 +179,22 @@ CASES = [
     dict(name="ks3d_16", mesh=[(0, 20, 16)] * 3, B=2, C=1,
          terms=[("laplacian", -1, {}), ("biharmonic", -1, {}), ("ks_convection", -1, {"remove_mean": True})],
          integrator="SETDRK4", dt=0.05, steps=3, ic="smooth_noise"),
+    # 1-D Kuramoto-Sivashinsky preset (pde.py:27-39) and odd-order linear terms: complex exp(L dt) (KdV, pde.py:51-64)
+    dict(name="ks1d_64", mesh=[(0, 32, 64)], B=2, C=1,
+         terms=[("laplacian", -1, {}), ("biharmonic", -1, {}), ("convection", -1, {})],
+         integrator="auto", dt=0.05, steps=4, ic="smooth_noise"),
+    dict(name="kdv1d_64_setdrk4", mesh=[(0, 20, 64)], B=2, C=1,
+         terms=[("spatial_derivative", -1, {"dim_index": 0, "order": 3}), ("convection", 6.0, {})],
+         integrator="auto", dt=0.001, steps=4, ic="smooth_noise"),
+    dict(name="kdv1d_64_etdrk2", mesh=[(0, 20, 64)], B=2, C=1,
+         terms=[("spatial_derivative", -1, {"dim_index": 0, "order": 3}), ("convection", 6.0, {})],
+         integrator="ETDRK2", dt=0.001, steps=4, ic="smooth_noise"),
+    dict(name="kdv1d_64_rk4", mesh=[(0, 20, 64)], B=2, C=1,
+         terms=[("spatial_derivative", -1, {"dim_index": 0, "order": 3}), ("convection", 6.0, {})],
+         integrator="RK4", dt=0.0001, steps=4, ic="smooth_noise"),
+    dict(name="advdiff1d_32_etdrk0", mesh=[(0, 1, 32)], B=2, C=1,
+         terms=[("spatial_derivative", -0.7, {"dim_index": 0, "order": 1}), ("laplacian", 0.01, {})],
+         integrator="ETDRK0", dt=0.01, steps=5, ic="smooth_noise"),
 ]
 
 

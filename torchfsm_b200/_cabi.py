@@ -25,7 +25,7 @@ class FsmDesc(ctypes.Structure):
         ("program", ctypes.c_int32), ("integrator", ctypes.c_int32), ("kmax", ctypes.c_int32 * 3),
         ("ks_remove_mean", ctypes.c_int32), ("tab_channels", ctypes.c_int32), ("chunk", ctypes.c_int32),
         ("dt", ctypes.c_double), ("nl_coef", ctypes.c_double), ("ks_ext_sum", ctypes.c_double),
-        ("ks_ext_count", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("ks_ext_count", ctypes.c_int32), ("tab_complex", ctypes.c_int32),
         ("dk", ctypes.c_void_p * 3), ("dkraw", ctypes.c_void_p * 3),
         ("tab_exp", ctypes.c_void_p), ("tab_half_exp", ctypes.c_void_p), ("tab_coef", ctypes.c_void_p * 6),
         ("tab_lin", ctypes.c_void_p), ("source_hat", ctypes.c_void_p),

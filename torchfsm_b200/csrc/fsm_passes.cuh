@@ -996,6 +996,7 @@ struct Combine {
     // in registers to the fused inverse transforms and never stored.
     int has_next;
     int kind;                                   // index of the matching CombineShape (compile-time structure), -1 = generic
+    int tab_cplx;                               // tables hold cplx<T> entries (1-D grids, complex linear symbol)
     int any_ct2;                                // some coefficient uses a second table
     int ct[FSM_MAX_OUT + 1][FSM_MAX_IN + 1];    // table index, -1 = scalar only, -2 = term absent
     int ct2[FSM_MAX_OUT + 1][FSM_MAX_IN + 1];   // optional second table, -1 = none
@@ -1054,7 +1055,7 @@ FSM_CSHAPE(6, 1, 1, 1, {{0, -1, -2, -2}, {-2, -2, -2, -2}, {-2, -2, -2, -2}});
 template <int KIND, typename T>
 FSM_HD inline bool combine_matches(const Combine<T>& cb) {
     using S = CShape<KIND>;
-    if (cb.n_in != S::n_in || cb.n_out != S::n_out || cb.n_tab != S::n_tab || cb.has_next || cb.any_ct2 || !cb.use_fresh)
+    if (cb.n_in != S::n_in || cb.n_out != S::n_out || cb.n_tab != S::n_tab || cb.has_next || cb.any_ct2 || !cb.use_fresh || cb.tab_cplx)
         return false;
     for (int r = 0; r < FSM_MAX_OUT; ++r)
         for (int m = 0; m < FSM_MAX_IN + 1; ++m)
@@ -1168,9 +1169,44 @@ __device__ __forceinline__ void combine_block(const Combine<T>& cb, const cplx<T
     combine_apply<T, NB, KIND>(cb, fresh, op, bc_off, mode0, mstride, next);
 }
 
+// One mode with COMPLEX coefficient tables (odd-order linear terms make exp(L dt) complex; 1-D kernels and the
+// point-wise linear step only — the fused 2-D/3-D epilogue keeps real tables).
+template <typename T>
+__device__ __forceinline__ void combine_mode_cplx(const Combine<T>& cb, cplx<T> fresh, long bc_off, long tab_off, long mode) {
+    cplx<T> X[FSM_MAX_IN + 1];
+    cplx<T> tv[FSM_MAX_TAB];
+    X[0] = fresh;
+    FSM_UNROLL
+    for (int i = 0; i < FSM_MAX_IN; ++i) X[i + 1] = (i < cb.n_in) ? cb.in[i][bc_off + mode] : mk<T>(T(0), T(0));
+    FSM_UNROLL
+    for (int q = 0; q < FSM_MAX_TAB; ++q)
+        tv[q] = (q < cb.n_tab) ? reinterpret_cast<const cplx<T>*>(cb.tab[q])[tab_off + mode] : mk<T>(T(0), T(0));
+    FSM_UNROLL
+    for (int r = 0; r < FSM_MAX_OUT; ++r) {
+        if (r < cb.n_out) {
+            cplx<T> s = mk<T>(T(0), T(0));
+            FSM_UNROLL
+            for (int m = 0; m < FSM_MAX_IN + 1; ++m) {
+                const int ti = cb.ct[r][m], ti2 = cb.ct2[r][m];
+                if (ti != -2) {
+                    cplx<T> coef = mk<T>(cb.ca[r][m], T(0));
+                    FSM_UNROLL
+                    for (int q = 0; q < FSM_MAX_TAB; ++q) {
+                        if (ti == q) coef = coef + cscale(tv[q], cb.cb[r][m]);
+                        if (ti2 == q) coef = coef + cscale(tv[q], cb.cb2[r][m]);
+                    }
+                    s = s + cmul(coef, X[m]);
+                }
+            }
+            cb.out[r][bc_off + mode] = s;
+        }
+    }
+}
+
 template <typename T>
 __device__ __forceinline__ void combine_mode(const Combine<T>& cb, cplx<T> fresh, long bc_off, long tab_off, long mode) {
-    combine_block<T, 1>(cb, &fresh, bc_off, tab_off, mode, 0);
+    if (cb.tab_cplx) combine_mode_cplx<T>(cb, fresh, bc_off, tab_off, mode);
+    else combine_block<T, 1>(cb, &fresh, bc_off, tab_off, mode, 0);
 }
 
 template <typename T, class Cfg, int C>

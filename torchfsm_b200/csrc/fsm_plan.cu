@@ -300,6 +300,7 @@ int make_combine(const fsm_plan* p, const Stage& s, cplx<T>* const* arr, bool fr
     cb.n_out = s.n_out;
     cb.use_fresh = fresh ? 1 : 0;
     cb.tab_cstride = (p->d.tab_channels > 1) ? p->nmodes : 0;
+    cb.tab_cplx = p->d.tab_complex ? 1 : 0;
     int slot_of[TAB_COUNT];
     for (int i = 0; i < TAB_COUNT; ++i) slot_of[i] = -1;
     for (int i = 0; i < s.n_in; ++i) cb.in[i] = arr[s.in[i]];
@@ -928,6 +929,10 @@ int fsm_plan_create(fsm_plan** out, const fsm_desc* d) {
     if (p->prog != FSM_PROG_LINEAR && d->integrator == FSM_INT_ETDRK0) {
         delete p;
         return fail(-EINVAL, "The ETDRK0 integrator only supports linear term");
+    }
+    if (d->tab_complex && p->ndim != 1) {
+        delete p;
+        return fail(-ENOSYS, "complex coefficient tables (odd-order linear terms) are supported on 1-D grids only");
     }
     for (int i = 0; i < p->ndim; ++i) {
         const int e = p->f64 ? launch_table<double>(p->n[i])->prepare() : launch_table<float>(p->n[i])->prepare();

@@ -119,16 +119,21 @@ class FusedStepper:
         self.integrator = integrator
         self._keep = []  # tensors referenced by the plan descriptor
 
+        def has_imag(t):
+            return t is not None and t.is_complex() and float(t.imag.abs().max()) != 0.0
+
         def real_table(t):
             t = _expand_table(t, self.shape)
-            if t.is_complex():
-                if float(t.imag.abs().max()) != 0.0:
+            if self.complex_tables:
+                t = t.to(self.cdtype)                 # every table carries complex entries (include/fsm_b200.h)
+            elif t.is_complex():
+                if has_imag(t):
                     raise NotImplementedError(
-                        "complex linear coefficients (odd-order linear terms) are not supported by the fused CUDA path")
+                        "complex linear coefficients (odd-order linear terms) are supported on 1-D grids only")
                 t = t.real
             if t.shape[0] > 1 and bool((t == t[:1]).all()):
                 t = t[:1]
-            return t.to(self.rdtype)
+            return t if self.complex_tables else t.to(self.rdtype)
 
         desc = _cabi.FsmDesc()
         desc.struct_size = ctypes.sizeof(_cabi.FsmDesc)
@@ -158,6 +163,12 @@ class FusedStepper:
                 L = torch.tensor([0.0], dtype=self.cdtype, device=self.device).reshape([1] * (self.n_dim + 2))
             tables = build_tables(integrator, dt, L, **integrator_cfg)
         self.tables_full = tables
+        # odd-order linear terms (KdV dispersion, advection) make exp(L dt) complex: 1-D kernels take complex tables
+        self.complex_tables = self.n_dim == 1 and (has_imag(linear_coef) or any(has_imag(t) for t in tables.values()))
+        if self.complex_tables and any(int(k) >= n // 2 for k, n in zip(kmax, self.shape)) and program != _cabi.PROG_LINEAR:
+            raise NotImplementedError("complex linear coefficients need a dealiasing rate below 1 on the fused path "
+                                      "(the Nyquist mode of the half spectrum is not Hermitian under a complex symbol)")
+        desc.tab_complex = 1 if self.complex_tables else 0
         rot = {}
         for k, t in tables.items():
             rt = real_table(t)

@@ -2,12 +2,24 @@
 from typing import Optional
 
 from .operator import (Operator, Convection, Laplacian, Biharmonic, KSConvection, VorticityConvection,
-                       NSPressureConvection)
+                       NSPressureConvection, SpatialDerivative)
 
 
 def Burgers(nu: float) -> Operator:
     """du/dt = -u.grad(u) + nu lap(u)   (pde.py:13-26)"""
     return nu * Laplacian() - Convection()
+
+
+def KuramotoSivashinsky() -> Operator:
+    """1-D KS: dphi/dt = -phi_xx - phi_xxxx - phi phi_x   (pde.py:27-39)"""
+    ks_eqn = -Laplacian() - Biharmonic() - Convection()
+    ks_eqn.register_additional_check(lambda dim_value, dim_mesh: dim_value == 1 and dim_mesh == 1)
+    return ks_eqn
+
+
+def KortewegDeVries(dispersion_coef=1, convection_coef: float = 6.0) -> Operator:
+    """dphi/dt = -c1 phi_xxx + c2 phi phi_x   (pde.py:51-64); the dispersion makes exp(L dt) complex"""
+    return -dispersion_coef * SpatialDerivative(0, 3) + convection_coef * Convection()
 
 
 def KuramotoSivashinskyHighDim() -> Operator:
