@@ -70,3 +70,33 @@ def test_cpu_tensors_are_rejected_by_the_cuda_build():
             (0.1 * fsm.Laplacian()).integrate(u, mesh=[(0, 1, 32), (0, 1, 32)], dt=0.1, step=1)
     finally:
         _cabi._lib = None
+
+
+def test_multi_gpu_options_are_validated_before_any_work():
+    """Host-side checks of the sharding API: bad exchange names, KS ensembles with an integrator whose zero-mode
+    weights are not known, and the direct-exchange registration on a plan without slab decomposition."""
+    import torch
+    import torchfsm_b200 as fsm
+    from product_util import build_emulator
+    from torchfsm_b200 import _cabi
+    _cabi.use_library(build_emulator())
+    op = fsm.pde.NavierStokes(Re=100)
+    with pytest.raises(ValueError):
+        op.set_slab_decomposition(rank=0, nranks=2, exchange="carrier-pigeon")
+    mesh = fsm.MeshGrid([(0, 20, 16)] * 2, device="cpu", dtype=torch.float64)
+    ks = fsm.pde.KuramotoSivashinskyHighDim()
+    ks.set_integrator(fsm.RKIntegrator.RK4)
+    ks.set_ensemble_group(object())                      # any non-None group: the check happens before the collective
+    u0 = torch.randn(2, 1, 16, 16, dtype=torch.float64)
+    with pytest.raises(NotImplementedError):
+        ks.integrate(u0, mesh=mesh, dt=1e-3, step=1)
+    ks2 = fsm.pde.KuramotoSivashinskyHighDim()
+    ks2.integrate(u0, mesh=mesh, dt=1e-2, step=1)
+    st = ks2._state_dict["integrator"]
+    ptrs = (ctypes.c_void_p * 2)(1, 2)
+    assert st._lib.fsm_slab_peers(st._plan, 1, ptrs, 2) != 0           # no slab decomposition on this plan
+    assert b"slab" in st._lib.fsm_last_error()
+    # complex linear symbols are a 1-D feature: a 2-D advection term must be refused, not silently dropped
+    adv = -1.0 * fsm.SpatialDerivative(0, 1) + 0.01 * fsm.Laplacian()
+    with pytest.raises(NotImplementedError):
+        adv.integrate(u0, mesh=mesh, dt=1e-2, step=1)
