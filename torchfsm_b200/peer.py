@@ -27,10 +27,13 @@ class SymmetricMemoryPeers:
         self.group = group if group is not None else dist.group.WORLD
         self._handles = []
         self._tensors = []
-        try:
-            symm_mem.enable_symm_mem_for_group(self.group.group_name)
-        except Exception:
-            pass                      # newer releases enable groups implicitly at rendezvous
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")            # deprecated (a no-op) in recent releases, required in older ones
+            try:
+                symm_mem.enable_symm_mem_for_group(self.group.group_name)
+            except Exception:
+                pass
 
     def alloc(self, numel, dtype, device):
         t = self._symm_mem.empty(int(numel), dtype=dtype, device=device)
