@@ -1,7 +1,7 @@
 import os
 import sys
 
-import pytest
+import pytest  # noqa: F401  (marker registration below uses the pytest hooks)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:

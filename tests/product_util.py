@@ -1,8 +1,6 @@
 """Build torchfsm_b200 operators from golden-fixture specs (shared by emulator and GPU tests)."""
 import os
-import sys
 
-import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -1,7 +1,10 @@
 #!/usr/bin/env python
 """Dynamic (executed) instruction mix of one kernel of an ncu report taken with --import-source on.
 Usage: tools/ncu_dynmix.py <report.ncu-rep> <kernel-name-substring>"""
-import csv, subprocess, sys, collections
+import collections
+import csv
+import subprocess
+import sys
 rep = sys.argv[1]; kern = sys.argv[2]
 out = subprocess.run(["ncu","-i",rep,"--page","source","--csv","--print-kernel-base","function"],capture_output=True,text=True).stdout
 for b in out.split('"Kernel Name",')[1:]:

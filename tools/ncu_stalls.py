@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Warp-stall sampling per SASS line of one kernel of an ncu report taken with --import-source on.
 Usage: tools/ncu_stalls.py <report.ncu-rep> <kernel-name-substring> [top-n]"""
-import csv, subprocess, sys, io, collections
+import csv
+import subprocess
+import sys
 rep = sys.argv[1]; kern = sys.argv[2]; topn = int(sys.argv[3]) if len(sys.argv) > 3 else 25
 out = subprocess.run(["ncu","-i",rep,"--page","source","--csv","--print-kernel-base","function"],capture_output=True,text=True).stdout
 # split per kernel

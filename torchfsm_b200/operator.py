@@ -11,7 +11,7 @@ operator is lowered to a *fused step program* executed by the CUDA library throu
 """
 import ctypes
 import os
-from typing import Callable, List, Optional, Sequence, Union
+from typing import Callable, List, Optional, Sequence
 
 import torch
 

@@ -16,7 +16,6 @@ Two exchange paths use them (`OperatorLike.set_slab_decomposition(exchange=...)`
 `SymmetricMemoryPeers` is the CUDA provider: torch symmetric memory (NVLink peer mappings inside one NVSwitch
 domain, device-side signal barrier). PyTorch is plumbing here; the data path is this repo's kernels.
 """
-import torch
 
 
 class SymmetricMemoryPeers:
