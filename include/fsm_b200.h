@@ -155,7 +155,7 @@ int fsm_slab_peers(fsm_plan* plan, int exchange, const void* const* ptrs, int32_
  * touches the k=0 bin, which never feeds back. With a log attached, every nonlinear evaluation appends the
  * LOCAL sum of the per-sample zero modes (plan dtype, `capacity` entries, device memory owned by the caller;
  * a new call resets the position). One all-reduce of the log after the run gives the exact zero-mode correction
- * (torchfsm_b200.FusedStepper.ks_allreduce_correction) - no collective inside the step. */
+ * (torchfsm_b200.FusedStepper._step_half_ks_sharded, Operator.set_ensemble_group) - no collective inside the step. */
 int fsm_ks_log(fsm_plan* plan, void* log, int64_t capacity);
 
 /* per-pass device timing for benchmarks: when enabled every pass launch is bracketed by CUDA
