@@ -255,6 +255,9 @@ class FusedStepper:
                 nsub //= 2
             self.nsub = max(1, nsub)
             self._comm_stream = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
+            n_copy = int(os.environ.get("FSM_DMA_STREAMS", "1"))
+            self._copy_streams = [torch.cuda.Stream(self.device) for _ in range(n_copy)] \
+                if (n_copy > 1 and self.device.type == "cuda") else []
 
     def _local_slab(self, t):
         """(X, n1, nh, n0) rot-half table -> contiguous local ky slab when the grid is slab-decomposed."""
@@ -273,10 +276,25 @@ class FusedStepper:
             # engines (+ one local), then a device-side barrier; nothing here occupies an SM for long
             blk = count // self.P
             src = self._send[which]
+            fan = self._copy_streams if self.device.type == "cuda" else []
+            if fan:     # FSM_DMA_STREAMS > 1 (experiment): the block copies of one exchange on several streams
+                cur = torch.cuda.current_stream(self.device)
+                start = torch.cuda.Event()
+                start.record(cur)
             for i in range(self.P):
                 q = (self.rank + i) % self.P                 # stagger the destinations across ranks
-                self._remote[which][q][offset + self.rank * blk: offset + (self.rank + 1) * blk].copy_(
-                    src[offset + q * blk: offset + (q + 1) * blk], non_blocking=True)
+                dst = self._remote[which][q][offset + self.rank * blk: offset + (self.rank + 1) * blk]
+                if fan:
+                    side = fan[i % len(fan)]
+                    side.wait_event(start)
+                    with torch.cuda.stream(side):
+                        dst.copy_(src[offset + q * blk: offset + (q + 1) * blk], non_blocking=True)
+                else:
+                    dst.copy_(src[offset + q * blk: offset + (q + 1) * blk], non_blocking=True)
+            for side in fan[:self.P]:
+                done = torch.cuda.Event()
+                done.record(side)
+                cur.wait_event(done)
             self._peer.barrier(self._peer_idx[which])
             return _StreamWork(self.device) if async_op else None
         return dist.all_to_all_single(self._recv[which][offset:offset + count], self._send[which][offset:offset + count],
