@@ -198,3 +198,41 @@ def test_recorders_real_frames_equal_the_spectrum_protocol():
     spec_traj = op.integrate(u0, dt=spec["dt"], step=5, trajectory_recorder=rec, return_in_fourier=True)
     assert rec._real is False and spec_traj.is_complex()
     assert rel_l2(torch.fft.ifftn(spec_traj, dim=(-1, -2)).real.numpy(), want.numpy()) <= 1e-13
+
+
+@pytest.mark.parametrize("shape", [(8, 8), (16, 8), (8, 16), (64, 8), (8, 64), (256, 8), (8, 256), (512, 8), (8, 512),
+                                   (1024, 8), (8, 1024), (8, 128, 8), (8, 256, 8), (8, 512, 8), (512, 8, 8), (8, 8, 512)])
+def test_every_line_length_and_axis_role(shape):
+    """Each supported line length (8..1024) in each role (first axis = IX/FX, middle axis = MID, last axis = PHYS):
+    the plain transforms against torch.fft and one Burgers step against the numpy oracle. Guards the per-size FFT
+    decompositions and their compile-time index splits, including the sizes no fixture covers."""
+    import torchfsm_b200 as fsm
+    from oracle import OracleOperator
+    nd = len(shape)
+    mesh_info = [(0.0, 1.0 + 0.5 * i, n) for i, n in enumerate(shape)]
+    gen = torch.Generator().manual_seed(sum(shape))
+    u0 = torch.randn(2, nd, *shape, generator=gen, dtype=torch.float64)
+    dims = tuple(range(2, 2 + nd))
+    u_hat_full = torch.fft.fftn(u0, dim=dims)
+    for d, n in zip(dims, shape):                          # band-limit so that one step stays smooth
+        f = torch.fft.fftfreq(n, 1.0 / n).abs()
+        view = [1] * u0.dim()
+        view[d] = n
+        u_hat_full = u_hat_full * (f <= max(1, n // 4)).to(u_hat_full.dtype).reshape(view)
+    u0 = torch.fft.ifftn(u_hat_full, dim=dims).real.contiguous()
+    u0 = u0 / u0.abs().max()
+    terms = [("laplacian", 0.01, {}), ("convection", -1, {})]
+    op = product_operator(terms)
+    op.set_integrator(fsm.ETDRKIntegrator.ETDRK2)
+    mesh = fsm.MeshGrid(mesh_info, device="cpu", dtype=torch.float64)
+    dt = 1e-4
+    u1 = op.integrate(u0, mesh=mesh, dt=dt, step=1)
+    st = op._state_dict["integrator"]
+    u_hat = st.r2c(u0)
+    assert rel_l2(st.half_to_full(u_hat).numpy(), torch.fft.fftn(u0, dim=dims).numpy()) < 1e-13
+    assert rel_l2(st.c2r(u_hat).numpy(), u0.numpy()) < 1e-13
+    ora = OracleOperator(terms).register_mesh(mesh_info, nd, dtype="float64")
+    ora.set_integrator("ETDRK2")
+    integ = ora.build_integrator(dt)
+    want = ora.mesh.ifft(integ.step(ora.mesh.fft(u0.numpy()))).real
+    assert rel_l2(u1.numpy(), want) < 1e-12

@@ -187,3 +187,35 @@ def test_pure_diffusion_is_exact_on_gpu():
     uT = (nu * fsm.Laplacian()).integrate(u0, mesh=mesh, dt=dt, step=steps)
     want = np.exp(-nu * (2 * np.pi) ** 2 * 13 * dt * steps) * u0
     assert float((uT - want).abs().max()) < 1e-12
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.float64, 1e-12)])
+@pytest.mark.parametrize("shape", [(8, 256, 8), (256, 8, 8), (8, 8, 256), (8, 512, 8), (512, 8, 8), (8, 8, 512),
+                                   (512, 8), (8, 512), (256, 16), (16, 256)])
+def test_long_lines_in_every_axis_role_vs_oracle(shape, dtype, tol):
+    """The 256/512-point decompositions of C4/C5 (and their 2-D counterparts) in each role (x, middle, last
+    axis) on thin grids the oracle finishes instantly: transforms vs torch.fft, one Burgers ETDRK2 step vs the oracle."""
+    import torchfsm_b200 as fsm
+    from oracle import OracleOperator
+    nd = len(shape)
+    mesh_info = [(0.0, 1.0 + 0.5 * i, n) for i, n in enumerate(shape)]
+    u0 = _smooth((2, nd) + tuple(shape), torch.float64, seed=sum(shape)).to(dtype)
+    terms = [("laplacian", 0.01, {}), ("convection", -1, {})]
+    dt = 1e-4
+    ora = OracleOperator(terms).register_mesh(mesh_info, nd, dtype="float32" if dtype == torch.float32 else "float64")
+    ora.set_integrator("ETDRK2")
+    integ = ora.build_integrator(dt)
+    op = product_operator(terms)
+    op.set_integrator(fsm.ETDRKIntegrator.ETDRK2)
+    mesh = fsm.MeshGrid(mesh_info, device="cuda", dtype=dtype)
+    m, c = op._pre_check(u0.cuda(), None, mesh)
+    op.register_mesh(m, c)
+    tabs = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in integ.tables.items()}
+    st = op._build_integrator(dt, u0.shape[0], tables=tabs)
+    u_hat = st.r2c(u0.cuda())
+    dims = tuple(range(2, 2 + nd))
+    assert rel_l2(st.half_to_full(u_hat).cpu().numpy(), torch.fft.fftn(u0.double(), dim=dims).numpy()) <= tol
+    assert rel_l2(st.c2r(u_hat).cpu().numpy(), u0.numpy()) <= tol
+    got = st.c2r(st.step_half(u_hat, 1)).cpu().numpy()
+    want = ora.mesh.ifft(integ.step(ora.mesh.fft(u0.numpy()))).real
+    assert rel_l2(got, want) <= tol
