@@ -189,9 +189,24 @@ def test_pure_diffusion_is_exact_on_gpu():
     assert float((uT - want).abs().max()) < 1e-12
 
 
-@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.float64, 1e-12)])
-@pytest.mark.parametrize("shape", [(8, 256, 8), (256, 8, 8), (8, 8, 256), (8, 512, 8), (512, 8, 8), (8, 8, 512),
-                                   (512, 8), (8, 512), (256, 16), (16, 256)])
+_ROLE_SHAPES = [(8, 256, 8), (256, 8, 8), (8, 8, 256), (8, 512, 8), (512, 8, 8), (8, 8, 512),
+                (512, 8), (8, 512), (256, 16), (16, 256)]
+
+
+def test_fp64_shared_memory_limits_are_refused_up_front():
+    """fp64 line buffers of 1024-point lines (and of 512-point last-axis lines of 3-D convection) exceed an SM's
+    shared memory: the host layer says so instead of failing at launch."""
+    import torchfsm_b200 as fsm
+    for shape in [(1024, 16), (16, 1024), (8, 8, 512)]:
+        nd = len(shape)
+        mesh = fsm.MeshGrid([(0.0, 1.0, n) for n in shape], device="cuda", dtype=torch.float64)
+        u0 = torch.zeros((1, nd) + shape, dtype=torch.float64, device="cuda")
+        with pytest.raises(NotImplementedError):
+            fsm.pde.Burgers(0.01).integrate(u0, mesh=mesh, dt=1e-3, step=1)
+
+
+@pytest.mark.parametrize("shape,dtype,tol", [(s, torch.float32, 1e-5) for s in _ROLE_SHAPES] +
+                         [(s, torch.float64, 1e-12) for s in _ROLE_SHAPES if s != (8, 8, 512)])
 def test_long_lines_in_every_axis_role_vs_oracle(shape, dtype, tol):
     """The 256/512-point decompositions of C4/C5 (and their 2-D counterparts) in each role (x, middle, last
     axis) on thin grids the oracle finishes instantly: transforms vs torch.fft, one Burgers ETDRK2 step vs the oracle."""
