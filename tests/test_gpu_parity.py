@@ -234,3 +234,27 @@ def test_long_lines_in_every_axis_role_vs_oracle(shape, dtype, tol):
     got = st.c2r(st.step_half(u_hat, 1)).cpu().numpy()
     want = ora.mesh.ifft(integ.step(ora.mesh.fft(u0.numpy()))).real
     assert rel_l2(got, want) <= tol
+
+
+def test_full_run_drift_stays_small_on_gpu():
+    """North star: drift over the full run. C1 at full size and C3 bounded to 256^2 x 2, 200 steps each, product vs
+    oracle from the same state and tables. Chaotic growth is slow on these runs; the bound is generous on purpose."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import trajectory_drift as td
+    dev = torch.device("cuda", 0)
+    marks = [1, 50, 200]
+    x = (np.arange(128) / 128.0).astype(np.float32).reshape(1, 1, 128)
+    r1 = td.drift("C1", [(0.0, 1.0, 128)], lambda cv: [("laplacian", 0.01, {}), ("convection", -1, {})], "SETDRK4",
+                  0.01, 200, (np.sin(2 * np.pi * x) + 0.5).astype(np.float32), torch.float32, dev, marks)
+    assert max(r1["rel_l2_after_steps"].values()) <= 1e-4, r1
+    n = 256
+    ax = (np.arange(n) * (2 * np.pi / n)).astype(np.float32)
+    src = (4.0 * np.cos(4.0 * ax)).reshape(1, 1, 1, n).repeat(n, axis=2).astype(np.float32)
+    u0 = _smooth((2, 1, n, n), torch.float32, seed=3).numpy()
+    r3 = td.drift("C3 bounded", [(0, 2 * np.pi, n)] * 2,
+                  lambda cv: [("vorticity_convection", -1, {}), ("laplacian", 1 / 100, {}),
+                              ("implicit_unit_source", -0.1, {}), ("explicit_source", -1, {"source": cv(src)})],
+                  "ETDRK2", 0.01, 200, u0, torch.float32, dev, marks)
+    assert max(r3["rel_l2_after_steps"].values()) <= 1e-4, r3
