@@ -236,3 +236,15 @@ def test_every_line_length_and_axis_role(shape):
     integ = ora.build_integrator(dt)
     want = ora.mesh.ifft(integ.step(ora.mesh.fft(u0.numpy()))).real
     assert rel_l2(u1.numpy(), want) < 1e-12
+
+
+def test_operator_to_changes_the_working_precision():
+    """Operator.to(dtype=...) (operator/_base.py:792-803) re-registers the mesh: same operator, fp64 then fp32."""
+    g = load_golden("c3_ns2d_32_etdrk2_f64")
+    spec = g["spec"]
+    op, mesh, u0 = product_from_golden(g, "cpu")
+    u64 = op.integrate(u0, mesh=mesh, dt=spec["dt"], step=2)
+    op.to(dtype=torch.float32)
+    u32 = op.integrate(u0.float(), dt=spec["dt"], step=2)
+    assert u32.dtype == torch.float32 and rel_l2(u32.double().numpy(), u64.numpy()) < 1e-5
+    assert op._state_dict["integrator"].rdtype == torch.float32

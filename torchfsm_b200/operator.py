@@ -630,6 +630,14 @@ class OperatorLike:
         if self._state_dict.get("integrator") is not None:
             self._state_dict["integrator"].ks_group = group
 
+    def to(self, device=None, dtype=None):
+        """operator/_base.py:792-803: move the registered mesh (and with it every table) to another device / dtype;
+        the integrator is rebuilt on the next call."""
+        sd = self._state_dict
+        if sd is not None and sd.get("f_mesh") is not None:
+            self.register_mesh(FourierMesh(sd["f_mesh"], device=device, dtype=dtype), sd["n_channel"])
+        return self
+
     def set_chunk(self, chunk: int):
         """Samples per pass launch (0 = library default); a tuning knob of the CUDA path."""
         self._chunk = int(chunk)
