@@ -258,3 +258,119 @@ def test_full_run_drift_stays_small_on_gpu():
                               ("implicit_unit_source", -0.1, {}), ("explicit_source", -1, {"source": cv(src)})],
                   "ETDRK2", 0.01, 200, u0, torch.float32, dev, marks)
     assert max(r3["rel_l2_after_steps"].values()) <= 1e-4, r3
+
+
+# ---------------------------------------------------------------- round 2: the configs at size, per step, vs the oracle
+def _per_step_vs_oracle(mesh_info, terms, n_channel, integrator, dt, u0, steps, tol, device="cuda", workers=8):
+    """Product (CUDA library, oracle-built tables injected) against the oracle after EVERY step."""
+    import torchfsm_b200 as fsm
+    from oracle import OracleOperator
+    from product_util import integrator_enum
+    dtype = u0.dtype
+    ora = OracleOperator(_conv(terms, lambda t: t.numpy()))
+    ora.register_mesh(mesh_info, n_channel, dtype="float32" if dtype == torch.float32 else "float64", workers=workers)
+    ora.set_integrator(integrator)
+    integ = ora.build_integrator(dt)
+    op = product_operator(_conv(terms, lambda t: t.to(device)))
+    op.set_integrator(integrator_enum(integrator))
+    mesh = fsm.MeshGrid(mesh_info, device=device, dtype=dtype)
+    m, c = op._pre_check(u0.to(device), None, mesh)
+    op.register_mesh(m, c)
+    tabs = {k: torch.from_numpy(np.ascontiguousarray(v)).to(device) for k, v in integ.tables.items()}
+    st = op._build_integrator(dt, u0.shape[0], tables=tabs)
+    u_hat = st.r2c(u0.to(device))
+    ref_hat = ora.mesh.fft(u0.numpy())
+    errs = []
+    for step in range(steps):
+        u_hat = st.step_half(u_hat, 1)
+        ref_hat = integ.step(ref_hat)
+        errs.append(rel_l2(st.c2r(u_hat).cpu().numpy(), ora.mesh.ifft(ref_hat).real))
+        assert errs[-1] <= tol, f"step {step}: {errs}"
+    return errs
+
+
+def _taylor_green(n, dtype, amp=0.05):
+    ax = torch.arange(n, dtype=dtype) * (2 * np.pi / n)
+    x, y, z = ax.reshape(1, 1, n, 1, 1), ax.reshape(1, 1, 1, n, 1), ax.reshape(1, 1, 1, 1, n)
+    u = torch.cat([torch.sin(x) * torch.cos(y) * torch.cos(z), -torch.cos(x) * torch.sin(y) * torch.cos(z),
+                   torch.zeros(1, 1, n, n, n, dtype=dtype)], dim=1)
+    return u + amp * _smooth((1, 3, n, n, n), dtype, seed=5)
+
+
+@pytest.mark.parametrize("n", [64, 128])
+def test_c5_ns3d_setdrk4_vs_oracle(n):
+    """C5's program and integrator (NS velocity form with pressure projection, SETDRK4, 2/3 dealiasing) at 64^3 and
+    128^3: Taylor-Green + noise, three steps, each within 1e-5 of the oracle (_navier_stokes.py:231-254,
+    _setdrk_step.py:55-82)."""
+    terms = [("ns_pressure_convection", 1, {}), ("laplacian", 1 / 1600, {})]
+    _per_step_vs_oracle([(0, 2 * np.pi, n)] * 3, terms, 3, "SETDRK4", 0.01, _taylor_green(n, torch.float32), 3, 1e-5)
+
+
+def test_c5_ns3d_setdrk4_fp64_vs_oracle():
+    terms = [("ns_pressure_convection", 1, {}), ("laplacian", 1 / 1600, {})]
+    _per_step_vs_oracle([(0, 2 * np.pi, 64)] * 3, terms, 3, "SETDRK4", 0.01, _taylor_green(64, torch.float64), 3, 1e-12)
+
+
+def test_c4_burgers3d_setdrk4_vs_oracle():
+    """C4's program and integrator at 128^3 x 2 (the fixture-sized cases stop at 16^3)."""
+    terms = [("laplacian", 0.01, {}), ("convection", -1, {})]
+    u0 = _smooth((2, 3, 128, 128, 128), torch.float32, seed=11)
+    _per_step_vs_oracle([(0, 1, 128)] * 3, terms, 3, "SETDRK4", 0.002, u0, 3, 1e-5)
+
+
+def test_c2_ks2d_setdrk4_vs_oracle_at_size():
+    """C2 at its own grid (256^2, L = 60) with SETDRK4 and a batch of 8: per-step parity, including the batch mean
+    that couples the samples through the k = 0 bin (_ks_convection.py:34-36)."""
+    terms = [("laplacian", -1, {}), ("biharmonic", -1, {}), ("ks_convection", -1, {})]
+    u0 = torch.randn(8, 1, 256, 256, generator=torch.Generator().manual_seed(0))
+    _per_step_vs_oracle([(0, 60, 256)] * 2, terms, 1, "SETDRK4", 0.5, u0, 3, 1e-5)
+
+
+def test_plan_follows_the_tensor_device_not_the_current_device():
+    """A mesh on cuda:1 while cuda:0 is current: tables, kernels and results must live on cuda:1."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    g = load_golden("c3_ns2d_32_etdrk2_f32")
+    torch.cuda.set_device(0)
+    op, mesh, u0 = product_from_golden(g, "cuda:1")
+    uT = op.integrate(u0, mesh=mesh, dt=g["spec"]["dt"], step=g["spec"]["steps"])
+    assert uT.device == torch.device("cuda", 1) and torch.cuda.current_device() == 0
+    assert rel_l2(uT.cpu().numpy(), g["uT"]) <= 1e-5 * g["spec"]["steps"]
+
+
+def test_integrate_stream_equals_integrate():
+    """The pipelined host entry point (three streams, double-buffered staging) returns exactly what integrate() does."""
+    import torchfsm_b200 as fsm
+    n, B = 256, 4
+    mesh = fsm.MeshGrid([(0, 2 * np.pi, n)] * 2, device="cuda", dtype=torch.float32)
+    _, y = mesh.bc_mesh_grid()
+    op = fsm.pde.NavierStokesVorticity(Re=100, force=fsm.field.kolm_force(y))
+    op.set_integrator(fsm.ETDRKIntegrator.ETDRK2)
+    batches = [_smooth((B, 1, n, n), torch.float32, seed=s).pin_memory() for s in range(5)]
+    outs = op.integrate_stream(batches, dt=0.01, step=3, mesh=mesh)
+    torch.cuda.synchronize()
+    for b, o in zip(batches, outs):
+        want = op.integrate(b.cuda(), dt=0.01, step=3)
+        assert o.device.type == "cpu" and torch.equal(o, want.cpu())
+
+
+def test_recorders_and_solve_on_gpu():
+    """§8(f2)/(f4): physical frames straight from the C2R pass (AutoRecorder, CPURecorder) and LinearOperator.solve
+    on the CUDA library (traj_recorder.py:95-148, operator/_base.py:217-262)."""
+    import torchfsm_b200 as fsm
+    g = load_golden("c3_ns2d_32_etdrk2_f32")
+    op, mesh, u0 = product_from_golden(g, "cuda")
+    dt, steps = g["spec"]["dt"], g["spec"]["steps"]
+    final = op.integrate(u0, mesh=mesh, dt=dt, step=steps)
+    for rec in (fsm.AutoRecorder(), fsm.CPURecorder()):
+        traj = op.integrate(u0, dt=dt, step=steps, trajectory_recorder=rec)
+        assert traj.shape == (u0.shape[0], steps + 1) + tuple(u0.shape[1:])
+        assert float((traj[:, 0].to(u0.device) - u0).abs().max()) < 1e-5
+        assert float((traj[:, -1].to(u0.device) - final).abs().max()) < 1e-6
+    n = 64
+    mesh2 = fsm.MeshGrid([(0, 2 * np.pi, n)] * 2, device="cuda", dtype=torch.float64)
+    x, y = mesh2.bc_mesh_grid()
+    phi = torch.sin(3 * x) * torch.cos(2 * y)
+    rhs = -13.0 * phi                                           # lap(phi)
+    sol = fsm.Laplacian().solve(b=rhs, mesh=mesh2, n_channel=1)
+    assert float((sol - phi).abs().max()) < 1e-12

@@ -258,6 +258,16 @@ struct ProfScope {
 struct ProfScope { ProfScope(const fsm_plan*, int, cudaStream_t) {} };
 #endif
 
+// error of the launch just issued (the pass launches check theirs in the launch layer)
+int launch_status(const char* what) {
+#ifndef FSM_EMU
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(-EIO, "%s launch failed: %s", what, cudaGetErrorString(e));
+#endif
+    (void)what;
+    return 0;
+}
+
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
 
@@ -435,7 +445,7 @@ int run_stage(const fsm_plan* p, const Buffers<T>& bf, const Stage& s, cudaStrea
         const long total = (long)p->B * p->C * p->nmodes;
         auto kern = k_combine_only<T>;
         FSM_LAUNCH(kern, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, cb, p->nmodes, p->C, total);
-        return 0;
+        return launch_status("linear combine");
     }
     const Geom<T> g = make_geom<T>(p, false);
     const cplx<T>* stage_in = bf.arr[s.input];
@@ -492,6 +502,7 @@ int run_stage(const fsm_plan* p, const Buffers<T>& bf, const Stage& s, cudaStrea
         T* slot = nullptr;
         if (p->ks_log && p->ks_log_pos < p->ks_log_cap) slot = static_cast<T*>(p->ks_log) + p->ks_log_pos++;
         FSM_LAUNCH(kern, dim3(1), dim3(128), sizeof(T) * 2, st, cb, (const T*)bf.dc, p->B, p->nmodes, slot);
+        if (int e = launch_status("KS zero-mode fix")) return e;
     }
     return 0;
 }
@@ -1228,7 +1239,7 @@ int fsm_half_to_full(fsm_plan* plan, const void* u_hat, void* full_hat, void* st
         auto kern = k_half_to_full<float>;
         FSM_LAUNCH(kern, grid, block, 0, st, make_geom<float>(plan, true), (const cplx<float>*)u_hat, (cplx<float>*)full_hat, nf);
     }
-    return 0;
+    return launch_status("half_to_full");
 }
 
 int fsm_full_to_half(fsm_plan* plan, const void* full_hat, void* u_hat, void* stream) {
@@ -1244,7 +1255,7 @@ int fsm_full_to_half(fsm_plan* plan, const void* full_hat, void* u_hat, void* st
         auto kern = k_full_to_half<float>;
         FSM_LAUNCH(kern, grid, block, 0, st, make_geom<float>(plan, true), (const cplx<float>*)full_hat, (cplx<float>*)u_hat, nf);
     }
-    return 0;
+    return launch_status("full_to_half");
 }
 
 }  // extern "C"

@@ -28,8 +28,10 @@ class MeshGrid:
         return self.n_dim
 
     def __getitem__(self, i):
+        # mesh.py:56-62: coordinates start at 0 whatever `start` is (kept as the reference has it, so that forcing
+        # and initial conditions built from bc_mesh_grid() match for the same user script)
         a, b, n = self.mesh_info[i]
-        return a + (b - a) * torch.arange(0, n, device=self.device, dtype=self.dtype) / n
+        return (b - a) * torch.arange(0, n, device=self.device, dtype=self.dtype) / n
 
     x = property(lambda self: self[0])
     y = property(lambda self: self[1])
