@@ -143,14 +143,14 @@ struct Dft {
     static_assert(R == 4 || R == 8 || R == 16 || R == 32, "radix");
     static FSM_HD __forceinline__ void run(cplx<T>* a) {
         cplx<T> e[R / 2], o[R / 2];
-        static_for<0, R / 2>([&](auto kc) {
+        static_for<0, R / 2>([&](auto kc) FSM_INLINE_LAMBDA {
             constexpr int k = decltype(kc)::value;
             e[k] = a[2 * k];
             o[k] = a[2 * k + 1];
         });
         Dft<R / 2, DIR, T>::run(e);
         Dft<R / 2, DIR, T>::run(o);
-        static_for<0, R / 2>([&](auto kc) {
+        static_for<0, R / 2>([&](auto kc) FSM_INLINE_LAMBDA {
             constexpr int k = decltype(kc)::value;
             constexpr int j = k * (32 / R);  // W_R^k = W_32^j, 0 <= j < 16
             if constexpr (j == 0) {
@@ -182,6 +182,14 @@ struct Dft<1, DIR, T> {
 // ------------------------------------------------------------------------------------
 // FFT configuration: N = R0*R1*R2, every radix divides EPT, TL = N/EPT threads per line.
 // ------------------------------------------------------------------------------------
+// Stage twiddles W^(j*t), t = 1..R-1: with FSM_TW_RECUR only the t = 1 row is stored and read (one LDS per
+// butterfly group); the other rows are its powers, formed in registers by repeated multiplication
+// p[t] = p[t/2] * p[t - t/2] (depth <= log2 R, a few 1e-8 of extra rounding in fp32). The passes are bound by the
+// shared-memory pipe (ncu: 41-70 % of the wavefront peak with 28 twiddle LDS per 1024-point transform), and the
+// packed-FMA pipe has room.
+#ifndef FSM_TW_RECUR
+#define FSM_TW_RECUR 1
+#endif
 template <int N_, int EPT_, int R0_, int R1_ = 1, int R2_ = 1>
 struct FftCfg {
     static constexpr int N = N_, EPT = EPT_, TL = N_ / EPT_;
@@ -201,9 +209,12 @@ struct FftCfg {
     // read "column-wise" by consecutive lanes (transposed stores) hit distinct banks.
     static constexpr int RAWLEN = N_ + (N_ >> PADSHIFT) + 1;
     static constexpr int LINE_PITCH = RAWLEN + ((2 - RAWLEN % 16) + 16) % 16;
-    // twiddle tables (complex entries): stage 1 uses (R1-1)*R0, stage 2 uses (R2-1)*R0*R1
-    static constexpr int TW1 = (R1_ > 1) ? (R1_ - 1) * R0_ : 0;
-    static constexpr int TW2 = (R2_ > 1) ? (R2_ - 1) * R0_ * R1_ : 0;
+    // twiddle tables (complex entries): stage 1 uses (R1-1)*R0, stage 2 uses (R2-1)*R0*R1 -- or only their
+    // first rows (R0, R0*R1 entries) when the other rows are formed by recurrence
+    static constexpr bool RECUR = (FSM_TW_RECUR != 0);
+    static constexpr int TWROWS1 = RECUR ? 1 : (R1_ - 1), TWROWS2 = RECUR ? 1 : (R2_ - 1);
+    static constexpr int TW1 = (R1_ > 1) ? TWROWS1 * R0_ : 0;
+    static constexpr int TW2 = (R2_ > 1) ? TWROWS2 * R0_ * R1_ : 0;
     static constexpr int TW_TOTAL = TW1 + TW2;
 };
 
@@ -220,6 +231,16 @@ struct LineSync {
     }
 };
 
+// p[t] = b^t for t = 1..R-1 (p[0] unused)
+template <int R, typename T>
+FSM_HD __forceinline__ void twiddle_powers(cplx<T> b, cplx<T>* p) {
+    p[1] = b;
+    static_for<2, R>([&](auto tc) FSM_INLINE_LAMBDA {
+        constexpr int t = decltype(tc)::value;
+        p[t] = cmul(p[t >> 1], p[t - (t >> 1)]);
+    });
+}
+
 // ---- building blocks -----------------------------------------------------------------------
 // line_fft_head: all stages but the last. On exit the input of the last stage sits in `buf`
 // (padded layout); the caller synchronises before the last stage reads it.
@@ -230,16 +251,16 @@ __device__ __forceinline__ void line_fft_head(cplx<T>* v, cplx<T>* buf, const cp
     constexpr int R0 = Cfg::R0, R1 = Cfg::R1;
     static_assert(Cfg::NST >= 2, "head/last split needs at least two stages");
     // ---- stage 0: Ns = 1, no twiddles
-    static_for<0, EPT / R0>([&](auto qc) {
+    static_for<0, EPT / R0>([&](auto qc) FSM_INLINE_LAMBDA {
         constexpr int q = decltype(qc)::value;
         cplx<T> a[R0];
-        static_for<0, R0>([&](auto tc) {
+        static_for<0, R0>([&](auto tc) FSM_INLINE_LAMBDA {
             constexpr int t = decltype(tc)::value;
             a[t] = v[q + t * (EPT / R0)];
         });
         Dft<R0, DIR, T>::run(a);
         const int w = tau + q * TL;
-        static_for<0, R0>([&](auto tc) {
+        static_for<0, R0>([&](auto tc) FSM_INLINE_LAMBDA {
             constexpr int t = decltype(tc)::value;
             buf[Cfg::pad(w * R0 + t)] = a[t];
         });
@@ -250,10 +271,10 @@ __device__ __forceinline__ void line_fft_head(cplx<T>* v, cplx<T>* buf, const cp
         constexpr int Ns = R0;
         constexpr bool kAffLd = ((N / R1) % Cfg::TLG == 0);
         const cplx<T>* ldb = buf + Cfg::pad(tau);
-        static_for<0, EPT / R1>([&](auto qc) {
+        static_for<0, EPT / R1>([&](auto qc) FSM_INLINE_LAMBDA {
             constexpr int q = decltype(qc)::value;
             const int w = tau + q * TL;
-            static_for<0, R1>([&](auto tc) {
+            static_for<0, R1>([&](auto tc) FSM_INLINE_LAMBDA {
                 constexpr int t = decltype(tc)::value;
                 if constexpr (kAffLd) v[q * R1 + t] = ldb[Cfg::pad(q * TL + t * (N / R1))];
                 else v[q * R1 + t] = buf[Cfg::pad(w + t * (N / R1))];
@@ -265,20 +286,25 @@ __device__ __forceinline__ void line_fft_head(cplx<T>* v, cplx<T>* buf, const cp
                                 ((TL * R1) % Cfg::PADG == 0);
         const int jt = tau & (Ns - 1);
         cplx<T>* stb = buf + Cfg::pad((tau / Ns) * Ns * R1 + jt);
-        static_for<0, EPT / R1>([&](auto qc) {
+        cplx<T> pw[R1];   // twiddle row of this thread (same for every q when the split is affine)
+        if constexpr (Cfg::RECUR && kAffSt) twiddle_powers<R1, T>(tw[jt], pw);
+        static_for<0, EPT / R1>([&](auto qc) FSM_INLINE_LAMBDA {
             constexpr int q = decltype(qc)::value;
             const int w = tau + q * TL;
             const int j = kAffSt ? jt : (w & (Ns - 1));
+            if constexpr (Cfg::RECUR && !kAffSt) twiddle_powers<R1, T>(tw[j], pw);
             cplx<T> a[R1];
             a[0] = v[q * R1];
-            static_for<1, R1>([&](auto tc) {
+            static_for<1, R1>([&](auto tc) FSM_INLINE_LAMBDA {
                 constexpr int t = decltype(tc)::value;
-                const cplx<T> wv = tw[(t - 1) * Ns + j];
+                cplx<T> wv;
+                if constexpr (Cfg::RECUR) wv = pw[t];
+                else wv = tw[(t - 1) * Ns + j];
                 a[t] = (DIR < 0) ? cmul(v[q * R1 + t], wv) : cmulc(v[q * R1 + t], wv);
             });
             Dft<R1, DIR, T>::run(a);
             const int base = (w / Ns) * Ns * R1 + j;
-            static_for<0, R1>([&](auto tc) {
+            static_for<0, R1>([&](auto tc) FSM_INLINE_LAMBDA {
                 constexpr int t = decltype(tc)::value;
                 if constexpr (kAffSt) stb[Cfg::pad(q * TL * R1 + t * Ns)] = a[t];
                 else buf[Cfg::pad(base + t * Ns)] = a[t];
@@ -304,12 +330,16 @@ __device__ __forceinline__ void fft_last_item(const cplx<T>* buf, const cplx<T>*
     const cplx<T>* ldb = buf + Cfg::pad(wt);
     if constexpr (kAff) a[0] = ldb[Cfg::pad(WC)];
     else a[0] = buf[Cfg::pad(w)];
-    static_for<1, RL>([&](auto tc) {
+    cplx<T> pw[RL];
+    if constexpr (Cfg::RECUR) twiddle_powers<RL, T>(twl[WC], pw);
+    static_for<1, RL>([&](auto tc) FSM_INLINE_LAMBDA {
         constexpr int t = decltype(tc)::value;
         cplx<T> x;
         if constexpr (kAff) x = ldb[Cfg::pad(WC + t * NS)];
         else x = buf[Cfg::pad(w + t * NS)];
-        const cplx<T> wv = twl[(t - 1) * NS + WC];
+        cplx<T> wv;
+        if constexpr (Cfg::RECUR) wv = pw[t];
+        else wv = twl[(t - 1) * NS + WC];
         a[t] = (DIR < 0) ? cmul(x, wv) : cmulc(x, wv);
     });
     Dft<RL, DIR, T>::run(a);
@@ -329,16 +359,16 @@ __device__ __forceinline__ void line_fft(cplx<T>* v, cplx<T>* buf, const cplx<T>
         line_fft_head<Cfg, DIR, T>(v, buf, tw, tau, sync);
         sync();
         cplx<T> out[EPT];
-        static_for<0, EPT / RL>([&](auto qc) {
+        static_for<0, EPT / RL>([&](auto qc) FSM_INLINE_LAMBDA {
             constexpr int q = decltype(qc)::value;
             cplx<T> a[RL];
             fft_last_item<Cfg, DIR, T, q * TL>(buf, tw, tau, a);
-            static_for<0, RL>([&](auto tc) {
+            static_for<0, RL>([&](auto tc) FSM_INLINE_LAMBDA {
                 constexpr int t = decltype(tc)::value;
                 out[q + t * (EPT / RL)] = a[t];
             });
         });
-        static_for<0, EPT>([&](auto mc) {
+        static_for<0, EPT>([&](auto mc) FSM_INLINE_LAMBDA {
             constexpr int m = decltype(mc)::value;
             v[m] = out[m];
         });
@@ -351,7 +381,7 @@ inline void fill_twiddles(cplx<T>* tw) {
     const double two_pi = 6.283185307179586476925286766559;
     if (Cfg::R1 > 1) {
         const int Ns = Cfg::R0;
-        for (int t = 1; t < Cfg::R1; ++t)
+        for (int t = 1; t <= Cfg::TWROWS1; ++t)
             for (int j = 0; j < Ns; ++j) {
                 double ang = -two_pi * (double)(j * t) / (double)(Ns * Cfg::R1);
                 tw[(t - 1) * Ns + j] = mk<T>((T)__builtin_cos(ang), (T)__builtin_sin(ang));
@@ -360,7 +390,7 @@ inline void fill_twiddles(cplx<T>* tw) {
     if (Cfg::R2 > 1) {
         const int Ns = Cfg::R0 * Cfg::R1;
         cplx<T>* tw2 = tw + Cfg::TW1;
-        for (int t = 1; t < Cfg::R2; ++t)
+        for (int t = 1; t <= Cfg::TWROWS2; ++t)
             for (int j = 0; j < Ns; ++j) {
                 double ang = -two_pi * (double)(j * t) / (double)(Ns * Cfg::R2);
                 tw2[(t - 1) * Ns + j] = mk<T>((T)__builtin_cos(ang), (T)__builtin_sin(ang));

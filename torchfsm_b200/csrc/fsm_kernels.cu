@@ -125,8 +125,27 @@ static int launch_phys_p(const PhysArgs<T>& a, cudaStream_t s) {
                a.in_t_stride, a.in_o_stride, a.out_o_stride, a.out_e_stride, a.n_t, 1);
     return check_launch();
 }
+#ifndef FSM_PHYSZ
+#define FSM_PHYSZ 1   // Z-line programs run the phase-overlapping last-axis kernel (k_pass_physz)
+#endif
+template <typename T, int N, int PROG>
+static int launch_physz_p(const PhysArgs<T>& a, cudaStream_t s) {
+    using Cfg = typename CfgFor<N>::type;
+    using Z = PhysZ<Cfg>;
+    auto kern = k_pass_physz<T, Cfg, PROG>;
+    const size_t smem = Z::smem_bytes(sizeof(cplx<T>));
+    if (int e = set_smem(kern, smem)) return e;
+    dim3 grid((a.n_t + Z::K - 1) / Z::K, 1, a.nb), block(Z::NT);
+    FSM_LAUNCH(kern, grid, block, smem, s, a.g, a.win, a.wout, a.win_fstride, a.wout_fstride, a.in_t_stride, a.out_e_stride,
+               a.n_t);
+    return check_launch();
+}
 template <typename T, int N>
 static int launch_phys(int prog, int ndim, const PhysArgs<T>& a, cudaStream_t s) {
+    if (FSM_PHYSZ && ndim == 2 && a.n_outer == 1) {
+        if (prog == PROG_NS2D) return launch_physz_p<T, N, PROG_NS2D>(a, s);
+        if (prog == PROG_KS2D) return launch_physz_p<T, N, PROG_KS2D>(a, s);
+    }
     if (prog == PROG_C2R) return launch_phys_p<T, N, PROG_C2R, 2>(a, s);
     if (prog == PROG_R2C) return launch_phys_p<T, N, PROG_R2C, 2>(a, s);
     if (ndim == 2) {
@@ -170,21 +189,6 @@ static int launch_fx(int C, const FxArgs<T>& a, cudaStream_t s) {
     return -ENOSYS;
 }
 
-template <typename T, int N>
-static int launch_fxix_ns2d(const FxIxArgs<T>& a, cudaStream_t s) {
-    using Cfg = typename CfgFor<N>::type;
-    if constexpr (Cfg::NST < 2) {
-        return -ENOSYS;
-    } else {
-        auto kern = k_pass_fxix_ns2d<T, Cfg>;
-        const size_t smem = Smem<Cfg, T>::bytes(2 * kKL);
-        if (int e = set_smem(kern, smem)) return e;
-        dim3 grid((a.fx.nlines + kKL - 1) / kKL, 1, a.fx.nb), block(kKL * Cfg::TL);
-        FSM_LAUNCH(kern, grid, block, smem, s, a.fx.g, a.fx.win, a.fx.win_fstride, a.fx.cb, a.fx.ep, a.fx.nlines, a.fx.b0,
-                   a.w1, a.w1_fstride, a.out_e_stride, a.n_keep, a.do_ix);
-        return check_launch();
-    }
-}
 template <typename T, int N>
 static int launch_step1d(const Step1dArgs<T>& a, cudaStream_t s) {
     using Cfg = typename CfgFor<N>::type;
@@ -246,14 +250,14 @@ template <typename T, int N> static int prepare_tables() { return 0; }
 #define FSM_CAT(a, b) FSM_CAT2(a, b)
 const LaunchTable<float>* FSM_CAT(table_f32_, FSM_N)() {
     static const LaunchTable<float> t = {FSM_N, launch_ix<float, FSM_N>, launch_mid<float, FSM_N>,
-                                         launch_phys<float, FSM_N>, launch_fx<float, FSM_N>, launch_fxix_ns2d<float, FSM_N>,
+                                         launch_phys<float, FSM_N>, launch_fx<float, FSM_N>,
                                          launch_step1d<float, FSM_N>, launch_line1d<float, FSM_N>,
                                          prepare_tables<float, FSM_N>};
     return &t;
 }
 const LaunchTable<double>* FSM_CAT(table_f64_, FSM_N)() {
     static const LaunchTable<double> t = {FSM_N, launch_ix<double, FSM_N>, launch_mid<double, FSM_N>,
-                                          launch_phys<double, FSM_N>, launch_fx<double, FSM_N>, launch_fxix_ns2d<double, FSM_N>,
+                                          launch_phys<double, FSM_N>, launch_fx<double, FSM_N>,
                                           launch_step1d<double, FSM_N>, launch_line1d<double, FSM_N>,
                                           prepare_tables<double, FSM_N>};
     return &t;

@@ -49,14 +49,6 @@ struct FxArgs {
 };
 
 template <typename T>
-struct FxIxArgs {
-    FxArgs<T> fx;
-    cplx<T>* w1;
-    long w1_fstride, out_e_stride;
-    int n_keep, do_ix;
-};
-
-template <typename T>
 struct Step1dArgs {
     Geom<T> g;
     StageList<T> sl;
@@ -72,7 +64,6 @@ struct LaunchTable {
     int (*mid)(int dir, const MidArgs<T>&, cudaStream_t);
     int (*phys)(int prog, int ndim, const PhysArgs<T>&, cudaStream_t);
     int (*fx)(int C, const FxArgs<T>&, cudaStream_t);
-    int (*fxix_ns2d)(const FxIxArgs<T>&, cudaStream_t);
     int (*step1d)(const Step1dArgs<T>&, cudaStream_t);
     int (*line1d)(int mode, const void* in, void* out, long nfields, cudaStream_t);
     int (*prepare)();   // once per device: fill the static twiddle tables of this line length (synchronous)

@@ -258,12 +258,12 @@ __device__ __forceinline__ void rotated_last_stage(const cplx<T>* bufs, const cp
     constexpr int RL = LastStage<Cfg>::RL, NS = LastStage<Cfg>::NS;
     const int t = threadIdx.x % kKL, widx = threadIdx.x / kKL;
     const cplx<T>* buf = bufs + t * Cfg::LINE_PITCH;
-    static_for<0, Cfg::EPT / RL>([&](auto qc) {
+    static_for<0, Cfg::EPT / RL>([&](auto qc) FSM_INLINE_LAMBDA {
         constexpr int q = decltype(qc)::value;
         const int w = widx + q * Cfg::TL;
         cplx<T> a[RL];
         fft_last_item<Cfg, DIR, T, q * Cfg::TL>(buf, tw, widx, a);
-        static_for<0, RL>([&](auto tc) {
+        static_for<0, RL>([&](auto tc) FSM_INLINE_LAMBDA {
             constexpr int tp = decltype(tc)::value;
             emit(w + tp * NS, a[tp]);
         });
@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
         twiddles_ready();   // the line is in flight; now wait for the twiddle copy
         FSM_UNROLL
         for (int m = 0; m < EPT; ++m) u[m] = cscale(u[m], g.inv_ntot);
-        static_for<0, 2 * NPAIR>([&](auto fc) {
+        static_for<0, 2 * NPAIR>([&](auto fc) FSM_INLINE_LAMBDA {
             constexpr int f = decltype(fc)::value;
             cplx<T> v[EPT];
             FSM_UNROLL
@@ -407,14 +407,14 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
                 cplx<T>* dm = w1 + (bc * NPAIR + pair) * w1_fstride + (n1 - tg);
                 FSM_PIN(dp);
                 FSM_PIN(dm);
-                static_for<0, EPT / RL>([&](auto qc) {
+                static_for<0, EPT / RL>([&](auto qc) FSM_INLINE_LAMBDA {
                     constexpr int q = decltype(qc)::value;
                     const int w = widx + q * TL;
                     cplx<T> a[RL], b[RL];
                     fft_last_item<Cfg, +1, T, q * TL>(s0, tw, widx, a);
                     fft_last_item<Cfg, +1, T, q * TL>(s1, tw, widx, b);
                     if (valid) {
-                        static_for<0, RL>([&](auto tc) {
+                        static_for<0, RL>([&](auto tc) FSM_INLINE_LAMBDA {
                             constexpr int tp = decltype(tc)::value;
                             const int off = (w + tp * NS) * (int)out_e_stride;   // inside one field: fits 32 bits
                             cplx<T> zp, zm;
@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
     FSM_UNROLL
     for (int m = 0; m < EPT; ++m) u[m] = cscale(u[m], g.inv_ntot);
 
-    static_for<0, NF>([&](auto fc) {
+    static_for<0, NF>([&](auto fc) FSM_INLINE_LAMBDA {
         constexpr int f = decltype(fc)::value;
         cplx<T> v[EPT];
         FSM_UNROLL
@@ -468,16 +468,16 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
         const bool valid = (int)(threadIdx.x % kKL) < k_valid;
         if (eb.shift >= 30) {   // one GPU: plain strided store, 32-bit index inside the field
             const int es = (int)out_e_stride;
-            rotated_last_stage<Cfg, +1, T>(pbufs, tw, [&](int e, cplx<T> val) {
+            rotated_last_stage<Cfg, +1, T>(pbufs, tw, [&](int e, cplx<T> val) FSM_INLINE_LAMBDA {
                 if (valid) dst[e * es] = val;
             });
         } else if (pe.n > 0) {  // direct exchange: the x-slab owner's receive buffer
             const long off0 = dst - w1;
-            rotated_last_stage<Cfg, +1, T>(pbufs, tw, [&](int e, cplx<T> val) {
+            rotated_last_stage<Cfg, +1, T>(pbufs, tw, [&](int e, cplx<T> val) FSM_INLINE_LAMBDA {
                 if (valid) *peer_ptr<T>(pe, eb, e, off0, out_e_stride) = val;
             });
         } else {
-            rotated_last_stage<Cfg, +1, T>(pbufs, tw, [&](int e, cplx<T> val) {
+            rotated_last_stage<Cfg, +1, T>(pbufs, tw, [&](int e, cplx<T> val) FSM_INLINE_LAMBDA {
                 if (valid) dst[blk_off(e, eb, out_e_stride)] = val;
             });
         }
@@ -524,7 +524,7 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
         const int p = tau + m * TL;
         if (line_ok && (DIR < 0 || iabs(signed_mode<N>(p)) <= g.kmax[1])) keepmask |= 1u << m;
     }
-    auto load_line = [&](int j, cplx<T>* raw) {
+    auto load_line = [&](int j, cplx<T>* raw) FSM_INLINE_LAMBDA {
         const cplx<T>* src = in + (b * nfi + spec.src[j]) * in_fstride + (long)(line_ok ? t : 0) * in_t_stride + (long)o * in_o_stride;
         if (one_block) {
             src += tau;
@@ -553,16 +553,16 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
         const bool valid = (int)(threadIdx.x % kKL) < k_valid;
         if (eb.shift >= 30) {
             const int es = (int)out_e_stride;
-            rotated_last_stage<Cfg, DIR, T>(pbufs, tw, [&](int e, cplx<T> val) {
+            rotated_last_stage<Cfg, DIR, T>(pbufs, tw, [&](int e, cplx<T> val) FSM_INLINE_LAMBDA {
                 if (valid) dst[e * es] = val;
             });
         } else if (pe.n > 0) {  // direct exchange: the ky-slab owner's receive buffer
             const long off0 = dst - out;
-            rotated_last_stage<Cfg, DIR, T>(pbufs, tw, [&](int e, cplx<T> val) {
+            rotated_last_stage<Cfg, DIR, T>(pbufs, tw, [&](int e, cplx<T> val) FSM_INLINE_LAMBDA {
                 if (valid) *peer_ptr<T>(pe, eb, e, off0, out_e_stride) = val;
             });
         } else {
-            rotated_last_stage<Cfg, DIR, T>(pbufs, tw, [&](int e, cplx<T> val) {
+            rotated_last_stage<Cfg, DIR, T>(pbufs, tw, [&](int e, cplx<T> val) FSM_INLINE_LAMBDA {
                 if (valid) dst[blk_off(e, eb, out_e_stride)] = val;
             });
         }
@@ -606,7 +606,7 @@ __device__ __forceinline__ void pair_load_raw(cplx<T>* A, cplx<T>* B, const cplx
     const cplx<T>* blo = (b ? b : a) + tau;
     const cplx<T>* bhi = (b ? b : a) + (N - tau);
     FSM_PIN(alo); FSM_PIN(ahi); FSM_PIN(blo); FSM_PIN(bhi);   // (never dereferenced for a row beyond the end)
-    static_for<0, EPT>([&](auto mc) {
+    static_for<0, EPT>([&](auto mc) FSM_INLINE_LAMBDA {
         constexpr int m = decltype(mc)::value;
         constexpr bool mirrored = (2 * m * TL >= N);
         const int p = tau + m * TL;
@@ -625,7 +625,7 @@ template <typename T, class Cfg>
 __device__ __forceinline__ void pair_combine(cplx<T>* v, const cplx<T>* Ar, const cplx<T>* Br, bool da, bool db, const T* dk,
                                              int tau, int kmax) {
     constexpr int N = Cfg::N, EPT = Cfg::EPT, TL = Cfg::TL;
-    static_for<0, EPT>([&](auto mc) {
+    static_for<0, EPT>([&](auto mc) FSM_INLINE_LAMBDA {
         constexpr int m = decltype(mc)::value;
         constexpr bool mirrored = (2 * m * TL >= N);          // p >= N/2 for every tau (p == N/2 only if tau == 0)
         const int p = tau + m * TL;
@@ -699,7 +699,7 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
     twiddles_begin<Cfg, T>(tw);
     if (g.pf & PF_TW_EARLY) twiddles_ready();
     bool tw_pending = true;   // resolved at compile time: the code below is straight-line
-    auto tw_ready_once = [&]() {
+    auto tw_ready_once = [&]() FSM_INLINE_LAMBDA {
         if (tw_pending) { twiddles_ready(); tw_pending = false; }
     };
     const int t0 = blockIdx.x * K;
@@ -723,13 +723,13 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
     (void)rawA; (void)rawB;
     T acc[(NOUT > 0 ? NOUT : 1)][EPT];
     (void)keep2;
-    static_for<0, RPT>([&](auto rc) {
+    static_for<0, RPT>([&](auto rc) FSM_INLINE_LAMBDA {
         constexpr int r = decltype(rc)::value;
         const int row = t0 + lt * RPT + r;
         const bool row_ok = row < n_t;
         const long roff = (long)row * in_t_stride;
         cplx<T> v[EPT];
-        auto inverse_pair = [&](int fa, int fb, bool da, bool db) {
+        auto inverse_pair = [&](int fa, int fb, bool da, bool db) FSM_INLINE_LAMBDA {
             const cplx<T>* pa = (fa >= 0) ? wb + fa * win_fstride + roff : nullptr;
             const cplx<T>* pb = (fb >= 0) ? wb + fb * win_fstride + roff : nullptr;
             pair_fill<T, Cfg>(v, pa, pb, da, db, dkl, tau, kmaxl, row_ok);
@@ -740,7 +740,7 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
         if constexpr (PROG == PROG_NS2D || PROG == PROG_KS2D) {
             // Z-lines written by IX: NS2D field 0 = u_x + i d_x w, field 1 = u_y + i d_y w; KS2D field 0 =
             // phi_x + i phi_y (full complex rows)
-            auto inverse_z = [&](int f) {
+            auto inverse_z = [&](int f) FSM_INLINE_LAMBDA {
                 const cplx<T>* z = wb + f * win_fstride + (row_ok ? roff : 0) + tau;
                 FSM_PIN(z);
                 const unsigned km = row_ok ? keepmask : 0u;
@@ -796,7 +796,7 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
             if constexpr (r == 0) pair_load_raw<T, Cfg>(rawA, rawB, wb + FA[0] * win_fstride + roff, wb + FB[0] * win_fstride + roff,
                                                         tau, kmaxl, row_ok);
             tw_ready_once();
-            static_for<0, 6>([&](auto ic) {
+            static_for<0, 6>([&](auto ic) FSM_INLINE_LAMBDA {
                 constexpr int i = decltype(ic)::value;
                 pair_combine<T, Cfg>(v, rawA, rawB, DA[i], DB[i], dkl, tau, kmaxl);
                 if constexpr (i + 1 < 6) {
@@ -930,9 +930,9 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
         const cplx<T>* st0 = bufs + NL * Cfg::LINE_PITCH;
         constexpr int NLc = kKL;
         const int es = (int)out_e_stride;   // offsets inside one field fit 32 bits
-        auto emit = [&](int l, int k, int kn) {
+        auto emit = [&](int l, int k, int kn) FSM_INLINE_LAMBDA {
             const cplx<T>* sl = st0 + l * NFW * Cfg::LINE_PITCH;
-            auto split = [&](const cplx<T>* line, cplx<T>& s0, cplx<T>& s1) {
+            auto split = [&](const cplx<T>* line, cplx<T>& s0, cplx<T>& s1) FSM_INLINE_LAMBDA {
                 const cplx<T> zk = line[k], zn = line[kn];
                 s0 = mk<T>(T(0.5) * (zk.x + zn.x), T(0.5) * (zk.y - zn.y));
                 s1 = mk<T>(T(0.5) * (zk.y + zn.y), T(0.5) * (zn.x - zk.x));
@@ -964,7 +964,7 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
         };
         {
             const int l = threadIdx.x % NLc, k0 = threadIdx.x / NLc;   // k0 < TL
-            static_for<0, EPT / 2>([&](auto itc) {
+            static_for<0, EPT / 2>([&](auto itc) FSM_INLINE_LAMBDA {
                 constexpr int it = decltype(itc)::value;
                 const int k = k0 + it * TL;
                 if constexpr (it == 0) emit(l, k, (k == 0) ? 0 : N - k);
@@ -973,6 +973,168 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
             if (threadIdx.x < NLc) emit(threadIdx.x, N / 2, N / 2);
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// Pass PHYS-Z: last-axis pass of the Z-line programs (NS2D, KS2D), organised for phase overlap and for the
+// shared-memory pipe (ncu, round 1: the generic kernel above ran "DRAM phase + shared-memory phase" back to
+// back in the ONE 512-thread CTA an SM could hold -- 152 us + 225 us of the 388 us it took on C3).
+//   * NLZ thread-lines per CTA, each taking FOUR rows -> at 1024 points 256 threads and 86 KB of shared memory
+//     per CTA: two independent CTAs per SM whose load / transform / store phases interleave;
+//   * rows (4 lt + 2h, 4 lt + 2h + 1) ride as one packed forward transform whose head lands in head buffer
+//     2 lt + h; the LAST stage of all 2 NLZ heads runs in the rotated distribution (lanes across buffers), each
+//     thread taking the work items j and NS - j so that Z(k) and Z(N - k) meet in registers: the split
+//     S0 = (Z(k) + conj Z(N-k))/2, S1 = (Z(k) - conj Z(N-k))/2i needs no staging line, and the two rows of a
+//     buffer leave as ONE 16-byte store, 128-byte segments per k across the lanes.
+// ------------------------------------------------------------------------------------------
+template <class Cfg>
+struct PhysZ {
+    static constexpr int NLZ = (Cfg::TL <= 16) ? 8 : 4;     // thread-lines per CTA
+    static constexpr int KS = 2 * NLZ;                      // head buffers = rotated lanes
+    static constexpr int NT = NLZ * Cfg::TL;
+    static constexpr int K = 4 * NLZ;                       // rows per CTA
+    static constexpr bool PARK = (Cfg::EPT >= 16);          // product of the even row waits in shared memory
+    static constexpr int PARK_PITCH = Cfg::N / 2;           // complex slots per thread-line
+    static size_t smem_bytes(size_t elem) {
+        return elem * (size_t)(((Cfg::TW_TOTAL + 1) & ~1) + KS * Cfg::LINE_PITCH + (PARK ? NLZ * PARK_PITCH : 0));
+    }
+};
+
+template <typename T>
+__device__ __forceinline__ void store_pair(cplx<T>* dst, cplx<T> a, cplx<T> b) {
+    dst[0] = a;
+    dst[1] = b;
+}
+#if defined(__CUDACC__) && !defined(FSM_EMU)
+__device__ __forceinline__ void store_pair(cplx<float>* dst, cplx<float> a, cplx<float> b) {
+    *reinterpret_cast<float4*>(dst) = make_float4(a.x, a.y, b.x, b.y);   // dst is 16-byte aligned (even row)
+}
+#endif
+
+template <typename T, class Cfg, int PROG>
+__global__ void __launch_bounds__(PhysZ<Cfg>::NT, FSM_MINB(PhysZ<Cfg>::NT))
+k_pass_physz(Geom<T> g, const cplx<T>* __restrict__ win, cplx<T>* __restrict__ wout, long win_fstride, long wout_fstride,
+             long in_t_stride, long out_e_stride, int n_t) {
+    static_assert(PROG == PROG_NS2D || PROG == PROG_KS2D, "Z-line programs only");
+    constexpr int N = Cfg::N, EPT = Cfg::EPT, TL = Cfg::TL;
+    using Z = PhysZ<Cfg>;
+    constexpr int NLZ = Z::NLZ, KS = Z::KS, K = Z::K;
+    constexpr int NFI = (PROG == PROG_NS2D) ? 2 : 1;
+    constexpr int RL = LastStage<Cfg>::RL, NS = LastStage<Cfg>::NS;
+    static_assert(Cfg::NST >= 2 && TL % 2 == 0 && (NS / 2) % (TL / 2) == 0, "rotated paired last stage");
+    FSM_DYN_SMEM(smem_raw);
+    cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);
+    cplx<T>* hb = tw + Smem<Cfg, T>::TWPAD;
+    const int lt = threadIdx.x / TL, tau = threadIdx.x % TL;
+    twiddles_begin<Cfg, T>(tw);
+    const int t0 = blockIdx.x * K;
+    const long b = blockIdx.z;
+    const int kmaxl = g.kmax[1];
+    LineSync<TL> sync{1 + lt};
+    cplx<T>* bufB = hb + (2 * lt) * Cfg::LINE_PITCH;        // head of rows 0,1 of this thread-line
+    cplx<T>* bufA = bufB + Cfg::LINE_PITCH;                 // exchange buffer of the inverse transforms, head of rows 2,3
+    cplx<T>* park = hb + KS * Cfg::LINE_PITCH + lt * Z::PARK_PITCH;
+    const cplx<T>* wb = win + b * NFI * win_fstride;
+
+    unsigned keepmask = 0;   // bit m: element p = tau + m*TL of a full complex row survives the dealiasing
+    FSM_UNROLL
+    for (int m = 0; m < EPT; ++m) {
+        const int p = tau + m * TL;
+        if (p <= kmaxl || p >= N - kmaxl) keepmask |= 1u << m;
+    }
+    bool tw_pending = true;
+    T keep2[Z::PARK ? 1 : EPT];
+    (void)keep2;
+    static_for<0, 4>([&](auto rc) FSM_INLINE_LAMBDA {
+        constexpr int r = decltype(rc)::value;
+        const int row = t0 + 4 * lt + r;
+        const bool row_ok = row < n_t;
+        cplx<T> v[EPT];
+        T acc[EPT];
+        auto inverse_z = [&](int f) FSM_INLINE_LAMBDA {
+            const cplx<T>* z = wb + f * win_fstride + (row_ok ? (long)row * in_t_stride : 0) + tau;
+            FSM_PIN(z);
+            const unsigned km = row_ok ? keepmask : 0u;
+            FSM_UNROLL
+            for (int m = 0; m < EPT; ++m) v[m] = ((km >> m) & 1u) ? z[m * TL] : mk<T>(T(0), T(0));
+            if (tw_pending) { twiddles_ready(); tw_pending = false; }
+            sync();
+            line_fft<Cfg, +1, T>(v, bufA, tw, tau, sync);
+        };
+        inverse_z(0);
+        if constexpr (PROG == PROG_KS2D) {
+            FSM_UNROLL
+            for (int m = 0; m < EPT; ++m) acc[m] = T(0.5) * (v[m].x * v[m].x + v[m].y * v[m].y);
+        } else {
+            FSM_UNROLL
+            for (int m = 0; m < EPT; ++m) acc[m] = v[m].x * v[m].y;
+            inverse_z(1);
+            FSM_UNROLL
+            for (int m = 0; m < EPT; ++m) acc[m] += v[m].x * v[m].y;
+        }
+        if constexpr ((r & 1) == 0) {
+            FSM_UNROLL
+            for (int m = 0; m < EPT; m += 2) {
+                if constexpr (Z::PARK) park[tau + (m / 2) * TL] = mk<T>(acc[m], acc[m + 1]);
+                else { keep2[m] = acc[m]; keep2[m + 1] = acc[m + 1]; }
+            }
+        } else {
+            FSM_UNROLL
+            for (int m = 0; m < EPT; m += 2) {
+                if constexpr (Z::PARK) {
+                    const cplx<T> pk2 = park[tau + (m / 2) * TL];
+                    v[m] = mk<T>(pk2.x, acc[m]);
+                    v[m + 1] = mk<T>(pk2.y, acc[m + 1]);
+                } else {
+                    v[m] = mk<T>(keep2[m], acc[m]);
+                    v[m + 1] = mk<T>(keep2[m + 1], acc[m + 1]);
+                }
+            }
+            sync();   // every thread of the line is done reading bufA (last stage of the inverse transform)
+            line_fft_head<Cfg, -1, T>(v, (r == 1) ? bufB : bufA, tw, tau, sync);
+        }
+    });
+    __syncthreads();
+
+    // ---- rotated, paired last stage of the KS head buffers: split and store wout[k * out_e_stride + row]
+    const int s = threadIdx.x % KS, widx = threadIdx.x / KS;     // widx < TL / 2
+    const cplx<T>* buf = hb + s * Cfg::LINE_PITCH;
+    const bool ok0 = t0 + 2 * s < n_t, ok1 = t0 + 2 * s + 1 < n_t;
+    cplx<T>* ob = wout + b * wout_fstride + t0 + 2 * s;
+    FSM_PIN(ob);
+    const int es = (int)out_e_stride;   // offsets inside one field fit 32 bits
+    auto emit = [&](int k, cplx<T> zk, cplx<T> zn) FSM_INLINE_LAMBDA {
+        const cplx<T> s0 = mk<T>(T(0.5) * (zk.x + zn.x), T(0.5) * (zk.y - zn.y));
+        const cplx<T> s1 = mk<T>(T(0.5) * (zk.y + zn.y), T(0.5) * (zn.x - zk.x));
+        cplx<T>* dst = ob + k * es;
+        if (ok1) store_pair(dst, s0, s1);
+        else if (ok0) dst[0] = s0;
+    };
+    static_for<0, EPT / RL>([&](auto qc) FSM_INLINE_LAMBDA {
+        constexpr int q = decltype(qc)::value;
+        const int u = widx + q * (TL / 2);                       // pair unit: work items u and NS - u
+        const int w1 = u, w2 = (u == 0) ? NS / 2 : NS - u;
+        cplx<T> a[RL], c[RL];
+        fft_last_item<Cfg, -1, T, 0>(buf, tw, w1, a);            // a[t] = X[w1 + t*NS]
+        fft_last_item<Cfg, -1, T, 0>(buf, tw, w2, c);            // c[t] = X[w2 + t*NS]
+        if (q == 0 && u == 0) {
+            // item 0 pairs with itself: k = t*NS <-> N - k = (RL - t)*NS; item NS/2 likewise: t <-> RL-1-t
+            static_for<0, RL / 2 + 1>([&](auto tc) FSM_INLINE_LAMBDA {
+                constexpr int t = decltype(tc)::value;
+                emit(t * NS, a[t], a[(RL - t) % RL]);
+            });
+            static_for<0, RL / 2>([&](auto tc) FSM_INLINE_LAMBDA {
+                constexpr int t = decltype(tc)::value;
+                emit(NS / 2 + t * NS, c[t], c[RL - 1 - t]);
+            });
+        } else {
+            static_for<0, RL / 2>([&](auto tc) FSM_INLINE_LAMBDA {
+                constexpr int t = decltype(tc)::value;
+                emit(w1 + t * NS, a[t], c[RL - 1 - t]);
+                emit(w2 + t * NS, c[t], a[RL - 1 - t]);
+            });
+        }
+    });
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1261,7 +1423,7 @@ k_pass_fx(Geom<T> g, const cplx<T>* __restrict__ win, long win_fstride,
         if (line < nlines) combine_load<T, NB>(cb, b * g.nmodes, 0, line_mode0 + tau, TL, opq[0]);
     }
     cplx<T> nhat[C][EPT];
-    auto load_channel = [&](int c, cplx<T>* dst) {
+    auto load_channel = [&](int c, cplx<T>* dst) FSM_INLINE_LAMBDA {
         const cplx<T>* src = win + (bl * C + c) * win_fstride + (long)line * line_stride;
         FSM_UNROLL
         for (int m = 0; m < EPT; ++m) dst[m] = src[(ib.shift >= 30) ? (long)(tau + m * TL) : blk_off(tau + m * TL, ib, 1)];
@@ -1269,7 +1431,7 @@ k_pass_fx(Geom<T> g, const cplx<T>* __restrict__ win, long win_fstride,
     if (line < nlines) load_channel(0, nhat[0]);
     twiddles_ready();      // first channel in flight while the twiddle copy lands
     if (line >= nlines) return;
-    static_for<0, C>([&](auto cc) {
+    static_for<0, C>([&](auto cc) FSM_INLINE_LAMBDA {
         constexpr int c = decltype(cc)::value;
         if constexpr (c > 0) load_channel(c, nhat[c]);
         if (c > 0) sync();
@@ -1279,9 +1441,9 @@ k_pass_fx(Geom<T> g, const cplx<T>* __restrict__ win, long win_fstride,
     int ky, kz = 0;
     if (g.ndim == 3) { ky = line / g.nh + g.ky0; kz = line % g.nh; } else { ky = line; }
     // the epilogue is instantiated once per compile-time combine shape (and once generic); cb.kind is uniform
-    with_combine_kind(cb.kind, [&](auto kindc) {
+    with_combine_kind(cb.kind, [&](auto kindc) FSM_INLINE_LAMBDA {
     constexpr int KIND = decltype(kindc)::value;
-    static_for<0, EPT / NB>([&](auto mbc) {
+    static_for<0, EPT / NB>([&](auto mbc) FSM_INLINE_LAMBDA {
         constexpr int mb = decltype(mbc)::value * NB;
         constexpr int cur = decltype(mbc)::value & 1;
         if constexpr (kPipe && mb + NB < EPT)
@@ -1444,132 +1606,6 @@ __global__ void __launch_bounds__(Cfg::TL) k_line1d(const void* __restrict__ in_
         FSM_UNROLL
         for (int m = 0; m < EPT; ++m) out[tau + m * TL] = v[m].x;
     }
-}
-
-// ------------------------------------------------------------------------------------------
-// Pass FXIX (2-D vorticity program): FX of stage s fused with IX of stage s+1 on the same ky line.
-// The combine hands the next stage state over in registers (Combine::has_next), so that state is never
-// written to or read from HBM; lines beyond the dealiasing cut only do the FX half.
-// ------------------------------------------------------------------------------------------
-template <typename T, class Cfg>
-__global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL))
-k_pass_fxix_ns2d(Geom<T> g, const cplx<T>* __restrict__ win, long win_fstride, Combine<T> cb, FxEpilogue<T> ep, int nlines,
-                 int b0, cplx<T>* __restrict__ w1, long w1_fstride, long out_e_stride, int n_keep, int do_ix) {
-    constexpr int N = Cfg::N, EPT = Cfg::EPT, TL = Cfg::TL;
-    FSM_DYN_SMEM(smem_raw);
-    cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);
-    cplx<T>* bufs = tw + Smem<Cfg, T>::TWPAD;
-    make_twiddles<Cfg, T>(tw);
-    const int lt = threadIdx.x / TL, tau = threadIdx.x % TL;
-    const int t0 = blockIdx.x * kKL;
-    const int line = t0 + lt;
-    const bool line_ok = line < nlines;
-    const long bl = blockIdx.z;
-    const long b = b0 + bl;
-    LineSync<TL> sync{1 + lt};
-    cplx<T> u[EPT];
-    // ---- FX half: forward x-transform of the nonlinear term, epilogue, combine
-    {
-        const cplx<T>* src = win + bl * win_fstride + (long)(line_ok ? line : 0) * N;
-        FSM_UNROLL
-        for (int m = 0; m < EPT; ++m) u[m] = line_ok ? src[tau + m * TL] : mk<T>(T(0), T(0));
-        line_fft<Cfg, -1, T>(u, bufs + lt * Cfg::LINE_PITCH, tw, tau, sync);
-        constexpr int NB = (EPT >= 4) ? 4 : EPT;
-        const long line_mode0 = (long)(line_ok ? line : 0) * N;
-        static_for<0, EPT / NB>([&](auto mbc) {
-            constexpr int mb = decltype(mbc)::value * NB;
-            cplx<T> f[NB], nx[NB];
-            FSM_UNROLL
-            for (int j = 0; j < NB; ++j) {
-                f[j] = cscale(u[mb + j], ep.nl_coef);
-                nx[j] = mk<T>(T(0), T(0));
-            }
-            if (ep.source) {
-                FSM_UNROLL
-                for (int j = 0; j < NB; ++j) f[j] = f[j] + ep.source[line_mode0 + tau + (mb + j) * TL];
-            }
-            if (line_ok)
-                combine_block<T, NB>(cb, f, b * g.nmodes, 0, line_mode0 + tau + mb * TL, TL, nx, true);
-            FSM_UNROLL
-            for (int j = 0; j < NB; ++j) u[mb + j] = nx[j];
-        });
-    }
-    if (!do_ix || t0 >= n_keep) return;   // block-uniform
-    // ---- IX half (see k_pass_ix, PROG_NS2D): four plain transforms, paired Z-lines formed at store time
-    const int k_valid = (kKL < n_keep - t0) ? kKL : (n_keep - t0);
-    const bool line_kept = line < n_keep;
-    const int n1 = g.n[1];
-    const T dky = line_kept ? g.dk[1][line] : T(0);
-    const T dkyraw = line_kept ? g.dkraw[1][line] : T(0);
-    FSM_UNROLL
-    for (int m = 0; m < EPT; ++m) {
-        const int p = tau + m * TL;
-        const bool kept = line_kept && (iabs(signed_mode<N>(p)) <= g.kmax[0]);
-        u[m] = kept ? cscale(u[m], g.inv_ntot) : mk<T>(T(0), T(0));
-    }
-    __syncthreads();   // every line is done with its forward-transform buffer
-    static_for<0, 4>([&](auto fc) {
-        constexpr int f = decltype(fc)::value;
-        cplx<T> v[EPT];
-        FSM_UNROLL
-        for (int m = 0; m < EPT; ++m) {
-            const int p = tau + m * TL;
-            if constexpr (f == 2) {
-                v[m] = u[m];
-            } else {
-                const T dkx = g.dk[0][p];
-                if constexpr (f == 0) {
-                    v[m] = cscale(u[m], dkx);
-                } else {
-                    const T dkxraw = g.dkraw[0][p];
-                    const T lap = -(dkxraw * dkxraw) - (dkyraw * dkyraw);
-                    const T ninv = (lap == T(0)) ? T(-1) : neg_recip(lap);
-                    v[m] = cmul_i(u[m], (f == 1 ? dky : dkx) * ninv);
-                }
-            }
-        }
-        cplx<T>* pbufs = bufs + (f & 1) * kKL * Cfg::LINE_PITCH;
-        line_fft_head<Cfg, +1, T>(v, pbufs + lt * Cfg::LINE_PITCH, tw, tau, sync);
-        if constexpr (f & 1) {
-            __syncthreads();
-            constexpr int pair = f >> 1;
-            constexpr int RL = LastStage<Cfg>::RL, NS = LastStage<Cfg>::NS;
-            const int ts = threadIdx.x % kKL, widx = threadIdx.x / kKL;
-            const int tg = t0 + ts;
-            const bool valid = ts < k_valid;
-            const bool selfc = (tg == 0) || (2 * tg == n1);
-            const T dky_s = valid ? g.dk[1][tg] : T(0);
-            const cplx<T>* s0 = bufs + ts * Cfg::LINE_PITCH;
-            const cplx<T>* s1 = s0 + kKL * Cfg::LINE_PITCH;
-            cplx<T>* dp = w1 + (bl * 2 + pair) * w1_fstride + tg;
-            cplx<T>* dm = w1 + (bl * 2 + pair) * w1_fstride + (n1 - tg);
-            static_for<0, EPT / RL>([&](auto qc) {
-                constexpr int q = decltype(qc)::value;
-                const int w = widx + q * TL;
-                cplx<T> a[RL], bb[RL];
-                fft_last_item<Cfg, +1, T>(s0, tw, w, a);
-                fft_last_item<Cfg, +1, T>(s1, tw, w, bb);
-                if (valid) {
-                    static_for<0, RL>([&](auto tc) {
-                        constexpr int tp = decltype(tc)::value;
-                        const int off = (w + tp * NS) * (int)out_e_stride;
-                        cplx<T> zp, zm;
-                        if constexpr (pair == 0) {
-                            zp = selfc ? mk<T>(bb[tp].x, -a[tp].y) : bb[tp] - a[tp];
-                            zm = mk<T>(a[tp].x + bb[tp].x, -(a[tp].y + bb[tp].y));
-                        } else {
-                            zp = selfc ? mk<T>(-bb[tp].x, -dky_s * a[tp].y)
-                                       : mk<T>(-dky_s * a[tp].x - bb[tp].x, -dky_s * a[tp].y - bb[tp].y);
-                            zm = mk<T>(dky_s * a[tp].x - bb[tp].x, bb[tp].y - dky_s * a[tp].y);
-                        }
-                        dp[off] = zp;
-                        if (!selfc) dm[off] = zm;
-                    });
-                }
-            });
-            if constexpr (f == 1) __syncthreads();
-        }
-    });
 }
 
 // Combine without a nonlinear term (ETDRK0) or point-wise fix-ups: one thread per mode.

@@ -177,28 +177,6 @@ static std::vector<Stage> build_stages(int integ, double dt, bool has_lin) {
     return st;
 }
 
-// Fused FX+IX programs (2-D vorticity): the stage state travels in registers, so ETDRK2 keeps a single
-// scratch array g = a - c2 N0 = E u + (c1 - c2) N0 and finishes with u' = g + c2 N1 (_etdrk.py:72-82 regrouped).
-static std::vector<Stage> build_stages_fused(int integ) {
-    std::vector<Stage> st;
-    if (integ != FSM_INT_ETDRK2 && integ != FSM_INT_SETDRK2) return st;
-    Stage s1;
-    s1.input = ARR_U; s1.n_in = 1; s1.in[0] = ARR_U; s1.n_out = 1; s1.out[0] = ARR_S1; s1.has_next = true;
-    s1.c[0][0] = tab2c(TAB_C1, 1.0, TAB_C2, -1.0);
-    s1.c[0][1] = tabc(TAB_EXP);
-    s1.c[FSM_MAX_OUT][0] = tabc(TAB_C1);
-    s1.c[FSM_MAX_OUT][1] = tabc(TAB_EXP);
-    Stage s2;
-    s2.input = ARR_S1; s2.n_in = 1; s2.in[0] = ARR_S1; s2.n_out = 1; s2.out[0] = ARR_U; s2.has_next = true;
-    s2.c[0][0] = tabc(TAB_C2);
-    s2.c[0][1] = scal(1.0);
-    s2.c[FSM_MAX_OUT][0] = tabc(TAB_C2);
-    s2.c[FSM_MAX_OUT][1] = scal(1.0);
-    st.push_back(s1);
-    st.push_back(s2);
-    return st;
-}
-
 }  // namespace fsm
 
 using namespace fsm;
@@ -218,7 +196,6 @@ struct fsm_plan {
     mutable long ks_log_pos = 0;
     int P = 1, rank = 0, kyl = 0, nxl = 0, nkz1 = 0;  // slab decomposition (P > 1): local ky / x extents, kept kz planes
     std::vector<Stage> stages;
-    std::vector<Stage> fused_stages;   // non-empty: FX of a stage is fused with IX of the next one
     Stage rhs_stage;
     // workspace (offsets in bytes)
     size_t off_arr[ARR_COUNT], off_w1, off_w2, off_w3, off_w2b, off_dc, ws_bytes;
@@ -353,7 +330,10 @@ int make_combine(const fsm_plan* p, const Stage& s, cplx<T>* const* arr, bool fr
                 cb.ct2[r][m] = sl;
             }
         }
-    cb.kind = (getenv("FSM_GENERIC_COMBINE") != nullptr) ? -1 : match_combine_shape(cb);
+    cb.kind = match_combine_shape(cb);
+#ifdef FSM_EMU   // test seam of the CPU suite only (generic vs specialised combine); the CUDA build reads no environment
+    if (getenv("FSM_GENERIC_COMBINE") != nullptr) cb.kind = -1;
+#endif
     *out = cb;
     return 0;
 }
@@ -529,55 +509,9 @@ int run_1d(const fsm_plan* p, const Buffers<T>& bf, const Stage* stages, int n_s
     return 0;
 }
 
-// 2-D vorticity program with FX of every stage fused into IX of the next: per chunk of samples
-//   IX | PHYS, FXIX(stage 1) | PHYS, FXIX(stage 2) | ... | PHYS, FX-half only (last stage of the last step)
-template <typename T>
-int run_fused_ns2d(const fsm_plan* p, const Buffers<T>& bf, int n_steps, cudaStream_t st) {
-    const Geom<T> g = make_geom<T>(p, false);
-    const LaunchTable<T>* tx = launch_table<T>(p->n[0]);
-    const LaunchTable<T>* tl = launch_table<T>(p->n[1]);
-    const int n_keep = (p->d.kmax[1] + 1 < p->nh) ? p->d.kmax[1] + 1 : p->nh;
-    const long w1_fstride = (long)p->n[0] * p->n[1];
-    const int nst = (int)p->fused_stages.size();
-    std::vector<Combine<T>> cbs(nst);
-    for (int i = 0; i < nst; ++i)
-        if (int e = make_combine<T>(p, p->fused_stages[i], bf.arr, true, &cbs[i])) return e;
-    FxEpilogue<T> ep;
-    ep.nl_coef = (T)p->d.nl_coef;
-    ep.source = static_cast<const cplx<T>*>(p->d.source_hat);
-    ep.dc_out = nullptr;
-    ep.project = 0;
-    for (int b0 = 0; b0 < p->B; b0 += p->chunk) {
-        const int nb = (p->B - b0 < p->chunk) ? (p->B - b0) : p->chunk;
-        IxArgs<T> a;
-        a.g = g; a.state = bf.arr[ARR_U] + (long)b0 * p->nmodes; a.w1 = bf.w1;
-        a.state_bstride = p->nmodes; a.nbc = nb; a.w1_fstride = w1_fstride;
-        a.in_t_stride = p->n[0]; a.in_o_stride = 0; a.out_o_stride = 0; a.out_e_stride = p->n[1];
-        a.n_t = n_keep; a.n_outer = 1;
-        { ProfScope ps(p, PASS_IX, st); if (int e = tx->ix(PROG_NS2D, a, st)) return fail(e, "IX launch failed"); }
-        for (int step = 0; step < n_steps; ++step)
-            for (int si = 0; si < nst; ++si) {
-                PhysArgs<T> ph;
-                ph.g = g; ph.win = bf.w1; ph.wout = bf.w2; ph.phys_in = nullptr; ph.phys_out = nullptr; ph.nb = nb;
-                ph.win_fstride = w1_fstride; ph.wout_fstride = p->nmodes;
-                ph.in_t_stride = p->n[1]; ph.in_o_stride = 0; ph.out_o_stride = 0; ph.out_e_stride = p->n[0];
-                ph.n_t = p->n[0]; ph.n_outer = 1;
-                { ProfScope ps(p, PASS_PHYS, st); if (int e = tl->phys(PROG_NS2D, 2, ph, st)) return fail(e, "PHYS launch failed"); }
-                FxIxArgs<T> f;
-                f.fx.g = g; f.fx.win = bf.w2; f.fx.win_fstride = p->nmodes; f.fx.cb = cbs[si]; f.fx.ep = ep;
-                f.fx.nlines = p->nh; f.fx.b0 = b0; f.fx.nb = nb;
-                f.w1 = bf.w1; f.w1_fstride = w1_fstride; f.out_e_stride = p->n[1]; f.n_keep = n_keep;
-                f.do_ix = (step == n_steps - 1 && si == nst - 1) ? 0 : 1;
-                { ProfScope ps(p, PASS_FX, st); if (int e = tx->fxix_ns2d(f, st)) return fail(e, "FXIX launch failed"); }
-            }
-    }
-    return 0;
-}
-
 template <typename T>
 int do_step(fsm_plan* p, void* u_hat, void* ws, int n_steps, cudaStream_t st) {
     Buffers<T> bf = carve<T>(p, u_hat, ws, nullptr);
-    if (!p->fused_stages.empty() && n_steps > 0) return run_fused_ns2d<T>(p, bf, n_steps, st);
     if (p->ndim == 1 && p->prog != FSM_PROG_LINEAR) {
         if (p->stages.size() > FSM_MAX_STAGES) return fail(-ENOSYS, "too many stages for the 1-D kernel");
         return run_1d<T>(p, bf, p->stages.data(), (int)p->stages.size(), n_steps, st);
@@ -951,11 +885,7 @@ int fsm_plan_create(fsm_plan** out, const fsm_desc* d) {
     }
     p->stages = build_stages(d->integrator, d->dt, d->tab_lin != nullptr);
     if (p->stages.empty()) { delete p; return fail(-ENOSYS, "unknown integrator %d", d->integrator); }
-    // FX(stage s) + IX(stage s+1) fusion for the 2-D vorticity program: opt-in experiment (FSM_FUSE=1). Measured on
-    // C3 it is 8 % slower than the two separate kernels (the halves serialise inside the one CTA an SM holds).
     p->pf = FSM_PF_DEFAULT;
-    if (const char* e = getenv("FSM_PF")) p->pf = atoi(e);    // tuning hook
-    if (p->kprog == PROG_NS2D && getenv("FSM_FUSE") && p->n[0] >= 16) p->fused_stages = build_stages_fused(d->integrator);
     // right-hand side L u + N(u)
     {
         Stage s;
@@ -1066,7 +996,6 @@ int fsm_plan_create(fsm_plan** out, const fsm_desc* d) {
             p->pass_units[PASS_FX] += (int64_t)(s.n_in + s.n_out) * p->C;
         }
         for (int i = 0; i < 4; ++i) units += p->pass_units[i];
-        if (!p->fused_stages.empty()) launches = (int64_t)nchunks * 2 * (int64_t)p->fused_stages.size();
         p->launches_per_step = launches;
         p->algo_bytes_per_step = units * (int64_t)p->ntot * (p->f64 ? 8 : 4) * p->B;
     }
