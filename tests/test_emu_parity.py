@@ -248,3 +248,43 @@ def test_operator_to_changes_the_working_precision():
     u32 = op.integrate(u0.float(), dt=spec["dt"], step=2)
     assert u32.dtype == torch.float32 and rel_l2(u32.double().numpy(), u64.numpy()) < 1e-5
     assert op._state_dict["integrator"].rdtype == torch.float32
+
+
+@pytest.mark.parametrize("prog,shape,batch", [("ns2d", (512, 16), 3), ("ns2d", (1024, 8), 2), ("ks2d", (512, 8), 5),
+                                              ("ns2d", (16, 512), 2), ("ks2d", (8, 1024), 2), ("ns2d", (256, 32), 3)])
+def test_zline_programs_with_long_lines_vs_oracle(prog, shape, batch):
+    """The Z-line kernels of the 2-D vorticity / KS programs at the line lengths of C3 (persistent inverse-x kernel with
+    cp.async staging for >= 512-point x lines, two-CTA kernels below; phase-overlapping last-axis kernel) on thin grids:
+    fp32, two steps, several samples so that the persistent loop iterates."""
+    import torchfsm_b200 as fsm
+    from oracle import OracleOperator
+    mesh_info = [(0.0, 2 * np.pi, shape[0]), (0.0, 2 * np.pi * 1.5, shape[1])]
+    g = torch.Generator().manual_seed(sum(shape) + batch)
+    u0 = torch.randn((batch, 1) + shape, generator=g, dtype=torch.float64)
+    u_hat = torch.fft.fftn(u0, dim=(2, 3))
+    for d, n in zip((2, 3), shape):
+        f = torch.fft.fftfreq(n, 1.0 / n).abs()
+        view = [1, 1, 1, 1]
+        view[d] = n
+        u_hat = u_hat * (f <= max(1, n // 4)).to(u_hat.dtype).reshape(view)
+    u0 = torch.fft.ifftn(u_hat, dim=(2, 3)).real
+    u0 = (u0 / u0.abs().max()).float().contiguous()
+    if prog == "ns2d":
+        terms = [("vorticity_convection", -1, {}), ("laplacian", 0.01, {}), ("implicit_unit_source", -0.1, {})]
+        integ_name, dt = "ETDRK2", 1e-3
+    else:
+        terms = [("laplacian", -0.1, {}), ("biharmonic", -0.01, {}), ("ks_convection", -1, {})]
+        integ_name, dt = "SETDRK2", 1e-3
+    ora = OracleOperator(terms).register_mesh(mesh_info, 1, dtype="float32")
+    ora.set_integrator(integ_name)
+    integ = ora.build_integrator(dt)
+    op = product_operator(terms)
+    op.set_integrator(fsm.ETDRKIntegrator.ETDRK2 if prog == "ns2d" else fsm.SETDRKIntegrator.SETDRK2)
+    mesh = fsm.MeshGrid(mesh_info, device="cpu", dtype=torch.float32)
+    m, c = op._pre_check(u0, None, mesh)
+    op.register_mesh(m, c)
+    tabs = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in integ.tables.items()}
+    st = op._build_integrator(dt, batch, tables=tabs)
+    got = st.c2r(st.step_half(st.r2c(u0), 2)).numpy()
+    want = ora.mesh.ifft(integ.step(integ.step(ora.mesh.fft(u0.numpy())))).real
+    assert rel_l2(got, want) < 1e-5

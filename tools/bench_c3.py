@@ -24,6 +24,8 @@ def one(a):
     op.set_integrator(fsm.ETDRKIntegrator.ETDRK2)
     if a.chunk:
         op.set_chunk(a.chunk)
+    if a.lanes:
+        op.set_lanes(a.lanes)
     u0 = fsm.field.diffused_noise(mesh, batch_size=B, generator=torch.Generator().manual_seed(0))
     op.integrate(u0, mesh=mesh, dt=0.01, step=1)
     st = op._state_dict["integrator"]
@@ -45,7 +47,7 @@ def one(a):
     st.profile(False)
     out = {"lib": os.path.basename(os.environ.get("FSM_B200_LIB", "libfsm_b200.so")), "ms_per_step": round(best, 4),
            "passes_ms": {k: round(v["ms"] / 10, 4) for k, v in prof.items() if v["launches"]},
-           "finite": bool(torch.isfinite(u_hat.real).all()), "chunk": st.info()["chunk"]}
+           "finite": bool(torch.isfinite(u_hat.real).all()), "chunk": st.info()["chunk"], "lanes": a.lanes}
     if a.parity:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import test_gpu_parity as t
@@ -60,6 +62,7 @@ if __name__ == "__main__":
     ap.add_argument("--libs", default="")
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--chunk", type=int, default=0)
+    ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--n", type=int, default=1024)
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--parity", action="store_true")
@@ -72,7 +75,7 @@ if __name__ == "__main__":
             env = dict(os.environ)
             if lib and lib != "default":
                 env["FSM_B200_LIB"] = lib if os.path.isabs(lib) else os.path.join(ROOT, lib)
-            args = [sys.executable, os.path.abspath(__file__), "--child", "--steps", str(a.steps), "--chunk", str(a.chunk),
+            args = [sys.executable, os.path.abspath(__file__), "--child", "--steps", str(a.steps), "--chunk", str(a.chunk), "--lanes", str(a.lanes),
                     "--n", str(a.n), "--batch", str(a.batch)] + (["--parity"] if a.parity else [])
             r = subprocess.run(args, env=env, capture_output=True, text=True)
             sys.stdout.write(r.stdout if r.returncode == 0 else json.dumps({"lib": lib, "error": r.stderr[-400:]}) + "\n")

@@ -30,6 +30,7 @@ class FsmDesc(ctypes.Structure):
         ("tab_exp", ctypes.c_void_p), ("tab_half_exp", ctypes.c_void_p), ("tab_coef", ctypes.c_void_p * 6),
         ("tab_lin", ctypes.c_void_p), ("source_hat", ctypes.c_void_p),
         ("slab_rank", ctypes.c_int32), ("slab_nranks", ctypes.c_int32),
+        ("lanes", ctypes.c_int32), ("reserved0", ctypes.c_int32),
     ]
 
 

@@ -81,8 +81,80 @@ static int launch_ix_p(const IxArgs<T>& a, cudaStream_t s) {
                a.in_o_stride, a.out_o_stride, a.out_e_stride, a.n_t, a.eb, a.pe);
     return check_launch();
 }
+#ifndef FSM_IXZ
+#define FSM_IXZ 1   // Z-line programs on one GPU run the phase-overlapping inverse-x kernel (k_pass_ixz)
+#endif
+template <typename T, int N, int PROG>
+static int launch_ixz_p(const IxArgs<T>& a, cudaStream_t s) {
+    using Cfg = typename CfgFor<N>::type;
+    using Z = PhysZ<Cfg>;
+    auto kern = k_pass_ixz<T, Cfg, PROG>;
+    const size_t smem = Z::smem_bytes(sizeof(cplx<T>));
+    if (int e = set_smem(kern, smem)) return e;
+    dim3 grid((a.n_t + Z::KS - 1) / Z::KS, 1, a.nbc), block(Z::NT);
+    FSM_LAUNCH(kern, grid, block, smem, s, a.g, a.state, a.w1, a.state_bstride, a.w1_fstride, a.in_t_stride, a.out_e_stride,
+               a.n_t);
+    return check_launch();
+}
+#ifndef FSM_IXP
+// Persistent inverse-x kernel with cp.async staging of the next tile's state lines (k_pass_ixp). Measured on C3
+// (profiles/r2_kernel_variants.md): 0.700 ms/step against 0.685 for the one-tile-per-CTA kernel, 0.363 against
+// 0.319 at 512 points: hiding the first-load latency buys nothing, the pass is not bound by it. Kept off.
+#define FSM_IXP 0
+#endif
+#ifndef FSM_EMU
+static inline int sm_count() {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    return sms;
+}
+#else
+static inline int sm_count() { return 3; }   // the emulator runs a few "SMs" so that the persistent loops iterate
+#endif
+template <typename T, int N, int PROG>
+static int launch_ixp_p(const IxArgs<T>& a, cudaStream_t s) {
+    using Cfg = typename CfgFor<N>::type;
+    if constexpr (Cfg::NST < 2) {
+        return -ENOSYS;
+    } else {
+        auto kern = k_pass_ixp<T, Cfg, PROG>;
+        const size_t smem = Smem<Cfg, T>::bytes(2 * kKL) + sizeof(cplx<T>) * (size_t)kKL * Cfg::N;
+        if (int e = set_smem(kern, smem)) return e;
+        const int tiles = (a.n_t + kKL - 1) / kKL;
+        const int items = tiles * a.nbc;
+        static const int per_sm = [&] {
+#ifndef FSM_EMU
+            int n = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kKL * Cfg::TL, smem) != cudaSuccess) n = 1;
+            return n < 1 ? 1 : n;
+#else
+            return 1;
+#endif
+        }();
+        int ctas = sm_count() * per_sm;
+        if (ctas < 1) ctas = 1;
+        if (ctas > items) ctas = items;
+        FSM_LAUNCH(kern, dim3(ctas), dim3(kKL * Cfg::TL), smem, s, a.g, a.state, a.w1, a.state_bstride, a.w1_fstride,
+                   a.in_t_stride, a.out_e_stride, a.n_t, tiles, items);
+        return check_launch();
+    }
+}
 template <typename T, int N>
 static int launch_ix(int prog, const IxArgs<T>& a, cudaStream_t s) {
+    if (a.n_outer == 1 && a.eb.shift >= 30 && a.g.ndim == 2 && (prog == PROG_NS2D || prog == PROG_KS2D)) {
+        using Cfg = typename CfgFor<N>::type;
+        if (FSM_IXZ && Cfg::TL <= 16) {      // measured: the two-CTA form wins up to 256 points, loses from 512 on
+            if (prog == PROG_NS2D) return launch_ixz_p<T, N, PROG_NS2D>(a, s);
+            return launch_ixz_p<T, N, PROG_KS2D>(a, s);
+        }
+        if constexpr (FSM_IXP != 0) {
+            if (Cfg::TL >= 32 && sizeof(T) == 4) {
+                if (prog == PROG_NS2D) return launch_ixp_p<T, N, PROG_NS2D>(a, s);
+                return launch_ixp_p<T, N, PROG_KS2D>(a, s);
+            }
+        }
+    }
     switch (prog) {
         case PROG_NS2D: return launch_ix_p<T, N, PROG_NS2D>(a, s);
         case PROG_KS2D: return launch_ix_p<T, N, PROG_KS2D>(a, s);
@@ -108,17 +180,23 @@ static int launch_mid(int dir, const MidArgs<T>& a, cudaStream_t s) {
     return dir > 0 ? launch_mid_d<T, N, +1>(a, s) : launch_mid_d<T, N, -1>(a, s);
 }
 
+#ifndef FSM_PHYS3D_NL512
+// thread-lines per CTA of the 3-D convection last-axis pass at 512 points. Measured on C5: 4 (two 256-thread CTAs per
+// SM, 64-byte store segments, 80 B of spills) 9.68 ms/step against 9.75 with 8 (one CTA per SM): no gain, kept at 8.
+#define FSM_PHYS3D_NL512 8
+#endif
 template <typename T, int N, int PROG, int NDIM>
 static int launch_phys_p(const PhysArgs<T>& a, cudaStream_t s) {
     using Cfg = typename CfgPhys<N, NDIM>::type;
     using PT = PhysTraits<PROG, NDIM>;
     constexpr int NFW = (PT::NOUT * PT::RPT + 1) / 2;
-    auto kern = k_pass_phys<T, Cfg, PROG, NDIM>;
-    const int K = kKL * PT::RPT;
-    const size_t smem = Smem<Cfg, T>::bytes(kKL * (1 + (NFW > 0 ? NFW : 0)));
+    constexpr int NLP = (PROG == PROG_CONV && NDIM == 3 && N == 512 && sizeof(T) == 4) ? FSM_PHYS3D_NL512 : kKL;
+    auto kern = k_pass_phys<T, Cfg, PROG, NDIM, NLP>;
+    const int K = NLP * PT::RPT;
+    const size_t smem = Smem<Cfg, T>::bytes(NLP * (1 + (NFW > 0 ? NFW : 0)));
     if (int e = set_smem(kern, smem)) return e;
-    dim3 grid((a.n_t + K - 1) / K, a.n_outer, a.nb), block(kKL * Cfg::TL);
-    static const int wave = resident_ctas(kern, kKL * Cfg::TL, smem);
+    dim3 grid((a.n_t + K - 1) / K, a.n_outer, a.nb), block(NLP * Cfg::TL);
+    static const int wave = resident_ctas(kern, NLP * Cfg::TL, smem);
     Geom<T> g = a.g;
     g.pf_wave = wave;
     FSM_LAUNCH(kern, grid, block, smem, s, g, a.win, a.wout, a.phys_in, a.phys_out, a.win_fstride, a.wout_fstride, K,

@@ -485,6 +485,336 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
 }
 
 // ------------------------------------------------------------------------------------------
+// Pass IX-P: k_pass_ix's Z-line branch (NS2D, KS2D) as a PERSISTENT kernel for long lines. One 512-thread CTA per
+// SM (register file) loops over (ky tile, sample) work items; the state lines of item i+1 are copied into a
+// staging area of shared memory with cp.async (thread-private: every thread copies exactly the elements it will
+// read back, so no barrier is involved) while the four transforms of item i run, and the stores of item i drain
+// while item i+1 computes. ncu on the one-tile-per-CTA kernel: 18 % of the warp-stall samples sat on the first
+// use of the freshly loaded line, 2 % on the store drain at exit, plus launch gaps.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void async_copy8(void* smem_dst, const void* gsrc) {
+#ifndef FSM_EMU
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(gsrc) : "memory");
+#else
+    *static_cast<unsigned long long*>(smem_dst) = *static_cast<const unsigned long long*>(gsrc);
+#endif
+}
+__device__ __forceinline__ void async_copy16(void* smem_dst, const void* gsrc) {
+#ifndef FSM_EMU
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gsrc) : "memory");
+#else
+    static_cast<unsigned long long*>(smem_dst)[0] = static_cast<const unsigned long long*>(gsrc)[0];
+    static_cast<unsigned long long*>(smem_dst)[1] = static_cast<const unsigned long long*>(gsrc)[1];
+#endif
+}
+__device__ __forceinline__ void async_copy_wait() {
+#ifndef FSM_EMU
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
+
+template <typename T, class Cfg, int PROG>
+__global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL))
+k_pass_ixp(Geom<T> g, const cplx<T>* __restrict__ state, cplx<T>* __restrict__ w1, long state_bstride, long w1_fstride,
+           long in_t_stride, long out_e_stride, int n_t, int tiles_per_sample, int n_items) {
+    static_assert(PROG == PROG_NS2D || PROG == PROG_KS2D, "Z-line programs only");
+    constexpr int N = Cfg::N, EPT = Cfg::EPT, TL = Cfg::TL;
+    constexpr int NPAIR = IxFields<PROG>::NPAIR;
+    FSM_DYN_SMEM(smem_raw);
+    cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);
+    cplx<T>* bufs = tw + Smem<Cfg, T>::TWPAD;
+    cplx<T>* stage = bufs + 2 * kKL * Cfg::LINE_PITCH;          // [kKL][N] staging of the next item's state lines
+    const int lt = threadIdx.x / TL, tau = threadIdx.x % TL;
+    const int n1 = g.n[1];
+    twiddles_begin<Cfg, T>(tw);
+    LineSync<TL> sync{1 + lt};
+    cplx<T>* mystage = stage + lt * N + tau;
+    // element-wise constants of this thread: x wavenumbers and the dealiasing predicate along x
+    T dkxr[EPT];
+    unsigned keepx = 0;
+    {
+        const T* dkx_t = g.dkraw[0] + tau;
+        FSM_PIN(dkx_t);
+        FSM_UNROLL
+        for (int m = 0; m < EPT; ++m) {
+            dkxr[m] = dkx_t[m * TL];
+            if (iabs(signed_mode<N>(tau + m * TL)) <= g.kmax[0]) keepx |= 1u << m;
+        }
+    }
+    auto line_of = [&](int item, int& t, long& bc) FSM_INLINE_LAMBDA {
+        bc = item / tiles_per_sample;
+        t = (item - (int)bc * tiles_per_sample) * kKL + lt;
+    };
+    auto line_mask = [&](int t) FSM_INLINE_LAMBDA -> unsigned {
+        const bool kept = (t < n_t) && (iabs(signed_mode_rt(t, n1)) <= g.kmax[1]);
+        return kept ? keepx : 0u;
+    };
+    auto prefetch_item = [&](int item) FSM_INLINE_LAMBDA {
+        int t; long bc;
+        line_of(item, t, bc);
+        const unsigned km = line_mask(t);
+        const cplx<T>* src = state + bc * state_bstride + (long)(km ? t : 0) * in_t_stride + tau;
+        FSM_PIN(src);
+        FSM_UNROLL
+        for (int m = 0; m < EPT; ++m) {
+            if ((km >> m) & 1u) {
+                if constexpr (sizeof(cplx<T>) == 8) async_copy8(mystage + m * TL, src + m * TL);
+                else async_copy16(mystage + m * TL, src + m * TL);
+            }
+        }
+    };
+    int item = blockIdx.x;
+    if (item < n_items) prefetch_item(item);
+    twiddles_ready();
+    for (; item < n_items; item += gridDim.x) {
+        int t; long bc;
+        line_of(item, t, bc);
+        const int t0 = t - lt;
+        const int k_valid = (kKL < n_t - t0) ? kKL : (n_t - t0);
+        const unsigned km = line_mask(t);
+        const T dky = km ? g.dk[1][t] : T(0);
+        const T dkyraw = km ? g.dkraw[1][t] : T(0);
+        cplx<T> u[EPT];
+        async_copy_wait();
+        FSM_UNROLL
+        for (int m = 0; m < EPT; ++m) u[m] = ((km >> m) & 1u) ? cscale(mystage[m * TL], g.inv_ntot) : mk<T>(T(0), T(0));
+        if (item + (int)gridDim.x < n_items) prefetch_item(item + gridDim.x);   // own elements only: no barrier needed
+        static_for<0, 2 * NPAIR>([&](auto fc) FSM_INLINE_LAMBDA {
+            constexpr int f = decltype(fc)::value;
+            cplx<T> v[EPT];
+            FSM_UNROLL
+            for (int m = 0; m < EPT; ++m) {
+                const int p = tau + m * TL;
+                const T dkx_h = (2 * p == N) ? T(0) : dkxr[m];
+                if constexpr (PROG == PROG_KS2D) {
+                    if constexpr (f == 0) v[m] = cscale(u[m], dkx_h);
+                    else v[m] = u[m];
+                } else if constexpr (f == 2) {
+                    v[m] = u[m];
+                } else if constexpr (f == 0) {
+                    v[m] = cscale(u[m], dkx_h);
+                } else {
+                    const T lap = -(dkxr[m] * dkxr[m]) - (dkyraw * dkyraw);
+                    const T ninv = (lap == T(0)) ? T(-1) : neg_recip(lap);
+                    v[m] = cmul_i(u[m], (f == 1 ? dky : dkx_h) * ninv);
+                }
+            }
+            cplx<T>* pbufs = bufs + (f & 1) * kKL * Cfg::LINE_PITCH;
+            line_fft_head<Cfg, +1, T>(v, pbufs + lt * Cfg::LINE_PITCH, tw, tau, sync);
+            if constexpr (f & 1) {
+                __syncthreads();
+                constexpr int pair = f >> 1;
+                constexpr int RL = LastStage<Cfg>::RL, NS = LastStage<Cfg>::NS;
+                const int ts = threadIdx.x % kKL, widx = threadIdx.x / kKL;
+                const int tg = t0 + ts;
+                const bool valid = ts < k_valid;
+                const bool selfc = (tg == 0) || (2 * tg == n1);
+                const T dky_s = valid ? g.dk[1][tg] : T(0);
+                const cplx<T>* s0 = bufs + ts * Cfg::LINE_PITCH;
+                const cplx<T>* s1 = s0 + kKL * Cfg::LINE_PITCH;
+                cplx<T>* dp = w1 + (bc * NPAIR + pair) * w1_fstride + tg;
+                cplx<T>* dm = w1 + (bc * NPAIR + pair) * w1_fstride + (n1 - tg);
+                FSM_PIN(dp);
+                FSM_PIN(dm);
+                static_for<0, EPT / RL>([&](auto qc) FSM_INLINE_LAMBDA {
+                    constexpr int q = decltype(qc)::value;
+                    const int w = widx + q * TL;
+                    cplx<T> a[RL], b[RL];
+                    fft_last_item<Cfg, +1, T, q * TL>(s0, tw, widx, a);
+                    fft_last_item<Cfg, +1, T, q * TL>(s1, tw, widx, b);
+                    if (valid) {
+                        static_for<0, RL>([&](auto tc) FSM_INLINE_LAMBDA {
+                            constexpr int tp = decltype(tc)::value;
+                            const int off = (w + tp * NS) * (int)out_e_stride;
+                            cplx<T> zp, zm;
+                            if constexpr (PROG == PROG_KS2D) {
+                                zp = selfc ? mk<T>(-a[tp].y, -dky_s * b[tp].y)
+                                           : mk<T>(-a[tp].y - dky_s * b[tp].x, a[tp].x - dky_s * b[tp].y);
+                                zm = mk<T>(dky_s * b[tp].x - a[tp].y, -(a[tp].x + dky_s * b[tp].y));
+                            } else if constexpr (pair == 0) {
+                                zp = selfc ? mk<T>(b[tp].x, -a[tp].y) : b[tp] - a[tp];
+                                zm = mk<T>(a[tp].x + b[tp].x, -(a[tp].y + b[tp].y));
+                            } else {
+                                zp = selfc ? mk<T>(-b[tp].x, -dky_s * a[tp].y)
+                                           : mk<T>(-dky_s * a[tp].x - b[tp].x, -dky_s * a[tp].y - b[tp].y);
+                                zm = mk<T>(dky_s * a[tp].x - b[tp].x, b[tp].y - dky_s * a[tp].y);
+                            }
+                            dp[off] = zp;
+                            if (!selfc) dm[off] = zm;
+                        });
+                    }
+                });
+                __syncthreads();   // the next heads (this item's second pair or the next item) overwrite the buffers
+            }
+        });
+    }
+}
+
+// Tile geometry shared by the two Z-line kernels (k_pass_ixz below, k_pass_physz further down)
+template <class Cfg>
+struct PhysZ {
+    static constexpr int NLZ = (Cfg::TL <= 16) ? 8 : 4;     // thread-lines per CTA
+    static constexpr int KS = 2 * NLZ;                      // head buffers = rotated lanes
+    static constexpr int NT = NLZ * Cfg::TL;
+    static constexpr int K = 4 * NLZ;                       // rows per CTA
+    static constexpr bool PARK = (Cfg::EPT >= 16);          // product of the even row waits in shared memory
+    static constexpr int PARK_PITCH = Cfg::N / 2;           // complex slots per thread-line
+    static size_t smem_bytes(size_t elem) {
+        return elem * (size_t)(((Cfg::TW_TOTAL + 1) & ~1) + KS * Cfg::LINE_PITCH + (PARK ? NLZ * PARK_PITCH : 0));
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// Pass IX-Z: inverse-x pass of the Z-line programs (NS2D, KS2D) on one GPU, organised like PHYS-Z for phase
+// overlap: NLZ thread-lines per CTA, each taking TWO ky lines (256 threads and 70 KB of shared memory at 1024
+// points -> two independent CTAs per SM). Every stored line is ONE plain transform of (complex symbol) x state:
+//   NS2D  Z1+ = T[(-kx + i ky ninv) w]        Z1- = conj T[( kx + i ky ninv) w]      (psi = ninv w, ninv = -1/lap)
+//         Z2+ = T[(-ky - i kx ninv) w]        Z2- = conj T[( ky - i kx ninv) w]
+//   KS2D  Z+  = T[(-ky + i kx) phi]           Z-  = conj T[( ky + i kx) phi]
+// (the linear combinations of k_pass_ix's four transforms A..D moved in front of the transform), so a field needs
+// one set of head buffers only and the last stage stores straight from registers in the rotated distribution.
+// The state line is re-read per field (L1/L2 hits after the first touch) instead of being held in registers.
+// Lines that are their own mirror (ky = 0, ky = n1/2) keep the Hermitian projection k_pass_ix applies: the
+// component a real field cannot have is dropped.
+// ------------------------------------------------------------------------------------------
+#ifndef FSM_IXZ_PREFETCH
+#define FSM_IXZ_PREFETCH 1
+#endif
+template <typename T, class Cfg, int PROG>
+__global__ void __launch_bounds__(PhysZ<Cfg>::NT, FSM_MINB(PhysZ<Cfg>::NT))
+k_pass_ixz(Geom<T> g, const cplx<T>* __restrict__ state, cplx<T>* __restrict__ w1, long state_bstride, long w1_fstride,
+           long in_t_stride, long out_e_stride, int n_t) {
+    static_assert(PROG == PROG_NS2D || PROG == PROG_KS2D, "Z-line programs only");
+    constexpr int N = Cfg::N, EPT = Cfg::EPT, TL = Cfg::TL;
+    using Z = PhysZ<Cfg>;
+    constexpr int KS = Z::KS;                    // ky lines per CTA = head buffers = rotated lanes
+    constexpr int NPAIR = IxFields<PROG>::NPAIR;
+    constexpr int RL = LastStage<Cfg>::RL, NS = LastStage<Cfg>::NS;
+    FSM_DYN_SMEM(smem_raw);
+    cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);
+    cplx<T>* hb = tw + Smem<Cfg, T>::TWPAD;
+    const int lt = threadIdx.x / TL, tau = threadIdx.x % TL;
+    twiddles_begin<Cfg, T>(tw);
+    const int t0 = blockIdx.x * KS;
+    const long bc = blockIdx.z;
+    const int n1 = g.n[1];
+    LineSync<TL> sync{1 + lt};
+    // per element of this thread: x wavenumber (raw, and zero on the Nyquist index) and the dealiasing predicate
+    T dkxr[EPT];
+    unsigned keepmask = 0;
+    {
+        const T* dkx_t = g.dkraw[0] + tau;
+        FSM_PIN(dkx_t);
+        FSM_UNROLL
+        for (int m = 0; m < EPT; ++m) {
+            const int p = tau + m * TL;
+            dkxr[m] = dkx_t[m * TL];
+            if (iabs(signed_mode<N>(p)) <= g.kmax[0]) keepmask |= 1u << m;
+        }
+    }
+    // rotated distribution of the last stage / store
+    const int s = threadIdx.x % KS, widx = threadIdx.x / KS;     // widx < TL / 2
+    const int tg = t0 + s;
+    const bool valid = tg < n_t;
+    const bool selfc = (tg == 0) || (2 * tg == n1);
+    const cplx<T>* sbuf = hb + s * Cfg::LINE_PITCH;
+    const int es = (int)out_e_stride;
+    bool tw_pending = true;
+
+    // per line of this thread-line: y wavenumbers, source pointer, keep mask (loaded once, not per field)
+    T dky2[2], dkyraw2[2];
+    const cplx<T>* src2[2];
+    unsigned km2[2];
+    FSM_UNROLL
+    for (int r = 0; r < 2; ++r) {
+        const int t = t0 + 2 * lt + r;
+        const bool line_kept = (t < n_t) && (iabs(signed_mode_rt(t, n1)) <= g.kmax[1]);
+        dky2[r] = line_kept ? g.dk[1][t] * g.inv_ntot : T(0);
+        dkyraw2[r] = line_kept ? g.dkraw[1][t] : T(0);
+        src2[r] = state + bc * state_bstride + (long)(line_kept ? t : 0) * in_t_stride + tau;
+        FSM_PIN(src2[r]);
+        km2[r] = line_kept ? keepmask : 0u;
+    }
+    auto load_raw = [&](int r, cplx<T>* raw) FSM_INLINE_LAMBDA {
+        FSM_UNROLL
+        for (int m = 0; m < EPT; ++m) raw[m] = ((km2[r] >> m) & 1u) ? src2[r][m * TL] : mk<T>(T(0), T(0));
+    };
+    cplx<T> raw[EPT];
+    load_raw(0, raw);
+    static_for<0, 2 * NPAIR>([&](auto fc) FSM_INLINE_LAMBDA {
+        constexpr int f = decltype(fc)::value;
+        constexpr int pair = f >> 1;
+        constexpr bool minus = (f & 1) != 0;
+        static_for<0, 2>([&](auto rc) FSM_INLINE_LAMBDA {
+            constexpr int r = decltype(rc)::value;
+            const T dky = dky2[r], dkyraw = dkyraw2[r];     // dky carries the 1/N scale
+            cplx<T> v[EPT];
+            FSM_UNROLL
+            for (int m = 0; m < EPT; ++m) {
+                const int p = tau + m * TL;
+                const T dkx_h = ((2 * p == N) ? T(0) : dkxr[m]) * g.inv_ntot;
+                T sr, si;
+                if constexpr (PROG == PROG_KS2D) {
+                    sr = minus ? dky : -dky;
+                    si = dkx_h;
+                } else {
+                    const T lap = -(dkxr[m] * dkxr[m]) - (dkyraw * dkyraw);
+                    const T ninv = (lap == T(0)) ? T(-1) : neg_recip(lap);
+                    if constexpr (pair == 0) {
+                        sr = minus ? dkx_h : -dkx_h;
+                        si = dky * ninv;
+                    } else {
+                        sr = minus ? dky : -dky;
+                        si = -(dkx_h * ninv);
+                    }
+                }
+                v[m] = cmul(raw[m], mk<T>(sr, si));
+            }
+            if (tw_pending) { twiddles_ready(); tw_pending = false; }
+            line_fft_head<Cfg, +1, T>(v, hb + (2 * lt + r) * Cfg::LINE_PITCH, tw, tau, sync);
+            // next item's state line: (f, 1) is needed at once; (f + 1, 0) is requested before the block barrier and the
+            // last stage of this field, which hide its latency (holding it across a head would spill)
+            if constexpr (r == 0) load_raw(1, raw);
+            else if constexpr (FSM_IXZ_PREFETCH && f + 1 < 2 * NPAIR) load_raw(0, raw);
+        });
+        __syncthreads();
+        {
+            cplx<T>* dst = w1 + (bc * NPAIR + pair) * w1_fstride + (minus ? (n1 - tg) : tg);
+            FSM_PIN(dst);
+            const bool store = valid && !(minus && selfc);
+            static_for<0, 2 * Cfg::EPT / RL>([&](auto qc) FSM_INLINE_LAMBDA {
+                constexpr int q = decltype(qc)::value;
+                cplx<T> a[RL];
+                fft_last_item<Cfg, +1, T, q * (TL / 2)>(sbuf, tw, widx, a);
+                const int w = widx + q * (TL / 2);
+                if (store) {
+                    static_for<0, RL>([&](auto tc) FSM_INLINE_LAMBDA {
+                        constexpr int tp = decltype(tc)::value;
+                        cplx<T> val = a[tp];
+                        if constexpr (minus) {
+                            val.y = -val.y;
+                        } else {
+                            // own mirror: NS2D pair 0 and KS2D keep (u . ) as real/imag parts of real fields
+                            if (selfc) {
+                                if constexpr (PROG == PROG_NS2D && pair == 0) val.x = T(0);
+                                else val.y = T(0);
+                            }
+                        }
+                        dst[(w + tp * NS) * es] = val;
+                    });
+                }
+            });
+        }
+        if constexpr (f + 1 < 2 * NPAIR) {
+            __syncthreads();
+            if constexpr (!FSM_IXZ_PREFETCH) load_raw(0, raw);
+        }
+    });
+}
+
+// ------------------------------------------------------------------------------------------
 // Pass MID (3-D only): C2C transform along y on NFI input fields, producing NFO output fields;
 // output field j = transform(in[src[j]] * (deriv[j] ? i*dk_y : 1)). Rotated output.
 //   inverse: W1 [kz][x][ky] -> W3 [x][y][kz];   forward: W2a [kz][x][y] -> W2b [ky][kz][x]
@@ -651,8 +981,9 @@ __device__ __forceinline__ void pair_fill(cplx<T>* v, const cplx<T>* a, const cp
     pair_combine<T, Cfg>(v, A, B, da, db, dk, tau, kmax);
 }
 
-template <typename T, class Cfg, int PROG, int NDIM>
-__global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass_phys(Geom<T> g, const cplx<T>* __restrict__ win, cplx<T>* __restrict__ wout,
+// NLP = thread-lines per CTA (kKL by default; a tuning parameter, see FSM_PHYS3D_NL512 in fsm_kernels.cu).
+template <typename T, class Cfg, int PROG, int NDIM, int NLP = kKL>
+__global__ void __launch_bounds__(NLP * Cfg::TL, FSM_MINB(NLP * Cfg::TL)) k_pass_phys(Geom<T> g, const cplx<T>* __restrict__ win, cplx<T>* __restrict__ wout,
                                                     const T* __restrict__ phys_in, T* __restrict__ phys_out,
                                                     long win_fstride, long wout_fstride, int K /*rows per CTA*/,
                                                     long in_t_stride, long in_o_stride, long out_o_stride,
@@ -664,7 +995,7 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
     FSM_DYN_SMEM(smem_raw);
     cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);
     cplx<T>* bufs = tw + Smem<Cfg, T>::TWPAD;
-    const int NL = K / RPT;  // thread-lines per CTA
+    constexpr int NL = NLP;  // thread-lines per CTA (K == NLP * RPT rows)
     const int lt = threadIdx.x / TL, tau = threadIdx.x % TL;
     const int kmaxl = (PROG == PROG_C2R) ? N / 2 : g.kmax[NDIM - 1];
     if constexpr (PROG == PROG_NS2D || PROG == PROG_KS2D) {
@@ -928,7 +1259,7 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
         cplx<T>* ob = wout + b * NOUT * wout_fstride + (long)o * out_o_stride + t0;
         FSM_PIN(ob);
         const cplx<T>* st0 = bufs + NL * Cfg::LINE_PITCH;
-        constexpr int NLc = kKL;
+        constexpr int NLc = NLP;
         const int es = (int)out_e_stride;   // offsets inside one field fit 32 bits
         auto emit = [&](int l, int k, int kn) FSM_INLINE_LAMBDA {
             const cplx<T>* sl = st0 + l * NFW * Cfg::LINE_PITCH;
@@ -987,19 +1318,6 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
 //     S0 = (Z(k) + conj Z(N-k))/2, S1 = (Z(k) - conj Z(N-k))/2i needs no staging line, and the two rows of a
 //     buffer leave as ONE 16-byte store, 128-byte segments per k across the lanes.
 // ------------------------------------------------------------------------------------------
-template <class Cfg>
-struct PhysZ {
-    static constexpr int NLZ = (Cfg::TL <= 16) ? 8 : 4;     // thread-lines per CTA
-    static constexpr int KS = 2 * NLZ;                      // head buffers = rotated lanes
-    static constexpr int NT = NLZ * Cfg::TL;
-    static constexpr int K = 4 * NLZ;                       // rows per CTA
-    static constexpr bool PARK = (Cfg::EPT >= 16);          // product of the even row waits in shared memory
-    static constexpr int PARK_PITCH = Cfg::N / 2;           // complex slots per thread-line
-    static size_t smem_bytes(size_t elem) {
-        return elem * (size_t)(((Cfg::TW_TOTAL + 1) & ~1) + KS * Cfg::LINE_PITCH + (PARK ? NLZ * PARK_PITCH : 0));
-    }
-};
-
 template <typename T>
 __device__ __forceinline__ void store_pair(cplx<T>* dst, cplx<T> a, cplx<T> b) {
     dst[0] = a;

@@ -10,6 +10,9 @@
 #include <vector>
 #include <utility>
 
+#ifndef FSM_LANES_DEFAULT
+#define FSM_LANES_DEFAULT 2
+#endif
 #ifndef FSM_PF_DEFAULT
 #define FSM_PF_DEFAULT 5   // PF_IX | PF_FX_OPS (measured on C3: 1.908 -> 1.861 ms/step; PF_PHYS and PF_FX_WIN cost time)
 #endif
@@ -181,12 +184,15 @@ static std::vector<Stage> build_stages(int integ, double dt, bool has_lin) {
 
 using namespace fsm;
 
+#define FSM_MAX_LANES 4
 struct fsm_plan {
     fsm_desc d;
     int ndim, n[3], nh, ph, B, C, prog, kprog;  // kprog = kernel-side Prog enum
     bool f64;
     long nmodes, ntot;
     int chunk;
+    int nlanes = 1;              // independent sample ranges stepped concurrently on internal streams (see do_step)
+    size_t lane_w_bytes[4] = {0, 0, 0, 0};   // per-lane size of the W1, W2, W3, W2b regions
     int nf_ix, nfi, nout;  // fields: IX per channel, PHYS inputs per sample, PHYS outputs per sample
     void* peers[2][FSM_MAX_PEERS] = {};   // direct exchange: receive buffers of every rank (exchange 1, 2)
     int n_peers[2] = {0, 0};
@@ -207,6 +213,9 @@ struct fsm_plan {
 #ifndef FSM_EMU
     std::vector<cudaEvent_t> ev_pool;
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev_used;
+    cudaStream_t lane_stream[FSM_MAX_LANES] = {};
+    cudaEvent_t lane_fork = nullptr, lane_join[FSM_MAX_LANES] = {};
+    int lane_device = -1;
 #endif
 };
 
@@ -346,16 +355,16 @@ struct Buffers {
 };
 
 template <typename T>
-Buffers<T> carve(const fsm_plan* p, void* u_hat, void* ws, void* ext) {
+Buffers<T> carve(const fsm_plan* p, void* u_hat, void* ws, void* ext, int lane = 0) {
     Buffers<T> b;
     char* base = static_cast<char*>(ws);
     b.arr[ARR_U] = static_cast<cplx<T>*>(u_hat);
     for (int i = ARR_S1; i <= ARR_S4; ++i) b.arr[i] = reinterpret_cast<cplx<T>*>(base + p->off_arr[i]);
     b.arr[ARR_EXT] = static_cast<cplx<T>*>(ext);
-    b.w1 = reinterpret_cast<cplx<T>*>(base + p->off_w1);
-    b.w2 = reinterpret_cast<cplx<T>*>(base + p->off_w2);
-    b.w3 = reinterpret_cast<cplx<T>*>(base + p->off_w3);
-    b.w2b = reinterpret_cast<cplx<T>*>(base + p->off_w2b);
+    b.w1 = reinterpret_cast<cplx<T>*>(base + p->off_w1 + lane * p->lane_w_bytes[0]);
+    b.w2 = reinterpret_cast<cplx<T>*>(base + p->off_w2 + lane * p->lane_w_bytes[1]);
+    b.w3 = reinterpret_cast<cplx<T>*>(base + p->off_w3 + lane * p->lane_w_bytes[2]);
+    b.w2b = reinterpret_cast<cplx<T>*>(base + p->off_w2b + lane * p->lane_w_bytes[3]);
     b.dc = reinterpret_cast<T*>(base + p->off_dc);
     return b;
 }
@@ -417,7 +426,8 @@ int run_forward_tail(const fsm_plan* p, const Buffers<T>& bf, const Geom<T>& g, 
 
 // One nonlinear evaluation of `stage_in` followed by the stage combine.
 template <typename T>
-int run_stage(const fsm_plan* p, const Buffers<T>& bf, const Stage& s, cudaStream_t st) {
+int run_stage(const fsm_plan* p, const Buffers<T>& bf, const Stage& s, cudaStream_t st, int b_lo = 0, int b_hi = -1) {
+    if (b_hi < 0) b_hi = p->B;
     Combine<T> cb;
     const bool fresh = p->prog != FSM_PROG_LINEAR;
     if (int e = make_combine<T>(p, s, bf.arr, fresh, &cb)) return e;
@@ -437,8 +447,8 @@ int run_stage(const fsm_plan* p, const Buffers<T>& bf, const Stage& s, cudaStrea
     ep.source = static_cast<const cplx<T>*>(p->d.source_hat);
     ep.dc_out = (p->prog == FSM_PROG_KS && p->d.ks_remove_mean) ? bf.dc : nullptr;
     ep.project = (p->prog == FSM_PROG_NS3D) ? 1 : 0;
-    for (int b0 = 0; b0 < p->B; b0 += p->chunk) {
-        const int nb = (p->B - b0 < p->chunk) ? (p->B - b0) : p->chunk;
+    for (int b0 = b_lo; b0 < b_hi; b0 += p->chunk) {
+        const int nb = (b_hi - b0 < p->chunk) ? (b_hi - b0) : p->chunk;
         IxArgs<T> a;
         a.g = g; a.state = stage_in + (long)b0 * p->C * p->nmodes; a.w1 = bf.w1;
         a.state_bstride = p->nmodes; a.nbc = nb * p->C;
@@ -516,6 +526,41 @@ int do_step(fsm_plan* p, void* u_hat, void* ws, int n_steps, cudaStream_t st) {
         if (p->stages.size() > FSM_MAX_STAGES) return fail(-ENOSYS, "too many stages for the 1-D kernel");
         return run_1d<T>(p, bf, p->stages.data(), (int)p->stages.size(), n_steps, st);
     }
+#ifndef FSM_EMU
+    // Samples are independent (every program but KS with its batch mean): the batch is split into `nlanes` ranges,
+    // each advanced through ALL steps on its own internal stream with its own intermediates. The kernels of one lane
+    // fill the wave tails of the other, and passes bound by different resources (FX: HBM, last-axis pass: shared
+    // memory, inverse-x: latency) share the SMs instead of following each other. Fork/join with events on the
+    // caller's stream; per-pass profiling keeps the single-stream order so that its timings do not overlap.
+    if (p->nlanes > 1 && !p->profile && n_steps > 0 && p->prog != FSM_PROG_LINEAR) {
+        int dev = -1;
+        cudaGetDevice(&dev);
+        if (p->lane_device != dev) {       // first use (or another device): create the streams and events here
+            for (int l = 0; l < p->nlanes; ++l) {
+                if (cudaStreamCreateWithFlags(&p->lane_stream[l], cudaStreamNonBlocking) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&p->lane_join[l], cudaEventDisableTiming) != cudaSuccess)
+                    return fail(-EIO, "could not create the lane streams");
+            }
+            if (cudaEventCreateWithFlags(&p->lane_fork, cudaEventDisableTiming) != cudaSuccess) return fail(-EIO, "event");
+            p->lane_device = dev;
+        }
+        const int per = (p->B + p->nlanes - 1) / p->nlanes;
+        cudaEventRecord(p->lane_fork, st);
+        for (int l = 0; l < p->nlanes; ++l) {
+            const int lo = l * per, hi = (lo + per < p->B) ? lo + per : p->B;
+            if (lo >= hi) continue;
+            cudaStream_t ls = p->lane_stream[l];
+            cudaStreamWaitEvent(ls, p->lane_fork, 0);
+            Buffers<T> lb = carve<T>(p, u_hat, ws, nullptr, l);
+            for (int i = 0; i < n_steps; ++i)
+                for (const Stage& s : p->stages)
+                    if (int e = run_stage<T>(p, lb, s, ls, lo, hi)) return e;
+            cudaEventRecord(p->lane_join[l], ls);
+            cudaStreamWaitEvent(st, p->lane_join[l], 0);
+        }
+        return 0;
+    }
+#endif
     for (int i = 0; i < n_steps; ++i)
         for (const Stage& s : p->stages)
             if (int e = run_stage<T>(p, bf, s, st)) return e;
@@ -918,6 +963,18 @@ int fsm_plan_create(fsm_plan** out, const fsm_desc* d) {
             w2b_per = (size_t)p->nout * p->nmodes * esz;
         }
     }
+    // lanes: independent sample ranges stepped concurrently (do_step). KS couples the samples through its batch mean.
+    int nlanes = d->lanes;
+    const bool independent = !(p->prog == FSM_PROG_KS && d->ks_remove_mean) && p->prog != FSM_PROG_LINEAR;
+    if (nlanes <= 0) nlanes = (independent && p->ndim >= 2 && p->P == 1 && p->B >= 4) ? FSM_LANES_DEFAULT : 1;
+    if (!independent || p->ndim == 1 || p->P > 1) nlanes = 1;
+    if (nlanes > FSM_MAX_LANES) nlanes = FSM_MAX_LANES;
+    if (nlanes > p->B) nlanes = p->B;
+#ifdef FSM_EMU
+    nlanes = 1;
+#endif
+    p->nlanes = nlanes;
+    const int lane_B = (p->B + nlanes - 1) / nlanes;   // samples per lane
     int chunk = d->chunk;
     if (chunk <= 0) {
         // as many samples per launch as an 8 GiB budget for the per-chunk intermediates allows (measured on
@@ -925,14 +982,15 @@ int fsm_plan_create(fsm_plan** out, const fsm_desc* d) {
         // and launch gaps better than L2 residency of the intermediates pays back), then balance the chunks.
         const size_t per = w1_per + w2_per + w3_per + w2b_per;
         const size_t budget = (size_t)8 << 30;
-        chunk = p->B;
+        chunk = lane_B;
         if (per > 0 && (size_t)chunk * per > budget && p->P == 1) chunk = (int)(budget / per);
         if (chunk < 1) chunk = 1;
-        if (chunk > p->B) chunk = p->B;
-        const int nch = (p->B + chunk - 1) / chunk;
-        chunk = (p->B + nch - 1) / nch;
+        if (chunk > lane_B) chunk = lane_B;
+        const int nch = (lane_B + chunk - 1) / chunk;
+        chunk = (lane_B + nch - 1) / nch;
     }
-    if (chunk > p->B || p->P > 1) chunk = p->B;
+    if (p->P > 1) chunk = p->B;
+    if (chunk > lane_B) chunk = lane_B;
     p->chunk = chunk;
     // workspace layout
     size_t off = 0;
@@ -946,10 +1004,14 @@ int fsm_plan_create(fsm_plan** out, const fsm_desc* d) {
         p->off_arr[i] = off;
         if (i <= n_scratch) off = align_up(off + state_bytes, 256);
     }
-    p->off_w1 = off; off = align_up(off + w1_per * chunk, 256);
-    p->off_w2 = off; off = align_up(off + w2_per * chunk, 256);
-    p->off_w3 = off; off = align_up(off + w3_per * chunk, 256);
-    p->off_w2b = off; off = align_up(off + w2b_per * chunk, 256);
+    p->lane_w_bytes[0] = align_up(w1_per * chunk, 256);
+    p->lane_w_bytes[1] = align_up(w2_per * chunk, 256);
+    p->lane_w_bytes[2] = align_up(w3_per * chunk, 256);
+    p->lane_w_bytes[3] = align_up(w2b_per * chunk, 256);
+    p->off_w1 = off; off += p->lane_w_bytes[0] * nlanes;
+    p->off_w2 = off; off += p->lane_w_bytes[1] * nlanes;
+    p->off_w3 = off; off += p->lane_w_bytes[2] * nlanes;
+    p->off_w2b = off; off += p->lane_w_bytes[3] * nlanes;
     p->off_dc = off; off = align_up(off + (size_t)p->B * (p->f64 ? 8 : 4), 256);
     p->ws_bytes = off;
     // generic transforms (r2c / c2r) process this many independent fields per launch: bounded by what
@@ -959,16 +1021,16 @@ int fsm_plan_create(fsm_plan** out, const fsm_desc* d) {
         if (p->ndim == 1) {
             cap = (size_t)p->B * p->C;
         } else if (p->ndim == 2) {
-            cap = (w1_per * chunk) / ((size_t)p->n[0] * p->ph * esz);
-            const size_t c2 = (w2_per * chunk) / ((size_t)p->nmodes * esz);
+            cap = (p->lane_w_bytes[0] * nlanes) / ((size_t)p->n[0] * p->ph * esz);    // the lane regions are contiguous
+            const size_t c2 = (p->lane_w_bytes[1] * nlanes) / ((size_t)p->nmodes * esz);
             if (c2 < cap) cap = c2;
         } else if (p->P > 1) {
             cap = (size_t)p->B * p->C;
         } else {
-            cap = (w1_per * chunk) / ((size_t)p->nh * plane * esz);
-            const size_t c3 = (w3_per * chunk) / ((size_t)plane * p->ph * esz);
-            const size_t c2 = (w2_per * chunk) / ((size_t)p->nh * plane * esz);
-            const size_t c2b = (w2b_per * chunk) / ((size_t)p->nmodes * esz);
+            cap = (p->lane_w_bytes[0] * nlanes) / ((size_t)p->nh * plane * esz);
+            const size_t c3 = (p->lane_w_bytes[2] * nlanes) / ((size_t)plane * p->ph * esz);
+            const size_t c2 = (p->lane_w_bytes[1] * nlanes) / ((size_t)p->nh * plane * esz);
+            const size_t c2b = (p->lane_w_bytes[3] * nlanes) / ((size_t)p->nmodes * esz);
             if (c3 < cap) cap = c3;
             if (c2 < cap) cap = c2;
             if (c2b < cap) cap = c2b;
@@ -977,7 +1039,7 @@ int fsm_plan_create(fsm_plan** out, const fsm_desc* d) {
     }
     // bookkeeping for benchmarks (SURVEY.md §8d transform-pass model)
     {
-        const int nchunks = (p->B + chunk - 1) / chunk;
+        const int nchunks = nlanes * ((lane_B + chunk - 1) / chunk);
         int64_t launches = 0, units = 0;  // units of one real field
         for (int i = 0; i < 4; ++i) p->pass_units[i] = 0;
         for (const Stage& s : p->stages) {
@@ -1008,6 +1070,13 @@ void fsm_plan_destroy(fsm_plan* plan) {
 #ifndef FSM_EMU
     for (auto& u : plan->ev_used) { cudaEventDestroy(u.second.first); cudaEventDestroy(u.second.second); }
     for (auto e : plan->ev_pool) cudaEventDestroy(e);
+    if (plan->lane_device >= 0) {
+        for (int l = 0; l < plan->nlanes; ++l) {
+            if (plan->lane_stream[l]) cudaStreamDestroy(plan->lane_stream[l]);
+            if (plan->lane_join[l]) cudaEventDestroy(plan->lane_join[l]);
+        }
+        if (plan->lane_fork) cudaEventDestroy(plan->lane_fork);
+    }
 #endif
     delete plan;
 }

@@ -113,7 +113,7 @@ class FusedStepper:
     def __init__(self, f_mesh: FourierMesh, batch: int, n_channel: int, program: int, integrator: str, dt: float,
                  linear_coef: Optional[torch.Tensor], nl_coef: float, source_hat: Optional[torch.Tensor],
                  kmax: Sequence[int], ks_remove_mean: bool, integrator_cfg: dict, chunk: int = 0,
-                 tables: Optional[dict] = None, slab=None):
+                 tables: Optional[dict] = None, slab=None, lanes: int = 0):
         lib = _GuardedLib(_cabi.lib(), f_mesh.device)
         # slab = (rank, nranks, process_group): ONE 3-D grid decomposed over nranks GPUs
         self.slab = slab
@@ -179,7 +179,8 @@ class FusedStepper:
         desc.program = program
         desc.integrator = _cabi.INTEGRATOR_IDS[integrator]
         desc.ks_remove_mean = 1 if ks_remove_mean else 0
-        desc.chunk = int(chunk or int(os.environ.get("FSM_CHUNK", "0")))
+        desc.chunk = int(chunk)
+        desc.lanes = int(lanes)
         desc.dt = float(dt)
         desc.nl_coef = float(nl_coef)
         dk, dkraw = f_mesh.wavenumber_tables()
@@ -558,6 +559,7 @@ class OperatorLike:
         self._state_dict = {"f_mesh": None, "n_channel": None, "linear_coef": None, "integrator": None}
         self._lowered = None
         self._chunk = 0
+        self._lanes = 0
         self._slab = None
 
     # ---- algebra (operator/_base.py:170-206, 826-850) ------------------------------------------
@@ -670,6 +672,12 @@ class OperatorLike:
     def set_chunk(self, chunk: int):
         """Samples per pass launch (0 = library default); a tuning knob of the CUDA path."""
         self._chunk = int(chunk)
+        self._state_dict["integrator"] = None
+
+    def set_lanes(self, lanes: int):
+        """Ensembles: number of independent sample ranges the library steps concurrently on internal streams
+        (0 = library default, 1 = everything on the caller's stream); a tuning knob of the CUDA path."""
+        self._lanes = int(lanes)
         self._state_dict["integrator"] = None
 
     def register_additional_check(self, func: Callable[[int, int], bool]):
@@ -792,7 +800,7 @@ class OperatorLike:
         try:
             st = FusedStepper(sd["f_mesh"], batch, sd["n_channel"], lo["program"], name, dt, sd["linear_coef"],
                               lo["nl_coef"], lo["source_hat"], lo["kmax"], lo["ks_remove_mean"], cfg,
-                              chunk=self._chunk, tables=tables, slab=self._slab)
+                              chunk=self._chunk, tables=tables, slab=self._slab, lanes=self._lanes)
         except torch.cuda.OutOfMemoryError as e:
             raise RuntimeError(os.linesep.join([
                 "Cuda out of memory when building the integrator.",
