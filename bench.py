@@ -359,7 +359,8 @@ def run_slab_c5(fsm, dist, world, rank, dev, steps, warmup):
             out["bare_exchange_error"] = repr(exc)[:200]
         gbs_total = info["algo_bytes_per_step"] * world / (ms * 1e-3) / 1e9
         out.update({"ms_per_step_1gpu": t1, "strong_efficiency_vs_n1": t1 / (world * ms), "exchange": st._exch_mode,
-                    "nsub": getattr(st, "nsub", 1), "pipeline": getattr(st, "pipeline", "x-sub-slabs"),
+                    "nsub": getattr(st, "nsub", 1), "cuda_graph": bool(getattr(st, "_graphs", None)),
+                    "graph_error": getattr(st, "_graph_error", None), "ky_ownership": "cyclic (kept lines only on the inverse exchange)",
                     "a2a_send_bytes_per_gpu_per_step": sent,
                     "a2a_bare_ms_per_step": bare,
                     "a2a_gbs_per_gpu": (sent / (bare * 1e-3) / 1e9) if bare else None,

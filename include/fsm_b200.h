@@ -87,8 +87,10 @@ typedef struct fsm_desc {
     const void* source_hat;   /* optional constant source spectrum, complex [C][modes], coefficient
                                  folded in (operator/_base.py:994-1015)                              */
     int32_t slab_rank;        /* slab decomposition of ONE 3-D grid over slab_nranks GPUs (0 / 1 = off):  */
-    int32_t slab_nranks;      /* spectral state and tables hold the local ky slab [n1/P][n2/2+1][n0],
-                                 physical fields the local x slab [n0/P][n1][n2]; see fsm_slab_phase      */
+    int32_t slab_nranks;      /* spectral state and tables hold the local ky lines [n1/P][n2/2+1][n0] with CYCLIC
+                                 ownership (local line t of rank r is ky = r + P t: every rank owns the same share of
+                                 the dealiased band, and the inverse-side exchange ships kept lines only); physical
+                                 fields the local x slab [n0/P][n1][n2] (blocked); see fsm_slab_phase      */
     int32_t lanes;            /* ensembles: independent sample ranges stepped concurrently on internal streams
                                  (fork/join on the caller's stream); 0 = choose, 1 = everything on the caller's stream */
     int32_t reserved0;

@@ -374,3 +374,14 @@ def test_recorders_and_solve_on_gpu():
     rhs = -13.0 * phi                                           # lap(phi)
     sol = fsm.Laplacian().solve(b=rhs, mesh=mesh2, n_channel=1)
     assert float((sol - phi).abs().max()) < 1e-12
+
+
+def test_genuine_reference_operator_on_the_gpu_dropin():
+    """the unmodified reference (baseline/_ref, its cuFFT + ATen path) against the same reference
+    operator object stepping through the fused kernels (torchfsm_b200.reference_adapter) on this GPU, same inputs."""
+    from test_reference_adapter import _reference, run_dropin
+    torchfsm = _reference()
+    if torchfsm is None:
+        pytest.skip("reference not importable on this box (baseline/_ref did not travel)")
+    run_dropin(torchfsm, "cuda", torch.float32, 1e-5)
+    run_dropin(torchfsm, "cuda", torch.float64, 1e-12)

@@ -31,7 +31,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--integrator", default="SETDRK4")
     ap.add_argument("--nsub", type=int, default=0, help="sub-slabs for exchange/compute overlap (0 = default)")
-    ap.add_argument("--modes", default="nccl", help="comma list of exchange paths to time: nccl, dma, store")
+    ap.add_argument("--modes", default="nccl", help="comma list of exchange[:nsub[:copy_streams[:graph]]] to time; "
+                                                    "exchange = nccl, dma or store")
+    ap.add_argument("--skip-parity", action="store_true")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -49,8 +51,12 @@ def main():
     for mode in a.modes.split(","):
         try:
             mode = mode.strip()
-            if ":" in mode:                      # "dma:4" = exchange path : sub-slabs
-                mode, a.nsub = mode.split(":")[0], int(mode.split(":")[1])
+            a.copy_streams, a.graph = 1, 1
+            if ":" in mode:                      # "dma:4:2:1" = exchange path : sub-slabs : copy streams : CUDA graph
+                f = mode.split(":")
+                mode, a.nsub = f[0], int(f[1])
+                a.copy_streams = int(f[2]) if len(f) > 2 else 1
+                a.graph = int(f[3]) if len(f) > 3 else 1
             run(a, mode, world, rank, dev)
         except Exception as exc:   # report and go on to the next mode
             if rank == 0:
@@ -62,7 +68,7 @@ def main():
 def run(a, mode, world, rank, dev):
     # ---- parity of the slab path on a golden fixture (16^3, fp32, SETDRK4)
     parity = None
-    if world > 1:
+    if world > 1 and not a.skip_parity:
         from golden_util import load_golden, rel_l2
         from product_util import product_from_golden
         g = load_golden("c5_ns3d_16_setdrk4_f32")
@@ -90,7 +96,7 @@ def run(a, mode, world, rank, dev):
     op.set_integrator(getattr(fsm.SETDRKIntegrator, a.integrator) if a.integrator.startswith("S")
                       else getattr(fsm.ETDRKIntegrator, a.integrator))
     if world > 1:
-        op.set_slab_decomposition(nsub=a.nsub, exchange=mode)
+        op.set_slab_decomposition(nsub=a.nsub, exchange=mode, copy_streams=a.copy_streams, graph=bool(a.graph))
     t0 = time.perf_counter()
     op.integrate(u, mesh=mesh, dt=0.0025, step=1)
     torch.cuda.synchronize()
@@ -139,7 +145,8 @@ def run(a, mode, world, rank, dev):
         info = st.info()
         print(json.dumps({"config": f"C5 ns3d {n}^3 B=1 C=3 {a.integrator} slab x{world}", "mode": mode, "n_gpus": world,
                           "ms_per_step": float(ms.item()), "steps_per_sec": 1e3 / float(ms.item()), "steps": a.steps,
-                          "finite": finite, "setup_s": setup_s, "nsub": getattr(st, "nsub", 1), "all_to_all": a2a, "parity_rel_l2_16cubed_fp32": parity,
+                          "finite": finite, "setup_s": setup_s, "nsub": getattr(st, "nsub", 1), "copy_streams": a.copy_streams,
+                          "graph": bool(getattr(st, "_graphs", None)), "graph_error": getattr(st, "_graph_error", None), "all_to_all": a2a, "parity_rel_l2_16cubed_fp32": parity,
                           "algo_gb_per_step_global": info["algo_bytes_per_step"] / 1e9}), flush=True)
     del st, op, u_hat
     torch.cuda.empty_cache()

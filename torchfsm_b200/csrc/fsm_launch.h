@@ -12,7 +12,7 @@ struct IxArgs {
     cplx<T>* w1;
     long state_bstride, w1_fstride, in_t_stride, in_o_stride, out_o_stride, out_e_stride;
     int n_t, n_outer, nbc;
-    Blk eb = {30, 0, 30, 0};
+    Blk eb = {30, 0, 30, 0, 0, 0, 0};
     Peers pe = {{nullptr}, 0, 0};
 };
 template <typename T>
@@ -23,7 +23,7 @@ struct MidArgs {
     long in_fstride, out_fstride, in_t_stride, in_o_stride, out_o_stride, out_e_stride;
     int nfi, n_t, n_outer, nb;
     MidSpec spec;
-    Blk ib = {30, 0, 30, 0}, eb = {30, 0, 30, 0};
+    Blk ib = {30, 0, 30, 0, 0, 0, 0}, eb = {30, 0, 30, 0, 0, 0, 0};
     Peers pe = {{nullptr}, 0, 0};
 };
 template <typename T>
@@ -44,7 +44,7 @@ struct FxArgs {
     Combine<T> cb;
     FxEpilogue<T> ep;
     int nlines, b0, nb;
-    Blk ib = {30, 0, 30, 0};
+    Blk ib = {30, 0, 30, 0, 0, 0, 0};
     long line_stride = 0;  // 0 = N (contiguous lines)
 };
 

@@ -55,7 +55,11 @@ struct Geom {
     int kmax[3];   // dealiasing: keep |m_i| <= kmax[i]
     long nmodes;   // complex modes per field in the rot-half layout
     T inv_ntot;    // 1 / (n0*n1*n2)
-    int ky0;       // slab decomposition: first global ky of the local spectral slab (0 on one GPU)
+    // slab decomposition (one GPU: ky0 = 0, kys = 1, gap = 0): ky ownership is CYCLIC, local line t holds the global
+    // ky = ky0 + kys * t (ky0 = rank, kys = ranks), so every rank owns the same share of the dealiased band. On the
+    // inverse side only the kept local lines are processed and shipped: compact index t' -> local line
+    // t' < gap_at ? t' : t' + gap (the dropped middle of the spectrum is a contiguous run of local lines).
+    int ky0, kys, gap_at, gap;
     int pf;        // L2 prefetch switches (PF_* bits)
     int pf_wave;   // CTAs resident on the whole GPU for this launch = prefetch distance in CTAs
     const T* dk[3];     // 2*pi*f_i(m), Nyquist entry zeroed (Hermitian projection of i*k)
@@ -69,6 +73,9 @@ struct Blk {
     long stride;
     int shift2;     // sub-slab block: (i & mask) >> shift2   (30 = none)
     long stride2;
+    // cyclic ownership (the ky axis of a slab-decomposed grid): rank = i & (2^cyc - 1), local index t = i >> cyc,
+    // stored at the compact position t < gap_at ? t : t - gap. cyc = 0: blocked ownership as described above.
+    int cyc, gap_at, gap;
 };
 // Direct exchange (slab decomposition): instead of a local send buffer the pass stores straight into the
 // receive buffers of the destination ranks (peer memory over NVLink; plain addresses in the emulator).
@@ -81,6 +88,10 @@ struct Peers {
     long self_off;    // elements: (this rank) * Blk::stride
 };
 __device__ __forceinline__ long blk_off(int i, const Blk& b, long elem_stride) {
+    if (b.cyc > 0) {
+        const int t = i >> b.cyc;
+        return (long)(i & ((1 << b.cyc) - 1)) * b.stride + (long)(t < b.gap_at ? t : t - b.gap) * elem_stride;
+    }
     const int r = i & ((1 << b.shift) - 1);
     const int lo = (b.shift2 < b.shift) ? b.shift2 : b.shift;
     return (long)(i >> b.shift) * b.stride + (long)(r >> b.shift2) * b.stride2 + (long)(r & ((1 << lo) - 1)) * elem_stride;
@@ -128,6 +139,11 @@ __device__ __forceinline__ bool next_wave_block(int wave, int& x, int& y, int& z
 
 template <typename T>
 __device__ __forceinline__ cplx<T>* peer_ptr(const Peers& pe, const Blk& b, int i, long off0, long elem_stride) {
+    if (b.cyc > 0) {
+        const int t = i >> b.cyc;
+        return static_cast<cplx<T>*>(pe.base[i & ((1 << b.cyc) - 1)]) + pe.self_off + off0 +
+               (long)(t < b.gap_at ? t : t - b.gap) * elem_stride;
+    }
     const int r = i & ((1 << b.shift) - 1);
     return static_cast<cplx<T>*>(pe.base[i >> b.shift]) + pe.self_off + off0 + (long)r * elem_stride;
 }
@@ -303,11 +319,11 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
             const int t2 = x2 * K + lt;
             bool want = t2 < n_t;
             if (want && PROG != PROG_C2R) {
-                want = iabs(signed_mode_rt(t2 + g.ky0, g.n[1])) <= g.kmax[1];
+                want = iabs(signed_mode_rt(g.ky0 + g.kys * (t2 < g.gap_at ? t2 : t2 + g.gap), g.n[1])) <= g.kmax[1];
                 if (g.ndim == 3) want = want && (o2 <= g.kmax[2]);
             }
             if (want)
-                l2_prefetch_line<T>(state + (long)z2 * state_bstride + (long)t2 * in_t_stride + (long)o2 * in_o_stride, N,
+                l2_prefetch_line<T>(state + (long)z2 * state_bstride + (long)(t2 < g.gap_at ? t2 : t2 + g.gap) * in_t_stride + (long)o2 * in_o_stride, N,
                                     PROG == PROG_C2R ? N : g.kmax[0]);
         }
     }
@@ -320,7 +336,8 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
     const int t = t0 + lt;  // ky index of this thread-line
     const int k_valid = (K < n_t - t0) ? K : (n_t - t0);
     // dealias test on the line coordinates
-    const int tglob = (t < n_t ? t : 0) + g.ky0;   // global ky of this line
+    const int tloc = (t < n_t) ? (t < g.gap_at ? t : t + g.gap) : 0;   // local line behind the compact index t
+    const int tglob = g.ky0 + g.kys * tloc;                             // its global ky
     const int my = signed_mode_rt(tglob, g.n[1]);
     bool line_kept = (t < n_t);
     if (PROG != PROG_C2R) {
@@ -331,7 +348,7 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
     const T dkyraw = (t < n_t) ? g.dkraw[1][tglob] : T(0);
 
     cplx<T> u[EPT];
-    const cplx<T>* src = state + bc * state_bstride + (long)(t < n_t ? t : 0) * in_t_stride + (long)o * in_o_stride + tau;
+    const cplx<T>* src = state + bc * state_bstride + (long)tloc * in_t_stride + (long)o * in_o_stride + tau;
     FSM_PIN(src);
     LineSync<TL> sync{1 + lt};
     cplx<T>* mybuf = bufs + lt * Cfg::LINE_PITCH;
@@ -1757,7 +1774,7 @@ k_pass_fx(Geom<T> g, const cplx<T>* __restrict__ win, long win_fstride,
     });
     // line coordinates
     int ky, kz = 0;
-    if (g.ndim == 3) { ky = line / g.nh + g.ky0; kz = line % g.nh; } else { ky = line; }
+    if (g.ndim == 3) { ky = g.ky0 + g.kys * (line / g.nh); kz = line % g.nh; } else { ky = line; }
     // the epilogue is instantiated once per compile-time combine shape (and once generic); cb.kind is uniform
     with_combine_kind(cb.kind, [&](auto kindc) FSM_INLINE_LAMBDA {
     constexpr int KIND = decltype(kindc)::value;

@@ -201,6 +201,7 @@ struct fsm_plan {
     long ks_log_cap = 0;
     mutable long ks_log_pos = 0;
     int P = 1, rank = 0, kyl = 0, nxl = 0, nkz1 = 0;  // slab decomposition (P > 1): local ky / x extents, kept kz planes
+    int gap_at = 0, gap = 0, nky1 = 0;                // cyclic ky ownership: dropped run of local lines, kept local lines
     std::vector<Stage> stages;
     Stage rhs_stage;
     // workspace (offsets in bytes)
@@ -267,7 +268,10 @@ Geom<T> make_geom(const fsm_plan* p, bool nomask) {
         g.dk[i] = static_cast<const T*>(p->d.dk[i]);
         g.dkraw[i] = static_cast<const T*>(p->d.dkraw[i]);
     }
-    g.ky0 = (p->P > 1) ? p->rank * p->kyl : 0;
+    g.ky0 = (p->P > 1) ? p->rank : 0;
+    g.kys = (p->P > 1) ? p->P : 1;
+    g.gap_at = (p->P > 1 && !nomask) ? p->gap_at : (1 << 30);
+    g.gap = (p->P > 1 && !nomask) ? p->gap : 0;
     g.pf = p->pf;
     g.pf_wave = 0;
     g.nh = p->nh;
@@ -682,12 +686,13 @@ int slab_ix(const fsm_plan* p, const Geom<T>& g, int kprog, const cplx<T>* state
             int nkz, int nsub, cudaStream_t st) {
     const LaunchTable<T>* tx = launch_table<T>(p->n[0]);
     const int nxh = p->nxl / nsub;
+    const int nky = p->kyl - g.gap;     // local lines shipped: the kept ones (everything for the plain transforms)
     IxArgs<T> a;
     a.g = g; a.state = state; a.w1 = send; a.state_bstride = p->nmodes; a.nbc = nfields_in;
-    a.w1_fstride = (long)nkz * nxh * p->kyl;
+    a.w1_fstride = (long)nkz * nxh * nky;
     a.in_t_stride = (long)p->nh * p->n[0]; a.in_o_stride = p->n[0];
-    a.out_o_stride = (long)nxh * p->kyl; a.out_e_stride = p->kyl;
-    a.n_t = p->kyl; a.n_outer = nkz;
+    a.out_o_stride = (long)nxh * nky; a.out_e_stride = nky;
+    a.n_t = nky; a.n_outer = nkz;
     a.eb.shift = ilog2(p->nxl); a.eb.stride = (long)nfields_in * nf * a.w1_fstride;
     a.eb.shift2 = ilog2(nxh); a.eb.stride2 = (long)p->P * a.eb.stride;
     if (p->n_peers[0] > 0) {
@@ -706,13 +711,15 @@ int slab_mid_inverse(const fsm_plan* p, const Geom<T>& g, const cplx<T>* recv, c
                      int nkz, int nb, int sub, int nsub, cudaStream_t st) {
     const LaunchTable<T>* ty = launch_table<T>(p->n[1]);
     const int nxh = p->nxl / nsub;
+    const int nky = p->kyl - g.gap;
     MidArgs<T> m;
     m.g = g;
-    m.in_fstride = (long)nkz * nxh * p->kyl; m.out_fstride = (long)p->nxl * p->n[1] * p->ph;
-    m.in_t_stride = (long)nxh * p->kyl; m.in_o_stride = p->kyl;
+    m.in_fstride = (long)nkz * nxh * nky; m.out_fstride = (long)p->nxl * p->n[1] * p->ph;
+    m.in_t_stride = (long)nxh * nky; m.in_o_stride = nky;
     m.out_o_stride = (long)p->n[1] * p->ph; m.out_e_stride = p->ph;
     m.nfi = nfi_in; m.n_t = nkz; m.n_outer = nxh; m.nb = nb; m.spec = spec;
-    m.ib.shift = ilog2(p->kyl); m.ib.stride = (long)nb * nfi_in * m.in_fstride;
+    m.ib.shift = 0; m.ib.cyc = ilog2(p->P); m.ib.gap_at = g.gap_at; m.ib.gap = g.gap;   // ky: cyclic owners, compact lines
+    m.ib.stride = (long)nb * nfi_in * m.in_fstride;
     m.in = recv + (long)sub * p->P * m.ib.stride;
     m.out = w3 + (long)sub * nxh * m.out_o_stride;
     ProfScope ps(p, PASS_MID, st);
@@ -731,7 +738,8 @@ int slab_mid_forward(const fsm_plan* p, const Geom<T>& g, const cplx<T>* w2a, cp
     m.in_t_stride = p->n[1]; m.in_o_stride = (long)p->nxl * p->n[1];
     m.out_o_stride = nxh; m.out_e_stride = (long)p->nh * nxh;
     m.nfi = nf; m.n_t = nxh; m.n_outer = p->nh; m.nb = nb; m.spec = mid_spec_identity(nf);
-    m.eb.shift = ilog2(p->kyl); m.eb.stride = (long)nb * nf * m.out_fstride;
+    m.eb.shift = 0; m.eb.cyc = ilog2(p->P); m.eb.gap_at = 1 << 30; m.eb.gap = 0;    // ky: cyclic owners, every line
+    m.eb.stride = (long)nb * nf * m.out_fstride;
     m.in = w2a + (long)sub * nxh * m.in_t_stride;
     m.out = send + (long)sub * p->P * m.eb.stride;
     if (p->n_peers[1] > 0) {
@@ -889,6 +897,19 @@ int fsm_plan_create(fsm_plan** out, const fsm_desc* d) {
         }
         p->P = P; p->rank = d->slab_rank; p->kyl = p->n[1] / P; p->nxl = p->n[0] / P;
         p->nkz1 = (d->kmax[2] + 1 < p->nh) ? d->kmax[2] + 1 : p->nh;
+        // cyclic ky ownership (rank r holds ky = r + P t): the same compact set of local lines covers the kept band
+        // |ky| <= kmax on every rank: t < Llo (largest count, rank 0) and t >= kyl - Lhi (largest count, rank P-1)
+        {
+            const int km = d->kmax[1], n1 = p->n[1];
+            int llo = km / P + 1;
+            int first_hi = (n1 - km - (P - 1) + P - 1) / P;      // ceil((n1 - km - (P-1)) / P)
+            if (first_hi < 0) first_hi = 0;
+            int lhi = p->kyl - first_hi;
+            if (llo + lhi >= p->kyl || p->prog == FSM_PROG_LINEAR) { llo = p->kyl; lhi = 0; }
+            p->gap_at = llo;
+            p->gap = p->kyl - llo - lhi;
+            p->nky1 = p->kyl - p->gap;
+        }
         p->nmodes = (long)p->kyl * p->nh * p->n[0];   // local spectral slab
     }
     // program -> kernel program and field counts
@@ -1130,7 +1151,7 @@ int fsm_slab_info(const fsm_plan* plan, int op, int64_t* exch1_elems, int64_t* e
     const int64_t blk1 = (int64_t)plan->nxl * plan->kyl, blk2 = (int64_t)plan->kyl * plan->nh * plan->nxl;
     int64_t e1, e2;
     if (op == FSM_SLAB_STEP || op == FSM_SLAB_RHS) {
-        e1 = (int64_t)plan->P * plan->B * plan->C * plan->nf_ix * plan->nkz1 * blk1;
+        e1 = (int64_t)plan->P * plan->B * plan->C * plan->nf_ix * plan->nkz1 * plan->nxl * plan->nky1;
         e2 = (int64_t)plan->P * plan->B * plan->nout * blk2;
     } else {
         e1 = (int64_t)plan->P * plan->B * plan->C * plan->nh * blk1;

@@ -113,7 +113,7 @@ class FusedStepper:
     def __init__(self, f_mesh: FourierMesh, batch: int, n_channel: int, program: int, integrator: str, dt: float,
                  linear_coef: Optional[torch.Tensor], nl_coef: float, source_hat: Optional[torch.Tensor],
                  kmax: Sequence[int], ks_remove_mean: bool, integrator_cfg: dict, chunk: int = 0,
-                 tables: Optional[dict] = None, slab=None, lanes: int = 0):
+                 tables: Optional[dict] = None, slab=None, lanes: int = 0, allocate: bool = True):
         lib = _GuardedLib(_cabi.lib(), f_mesh.device)
         # slab = (rank, nranks, process_group): ONE 3-D grid decomposed over nranks GPUs
         self.slab = slab
@@ -244,8 +244,11 @@ class FusedStepper:
         self._plan = plan
         self._lib = lib
         ws = lib.fsm_workspace_bytes(plan)
-        self.workspace = torch.empty(max(ws, 16), dtype=torch.uint8, device=self.device)
         self.ws_bytes = ws
+        if not allocate:          # validation only (reference_adapter.lower): the plan exists, nothing can run
+            self.workspace = None
+            return
+        self.workspace = torch.empty(max(ws, 16), dtype=torch.uint8, device=self.device)
         if self.P > 1:
             self._slab_counts = {}
             n1 = n2 = 0
@@ -280,24 +283,30 @@ class FusedStepper:
             else:
                 self._send = [torch.empty(n, dtype=self.cdtype, device=self.device) for n in (n1, n2)]
                 self._recv = [torch.empty(n, dtype=self.cdtype, device=self.device) for n in (n1, n2)]
-            nsub = int(slab[3]) if len(slab) > 3 and slab[3] else int(os.environ.get("FSM_SLAB_SUB", "0"))
+            nsub = int(slab[3]) if len(slab) > 3 and slab[3] else 0
             if self._exch_mode == "store":
                 nsub = 1
-            if nsub <= 0:       # measured on C5 (profiles/r1_slab_scaling_c5_v3.md): 2 sub-slabs at 8 ranks, 4 at 2 ranks (dma)
-                nsub = (4 if (self._exch_mode == "dma" and self.P <= 2 and self.nxl >= 32) else 2) if self.nxl >= 16 else 1
+            if nsub <= 0:       # sub-slabs pipeline the exchanges with the local y/z chain (profiles/r2_slab_scaling.md)
+                nsub = 4 if self.nxl >= 32 else (2 if self.nxl >= 16 else 1)
             while nsub > 1 and self.nxl % nsub:
                 nsub //= 2
             self.nsub = max(1, nsub)
             self._comm_stream = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
-            n_copy = int(os.environ.get("FSM_DMA_STREAMS", "1"))
+            n_copy = int(slab[6]) if len(slab) > 6 and slab[6] else 1
             self._copy_streams = [torch.cuda.Stream(self.device) for _ in range(n_copy)] \
                 if (n_copy > 1 and self.device.type == "cuda") else []
+            # the whole step (every phase launch, copy, barrier and stream dependency of its stages) is captured in
+            # ONE CUDA graph per state buffer and replayed: the phase loop is a few hundred host calls per step
+            self._graph_enabled = bool(slab[7]) if len(slab) > 7 else True
+            self._graphs, self._warm, self._graph_error = {}, False, None
 
     def _local_slab(self, t):
-        """(X, n1, nh, n0) rot-half table -> contiguous local ky slab when the grid is slab-decomposed."""
+        """(X, n1, nh, n0) rot-half table -> contiguous local ky lines when the grid is slab-decomposed. Ownership is
+        cyclic (rank r holds ky = r, r + P, ...), so every rank owns the same share of the dealiased band and the
+        inverse-side exchange ships kept lines only (include/fsm_b200.h)."""
         if self.P == 1:
             return t
-        return t[:, self.rank * self.kyl:(self.rank + 1) * self.kyl].contiguous()
+        return t[:, self.rank::self.P].contiguous()
 
     # ---- slab-decomposed phases ---------------------------------------------------------------------
     def _exchange(self, which, count, offset=0, async_op=False):
@@ -311,7 +320,7 @@ class FusedStepper:
             blk = count // self.P
             src = self._send[which]
             fan = self._copy_streams if self.device.type == "cuda" else []
-            if fan:     # FSM_DMA_STREAMS > 1 (experiment): the block copies of one exchange on several streams
+            if fan:     # copy_streams > 1: the block copies of one exchange spread over several streams
                 cur = torch.cuda.current_stream(self.device)
                 start = torch.cuda.Event()
                 start.record(cur)
@@ -477,13 +486,48 @@ class FusedStepper:
             return self._step_half_ks_sharded(u_hat, int(n_steps))
         if self.P > 1 and self.n_stages and self._desc.program != _cabi.PROG_LINEAR:
             self._slab_begin()
-            for _ in range(int(n_steps)):
-                for stage in range(self.n_stages):
-                    self._slab_eval(0, stage, u_hat)
+            self._slab_steps(u_hat, int(n_steps))
             return u_hat
         _cabi.check(self._lib.fsm_step(self._plan, u_hat.data_ptr(), self.workspace.data_ptr(), self.ws_bytes,
                                        int(n_steps), self._stream()), "step")
         return u_hat
+
+    def _slab_step_once(self, u_hat):
+        for stage in range(self.n_stages):
+            self._slab_eval(0, stage, u_hat)
+
+    def _slab_steps(self, u_hat, n):
+        """``n`` steps of a slab-decomposed grid. On CUDA the first step ever runs eagerly (it also warms every lazy
+        initialisation: NCCL channels, peer mappings), then one step is captured into a CUDA graph keyed by the state
+        buffer and replayed; every rank takes the same decisions, so collectives inside the graphs stay matched."""
+        if self.device.type != "cuda" or not self._graph_enabled:
+            for _ in range(n):
+                self._slab_step_once(u_hat)
+            return
+        if not self._warm and n > 0:
+            self._slab_step_once(u_hat)
+            self._warm = True
+            n -= 1
+        if n <= 0:
+            return
+        key = (u_hat.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream)
+        g = self._graphs.get(key)
+        if g is None:
+            try:
+                g = torch.cuda.CUDAGraph()
+                side = torch.cuda.Stream(self.device)
+                side.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):
+                    self._slab_step_once(u_hat)
+                torch.cuda.current_stream(self.device).wait_stream(side)
+                self._graphs[key] = g
+            except Exception as exc:      # capture unavailable: keep the eager phase loop
+                self._graph_enabled, self._graph_error, g = False, repr(exc), None
+        for _ in range(n):
+            if g is not None:
+                g.replay()
+            else:
+                self._slab_step_once(u_hat)
 
     _KS_FINAL_WEIGHTS = {"ETDRK1": [("coef_1", 1.0)], "SETDRK1": [("coef_1", 1.0)],
                          "ETDRK2": [("coef_1", 1.0, "coef_2", -1.0), ("coef_2", 1.0)],
@@ -627,7 +671,8 @@ class OperatorLike:
         self._lowered = None
 
     def set_slab_decomposition(self, group=None, rank: Optional[int] = None, nranks: Optional[int] = None,
-                               nsub: int = 0, exchange: str = "nccl", peers=None):
+                               nsub: int = 0, exchange: str = "nccl", peers=None, copy_streams: int = 1,
+                               graph: bool = True):
         """Decompose ONE 3-D grid over the ranks of a torch.distributed process group:
         ``integrate`` / ``__call__`` then take and return the local physical x-slab
         ``(B, C, n0/P, n1, n2)`` of the rank. The two transposes per evaluation run as ``exchange`` =
@@ -640,7 +685,11 @@ class OperatorLike:
 
         ``"dma"`` and ``"store"`` need peer-visible buffers: ``peers`` is a provider from ``torchfsm_b200.peer``
         (default: torch symmetric memory). ``nsub`` sub-slabs (0 = choose) pipeline the exchange of one part
-        with the local work on another ("nccl", "dma")."""
+        with the local work on another ("nccl", "dma"); ``copy_streams`` spreads the block copies of one "dma"
+        exchange over several streams; ``graph`` captures each step in one CUDA graph (replayed per step).
+
+        Spectral ownership is cyclic in ky (rank r holds ky = r, r + P, ...): every rank owns the same share of the
+        dealiased band and the inverse-side exchange ships kept lines only."""
         import torch.distributed as dist
         if exchange not in ("nccl", "dma", "store"):
             raise ValueError(f"unknown exchange {exchange!r}")
@@ -649,7 +698,7 @@ class OperatorLike:
             peers = SymmetricMemoryPeers(group)
         self._slab = (dist.get_rank(group) if rank is None else rank,
                       dist.get_world_size(group) if nranks is None else nranks, group, nsub,
-                      peers if exchange != "nccl" else None, exchange)
+                      peers if exchange != "nccl" else None, exchange, int(copy_streams), bool(graph))
         self._state_dict["integrator"] = None
         self._rhs_stepper = None
 
