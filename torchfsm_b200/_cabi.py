@@ -30,12 +30,19 @@ class FsmDesc(ctypes.Structure):
         ("tab_exp", ctypes.c_void_p), ("tab_half_exp", ctypes.c_void_p), ("tab_coef", ctypes.c_void_p * 6),
         ("tab_lin", ctypes.c_void_p), ("source_hat", ctypes.c_void_p),
         ("slab_rank", ctypes.c_int32), ("slab_nranks", ctypes.c_int32),
-        ("lanes", ctypes.c_int32), ("reserved0", ctypes.c_int32),
+        ("lanes", ctypes.c_int32), ("tab_batched", ctypes.c_int32),
+        ("force_hat", ctypes.c_void_p),
     ]
 
 
+class FsmMapTerm(ctypes.Structure):
+    """fsm_map_term of include/fsm_b200.h: one monomial-symbol term of a point-wise spectral map."""
+    _fields_ = [("out_channel", ctypes.c_int32), ("in_channel", ctypes.c_int32), ("power", ctypes.c_int32 * 3),
+                ("inv_laplacian", ctypes.c_int32), ("coef", ctypes.c_double)]
+
+
 EXPORTS = ["fsm_plan_create", "fsm_plan_destroy", "fsm_workspace_bytes", "fsm_step", "fsm_rhs", "fsm_r2c",
-           "fsm_c2r", "fsm_half_to_full", "fsm_full_to_half", "fsm_plan_info", "fsm_stage_kinds", "fsm_slab_phase", "fsm_slab_info", "fsm_slab_peers", "fsm_ks_log", "fsm_profile_enable", "fsm_profile_read", "fsm_last_error",
+           "fsm_c2r", "fsm_spectral_map", "fsm_stage_input", "fsm_stage_combine", "fsm_mask_state", "fsm_sym_outer", "fsm_half_to_full", "fsm_full_to_half", "fsm_plan_info", "fsm_stage_kinds", "fsm_slab_phase", "fsm_slab_info", "fsm_slab_peers", "fsm_ks_log", "fsm_profile_enable", "fsm_profile_read", "fsm_last_error",
            "fsm_abi_version", "fsm_backend"]
 
 _lib = None
@@ -58,6 +65,16 @@ def _declare(lib):
     lib.fsm_r2c.restype = i32
     lib.fsm_c2r.argtypes = [vp, vp, vp, vp, sz, vp]
     lib.fsm_c2r.restype = i32
+    lib.fsm_spectral_map.argtypes = [vp, vp, i32, vp, i32, ctypes.POINTER(FsmMapTerm), i32, i32, vp]
+    lib.fsm_spectral_map.restype = i32
+    lib.fsm_stage_input.argtypes = [vp, i32, i64p]
+    lib.fsm_stage_input.restype = i32
+    lib.fsm_stage_combine.argtypes = [vp, i32, vp, vp, vp, vp, sz, vp]
+    lib.fsm_stage_combine.restype = i32
+    lib.fsm_mask_state.argtypes = [vp, vp, i32, vp]
+    lib.fsm_mask_state.restype = i32
+    lib.fsm_sym_outer.argtypes = [vp, vp, vp, i32, vp]
+    lib.fsm_sym_outer.restype = i32
     lib.fsm_half_to_full.argtypes = [vp, vp, vp, vp]
     lib.fsm_half_to_full.restype = i32
     lib.fsm_full_to_half.argtypes = [vp, vp, vp, vp]

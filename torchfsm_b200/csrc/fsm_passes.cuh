@@ -1488,6 +1488,8 @@ struct Combine {
     cplx<T>* out[FSM_MAX_OUT];
     const T* tab[FSM_MAX_TAB];     // real tables [tab_channels][nmodes]
     long tab_cstride;              // 0 if one table serves every channel
+    long tab_bstride;              // 0 if one table serves every sample (else per-sample tables: batched coefficients,
+                                   // operator/_base.py:339-357 with tensor-valued coefficients)
     // row[r] = sum_m (ca + cb * tab[ct] + cb2 * tab[ct2])[r][m] * X_m,  X_0 = fresh N, X_{1+i} = in[i].
     // Rows 0..n_out-1 are stored to out[r]; row FSM_MAX_OUT (if has_next) is the next stage state, handed
     // in registers to the fused inverse transforms and never stored.
@@ -1507,7 +1509,9 @@ struct FxEpilogue {
     T nl_coef;                     // scalar coefficient of the convective term
     const cplx<T>* source;         // optional constant source spectrum [C][nmodes] (coef folded in)
     T* dc_out;                     // KS: per-sample zero-mode of the nonlinear term (captured, then zeroed)
-    int project;                   // NS3D pressure projection
+    int project;                   // NS pressure projection (2-D and 3-D velocity form)
+    const cplx<T>* force;          // optional constant term added BEFORE the projection [C][nmodes]: -coef * f_hat of
+                                   // NSPressureConvection(external_force) (_navier_stokes.py:237-254)
 };
 
 // ---- compile-time combine structures ---------------------------------------------------------------------
@@ -1729,7 +1733,7 @@ k_pass_fx(Geom<T> g, const cplx<T>* __restrict__ win, long win_fstride,
                     if (i < cb.n_in) l2_prefetch(cb.in[i] + (b * C + c) * g.nmodes + (long)line * N, (long)N * sizeof(cplx<T>));
                 FSM_UNROLL
                 for (int q = 0; q < FSM_MAX_TAB; ++q)
-                    if (q < cb.n_tab) l2_prefetch(cb.tab[q] + c * cb.tab_cstride + (long)line * N, (long)N * sizeof(T));
+                    if (q < cb.n_tab) l2_prefetch(cb.tab[q] + b * cb.tab_bstride + c * cb.tab_cstride + (long)line * N, (long)N * sizeof(T));
             }
         }
         int x2, y2, z2;
@@ -1755,7 +1759,7 @@ k_pass_fx(Geom<T> g, const cplx<T>* __restrict__ win, long win_fstride,
     constexpr bool kPipe = (C == 1) && (N <= 512);
     CombineOperands<T, NB> opq[2];   // dead (optimised away) when !kPipe
     if constexpr (kPipe) {
-        if (line < nlines) combine_load<T, NB>(cb, b * g.nmodes, 0, line_mode0 + tau, TL, opq[0]);
+        if (line < nlines) combine_load<T, NB>(cb, b * g.nmodes, b * cb.tab_bstride, line_mode0 + tau, TL, opq[0]);
     }
     cplx<T> nhat[C][EPT];
     auto load_channel = [&](int c, cplx<T>* dst) FSM_INLINE_LAMBDA {
@@ -1782,30 +1786,39 @@ k_pass_fx(Geom<T> g, const cplx<T>* __restrict__ win, long win_fstride,
         constexpr int mb = decltype(mbc)::value * NB;
         constexpr int cur = decltype(mbc)::value & 1;
         if constexpr (kPipe && mb + NB < EPT)
-            combine_load<T, NB, KIND>(cb, b * g.nmodes, 0, line_mode0 + tau + (mb + NB) * TL, TL, opq[cur ^ 1]);
+            combine_load<T, NB, KIND>(cb, b * g.nmodes, b * cb.tab_bstride, line_mode0 + tau + (mb + NB) * TL, TL, opq[cur ^ 1]);
         cplx<T> f[C][NB];
         FSM_UNROLL
         for (int j = 0; j < NB; ++j) {
             const int p = tau + (mb + j) * TL;
             FSM_UNROLL
             for (int c = 0; c < C; ++c) f[c][j] = cscale(nhat[c][mb + j], ep.nl_coef);
-            if constexpr (C == 3) {
+            if constexpr (C == 3 || C == 2) {
                 if (ep.project) {
                     // result_i = (ik_i) lap^-1 sum_j (ik_j) c_j - c_i   (_navier_stokes.py:249-254), with the
                     // Hermitian projection of the composite symbol: a cross term is dropped when exactly one
-                    // of its two axes sits on its Nyquist index.
-                    const T d0 = g.dkraw[0][p], d1 = g.dkraw[1][ky], d2 = g.dkraw[2][kz];
-                    const bool q0 = (p == g.n[0] / 2), q1 = (ky == g.n[1] / 2), q2 = (kz == g.n[2] / 2);
-                    const T k2 = d0 * d0 + d1 * d1 + d2 * d2;
-                    const T ik2 = (k2 == T(0)) ? T(0) : T(1) / k2;
-                    const T dd[3] = {d0, d1, d2};
-                    const bool qq[3] = {q0, q1, q2};
-                    cplx<T> r[3];
+                    // of its two axes sits on its Nyquist index. c = coef * (conv - force).
+                    if (ep.force) {
+                        FSM_UNROLL
+                        for (int c = 0; c < C; ++c) f[c][j] = f[c][j] + ep.force[(long)c * g.nmodes + line_mode0 + p];
+                    }
+                    const int kk[3] = {p, ky, kz};
+                    T dd[C];
+                    bool qq[C];
+                    T k2 = T(0);
                     FSM_UNROLL
-                    for (int i = 0; i < 3; ++i) {
+                    for (int i = 0; i < C; ++i) {
+                        dd[i] = g.dkraw[i][kk[i]];
+                        qq[i] = (kk[i] == g.n[i] / 2);
+                        k2 = fsm_fma(dd[i], dd[i], k2);
+                    }
+                    const T ik2 = (k2 == T(0)) ? T(0) : T(1) / k2;
+                    cplx<T> r[C];
+                    FSM_UNROLL
+                    for (int i = 0; i < C; ++i) {
                         cplx<T> s = mk<T>(T(0), T(0));
                         FSM_UNROLL
-                        for (int jj = 0; jj < 3; ++jj) {
+                        for (int jj = 0; jj < C; ++jj) {
                             const T w = (i == jj || qq[i] == qq[jj]) ? dd[i] * dd[jj] * ik2 : T(0);
                             s.x = fsm_fma(w, f[jj][j].x, s.x);
                             s.y = fsm_fma(w, f[jj][j].y, s.y);
@@ -1813,7 +1826,7 @@ k_pass_fx(Geom<T> g, const cplx<T>* __restrict__ win, long win_fstride,
                         r[i] = s - f[i][j];
                     }
                     FSM_UNROLL
-                    for (int i = 0; i < 3; ++i) f[i][j] = r[i];
+                    for (int i = 0; i < C; ++i) f[i][j] = r[i];
                 }
             }
         }
@@ -1834,7 +1847,7 @@ k_pass_fx(Geom<T> g, const cplx<T>* __restrict__ win, long win_fstride,
         } else {
             FSM_UNROLL
             for (int c = 0; c < C; ++c)
-                combine_block<T, NB, KIND>(cb, f[c], (b * C + c) * g.nmodes, c * cb.tab_cstride, line_mode0 + tau + mb * TL, TL);
+                combine_block<T, NB, KIND>(cb, f[c], (b * C + c) * g.nmodes, b * cb.tab_bstride + c * cb.tab_cstride, line_mode0 + tau + mb * TL, TL);
         }
     });
     });
@@ -1894,7 +1907,7 @@ __global__ void __launch_bounds__(Cfg::TL) k_step1d(Geom<T> g, StageList<T> sl, 
                 if (p <= N / 2) {
                     cplx<T> f = cscale(v[m], ep.nl_coef);
                     if (ep.source) f = f + ep.source[p];
-                    combine_mode<T>(sl.cb[si], f, boff, 0, p);
+                    combine_mode<T>(sl.cb[si], f, boff, b * sl.cb[si].tab_bstride, p);
                 }
             }
             __syncthreads();
@@ -1944,14 +1957,20 @@ __global__ void __launch_bounds__(Cfg::TL) k_line1d(const void* __restrict__ in_
 }
 
 // Combine without a nonlinear term (ETDRK0) or point-wise fix-ups: one thread per mode.
+// The fresh term X_0 is `fresh` ([B][C][nmodes], a nonlinear term evaluated outside the fused passes:
+// fsm_stage_combine) plus `source` ([C][nmodes], constant spectrum), either may be null.
 template <typename T>
-__global__ void k_combine_only(Combine<T> cb, long nmodes, int C, long total /*B*C*nmodes*/) {
+__global__ void k_combine_only(Combine<T> cb, long nmodes, int C, long total /*B*C*nmodes*/,
+                               const cplx<T>* __restrict__ fresh, const cplx<T>* __restrict__ source) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const long mode = i % nmodes;
     const long bc = i / nmodes;
     const int c = (int)(bc % C);
-    combine_mode<T>(cb, mk<T>(T(0), T(0)), bc * nmodes, c * cb.tab_cstride, mode);
+    cplx<T> f = mk<T>(T(0), T(0));
+    if (fresh) f = fresh[i];
+    if (source) f = f + source[(long)c * nmodes + mode];
+    combine_mode<T>(cb, f, bc * nmodes, (bc / C) * cb.tab_bstride + c * cb.tab_cstride, mode);
 }
 
 // KS: N_hat_b(0) = coef * (S_b - mean_b S_b). The FX pass stored coef*S_b in dc[b] and combined a zero.
@@ -1973,7 +1992,7 @@ __global__ void k_ks_dc_fix(Combine<T> cb, const T* dc, int B, long nmodes, T* l
             const int ti = cb.ct[r][0];
             if (ti == -2) continue;
             T coef = cb.ca[r][0];
-            if (ti >= 0) coef += cb.cb[r][0] * cb.tab[ti][0];
+            if (ti >= 0) coef += cb.cb[r][0] * cb.tab[ti][(long)b * cb.tab_bstride];
             cplx<T>* o = cb.out[r] + (long)b * nmodes;  // C == 1
             o[0].x += coef * delta;
         }

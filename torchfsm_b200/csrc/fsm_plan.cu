@@ -1,6 +1,7 @@
 // Plan, stage programs and the C ABI (include/fsm_b200.h) of libfsm_b200.so.
 #include "fsm_b200.h"
 #include "fsm_launch.h"
+#include "fsm_pointwise.cuh"
 
 #include <cerrno>
 #include <cstdarg>
@@ -300,6 +301,7 @@ int make_combine(const fsm_plan* p, const Stage& s, cplx<T>* const* arr, bool fr
     cb.n_out = s.n_out;
     cb.use_fresh = fresh ? 1 : 0;
     cb.tab_cstride = (p->d.tab_channels > 1) ? p->nmodes : 0;
+    cb.tab_bstride = p->d.tab_batched ? (long)p->d.tab_channels * p->nmodes : 0;
     cb.tab_cplx = p->d.tab_complex ? 1 : 0;
     int slot_of[TAB_COUNT];
     for (int i = 0; i < TAB_COUNT; ++i) slot_of[i] = -1;
@@ -420,7 +422,7 @@ int run_forward_tail(const fsm_plan* p, const Buffers<T>& bf, const Geom<T>& g, 
     f.nlines = (int)(p->nmodes / p->n[0]); f.b0 = b0; f.nb = nb;
     // independent channels (no projection, no per-channel table or source): run them as separate
     // single-channel fields -> no three-channel register tile, C times the parallelism
-    if (C > 1 && !ep.project && !ep.source && !ep.dc_out && cb.tab_cstride == 0) {
+    if (C > 1 && !ep.project && !ep.source && !ep.dc_out && cb.tab_cstride == 0 && cb.tab_bstride == 0) {
         f.b0 = b0 * C; f.nb = nb * C;
         C = 1;
     }
@@ -428,21 +430,39 @@ int run_forward_tail(const fsm_plan* p, const Buffers<T>& bf, const Geom<T>& g, 
     return 0;
 }
 
+// NSPressureConvection(external_force) dealiases the integrator's own stage state in place before it evaluates
+// (dedicated/_navier_stokes.py:241); every later use of that state sees the masked values, except in
+// the one-stage schemes, whose `exp * u` is formed before the evaluation runs (_etdrk.py:47-51, _setdrk_step.py:5-11), and
+// in the right-hand side (operator/_base.py:425-433: `linear_coef * u_fft` first).
+template <typename T>
+int mask_stage_input(const fsm_plan* p, const Geom<T>& g, const Stage& s, cplx<T>* arr, int b_lo, int b_hi, cudaStream_t st) {
+    if (!p->d.force_hat || &s == &p->rhs_stage || p->stages.size() < 2) return 0;
+    const long total = (long)(b_hi - b_lo) * p->C * p->nmodes;
+    auto kern = k_mask_state<T>;
+    FSM_LAUNCH(kern, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, g, arr + (long)b_lo * p->C * p->nmodes, total);
+    return launch_status("stage-state dealiasing");
+}
+
 // One nonlinear evaluation of `stage_in` followed by the stage combine.
 template <typename T>
-int run_stage(const fsm_plan* p, const Buffers<T>& bf, const Stage& s, cudaStream_t st, int b_lo = 0, int b_hi = -1) {
+int run_stage(const fsm_plan* p, const Buffers<T>& bf, const Stage& s, cudaStream_t st, int b_lo = 0, int b_hi = -1,
+              const cplx<T>* ext_fresh = nullptr) {
     if (b_hi < 0) b_hi = p->B;
     Combine<T> cb;
-    const bool fresh = p->prog != FSM_PROG_LINEAR;
+    const bool fused = p->prog != FSM_PROG_LINEAR;
+    // no convective term: the "nonlinear" term is the constant source (if any) or one evaluated outside (ext_fresh)
+    const bool fresh = fused || ext_fresh != nullptr || p->d.source_hat != nullptr;
     if (int e = make_combine<T>(p, s, bf.arr, fresh, &cb)) return e;
-    if (!fresh) {
+    if (!fused) {
         const long total = (long)p->B * p->C * p->nmodes;
         auto kern = k_combine_only<T>;
-        FSM_LAUNCH(kern, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, cb, p->nmodes, p->C, total);
+        FSM_LAUNCH(kern, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, cb, p->nmodes, p->C, total, ext_fresh,
+                   static_cast<const cplx<T>*>(p->d.source_hat));
         return launch_status("linear combine");
     }
     const Geom<T> g = make_geom<T>(p, false);
     const cplx<T>* stage_in = bf.arr[s.input];
+    if (int e = mask_stage_input<T>(p, g, s, bf.arr[s.input], b_lo, b_hi, st)) return e;
     const LaunchTable<T>* tx = launch_table<T>(p->n[0]);
     const LaunchTable<T>* tl = launch_table<T>(p->n[p->ndim - 1]);
     const LaunchTable<T>* ty = (p->ndim == 3) ? launch_table<T>(p->n[1]) : nullptr;
@@ -451,6 +471,7 @@ int run_stage(const fsm_plan* p, const Buffers<T>& bf, const Stage& s, cudaStrea
     ep.source = static_cast<const cplx<T>*>(p->d.source_hat);
     ep.dc_out = (p->prog == FSM_PROG_KS && p->d.ks_remove_mean) ? bf.dc : nullptr;
     ep.project = (p->prog == FSM_PROG_NS3D) ? 1 : 0;
+    ep.force = static_cast<const cplx<T>*>(p->d.force_hat);
     for (int b0 = b_lo; b0 < b_hi; b0 += p->chunk) {
         const int nb = (b_hi - b0 < p->chunk) ? (b_hi - b0) : p->chunk;
         IxArgs<T> a;
@@ -516,6 +537,7 @@ int run_1d(const fsm_plan* p, const Buffers<T>& bf, const Stage* stages, int n_s
     a.ep.source = static_cast<const cplx<T>*>(p->d.source_hat);
     a.ep.dc_out = nullptr;
     a.ep.project = 0;
+    a.ep.force = nullptr;
     a.n_steps = n_steps;
     a.nb = p->B;
     const LaunchTable<T>* tx = launch_table<T>(p->n[0]);
@@ -614,7 +636,7 @@ int do_r2c(fsm_plan* p, const void* u, void* u_hat, void* ws, cudaStream_t st) {
         tmp.d.tab_channels = 1;
         if (int e = make_combine<T>(&tmp, s, arr, true, &cb)) return e;
         FxEpilogue<T> ep;
-        ep.nl_coef = T(1); ep.source = nullptr; ep.dc_out = nullptr; ep.project = 0;
+        ep.nl_coef = T(1); ep.source = nullptr; ep.dc_out = nullptr; ep.project = 0; ep.force = nullptr;
         if (int e = run_forward_tail<T>(p, bf, g, 1, 1, cb, ep, 0, nf, st)) return e;
     }
     return 0;
@@ -795,9 +817,14 @@ int do_slab_phase(fsm_plan* p, int op, int stage, int phase, int sub, int nsub, 
     const cplx<T>* rcv = static_cast<const cplx<T>*>(recv);
     if (op == FSM_SLAB_STEP || op == FSM_SLAB_RHS) {
         if (p->prog == FSM_PROG_LINEAR) return fail(-EINVAL, "linear operators have no slab phases; call fsm_step");
+        if (op == FSM_SLAB_STEP && p->d.force_hat && p->d.integrator == FSM_INT_RK4)
+            return fail(-ENOSYS, "NS pressure convection with an external force is not supported with the RK integrators");
         const Stage& s = (op == FSM_SLAB_RHS) ? p->rhs_stage : p->stages[stage];
         const Geom<T> g = make_geom<T>(p, false);
-        if (phase == 0) return slab_ix<T>(p, g, p->kprog, bf.arr[s.input], snd, p->B * p->C, p->nf_ix, p->nkz1, nsub, st);
+        if (phase == 0) {
+            if (int e = mask_stage_input<T>(p, g, s, bf.arr[s.input], 0, p->B, st)) return e;
+            return slab_ix<T>(p, g, p->kprog, bf.arr[s.input], snd, p->B * p->C, p->nf_ix, p->nkz1, nsub, st);
+        }
         if (phase == 1) {
             if (int e = slab_mid_inverse<T>(p, g, rcv, bf.w3, p->C * p->nf_ix, mid_spec_inverse(p), p->nkz1, p->B, sub, nsub, st)) return e;
             if (int e = slab_phys<T>(p, g, p->kprog, bf.w3, bf.w2, nullptr, nullptr, p->B, sub, nsub, st)) return e;
@@ -810,6 +837,7 @@ int do_slab_phase(fsm_plan* p, int op, int stage, int phase, int sub, int nsub, 
         ep.source = static_cast<const cplx<T>*>(p->d.source_hat);
         ep.dc_out = nullptr;
         ep.project = (p->prog == FSM_PROG_NS3D) ? 1 : 0;
+        ep.force = static_cast<const cplx<T>*>(p->d.force_hat);
         return slab_fx<T>(p, g, rcv, p->C, p->B, cb, ep, nsub, st);
     }
     if (nsub != 1) return fail(-EINVAL, "the plain transforms run with one sub-slab");
@@ -828,7 +856,7 @@ int do_slab_phase(fsm_plan* p, int op, int stage, int phase, int sub, int nsub, 
         tmp.d.tab_channels = 1;
         if (int e = make_combine<T>(&tmp, s, bf.arr, true, &cb)) return e;
         FxEpilogue<T> ep;
-        ep.nl_coef = T(1); ep.source = nullptr; ep.dc_out = nullptr; ep.project = 0;
+        ep.nl_coef = T(1); ep.source = nullptr; ep.dc_out = nullptr; ep.project = 0; ep.force = nullptr;
         return slab_fx<T>(p, g, rcv, 1, nf, cb, ep, 1, st);
     }
     if (op == FSM_SLAB_C2R) {
@@ -837,6 +865,21 @@ int do_slab_phase(fsm_plan* p, int op, int stage, int phase, int sub, int nsub, 
         return slab_phys<T>(p, g, PROG_C2R, bf.w3, nullptr, nullptr, static_cast<T*>(aux), nf, 0, 1, st);
     }
     return fail(-EINVAL, "unknown slab op %d", op);
+}
+
+template <typename T>
+MapTerms<T> make_map_terms(const fsm_map_term* terms, int n_terms, int c_in, int c_out, int dealias) {
+    MapTerms<T> mt;
+    memset(&mt, 0, sizeof(mt));
+    mt.n_terms = n_terms; mt.c_in = c_in; mt.c_out = c_out; mt.dealias = dealias ? 1 : 0;
+    for (int t = 0; t < n_terms; ++t) {
+        mt.out_ch[t] = (signed char)terms[t].out_channel;
+        mt.in_ch[t] = (signed char)terms[t].in_channel;
+        for (int a = 0; a < 3; ++a) mt.pw[t][a] = (signed char)terms[t].power[a];
+        mt.inv_lap[t] = (signed char)terms[t].inv_laplacian;
+        mt.coef[t] = (T)terms[t].coef;
+    }
+    return mt;
 }
 
 }  // namespace
@@ -925,9 +968,9 @@ int fsm_plan_create(fsm_plan** out, const fsm_desc* d) {
         case FSM_PROG_NS2D_VORT:
             if (p->C != 1 || p->ndim != 2) { delete p; return fail(-EINVAL, "vorticity convection needs a 2-D scalar field"); }
             p->kprog = PROG_NS2D; p->nf_ix = 4; p->nfi = 4; p->nout = 1; break;
-        case FSM_PROG_NS3D:
-            if (p->C != 3 || p->ndim != 3) { delete p; return fail(-EINVAL, "NS pressure convection needs a 3-D, 3-channel field"); }
-            p->kprog = PROG_NS3D; p->nf_ix = 2; p->nfi = 9; p->nout = 3; break;
+        case FSM_PROG_NS3D:   // velocity form with the pressure projected out: the convection program + projection in FX
+            if (p->C != p->ndim || p->ndim < 2) { delete p; return fail(-EINVAL, "NS pressure convection needs a 2-D or 3-D field with channels == ndim"); }
+            p->kprog = (p->ndim == 3) ? PROG_NS3D : PROG_CONV; p->nf_ix = 2; p->nfi = (p->ndim == 2) ? 4 : 9; p->nout = p->C; break;
         default: delete p; return fail(-ENOSYS, "unknown program %d", p->prog);
     }
     if (p->prog == FSM_PROG_LINEAR && d->integrator != FSM_INT_ETDRK0 && d->integrator != FSM_INT_RK4) {
@@ -940,6 +983,10 @@ int fsm_plan_create(fsm_plan** out, const fsm_desc* d) {
     if (p->prog != FSM_PROG_LINEAR && d->integrator == FSM_INT_ETDRK0) {
         delete p;
         return fail(-EINVAL, "The ETDRK0 integrator only supports linear term");
+    }
+    if (d->force_hat && p->prog != FSM_PROG_NS3D) {
+        delete p;
+        return fail(-EINVAL, "force_hat belongs to the NS pressure-convection program");
     }
     if (d->tab_complex && p->ndim != 1) {
         delete p;
@@ -1220,6 +1267,10 @@ int fsm_step(fsm_plan* plan, void* u_hat, void* workspace, size_t ws_bytes, int 
     FSM_CHECK_WS(plan, workspace, ws_bytes);
     if (!u_hat || n_steps < 0) return fail(-EINVAL, "bad argument");
     if (plan->P > 1 && plan->prog != FSM_PROG_LINEAR) return fail(-EINVAL, "slab-decomposed plans are driven through fsm_slab_phase");
+    // the reference dealiases the stage state in place when a force is attached (quirk Q5); what that does to the
+    // temporaries of _rk.py:43-58 is an accident of evaluation order this path does not restate
+    if (plan->d.force_hat && plan->d.integrator == FSM_INT_RK4)
+        return fail(-ENOSYS, "NS pressure convection with an external force is not supported with the RK integrators");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     return plan->f64 ? do_step<double>(plan, u_hat, workspace, n_steps, st) : do_step<float>(plan, u_hat, workspace, n_steps, st);
 }
@@ -1275,6 +1326,94 @@ int fsm_full_to_half(fsm_plan* plan, const void* full_hat, void* u_hat, void* st
         FSM_LAUNCH(kern, grid, block, 0, st, make_geom<float>(plan, true), (const cplx<float>*)full_hat, (cplx<float>*)u_hat, nf);
     }
     return launch_status("full_to_half");
+}
+
+int fsm_spectral_map(fsm_plan* plan, const void* in_hat, int32_t c_in, void* out_hat, int32_t c_out,
+                     const fsm_map_term* terms, int32_t n_terms, int32_t dealias, void* stream) {
+    if (!plan || !in_hat || !out_hat || in_hat == out_hat || !terms) return fail(-EINVAL, "bad argument");
+    if (c_in < 1 || c_in > FSM_MAP_MAX_CH || c_out < 1 || c_out > FSM_MAP_MAX_CH)
+        return fail(-EINVAL, "spectral map: channel counts must lie in [1, %d]", FSM_MAP_MAX_CH);
+    if (n_terms < 0 || n_terms > FSM_MAP_MAX_TERMS) return fail(-EINVAL, "spectral map: at most %d terms", FSM_MAP_MAX_TERMS);
+    for (int t = 0; t < n_terms; ++t) {
+        const fsm_map_term& m = terms[t];
+        if (m.out_channel < 0 || m.out_channel >= c_out || m.in_channel < 0 || m.in_channel >= c_in)
+            return fail(-EINVAL, "spectral map: term %d refers to a channel outside the fields", t);
+        if (m.inv_laplacian < 0 || m.inv_laplacian > 8) return fail(-EINVAL, "spectral map: bad inverse-Laplacian power in term %d", t);
+        for (int a = 0; a < 3; ++a) {
+            if (m.power[a] < 0 || m.power[a] > 16) return fail(-EINVAL, "spectral map: bad derivative order in term %d", t);
+            if (a >= plan->ndim && m.power[a] != 0) return fail(-EINVAL, "spectral map: term %d differentiates along a missing axis", t);
+        }
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long total = (long)plan->B * plan->nmodes;
+    dim3 grid((unsigned)((total + 255) / 256)), block(256);
+    if (plan->f64) {
+        const MapTerms<double> mt = make_map_terms<double>(terms, n_terms, c_in, c_out, dealias);
+        auto kern = k_spectral_map<double>;
+        FSM_LAUNCH(kern, grid, block, 0, st, make_geom<double>(plan, dealias == 0), mt, (const cplx<double>*)in_hat, (cplx<double>*)out_hat, total);
+    } else {
+        const MapTerms<float> mt = make_map_terms<float>(terms, n_terms, c_in, c_out, dealias);
+        auto kern = k_spectral_map<float>;
+        FSM_LAUNCH(kern, grid, block, 0, st, make_geom<float>(plan, dealias == 0), mt, (const cplx<float>*)in_hat, (cplx<float>*)out_hat, total);
+    }
+    return launch_status("spectral map");
+}
+
+int fsm_stage_input(const fsm_plan* plan, int32_t stage, int64_t* ws_offset) {
+    if (!plan || !ws_offset) return fail(-EINVAL, "bad argument");
+    if (stage < -1 || stage >= (int)plan->stages.size()) return fail(-EINVAL, "bad stage %d", stage);
+    const int arr = (stage < 0) ? ARR_U : plan->stages[stage].input;
+    *ws_offset = (arr == ARR_U) ? -1 : (int64_t)plan->off_arr[arr];
+    return (int)plan->stages.size();
+}
+
+int fsm_stage_combine(fsm_plan* plan, int32_t stage, void* u_hat, const void* fresh_hat, void* rhs_out, void* workspace,
+                      size_t ws_bytes, void* stream) {
+    FSM_CHECK_WS(plan, workspace, ws_bytes);
+    if (!u_hat || !fresh_hat) return fail(-EINVAL, "bad argument");
+    if (plan->prog != FSM_PROG_LINEAR) return fail(-EINVAL, "fsm_stage_combine belongs to plans without a fused nonlinear program");
+    if (stage < -1 || stage >= (int)plan->stages.size()) return fail(-EINVAL, "bad stage %d", stage);
+    if (stage < 0 && (!rhs_out || rhs_out == u_hat)) return fail(-EINVAL, "the right-hand side needs its own output array");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const Stage& s = (stage < 0) ? plan->rhs_stage : plan->stages[stage];
+    if (plan->f64) {
+        Buffers<double> bf = carve<double>(plan, u_hat, workspace, rhs_out);
+        return run_stage<double>(plan, bf, s, st, 0, -1, static_cast<const cplx<double>*>(fresh_hat));
+    }
+    Buffers<float> bf = carve<float>(plan, u_hat, workspace, rhs_out);
+    return run_stage<float>(plan, bf, s, st, 0, -1, static_cast<const cplx<float>*>(fresh_hat));
+}
+
+int fsm_mask_state(fsm_plan* plan, void* state_hat, int32_t channels, void* stream) {
+    if (!plan || !state_hat || channels < 1) return fail(-EINVAL, "bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long total = (long)plan->B * channels * plan->nmodes;
+    dim3 grid((unsigned)((total + 255) / 256)), block(256);
+    if (plan->f64) {
+        auto kern = k_mask_state<double>;
+        FSM_LAUNCH(kern, grid, block, 0, st, make_geom<double>(plan, false), (cplx<double>*)state_hat, total);
+    } else {
+        auto kern = k_mask_state<float>;
+        FSM_LAUNCH(kern, grid, block, 0, st, make_geom<float>(plan, false), (cplx<float>*)state_hat, total);
+    }
+    return launch_status("mask state");
+}
+
+int fsm_sym_outer(fsm_plan* plan, const void* u, void* out, int32_t channels, void* stream) {
+    if (!plan || !u || !out || u == out) return fail(-EINVAL, "bad argument");
+    if (channels < 1 || channels > FSM_MAP_MAX_CH) return fail(-EINVAL, "channel count must lie in [1, %d]", FSM_MAP_MAX_CH);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long npts = plan->ntot / plan->P;      // local physical slab of a decomposed grid
+    const long total = (long)plan->B * npts;
+    dim3 grid((unsigned)((total + 255) / 256)), block(256);
+    if (plan->f64) {
+        auto kern = k_sym_outer<double>;
+        FSM_LAUNCH(kern, grid, block, 0, st, (const double*)u, (double*)out, (int)channels, npts, total);
+    } else {
+        auto kern = k_sym_outer<float>;
+        FSM_LAUNCH(kern, grid, block, 0, st, (const float*)u, (float*)out, (int)channels, npts, total);
+    }
+    return launch_status("symmetric products");
 }
 
 }  // extern "C"

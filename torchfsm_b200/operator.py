@@ -20,6 +20,13 @@ from .integrator import (ETDRKIntegrator, SETDRKIntegrator, RKIntegrator, integr
 from .mesh import FourierMesh, MeshGrid
 
 _LINEAR_KINDS = ("laplacian", "biharmonic", "spatial_derivative", "implicit_unit_source")
+# channel-changing cores that are pure symbol products: evaluated by the point-wise spectral map (fsm_spectral_map)
+_MAP_KINDS = ("grad", "div", "curl", "vorticity2velocity")
+# diagnostics composed of a map, one convection evaluation and a pressure solve
+_COMPOSITE_KINDS = ("velocity2pressure", "vorticity2pressure")
+# nonlinear cores without a fused program: evaluated by composing the library's passes on the host (c2r, a point-wise
+# physical-space function, r2c, spectral map) and handed to the integrator stage (fsm_stage_combine)
+_EXTERNAL_KINDS = ("implicit_func_source", "conservative_convection")
 _PROGRAM_OF = {"convection": _cabi.PROG_CONVECTION, "ks_convection": _cabi.PROG_KS,
                "vorticity_convection": _cabi.PROG_NS2D_VORT, "ns_pressure_convection": _cabi.PROG_NS3D}
 
@@ -50,11 +57,8 @@ def _rot_half(t: torch.Tensor, shape) -> torch.Tensor:
 
 
 def _expand_table(t: torch.Tensor, shape) -> torch.Tensor:
-    """Broadcastable (1|B, 1|C, ...) reference-layout table -> (Ct, *shape)."""
-    if t.shape[0] != 1:
-        raise NotImplementedError("batched (per-sample) coefficients are not supported by the fused CUDA path")
-    t = t[0]
-    return t.expand(t.shape[0], *shape)
+    """Broadcastable (1|B, 1|C, ...) reference-layout table -> (Bt, Ct, *shape) with Bt in {1, B}, Ct in {1, C}."""
+    return t.expand(t.shape[0], t.shape[1], *shape)
 
 
 def _same_device(a: torch.device, b: torch.device) -> bool:
@@ -113,7 +117,8 @@ class FusedStepper:
     def __init__(self, f_mesh: FourierMesh, batch: int, n_channel: int, program: int, integrator: str, dt: float,
                  linear_coef: Optional[torch.Tensor], nl_coef: float, source_hat: Optional[torch.Tensor],
                  kmax: Sequence[int], ks_remove_mean: bool, integrator_cfg: dict, chunk: int = 0,
-                 tables: Optional[dict] = None, slab=None, lanes: int = 0, allocate: bool = True):
+                 tables: Optional[dict] = None, slab=None, lanes: int = 0, allocate: bool = True,
+                 force_hat: Optional[torch.Tensor] = None):
         lib = _GuardedLib(_cabi.lib(), f_mesh.device)
         # slab = (rank, nranks, process_group): ONE 3-D grid decomposed over nranks GPUs
         self.slab = slab
@@ -157,6 +162,8 @@ class FusedStepper:
 
         def real_table(t):
             t = _expand_table(t, self.shape)
+            if t.shape[0] not in (1, batch):
+                raise ValueError("a batched coefficient must have one entry per sample")
             if self.complex_tables:
                 t = t.to(self.cdtype)                 # every table carries complex entries (include/fsm_b200.h)
             elif t.is_complex():
@@ -164,8 +171,8 @@ class FusedStepper:
                     raise NotImplementedError(
                         "complex linear coefficients (odd-order linear terms) are supported on 1-D grids only")
                 t = t.real
-            if t.shape[0] > 1 and bool((t == t[:1]).all()):
-                t = t[:1]
+            if t.shape[1] > 1 and bool((t == t[:, :1]).all()):
+                t = t[:, :1]
             return t if self.complex_tables else t.to(self.rdtype)
 
         desc = _cabi.FsmDesc()
@@ -204,20 +211,21 @@ class FusedStepper:
                                       "(the Nyquist mode of the half spectrum is not Hermitian under a complex symbol)")
         desc.tab_complex = 1 if self.complex_tables else 0
         rot = {}
+        tab_batch = 1       # tensor-valued coefficients of linear terms make every table per-sample (_base.py:339-357)
         for k, t in tables.items():
             rt = real_table(t)
             rot[k] = rt
-            tab_channels = max(tab_channels, rt.shape[0])
+            tab_batch, tab_channels = max(tab_batch, rt.shape[0]), max(tab_channels, rt.shape[1])
         if linear_coef is not None:
             rot["lin"] = real_table(linear_coef)
-            tab_channels = max(tab_channels, rot["lin"].shape[0])
+            tab_batch, tab_channels = max(tab_batch, rot["lin"].shape[0]), max(tab_channels, rot["lin"].shape[1])
         for k in list(rot):
-            t = rot[k]
-            if t.shape[0] != tab_channels:
-                t = t.expand(tab_channels, *t.shape[1:])
+            t = rot[k].expand(tab_batch, tab_channels, *self.shape).reshape(tab_batch * tab_channels, *self.shape)
             rot[k] = self._local_slab(_rot_half(t, self.shape))
             self._keep.append(rot[k])
         desc.tab_channels = tab_channels
+        desc.tab_batched = 1 if tab_batch > 1 else 0
+        self.tab_batch = tab_batch
         if "exp" in rot:
             desc.tab_exp = rot["exp"].data_ptr()
         if "half_exp" in rot:
@@ -227,14 +235,23 @@ class FusedStepper:
                 desc.tab_coef[i] = rot[f"coef_{i + 1}"].data_ptr()
         if "lin" in rot:
             desc.tab_lin = rot["lin"].data_ptr()
+        def const_spectrum(t, what):
+            t = _expand_table(t, self.shape)
+            if t.shape[0] != 1:
+                raise NotImplementedError(f"a per-sample {what} is not supported by the fused CUDA path")
+            if t.shape[1] not in (1, n_channel):
+                raise ValueError(f"{what} has an incompatible channel count")
+            t = t[0].expand(n_channel, *self.shape).to(self.cdtype)
+            t = self._local_slab(_rot_half(t, self.shape))
+            self._keep.append(t)
+            return t
+
         if source_hat is not None:
-            s = _expand_table(source_hat, self.shape)
-            if s.shape[0] not in (1, n_channel):
-                raise ValueError("explicit source has an incompatible channel count")
-            s = s.expand(n_channel, *self.shape).to(self.cdtype)
-            self.source_rot = self._local_slab(_rot_half(s, self.shape))
-            self._keep.append(self.source_rot)
+            self.source_rot = const_spectrum(source_hat, "explicit source")
             desc.source_hat = self.source_rot.data_ptr()
+        if force_hat is not None:
+            self.force_rot = const_spectrum(force_hat, "external force")
+            desc.force_hat = self.force_rot.data_ptr()
         if self.P > 1:
             desc.slab_rank, desc.slab_nranks = self.rank, self.P
         self.rot_tables = rot
@@ -462,6 +479,20 @@ class FusedStepper:
                                       self.ws_bytes, self._stream()), "c2r")
         return out
 
+    def spectral_map(self, u_hat: torch.Tensor, c_out: int, terms, dealias: bool = False) -> torch.Tensor:
+        """out[b][co] = sum of coef * prod_a (i k_a)^p_a * (1/lap)^q * u_hat[b][ci] over ``terms`` =
+        [(co, ci, (p0, p1, p2), q, coef)]; one point-wise kernel on the rot-half state (``fsm_spectral_map``)."""
+        arr = (_cabi.FsmMapTerm * max(1, len(terms)))()
+        for i, (co, ci, pw, q, coef) in enumerate(terms):
+            arr[i].out_channel, arr[i].in_channel, arr[i].inv_laplacian, arr[i].coef = int(co), int(ci), int(q), float(coef)
+            for a in range(3):
+                arr[i].power[a] = int(pw[a]) if a < len(pw) else 0
+        c_in = u_hat.shape[1]
+        out = torch.empty((self.B, c_out, self.nmodes), dtype=self.cdtype, device=self.device)
+        _cabi.check(self._lib.fsm_spectral_map(self._plan, u_hat.data_ptr(), c_in, out.data_ptr(), c_out, arr, len(terms),
+                                               1 if dealias else 0, self._stream()), "spectral_map")
+        return out
+
     def half_to_full(self, u_hat: torch.Tensor) -> torch.Tensor:
         if self.P > 1:
             raise NotImplementedError("full-spectrum frames are not available for slab-decomposed grids")
@@ -541,6 +572,8 @@ class FusedStepper:
         while the library logs the per-evaluation local zero-mode sums; ONE all-reduce of that log afterwards
         gives the exact correction of the zero mode (no collective inside the step)."""
         import torch.distributed as dist
+        if getattr(self, "tab_batch", 1) > 1:
+            raise NotImplementedError("sharded KS ensembles do not take per-sample coefficients")
         if self.integrator not in self._KS_FINAL_WEIGHTS:
             raise NotImplementedError(f"sharded KS ensembles are not supported with the {self.integrator} integrator")
         spec = self._KS_FINAL_WEIGHTS[self.integrator]
@@ -586,6 +619,61 @@ class FusedStepper:
 
     def forward(self, u_hat_full: torch.Tensor, dt: float) -> torch.Tensor:
         return self.step(u_hat_full)
+
+
+class HostComposedStepper(FusedStepper):
+    """Integrator for nonlinear cores without a fused program (``_EXTERNAL_KINDS``): the plan carries the linear part
+    and the stage formulas; each stage's nonlinear term is evaluated by ``nonlinear(stepper, stage_state_hat)`` from
+    the library's own passes and combined by ``fsm_stage_combine`` (same tables, same stage algebra as the fused
+    path; integrator/_etdrk.py:47-82, _setdrk_step.py:5-82, _rk.py:43-58)."""
+
+    def __init__(self, *args, nonlinear=None, **kwargs):
+        super().__init__(*args, **kwargs)
+        if self.P > 1:
+            raise NotImplementedError("host-composed nonlinear terms are not available on slab-decomposed grids")
+        self._nonlinear = nonlinear
+        self._stage_off = []
+        off = ctypes.c_int64()
+        n = self._lib.fsm_stage_input(self._plan, -1, ctypes.byref(off))
+        if n < 0:
+            _cabi.check(n, "stage_input")
+        for s in range(n):
+            _cabi.check(min(0, self._lib.fsm_stage_input(self._plan, s, ctypes.byref(off))), "stage_input")
+            self._stage_off.append(off.value)
+        self._state_bytes = self.B * self.C * self.nmodes * (8 if self.rdtype == torch.float32 else 16)
+
+    def _stage_state(self, s, u_hat):
+        off = self._stage_off[s]
+        if off < 0:
+            return u_hat
+        return self.workspace[off:off + self._state_bytes].view(self.cdtype).view(self.B, self.C, self.nmodes)
+
+    def mask_state(self, x_hat: torch.Tensor) -> torch.Tensor:
+        """Zero the modes outside the dealiasing box, in place (operator/_base.py:381-385)."""
+        _cabi.check(self._lib.fsm_mask_state(self._plan, x_hat.data_ptr(), x_hat.shape[1], self._stream()), "mask_state")
+        return x_hat
+
+    def sym_outer(self, u: torch.Tensor) -> torch.Tensor:
+        C = u.shape[1]
+        out = torch.empty((u.shape[0], C * (C + 1) // 2) + tuple(u.shape[2:]), dtype=u.dtype, device=u.device)
+        _cabi.check(self._lib.fsm_sym_outer(self._plan, u.data_ptr(), out.data_ptr(), C, self._stream()), "sym_outer")
+        return out
+
+    def step_half(self, u_hat: torch.Tensor, n_steps: int = 1) -> torch.Tensor:
+        for _ in range(int(n_steps)):
+            for s in range(len(self._stage_off)):
+                fresh = self._nonlinear(self, self._stage_state(s, u_hat))
+                _cabi.check(self._lib.fsm_stage_combine(self._plan, s, u_hat.data_ptr(), fresh.data_ptr(), None,
+                                                        self.workspace.data_ptr(), self.ws_bytes, self._stream()),
+                            "stage_combine")
+        return u_hat
+
+    def rhs_half(self, u_hat: torch.Tensor) -> torch.Tensor:
+        out = self.empty_half()
+        fresh = self._nonlinear(self, u_hat)
+        _cabi.check(self._lib.fsm_stage_combine(self._plan, -1, u_hat.data_ptr(), fresh.data_ptr(), out.data_ptr(),
+                                                self.workspace.data_ptr(), self.ws_bytes, self._stream()), "stage_combine")
+        return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -742,9 +830,27 @@ class OperatorLike:
         f_mesh = mesh if isinstance(mesh, FourierMesh) and device is None and dtype is None \
             else FourierMesh(mesh, device=device, dtype=dtype)
         self._state_dict = {"f_mesh": f_mesh, "n_channel": n_channel, "linear_coef": None, "integrator": None}
+        self._rhs_stepper = None
+        kinds = {t.kind for t in self.terms}
+        if kinds & set(_COMPOSITE_KINDS):
+            if len(self.terms) != 1 or isinstance(self.terms[0].coef, torch.Tensor):
+                raise NotImplementedError("Velocity2Pressure / Vorticity2Pressure cannot be summed with other operators "
+                                          "on the fused CUDA path")
+            t = self.terms[0]
+            if t.kind == "vorticity2pressure" and (f_mesh.n_dim != 2 or n_channel != 1):
+                raise ValueError("Only vorticity in 2Dmesh is supported")
+            if t.kind == "velocity2pressure" and f_mesh.n_dim != n_channel:
+                raise ValueError("convection operator only works for vector field with the same dimension as mesh")
+            self._lowered = dict(composite=t, c_out=1)
+            return
+        if kinds & set(_MAP_KINDS):
+            c_out, terms = self._lower_map(f_mesh, n_channel)
+            self._lowered = dict(map=terms, c_out=c_out)
+            return
         lin = []
         program, nl_coef, ks_remove_mean = _cabi.PROG_LINEAR, 0.0, True
-        source_hat = None
+        source_hat = force_hat = None
+        external = []
         for t in self.terms:
             if t.kind in _LINEAR_KINDS:
                 lin.append(t)
@@ -763,9 +869,33 @@ class OperatorLike:
                     if n_channel != 1:
                         raise NotImplementedError("KSConvection only supports scalar field")
                     ks_remove_mean = bool(t.params.get("remove_mean", True))
-                if t.kind == "ns_pressure_convection" and t.params.get("external_force") is not None:
-                    raise NotImplementedError("NSPressureConvection with an external force is not supported "
-                                              "by the fused CUDA path")
+                if t.kind == "ns_pressure_convection":
+                    if f_mesh.n_dim != n_channel or f_mesh.n_dim < 2:
+                        raise ValueError("convection operator only works for vector field with the same dimension as mesh")
+                    force = t.params.get("external_force")
+                    if force is not None:
+                        # _navier_stokes.py:237-254: coef * (grad lap^-1 div(conv - f) - (conv - f)); the fused epilogue
+                        # adds -coef * f_hat to coef * conv_hat before the projection. The force is evaluated once:
+                        # it must not depend on the state (explicit sources only).
+                        if any(ft.kind != "explicit_source" for ft in force.terms):
+                            raise NotImplementedError("NSPressureConvection takes state-independent external forces only "
+                                                      "(sums of ExplicitSource) on the fused CUDA path")
+                        f_hat = None
+                        for ft in force.terms:
+                            fs = ft.params["source"].to(device=f_mesh.device)
+                            fh = ft.coef * torch.fft.fftn(fs, dim=list(range(2, fs.dim())))
+                            f_hat = fh if f_hat is None else f_hat + fh
+                        # the reference subtracts the force from the convection in place and then adds it once more
+                        # (:241-254: `convection -= force` ... `- convection + force`): coef * (P(conv - f) + f) with
+                        # P(c) = grad lap^-1 div c - c. The second copy rides on the constant-source slot, after the projection.
+                        force_hat = -float(t.coef) * f_hat
+                        source_hat = float(t.coef) * f_hat if source_hat is None else source_hat + float(t.coef) * f_hat
+            elif t.kind in _EXTERNAL_KINDS:
+                if isinstance(t.coef, torch.Tensor):
+                    raise NotImplementedError("tensor-valued coefficients on nonlinear terms are not supported")
+                if t.kind == "conservative_convection" and f_mesh.n_dim != n_channel:
+                    raise ValueError("div operator only works for vector field with the same dimension as mesh")
+                external.append(t)
             elif t.kind == "explicit_source":
                 src = t.params["source"].to(device=f_mesh.device)
                 s_hat = torch.fft.fftn(src, dim=list(range(2, src.dim())))        # operator/_base.py:1002-1005
@@ -776,10 +906,10 @@ class OperatorLike:
         L = None
         if lin:                                                                   # operator/_base.py:339-357
             L = sum(t.coef * self._linear_core(t, f_mesh, n_channel) for t in lin)
-        if program == _cabi.PROG_LINEAR and source_hat is not None:
-            raise NotImplementedError("an explicit source without a convective term is not supported "
-                                      "by the fused CUDA path")
-        kmax = f_mesh.low_pass_kmax(self._de_aliasing_rate) if program != _cabi.PROG_LINEAR \
+        if external and program != _cabi.PROG_LINEAR:
+            raise NotImplementedError("ImplicitSource(func) / ConservativeConvection cannot be summed with a fused "
+                                      "convective term on the CUDA path")
+        kmax = f_mesh.low_pass_kmax(self._de_aliasing_rate) if (program != _cabi.PROG_LINEAR or external) \
             else [n // 2 for n in f_mesh.shape]
         if program == _cabi.PROG_NS3D and any(k >= n // 2 and n % 2 == 0 for k, n in zip(kmax, f_mesh.shape)):
             # the reference's pressure projection leaves anti-Hermitian content on the Nyquist planes of its full
@@ -789,7 +919,122 @@ class OperatorLike:
                                       "(rate < 1) on the fused CUDA path")
         self._state_dict["linear_coef"] = L
         self._lowered = dict(program=program, nl_coef=nl_coef, ks_remove_mean=ks_remove_mean,
-                             source_hat=source_hat, kmax=kmax)
+                             source_hat=source_hat, force_hat=force_hat, kmax=kmax, external=external)
+
+    def _lower_map(self, f_mesh: FourierMesh, n_channel: int):
+        """Operators made of symbol products only (Grad, Div, Curl, Vorticity2Velocity, optionally summed with linear
+        cores) -> (output channels, [(out, in, powers, inverse-Laplacian power, coefficient)]) for ``fsm_spectral_map``.
+        generic/_grad.py:6-28, _div.py:9-36, _curl.py:9-75, dedicated/_navier_stokes.py:75-104."""
+        d, C = f_mesh.n_dim, n_channel
+
+        def e(a, order=1):
+            return tuple(order if i == a else 0 for i in range(3))
+
+        per_term = []
+        for t in self.terms:
+            if isinstance(t.coef, torch.Tensor):
+                raise NotImplementedError("tensor-valued coefficients are not supported on channel-changing operators")
+            k, c = t.kind, float(t.coef)
+            if k == "grad":
+                if C != 1:
+                    raise ValueError("The Grad operator only supports scalar field.")
+                per_term.append((d, [(a, 0, e(a), 0, c) for a in range(d)]))
+            elif k == "div":
+                if d != C:
+                    raise ValueError("div operator only works for vector field with the same dimension as mesh")
+                per_term.append((1, [(0, a, e(a), 0, c) for a in range(d)]))
+            elif k == "curl":
+                if d != C:
+                    raise ValueError("div operator only works for vector field with the same dimension as mesh")
+                if C > 3 or C < 2:
+                    raise ValueError("div operator only works for 2D or 3D vector field")
+                if C == 2:
+                    per_term.append((1, [(0, 1, e(0), 0, c), (0, 0, e(1), 0, -c)]))
+                else:
+                    per_term.append((3, [(0, 2, e(1), 0, c), (0, 1, e(2), 0, -c), (1, 0, e(2), 0, c), (1, 2, e(0), 0, -c),
+                                         (2, 1, e(0), 0, c), (2, 0, e(1), 0, -c)]))
+            elif k == "vorticity2velocity":
+                if d != 2 or C != 1:
+                    raise ValueError("Only vorticity in 2Dmesh is supported")
+                per_term.append((2, [(0, 0, e(1), 1, -c), (1, 0, e(0), 1, c)]))
+            elif k == "laplacian":
+                per_term.append((C, [(ch, ch, e(a, 2), 0, c) for ch in range(C) for a in range(d)]))
+            elif k == "biharmonic":
+                per_term.append((C, [(ch, ch, tuple(x + y for x, y in zip(e(a, 2), e(b, 2))), 0, c * (1 if a == b else 2))
+                                     for ch in range(C) for a in range(d) for b in range(a, d)]))
+            elif k == "spatial_derivative":
+                if C != 1:
+                    raise ValueError("The SpatialDerivative operator only supports scalar field.")
+                per_term.append((1, [(0, 0, e(t.params["dim_index"], t.params["order"]), 0, c)]))
+            elif k == "implicit_unit_source":
+                per_term.append((C, [(ch, ch, (0, 0, 0), 0, c) for ch in range(C)]))
+            else:
+                raise NotImplementedError(f"{k} cannot be summed with a channel-changing operator on the fused CUDA path")
+        c_out = per_term[0][0]
+        if any(co != c_out for co, _ in per_term):
+            raise NotImplementedError("terms of one operator must produce the same number of channels on the fused CUDA path")
+        terms = [x for _, lst in per_term for x in lst]
+        if len(terms) > 32 or max(C, c_out) > 4:
+            raise NotImplementedError("too many symbol terms / channels for one point-wise map")
+        return c_out, terms
+
+    def _tf(self, batch: int, n_channel: int) -> "FusedStepper":
+        """Transform-only plan (r2c, c2r, layout converters, spectral map) for ``batch`` fields of ``n_channel`` channels."""
+        f_mesh = self._state_dict["f_mesh"]
+        cache = self.__dict__.setdefault("_tf_steppers", {})
+        key = (id(f_mesh), batch, n_channel, self._de_aliasing_rate, id(self._slab))
+        st = cache.get(key)
+        if st is None:
+            if len(cache) > 8:
+                cache.clear()
+            st = FusedStepper(f_mesh, batch, n_channel, _cabi.PROG_LINEAR, "RK4", 1.0, None, 0.0, None,
+                              f_mesh.low_pass_kmax(self._de_aliasing_rate), True, {}, slab=self._slab)
+            cache[key] = st
+        return st
+
+    def _eval_half(self, u_hat: torch.Tensor, f_mesh: FourierMesh, n_channel: int):
+        """Right-hand side L u + N(u) of this operator on a rot-half state (B, C, modes) -> (out_hat, output channels).
+        The body of ``__call__`` (operator/_base.py:753-790) between the transforms; also how a force operator handed to
+        the pressure diagnostics is evaluated (dedicated/_navier_stokes.py:128-131, 186-189)."""
+        if self._state_dict["f_mesh"] is not f_mesh or self._state_dict["n_channel"] != n_channel or self._lowered is None:
+            self.register_mesh(f_mesh, n_channel)
+        lo, B = self._lowered, u_hat.shape[0]
+        if "map" in lo:
+            return self._tf(B, n_channel).spectral_map(u_hat, lo["c_out"], lo["map"]), lo["c_out"]
+        if "composite" in lo:
+            return self._eval_composite(lo["composite"], u_hat, f_mesh, n_channel), 1
+        if self.is_linear and not any(isinstance(t.coef, torch.Tensor) for t in self.terms):
+            # a purely linear operator is a point-wise map too; this route also takes odd-order derivatives on 2-D/3-D
+            # grids, whose complex symbol the time-stepping tables refuse
+            if "linear_map" not in lo:
+                lo["linear_map"] = self._lower_map(f_mesh, n_channel)
+            c_out, terms = lo["linear_map"]
+            return self._tf(B, n_channel).spectral_map(u_hat, c_out, terms), c_out
+        st = getattr(self, "_rhs_stepper", None)
+        if st is None or st.B != B or st.f_mesh is not f_mesh:
+            st = self._build_integrator(1.0, B, rhs_only=True)
+        return st.rhs_half(u_hat), n_channel
+
+    def _eval_composite(self, t: _Term, u_hat: torch.Tensor, f_mesh: FourierMesh, n_channel: int) -> torch.Tensor:
+        """Velocity2Pressure / Vorticity2Pressure: p = -lap^-1 div((u . grad) u - f)
+        (dedicated/_navier_stokes.py:107-163, 166-217): [map to velocity ->] one evaluation of the convection program
+        (which dealiases its input on load, :136-137/:193) -> pressure solve as a point-wise map."""
+        B, d = u_hat.shape[0], f_mesh.n_dim
+        force = t.params.get("external_force")
+        conv_op = self.__dict__.get("_conv_op")
+        if conv_op is None:
+            conv_op = self._conv_op = Operator([_Term("convection")])
+        conv_op._de_aliasing_rate = self._de_aliasing_rate
+        conv_op._slab = self._slab
+        vel = u_hat
+        if t.kind == "vorticity2pressure":
+            vel = self._tf(B, 1).spectral_map(u_hat, 2, [(0, 0, (0, 1, 0), 1, -1.0), (1, 0, (1, 0, 0), 1, 1.0)])
+        conv, _ = conv_op._eval_half(vel, f_mesh, d)
+        if force is not None:
+            f_hat, _ = force._eval_half(u_hat, f_mesh, n_channel)      # the force sees the un-dealiased state
+            conv = conv - f_hat
+        e = [tuple(1 if i == a else 0 for i in range(3)) for a in range(d)]
+        return self._tf(B, d).spectral_map(conv, 1, [(0, a, e[a], 1, -float(t.coef)) for a in range(d)])
 
     @staticmethod
     def _linear_core(t: _Term, f_mesh: FourierMesh, n_channel: int) -> torch.Tensor:
@@ -835,6 +1080,35 @@ class OperatorLike:
             "Value and mesh do not match the requirement"
         return mesh, n_channel
 
+    def _external_nonlinear(self, terms, n_channel: int):
+        """sum_t coef_t * core_t(u_hat) for the host-composed cores (operator/_base.py:375-403): dealiased input for the
+        cores that ask for it, one inverse transform shared by all of them, every transform on the library's passes."""
+        d = self._state_dict["f_mesh"].n_dim
+        need_masked = any(t.kind == "conservative_convection" or t.params.get("non_linear", True) for t in terms)
+        need_plain = any(t.kind == "implicit_func_source" and not t.params.get("non_linear", True) for t in terms)
+        pairs = [(a, c) for a in range(n_channel) for c in range(a, n_channel)]
+
+        def evaluate(st, x_hat):
+            u_d = st.c2r(st.mask_state(x_hat.clone())) if need_masked else None
+            u = st.c2r(x_hat) if need_plain else None
+            out = None
+            for t in terms:
+                if t.kind == "implicit_func_source":                     # generic/_source.py:20-42
+                    v = t.params["source_func"](u_d if t.params.get("non_linear", True) else u)
+                    if v.shape != (st.B, st.C) + tuple(st.local_shape):
+                        raise ValueError("ImplicitSource: source_func must keep the shape of its argument")
+                    r = st.r2c(v)
+                    r = r * float(t.coef) if float(t.coef) != 1.0 else r
+                else:                                                    # generic/_conservative_convection.py:18-27
+                    uu_hat = self._tf(st.B, len(pairs)).r2c(st.sym_outer(u_d))
+                    e = [tuple(1 if i == a else 0 for i in range(3)) for a in range(d)]
+                    m = [(c, pairs.index((min(i, c), max(i, c))), e[i], 0, float(t.coef))
+                         for c in range(n_channel) for i in range(d)]
+                    r = self._tf(st.B, len(pairs)).spectral_map(uu_hat, n_channel, m)
+                out = r if out is None else out.add_(r)
+            return out
+        return evaluate
+
     def _build_integrator(self, dt: float, batch: int, tables: Optional[dict] = None, rhs_only: bool = False):
         """operator/_base.py:441-526: installs a FusedStepper in ``_state_dict['integrator']``.
 
@@ -843,13 +1117,21 @@ class OperatorLike:
         if rhs_only:
             name, cfg = "RK4", {}
         else:
-            name, cfg = integrator_name(self._integrator, lo["program"] == _cabi.PROG_LINEAR), self._integrator_config
+            # an explicit source is a nonlinear core in the reference (operator/_base.py:994-1015): "auto" -> SETDRK4
+            name, cfg = integrator_name(self._integrator, lo["program"] == _cabi.PROG_LINEAR and lo["source_hat"] is None
+                                        and not lo["external"]), self._integrator_config
         if name == "ETDRK0":
-            assert lo["program"] == _cabi.PROG_LINEAR, "The ETDRK0 integrator only supports linear term"
+            assert lo["program"] == _cabi.PROG_LINEAR and ((lo["source_hat"] is None and not lo["external"]) or rhs_only), \
+                "The ETDRK0 integrator only supports linear term"
         try:
-            st = FusedStepper(sd["f_mesh"], batch, sd["n_channel"], lo["program"], name, dt, sd["linear_coef"],
-                              lo["nl_coef"], lo["source_hat"], lo["kmax"], lo["ks_remove_mean"], cfg,
-                              chunk=self._chunk, tables=tables, slab=self._slab, lanes=self._lanes)
+            extra = {}
+            cls = FusedStepper
+            if lo["external"]:
+                cls, extra = HostComposedStepper, {"nonlinear": self._external_nonlinear(lo["external"], sd["n_channel"])}
+            st = cls(sd["f_mesh"], batch, sd["n_channel"], lo["program"], name, dt, sd["linear_coef"],
+                     lo["nl_coef"], lo["source_hat"], lo["kmax"], lo["ks_remove_mean"], cfg,
+                     chunk=self._chunk, tables=tables, slab=self._slab, lanes=self._lanes,
+                     force_hat=lo["force_hat"], **extra)
         except torch.cuda.OutOfMemoryError as e:
             raise RuntimeError(os.linesep.join([
                 "Cuda out of memory when building the integrator.",
@@ -868,6 +1150,9 @@ class OperatorLike:
             self.register_mesh(mesh, n_channel)
         else:
             self._pre_check(value[0], value[1], self._state_dict["f_mesh"])
+        if "map" in self._lowered or "composite" in self._lowered:
+            raise NotImplementedError("Grad/Div/Curl and the velocity/pressure diagnostics change the channel count: they "
+                                      "can be evaluated (operator(u)) but not integrated in time")
         v = value[0] if value[0] is not None else value[1]
         st = self._state_dict["integrator"]
         if st is None or st.dt != dt or st.B != v.shape[0]:
@@ -1008,16 +1293,24 @@ class OperatorLike:
         if self._state_dict["f_mesh"] is None or mesh is not None or self._lowered is None:
             m, n_channel = self._pre_check(u, u_fft, mesh if mesh is not None else self._state_dict["f_mesh"])
             self.register_mesh(m, n_channel)
-            self._rhs_stepper = None
         else:
             self._pre_check(u, u_fft, self._state_dict["f_mesh"])
+        f_mesh, n_channel = self._state_dict["f_mesh"], self._state_dict["n_channel"]
         v = u if u is not None else u_fft
-        st = getattr(self, "_rhs_stepper", None)
-        if st is None or st.B != v.shape[0] or st.f_mesh is not self._state_dict["f_mesh"]:
-            st = self._build_integrator(1.0, v.shape[0], rhs_only=True)
-        u_hat = st.r2c(u) if u_fft is None else st.full_to_half(u_fft)
-        out = st.rhs_half(u_hat)
-        return st.half_to_full(out) if return_in_fourier else st.c2r(out)
+        B = v.shape[0]
+        lo = self._lowered
+        if "map" in lo or "composite" in lo:
+            st_in, st_out = self._tf(B, n_channel), self._tf(B, lo["c_out"])
+        elif self.is_linear and not any(isinstance(t.coef, torch.Tensor) for t in self.terms):
+            st_in = st_out = self._tf(B, n_channel)
+        else:
+            st_in = getattr(self, "_rhs_stepper", None)
+            if st_in is None or st_in.B != B or st_in.f_mesh is not f_mesh:
+                st_in = self._build_integrator(1.0, B, rhs_only=True)
+            st_out = st_in
+        u_hat = st_in.r2c(u) if u_fft is None else st_in.full_to_half(u_fft)
+        out, _ = self._eval_half(u_hat, f_mesh, n_channel)
+        return st_out.half_to_full(out) if return_in_fourier else st_out.c2r(out)
 
 
 class Operator(OperatorLike):
@@ -1076,9 +1369,10 @@ def SpatialDerivative(dim_index: int, order: int) -> Operator:
 
 
 def ImplicitSource(source_func=None, non_linear: bool = True) -> Operator:
-    """operator/generic/_source.py:45-74 (unit form only on the fused path)"""
+    """operator/generic/_source.py:45-74. The unit form is a linear core; ``source_func`` (a callable on the physical
+    field) becomes a host-composed nonlinear term: c2r -> source_func -> r2c on the library's passes."""
     if source_func is not None:
-        raise NotImplementedError("ImplicitSource(source_func) is not supported by the fused CUDA path")
+        return Operator([_Term("implicit_func_source", 1, {"source_func": source_func, "non_linear": non_linear})])
     return Operator([_Term("implicit_unit_source")])
 
 
@@ -1105,3 +1399,55 @@ def VorticityConvection() -> Operator:
 def NSPressureConvection(external_force=None) -> Operator:
     """operator/dedicated/_navier_stokes.py:257-268"""
     return Operator([_Term("ns_pressure_convection", 1, {"external_force": external_force})])
+
+
+def ConservativeConvection() -> Operator:
+    """operator/generic/_conservative_convection.py:46-55: div(u u); host-composed from c2r, the symmetric products,
+    r2c of the d(d+1)/2 distinct products and the divergence as a spectral map."""
+    return Operator([_Term("conservative_convection")])
+
+
+def Grad() -> Operator:
+    """operator/generic/_grad.py:30-38"""
+    return Operator([_Term("grad")])
+
+
+def Div() -> Operator:
+    """operator/generic/_div.py:42-53"""
+    return Operator([_Term("div")])
+
+
+def Curl() -> Operator:
+    """operator/generic/_curl.py:78-93"""
+    return Operator([_Term("curl")])
+
+
+def Vorticity2Velocity() -> Operator:
+    """operator/dedicated/_navier_stokes.py:107-116"""
+    return Operator([_Term("vorticity2velocity")])
+
+
+def Vorticity2Pressure(external_force: Optional[OperatorLike] = None) -> Operator:
+    """operator/dedicated/_navier_stokes.py:166-176"""
+    return Operator([_Term("vorticity2pressure", 1, {"external_force": external_force})])
+
+
+def Velocity2Pressure(external_force: Optional[OperatorLike] = None) -> Operator:
+    """operator/dedicated/_navier_stokes.py:220-229"""
+    return Operator([_Term("velocity2pressure", 1, {"external_force": external_force})])
+
+
+def run_operators(u: torch.Tensor, operators: Sequence[OperatorLike], mesh):
+    """operator/__init__.py:12-31 — apply several operators to one field; the forward transform is shared."""
+    if not operators:
+        return iter(())
+    first = operators[0]
+    f_mesh, n_channel = first._pre_check(u, None, mesh)
+    first.register_mesh(f_mesh, n_channel)
+    st = first._tf(u.shape[0], n_channel)
+    u_hat = st.r2c(u)
+
+    def run(op):
+        out, c_out = op._eval_half(u_hat, f_mesh, n_channel)
+        return op._tf(u.shape[0], c_out).c2r(out)
+    return map(run, operators)
