@@ -336,7 +336,7 @@ def run_slab_c5(fsm, dist, world, rank, dev, steps, warmup):
     info = st.info()
     peak, _ = _peaks()
     out.update({"ms_per_step": ms, "steps_per_sec": 1e3 / ms, "finite": finite, "dt": C5_DT, "Re": C5_RE,
-                "algo_gb_per_step_global": info["algo_bytes_per_step"] * (world if world > 1 else 1) / 1e9})
+                "algo_gb_per_step_global": info["algo_bytes_per_step"] / 1e9})     # the plan counts the whole grid
     if world == 1:
         gbs = info["algo_bytes_per_step"] / (ms * 1e-3) / 1e9
         out.update({"ms_per_step_1gpu": ms, "strong_efficiency_vs_n1": 1.0, "hbm_frac_of_measured_peak": gbs / peak,
@@ -357,7 +357,7 @@ def run_slab_c5(fsm, dist, world, rank, dev, steps, warmup):
             bare = maxr(e0.elapsed_time(e1)) / 2
         except Exception as exc:
             out["bare_exchange_error"] = repr(exc)[:200]
-        gbs_total = info["algo_bytes_per_step"] * world / (ms * 1e-3) / 1e9
+        gbs_total = info["algo_bytes_per_step"] / (ms * 1e-3) / 1e9
         out.update({"ms_per_step_1gpu": t1, "strong_efficiency_vs_n1": t1 / (world * ms), "exchange": st._exch_mode,
                     "nsub": getattr(st, "nsub", 1), "cuda_graph": bool(getattr(st, "_graphs", None)),
                     "graph_error": getattr(st, "_graph_error", None), "ky_ownership": "cyclic (kept lines only on the inverse exchange)",

@@ -164,10 +164,10 @@ static int launch_ix(int prog, const IxArgs<T>& a, cudaStream_t s) {
     }
 }
 
-template <typename T, int N, int DIR>
-static int launch_mid_d(const MidArgs<T>& a, cudaStream_t s) {
+template <typename T, int N, int DIR, int IMODE, int EMODE>
+static int launch_mid_m(const MidArgs<T>& a, cudaStream_t s) {
     using Cfg = typename CfgFor<N>::type;
-    auto kern = k_pass_mid<T, Cfg, DIR>;
+    auto kern = k_pass_mid<T, Cfg, DIR, IMODE, EMODE>;
     const size_t smem = Smem<Cfg, T>::bytes(2 * kKL);
     if (int e = set_smem(kern, smem)) return e;
     dim3 grid((a.n_t + kKL - 1) / kKL, a.n_outer, a.nb), block(kKL * Cfg::TL);
@@ -175,9 +175,20 @@ static int launch_mid_d(const MidArgs<T>& a, cudaStream_t s) {
                a.in_t_stride, a.in_o_stride, a.out_o_stride, a.out_e_stride, a.n_t, a.ib, a.eb, a.pe);
     return check_launch();
 }
+// inverse side (dir > 0): contiguous input (one GPU) or the cyclic rank blocks of a receive buffer, plain store;
+// forward side: contiguous input, plain store / cyclic rank blocks of a send buffer / the peers' receive buffers
 template <typename T, int N>
 static int launch_mid(int dir, const MidArgs<T>& a, cudaStream_t s) {
-    return dir > 0 ? launch_mid_d<T, N, +1>(a, s) : launch_mid_d<T, N, -1>(a, s);
+    const bool in_blocked = a.ib.shift < 30, out_blocked = a.eb.shift < 30;
+    if (dir > 0) {
+        if (out_blocked || a.pe.n > 0) return -EINVAL;
+        if (in_blocked && a.ib.cyc <= 0) return -EINVAL;
+        return in_blocked ? launch_mid_m<T, N, +1, 1, 0>(a, s) : launch_mid_m<T, N, +1, 0, 0>(a, s);
+    }
+    if (in_blocked) return -EINVAL;
+    if (!out_blocked) return launch_mid_m<T, N, -1, 0, 0>(a, s);
+    if (a.eb.cyc <= 0) return -EINVAL;
+    return a.pe.n > 0 ? launch_mid_m<T, N, -1, 0, 2>(a, s) : launch_mid_m<T, N, -1, 0, 1>(a, s);
 }
 
 #ifndef FSM_PHYS3D_NL512

@@ -842,7 +842,12 @@ struct MidSpec {
     int deriv[12];
 };
 
-template <typename T, class Cfg, int DIR>
+// IMODE: 0 = input lines are contiguous (one GPU, forward side of a slab), 1 = the ky axis of the input is spread over
+// the rank blocks of a receive buffer with cyclic ownership (inverse side of a slab-decomposed grid).
+// EMODE: 0 = plain rotated store, 1 = the ky axis of the output goes to the rank blocks of a send buffer (cyclic
+// ownership), 2 = the same straight into the peers' receive buffers. One instantiation per combination keeps the
+// address arithmetic of the other paths (and their registers) out of each kernel.
+template <typename T, class Cfg, int DIR, int IMODE, int EMODE>
 __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass_mid(Geom<T> g, const cplx<T>* __restrict__ in, cplx<T>* __restrict__ out,
                                                    long in_fstride, long out_fstride, int nfi, MidSpec spec, int K,
                                                    long in_t_stride, long in_o_stride, long out_o_stride,
@@ -864,29 +869,45 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
     cplx<T>* mybuf = bufs + lt * Cfg::LINE_PITCH;
     // the line of output field j+1 is loaded (registers) before field j is transformed and stored, so its
     // latency hides behind the butterflies, the block barrier and the rotated stores of field j
-    const bool one_block = ib.shift >= 30;
     unsigned keepmask = 0;   // bit m: element p = tau + m*TL of an input line is read (dealiasing, valid line)
     FSM_UNROLL
     for (int m = 0; m < EPT; ++m) {
         const int p = tau + m * TL;
         if (line_ok && (DIR < 0 || iabs(signed_mode<N>(p)) <= g.kmax[1])) keepmask |= 1u << m;
     }
+    // cyclic input (IMODE 1): ky = tau + m*TL lives in rank block ky & (P-1) at slot ky >> log2(P), compacted by the
+    // dropped run of slots; TL is a multiple of P, so the block is fixed per thread and the slot advances by TL/P
+    const int icm = (IMODE == 1) ? ((1 << ib.cyc) - 1) : 0;
+    const long irank_off = (IMODE == 1) ? (long)(tau & icm) * ib.stride : 0;
+    const int islot0 = (IMODE == 1) ? (tau >> ib.cyc) : 0, islot_step = (IMODE == 1) ? (TL >> ib.cyc) : 0;
     auto load_line = [&](int j, cplx<T>* raw) FSM_INLINE_LAMBDA {
         const cplx<T>* src = in + (b * nfi + spec.src[j]) * in_fstride + (long)(line_ok ? t : 0) * in_t_stride + (long)o * in_o_stride;
-        if (one_block) {
+        if constexpr (IMODE == 0) {
             src += tau;
             FSM_PIN(src);
             FSM_UNROLL
             for (int m = 0; m < EPT; ++m) raw[m] = ((keepmask >> m) & 1u) ? src[m * TL] : mk<T>(T(0), T(0));
         } else {
-            FSM_UNROLL
-            for (int m = 0; m < EPT; ++m)
-                raw[m] = ((keepmask >> m) & 1u) ? src[blk_off(tau + m * TL, ib, 1)] : mk<T>(T(0), T(0));
+            if constexpr (TL >= FSM_MAX_PEERS) {
+                src += irank_off;
+                FSM_PIN(src);
+                FSM_UNROLL
+                for (int m = 0; m < EPT; ++m) {
+                    const int slot = islot0 + m * islot_step;
+                    raw[m] = ((keepmask >> m) & 1u) ? src[slot - (slot >= ib.gap_at ? ib.gap : 0)] : mk<T>(T(0), T(0));
+                }
+            } else {   // lines shorter than the rank count times the thread stride: plain per-element form
+                FSM_UNROLL
+                for (int m = 0; m < EPT; ++m)
+                    raw[m] = ((keepmask >> m) & 1u) ? src[blk_off(tau + m * TL, ib, 1)] : mk<T>(T(0), T(0));
+            }
         }
     };
     cplx<T> raw[EPT];
     load_line(0, raw);
     twiddles_ready();
+    const int ecm = (EMODE != 0) ? ((1 << eb.cyc) - 1) : 0;
+    const int es = (int)out_e_stride;     // one field of one rank block: fits 32 bits
     for (int j = 0; j < spec.nfo; ++j) {
         cplx<T> v[EPT];
         const bool deriv = spec.deriv[j] != 0;
@@ -898,19 +919,19 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
         __syncthreads();
         cplx<T>* dst = out + (b * spec.nfo + j) * out_fstride + (long)o * out_o_stride + t0 + threadIdx.x % kKL;
         const bool valid = (int)(threadIdx.x % kKL) < k_valid;
-        if (eb.shift >= 30) {
-            const int es = (int)out_e_stride;
+        if constexpr (EMODE == 0) {
+            FSM_PIN(dst);
             rotated_last_stage<Cfg, DIR, T>(pbufs, tw, [&](int e, cplx<T> val) FSM_INLINE_LAMBDA {
                 if (valid) dst[e * es] = val;
             });
-        } else if (pe.n > 0) {  // direct exchange: the ky-slab owner's receive buffer
+        } else if constexpr (EMODE == 2) {  // direct exchange: the ky-slab owner's receive buffer
             const long off0 = dst - out;
             rotated_last_stage<Cfg, DIR, T>(pbufs, tw, [&](int e, cplx<T> val) FSM_INLINE_LAMBDA {
                 if (valid) *peer_ptr<T>(pe, eb, e, off0, out_e_stride) = val;
             });
-        } else {
+        } else {                            // send buffer: rank block e & (P-1), slot e >> log2(P)
             rotated_last_stage<Cfg, DIR, T>(pbufs, tw, [&](int e, cplx<T> val) FSM_INLINE_LAMBDA {
-                if (valid) dst[blk_off(e, eb, out_e_stride)] = val;
+                if (valid) dst[(long)(e & ecm) * eb.stride + (e >> eb.cyc) * es] = val;
             });
         }
     }
