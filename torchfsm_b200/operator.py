@@ -303,8 +303,10 @@ class FusedStepper:
             nsub = int(slab[3]) if len(slab) > 3 and slab[3] else 0
             if self._exch_mode == "store":
                 nsub = 1
-            if nsub <= 0:       # sub-slabs pipeline the exchanges with the local y/z chain (profiles/r2_slab_scaling.md)
-                nsub = 4 if self.nxl >= 32 else (2 if self.nxl >= 16 else 1)
+            if nsub <= 0:       # sub-slabs pipeline the exchanges with the local y/z chain (profiles/r2_slab_scaling.md):
+                # four where a sub-slab still fills the GPU for several waves, two on thinner slabs (measured at 512^3:
+                # 4 ranks 8.82 ms with 4 sub-slabs against 9.17 with 2; 8 ranks 5.33 ms with 2 against 5.87 with 4)
+                nsub = 4 if self.nxl >= 128 else (2 if self.nxl >= 16 else 1)
             while nsub > 1 and self.nxl % nsub:
                 nsub //= 2
             self.nsub = max(1, nsub)
