@@ -418,3 +418,76 @@ def test_batched_viscosity_at_size_vs_per_sample_runs():
         one.set_integrator(fsm.ETDRKIntegrator.ETDRK2)
         want = one.integrate(u0[i:i + 1].contiguous(), mesh=mesh, dt=0.01, step=4)
         assert float((got[i:i + 1] - want).norm() / want.norm()) < 1e-6
+
+
+# ---------------------------------------------------------------- slab decomposition at size on ONE GPU
+def _slab_ranks_in_one_process(P, n, steps, integrator, nsub=1):
+    """Every rank's plan of a P-way slab decomposition lives in this process on one GPU; the all-to-all between the
+    phases is done by copying the rank blocks between the plans' exchange buffers (exactly what all_to_all_single /
+    the copy engines do between GPUs). Returns (slab result assembled over the ranks, single-plan result)."""
+    import torchfsm_b200 as fsm
+    dev = torch.device("cuda", 0)
+    mesh = fsm.MeshGrid([(0, 2 * np.pi, n)] * 3, device=dev, dtype=torch.float32)
+    u0 = _taylor_green(n, torch.float32).to(dev)
+    dt = 0.01
+
+    def make(rank=None):
+        op = fsm.pde.NavierStokes(Re=1600)
+        op.set_integrator(integrator)
+        if rank is not None:
+            op.set_slab_decomposition(group=None, rank=rank, nranks=P, nsub=nsub, exchange="nccl", graph=False)
+        nxl = n // P
+        u = u0 if rank is None else u0[:, :, rank * nxl:(rank + 1) * nxl].contiguous()
+        m, c = op._pre_check(u, None, mesh)
+        op.register_mesh(m, c)
+        return op, op._build_integrator(dt, 1), u
+
+    _, st1, _ = make()
+    want = st1.c2r(st1.step_half(st1.r2c(u0), steps))
+    ranks = [make(r) for r in range(P)]
+    sts = [st for _, st, _ in ranks]
+
+    def exchange(which, count, offset=0):
+        blk = count // P
+        for r in range(P):            # receive block q of rank r <- send block r of rank q
+            for q in range(P):
+                sts[r]._recv[which][offset + q * blk: offset + (q + 1) * blk].copy_(
+                    sts[q]._send[which][offset + r * blk: offset + (r + 1) * blk])
+
+    def phase(op, stage, ph, states, auxs, snd, rcv, sub=0, H=1):
+        for st, x, a in zip(sts, states, auxs):
+            st._slab_phase(op, stage, ph, x, a, snd, rcv, sub, H)
+
+    # forward transform of the local slabs
+    hats = [st.empty_half() for st in sts]
+    phys = [u for _, _, u in ranks]
+    c2 = sts[0]._slab_counts[2][1]
+    phase(2, 0, 1, hats, phys, 1, None)
+    exchange(1, c2)
+    phase(2, 0, 2, hats, phys, None, 1)
+    none = [None] * P
+    H = sts[0].nsub
+    c1s, c2s = sts[0]._slab_counts[0]
+    for _ in range(steps):
+        for stage in range(sts[0].n_stages):
+            phase(0, stage, 0, hats, none, 0, None, 0, H)
+            for h in range(H):
+                exchange(0, c1s // H, h * (c1s // H))
+                phase(0, stage, 1, hats, none, 1, 0, h, H)
+                exchange(1, c2s // H, h * (c2s // H))
+            phase(0, stage, 2, hats, none, None, 1, 0, H)
+    outs = [torch.empty_like(u) for u in phys]
+    c1 = sts[0]._slab_counts[3][0]
+    phase(3, 0, 0, hats, outs, 0, None)
+    exchange(0, c1)
+    phase(3, 0, 1, hats, outs, None, 0)
+    return torch.cat(outs, dim=2), want
+
+
+@pytest.mark.parametrize("P,nsub", [(2, 1), (4, 2), (8, 1)])
+def test_slab_decomposition_equals_single_plan_at_128cubed(P, nsub):
+    """C5's path at 128^3 (NS velocity form, SETDRK4, 2/3 dealiasing): the P-way slab-decomposed plans (cyclic ky
+    ownership, kept lines only on the inverse exchange, sub-slabs) against the single plan of the same grid, 2 steps."""
+    import torchfsm_b200 as fsm
+    got, want = _slab_ranks_in_one_process(P, 128, 2, fsm.SETDRKIntegrator.SETDRK4, nsub=nsub)
+    assert float((got - want).norm() / want.norm()) <= 1e-6

@@ -6,7 +6,7 @@ and the numpy oracle side by side from the same initial condition and the same c
 prints, per config, the relative L2 distance of the physical fields after 1, 10, 50, 100, ... steps up to the
 full run. Chaotic configs (KS, NS) amplify rounding differences: reported, not gated.
 
-    python tools/trajectory_drift.py [c1] [c3] [c2]     # bounded versions of the BASELINE configs
+    python tools/trajectory_drift.py [c1] [c3] [c2] [c2full] [c4] [c5]     # (bounded versions of) the BASELINE configs
 """
 import json
 import os
@@ -99,6 +99,35 @@ def main():
                                      lambda cv: [("laplacian", -1, {}), ("biharmonic", -1, {}),
                                                  ("ks_convection", -1, {"remove_mean": True})],
                                      "SETDRK4", 0.1, 200, u0, dtype, dev, marks))
+        if "c2full" in which:   # C2 at its own grid and time step: 2-D KS 256^2 (L = 60), batch bounded to 8, SETDRK4, dt = 0.5
+            n = 256
+            g = np.random.default_rng(0)
+            u0 = g.standard_normal((8, 1, n, n)).astype(npd)
+            res["runs"].append(drift("C2 ks2d (256^2 x 8 of 256^2 x 256)", [(0, 60.0, n)] * 2,
+                                     lambda cv: [("laplacian", -1, {}), ("biharmonic", -1, {}),
+                                                 ("ks_convection", -1, {"remove_mean": True})],
+                                     "SETDRK4", 0.5, 200, u0, dtype, dev, marks))
+        if "c4" in which:   # C4 bounded: 3-D Burgers 64^3 x 2 (full: 256^3 x 8), SETDRK4, dt = 0.002, 50 steps
+            n = 64
+            ax = (np.arange(n) / n).astype(npd) * 2 * np.pi
+            x, y, z = ax.reshape(1, 1, n, 1, 1), ax.reshape(1, 1, 1, n, 1), ax.reshape(1, 1, 1, 1, n)
+            base = np.concatenate([np.sin(x) * np.cos(y) * np.cos(z), -np.cos(x) * np.sin(y) * np.cos(z),
+                                   0.5 * np.sin(2 * x + z) * np.cos(y)], axis=1).astype(npd)
+            g = np.random.default_rng(1)
+            u0 = (np.repeat(base, 2, axis=0) + 0.05 * np.sin(x + 2 * y) * g.standard_normal((2, 3, 1, 1, 1))).astype(npd)
+            res["runs"].append(drift("C4 burgers3d (64^3 x 2 of 256^3 x 8)", [(0, 1.0, n)] * 3,
+                                     lambda cv: [("laplacian", 0.01, {}), ("convection", -1, {})], "SETDRK4", 0.002, 50, u0,
+                                     dtype, dev, [1, 10, 50]))
+        if "c5" in which:   # C5 bounded: 3-D NS 64^3 (full: 512^3), Taylor-Green + perturbation, SETDRK4, dt = 0.0025 * 8, 20 steps
+            n = 64
+            ax = (np.arange(n) / n).astype(npd) * 2 * np.pi
+            x, y, z = ax.reshape(1, 1, n, 1, 1), ax.reshape(1, 1, 1, n, 1), ax.reshape(1, 1, 1, 1, n)
+            u0 = np.concatenate([np.sin(x) * np.cos(y) * np.cos(z) + 0.05 * np.sin(2 * y) * np.cos(3 * z) + 0 * x,
+                                 -np.cos(x) * np.sin(y) * np.cos(z) + 0.05 * np.sin(3 * z + x) + 0 * y,
+                                 0.05 * np.sin(3 * y + x) * np.cos(2 * z)], axis=1).astype(npd)
+            res["runs"].append(drift("C5 ns3d velocity form (64^3 of 512^3)", [(0, 2 * np.pi, n)] * 3,
+                                     lambda cv: [("ns_pressure_convection", 1, {}), ("laplacian", 1 / 1600, {})], "SETDRK4",
+                                     0.02, 20, u0, dtype, dev, [1, 10, 20]))
     print(json.dumps(res, indent=1))
 
 
