@@ -467,20 +467,25 @@ def run_b200(args):
     peak, peak_src = _peaks()
     dom = max((k for k in prof if prof[k]["launches"] > 0), key=lambda k: prof[k]["ms"])
     passes = {}
+    touched = st.touched_bytes()
     for k, v in prof.items():
         if v["launches"] == 0:
             continue
         gbs = v["algo_bytes_per_step"] * prof_steps / (v["ms"] * 1e-3) / 1e9
+        tb = touched.get(k, 0)
         passes[k] = {"ms_per_step": v["ms"] / prof_steps, "launches_per_step": v["launches"] / prof_steps,
-                     "algo_gb_per_step": v["algo_bytes_per_step"] / 1e9, "achieved_gbs": gbs, "frac": gbs / peak}
+                     "algo_gb_per_step": v["algo_bytes_per_step"] / 1e9, "achieved_gbs": gbs, "frac": gbs / peak,
+                     "touched_gb_per_step": tb / 1e9,       # kept modes only, what the pass really reads + writes
+                     "touched_gbs": tb * prof_steps / (v["ms"] * 1e-3) / 1e9}
     # DRAM traffic per launch of the dominant kernel: NOT measured in this run (needs ncu); taken from the
     # committed ncu --set full capture of the same kernels and chunking, null when that does not apply
     traffic, traffic_src = None, None
-    for cand in ("r2_ncu_traffic.json", "r1_ncu_traffic.json"):
+    for cand in ("r2_ncu_traffic.json",):
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", cand)))
             if info["chunk"] == tj.get("chunk", 64):
-                traffic = tj["kernels"]["k_pass_" + dom.lower()]["dram_bytes_per_launch"]
+                kern = tj["kernels"].get("k_pass_" + dom.lower()) or tj["kernels"]["k_pass_" + dom.lower() + "z"]
+                traffic = kern["dram_bytes_per_launch"]
                 traffic_src = f"profiles/{cand} (committed ncu --set full capture, dram read+write bytes per launch; not re-measured in this run)"
                 break
         except Exception:
@@ -491,7 +496,9 @@ def run_b200(args):
                 "algo_bytes_per_launch": passes[dom]["algo_gb_per_step"] * 1e9 / passes[dom]["launches_per_step"],
                 "peak_source": peak_src, "passes": passes,
                 "whole_step": {"algo_gb_per_step": info["algo_bytes_per_step"] / 1e9, "achieved_gbs": step_gbs,
-                               "frac": step_gbs / peak, "frac_of_8000_nominal": step_gbs / 8000.0}}
+                               "frac": step_gbs / peak, "frac_of_8000_nominal": step_gbs / 8000.0,
+                               "touched_gb_per_step": sum(touched.values()) / 1e9,
+                               "touched_gbs": sum(touched.values()) / (ms_step * 1e-3) / 1e9}}
 
     # ---------------- end to end through the public API with host buffers (pipelined: upload, step, download of
     # consecutive batches on three streams; every step's input comes from pinned host memory and its result lands

@@ -76,14 +76,17 @@ typedef struct fsm_desc {
     double dt;                /* time step (RK4 only uses it; ETD tables already contain it)         */
     double nl_coef;           /* scalar coefficient of the convective nonlinear term                 */
     double ks_ext_sum;        /* reserved (0)                                                         */
-    int32_t ks_ext_count;     /* reserved (0)                                                         */
+    int32_t dynamic_force;    /* FSM_PROG_NS3D: 1 = the stages will be driven one by one through fsm_stage_run with a
+                                 state-dependent force spectrum (keeps the reference's grouping of the two-stage step)  */
     int32_t tab_complex;      /* 1: every coefficient table holds complex entries (2 reals per mode): odd-order
                                * linear terms such as KdV's dispersion (_spatial_derivative.py:7-20). 1-D grids only */
     const void* dk[3];        /* per-axis 2*pi*f(m), Nyquist entry zeroed (length n[i])  mesh.py:399-404 */
     const void* dkraw[3];     /* per-axis 2*pi*f(m) as the reference has it (length n[i])           */
     const void* tab_exp;      /* exp(dt L)            _etdrk.py:21 / _uncached.py:30                 */
     const void* tab_half_exp; /* exp(dt L / 2)        _uncached.py:135,191                           */
-    const void* tab_coef[6];  /* coef_1..coef_6       _etdrk.py:43-45,66-70 / _uncached.py:72-211    */
+    const void* tab_coef[6];  /* coef_1..coef_6       _etdrk.py:43-45,66-70 / _uncached.py:72-211. ETDRK2 / SETDRK2 use
+                                 coef_1 and coef_2 only; a caller may put coef_1 - coef_2 into the coef_3 slot, the step then
+                                 runs as d = E u + (coef_1 - coef_2) N0, u' = d + coef_2 N(a): one array read less */
     const void* tab_lin;      /* L itself (RK4 and fsm_rhs)   operator/_base.py:339-357              */
     const void* source_hat;   /* optional constant source spectrum, complex [C][modes], coefficient
                                  folded in (operator/_base.py:994-1015)                              */
@@ -164,12 +167,24 @@ int fsm_stage_input(const fsm_plan* plan, int32_t stage, int64_t* ws_offset);
 int fsm_stage_combine(fsm_plan* plan, int32_t stage, void* u_hat, const void* fresh_hat, void* rhs_out, void* workspace,
                       size_t ws_bytes, void* stream);
 int fsm_mask_state(fsm_plan* plan, void* state_hat, int32_t channels, void* stream);
+/* NSPressureConvection(external_force) with a force operator that DEPENDS on the state (_navier_stokes.py:237-254):
+ * the caller evaluates f_hat = external_force(stage input) [B][C][modes] with this library's passes BEFORE the stage
+ * runs (the reference evaluates the force on the un-dealiased state, then dealiases that state in place), and
+ * fsm_stage_run executes the fused evaluation + combine of stage `stage` with it: coef * (P(conv - f) + f).
+ * Plans must be created with dynamic_force = 1; stage -1 = the right-hand side into rhs_out. */
+int fsm_stage_run(fsm_plan* plan, int32_t stage, void* u_hat, const void* force_hat, void* rhs_out, void* workspace,
+                  size_t ws_bytes, void* stream);
 int fsm_sym_outer(fsm_plan* plan, const void* u, void* out, int32_t channels, void* stream);
 
 /* introspection for benchmarks: kernels launched per step, algorithmic bytes per step
  * (transform-pass model), modes per field, chunk size */
 int fsm_plan_info(const fsm_plan* plan, int64_t* launches_per_step, int64_t* algo_bytes_per_step,
                   int64_t* modes_per_field, int32_t* chunk);
+
+/* bytes the passes of each class {IX, MID, PHYS, FX + combine} really read + write per step: kept (dealiased) modes
+ * only on the inverse side, coefficient tables excluded. The section 8d model (fsm_plan_info / fsm_profile_read) counts
+ * whole fields per pass; this is what a pass's GB/s must be quoted on to stay below the HBM peak. */
+int fsm_plan_traffic(const fsm_plan* plan, int64_t* touched_bytes_per_step4);
 
 /* introspection for tests: number of integrator stages; kinds[i] = index of the compile-time combine
  * structure stage i runs with in the forward-x epilogue (-1 = generic data-driven path) */

@@ -6,7 +6,7 @@ It exists to CHECK the CUDA path; it is never the thing shipped or measured:
 
 * only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
   ``--impl reference`` legs of ``bench.py`` may import it;
-* nothing under ``torchfsm_b200/`` imports it (tests/test_no_oracle_in_product.py
+* nothing under ``torchfsm_b200/`` imports it (tests/test_product_boundary.py::test_product_does_not_import_oracle_or_emulator
   enforces that), and the product fails loudly when the CUDA library is missing.
 
 Arithmetic lives in a third-party dependency of the reference that is not under

@@ -73,6 +73,8 @@ def main():
         if only and case["name"] not in only:
             continue
         for dtype in (torch.float32, torch.float64):
+            if str(dtype).replace("torch.", "") not in case.get("dtypes", ["float32", "float64"]):
+                continue
             out = run_case(case, dtype)
             tag = "f32" if dtype == torch.float32 else "f64"
             path = os.path.join(OUT, f"{case['name']}_{tag}.npz")

@@ -171,6 +171,19 @@ OPS_CASES = [
     dict(name="ns2d_velocity_force_etdrk2", mode="integrate", mesh=_m((32, 16), TWO_PI, TWO_PI), B=2, C=2,
          terms=[("ns_pressure_convection", 1, {"force": [("explicit_source", 1, {"source": "force2d"})]}),
                 ("laplacian", 1 / 100, {})], integrator="ETDRK2", dt=0.005, steps=3),
+    # state-dependent forces: drag + body force (the 3-D analogue of kolm_force), and a force with its own derivative.
+    # fp32 only: the half-spectrum state reproduces the reference to ~1e-8 here (see DynamicForceStepper / DESIGN.md)
+    dict(name="ns3d_drag_force_setdrk4", mode="integrate", dtypes=["float32"], mesh=_m((16, 16, 8), TWO_PI, TWO_PI, TWO_PI), B=2, C=3,
+         terms=[("ns_pressure_convection", 1, {"force": [("implicit_unit_source", -0.1, {}),
+                                                        ("explicit_source", 1, {"source": "force3d"})]}),
+                ("laplacian", 1 / 100, {})], integrator="auto", dt=0.0025, steps=3),
+    dict(name="ns2d_velocity_drag_force_etdrk2", mode="integrate", dtypes=["float32"], mesh=_m((32, 16), TWO_PI, TWO_PI), B=2, C=2,
+         terms=[("ns_pressure_convection", 0.5, {"force": [("implicit_unit_source", -0.2, {}), ("laplacian", 0.01, {}),
+                                                          ("explicit_source", 1, {"source": "force2d"})]}),
+                ("laplacian", 1 / 100, {})], integrator="ETDRK2", dt=0.005, steps=3),
+    dict(name="ns3d_drag_force_etdrk1", mode="integrate", dtypes=["float32"], mesh=_m((8, 16, 16), TWO_PI, TWO_PI, TWO_PI), B=1, C=3,
+         terms=[("ns_pressure_convection", 1, {"force": [("implicit_unit_source", -0.1, {})]}),
+                ("laplacian", 1 / 100, {})], integrator="ETDRK1", dt=0.0025, steps=3),
     dict(name="burgers2d_batched_nu_etdrk2", mode="integrate", mesh=_m((32, 16), 1.0, 1.0), B=3, C=2,
          terms=[("laplacian", [0.01, 0.02, 0.05], {"_ndim": 2}), ("convection", -1, {})], integrator="ETDRK2", dt=0.002, steps=3),
     dict(name="burgers1d_batched_nu_setdrk4", mode="integrate", mesh=_m((64,), 1.0), B=3, C=1,

@@ -35,9 +35,18 @@ def test_channel_changing_operators_cannot_be_integrated():
         fsm.Curl()(torch.zeros(1, 1, 16, 16, dtype=torch.float64), mesh=mesh)
 
 
-def test_state_dependent_force_is_refused():
+def test_state_dependent_force_is_fp32_only():
+    """A force that depends on the state reaches the Nyquist planes of the un-dealiased state, where the reference's
+    full spectrum carries content a half spectrum cannot (1e-8 relative against the fixtures): fp32 runs, fp64 refuses."""
     import torchfsm_b200 as fsm
     mesh = fsm.MeshGrid([(0, 1, 16)] * 3, dtype=torch.float64)
     op = fsm.NSPressureConvection(-0.1 * fsm.ImplicitSource()) + 0.01 * fsm.Laplacian()
     with pytest.raises(NotImplementedError):
         op.integrate(torch.zeros(1, 3, 16, 16, 16, dtype=torch.float64), mesh=mesh, dt=0.1, step=1)
+    mesh32 = fsm.MeshGrid([(0, 1, 16)] * 3, dtype=torch.float32)
+    out = op.integrate(torch.zeros(1, 3, 16, 16, 16), mesh=mesh32, dt=0.1, step=1)
+    assert out.shape == (1, 3, 16, 16, 16) and float(out.abs().max()) == 0.0
+    rk = fsm.NSPressureConvection(-0.1 * fsm.ImplicitSource()) + 0.01 * fsm.Laplacian()
+    rk.set_integrator(fsm.RKIntegrator.RK4)
+    with pytest.raises(NotImplementedError):
+        rk.integrate(torch.zeros(1, 3, 16, 16, 16), mesh=mesh32, dt=0.1, step=1)

@@ -100,3 +100,27 @@ def test_multi_gpu_options_are_validated_before_any_work():
     adv = -1.0 * fsm.SpatialDerivative(0, 1) + 0.01 * fsm.Laplacian()
     with pytest.raises(NotImplementedError):
         adv.integrate(u0, mesh=mesh, dt=1e-2, step=1)
+
+
+def test_no_tuning_hooks_in_the_product_path():
+    """The CUDA build reads no environment variable (the only getenv sits behind FSM_EMU, a seam of the CPU test-suite)
+    and the Python layer knows exactly one: FSM_B200_LIB, the library path used by tools/ to compare kernel builds.
+    What bench.py runs is therefore what the defaults in the sources say."""
+    import re
+    csrc = os.path.join(ROOT, "torchfsm_b200", "csrc")
+    for name in os.listdir(csrc):
+        if not name.endswith((".cu", ".cuh", ".h")):
+            continue
+        lines = open(os.path.join(csrc, name)).read().split("\n")
+        for i, line in enumerate(lines):
+            if "getenv" in line:
+                assert "#ifdef FSM_EMU" in lines[i - 1], f"{name}:{i + 1} reads the environment in the CUDA build"
+    pkg = os.path.join(ROOT, "torchfsm_b200")
+    seen = set()
+    for name in os.listdir(pkg):
+        if name.endswith(".py"):
+            seen |= set(re.findall(r"environ(?:\.get)?\(?\[?[\"']([A-Z0-9_]+)[\"']", open(os.path.join(pkg, name)).read()))
+    assert seen == {"FSM_B200_LIB"}, seen
+    if "FSM_B200_LIB" not in os.environ:
+        from torchfsm_b200 import _cabi
+        assert _cabi.DEFAULT_LIB == os.path.join(pkg, "libfsm_b200.so")

@@ -52,8 +52,13 @@ def pass_breakdown(st, u_hat, steps=2):
     torch.cuda.synchronize()
     prof = st.profile_read()
     st.profile(False)
+    touched = st.touched_bytes()
+    # model_gbs: section 8d model bytes (whole fields per pass; may exceed the HBM peak where only kept modes move);
+    # touched_gbs / frac_of_peak: the bytes the pass really reads + writes (kept modes only, tables excluded)
     return {k: {"ms_per_step": round(v["ms"] / steps, 3), "launches_per_step": v["launches"] / steps,
-                "algo_gbs": round(v["algo_bytes_per_step"] * steps / max(v["ms"], 1e-9) / 1e6, 1)}
+                "model_gbs": round(v["algo_bytes_per_step"] * steps / max(v["ms"], 1e-9) / 1e6, 1),
+                "touched_gbs": round(touched[k] * steps / max(v["ms"], 1e-9) / 1e6, 1),
+                "frac_of_peak": round(touched[k] * steps / max(v["ms"], 1e-9) / 1e6 / peak(), 3)}
             for k, v in prof.items() if v["launches"]}
 
 
@@ -63,6 +68,10 @@ def report(name, st, ms, extra=None):
     line = {"config": name, "ms_per_step": ms, "steps_per_sec": 1e3 / ms, "algo_gb_per_step": info["algo_bytes_per_step"] / 1e9,
             "achieved_gbs": gbs, "frac_of_measured_hbm_peak": gbs / peak(), "launches_per_step": info["launches_per_step"],
             "chunk": info["chunk"]}
+    touched = sum(st.touched_bytes().values())
+    if touched:
+        line["touched_gb_per_step"] = touched / 1e9
+        line["frac_of_measured_hbm_peak_on_touched_bytes"] = touched / (ms * 1e-3) / 1e9 / peak()
     line.update(extra or {})
     print(json.dumps(line), flush=True)
 

@@ -46,10 +46,16 @@ if os.path.exists(path):
     print("wrote launches summary")
 
 # ---- full ncu report ------------------------------------------------------------------------
-rep = os.path.join(go, f"prof_{tag}_step.ncu-rep")
-if os.path.exists(rep):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(raw.splitlines()))
+def summarize_full(stem, header, traffic_workload, chunk):
+    rep = os.path.join(go, f"prof_{tag}_{stem}.ncu-rep")
+    rawcsv = os.path.join(go, f"prof_{tag}_{stem}_raw.csv")
+    if os.path.exists(rawcsv):
+        raw = open(rawcsv).read()
+    elif os.path.exists(rep):
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    else:
+        return
+    rows = list(csv.reader([l for l in raw.splitlines() if not l.startswith("==")]))
     hdr, units, data = rows[0], rows[1], rows[2:]
     want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
             "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum",
@@ -68,9 +74,8 @@ if os.path.exists(rep):
             "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
             "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio"]
     traffic = {}
-    with open(os.path.join(out_dir, f"{tag}_ncu_step_summary.txt"), "w") as f:
-        f.write("# ncu --set full --clock-control none --import-source on --profile-from-start off -c 3 python tools/profile_c3.py\n")
-        f.write("# one ETDRK2 step of C3 (1024^2 x 64, chunk 64): first evaluation's IX, PHYS, FX\n")
+    with open(os.path.join(out_dir, f"{tag}_ncu_{stem}_summary.txt"), "w") as f:
+        f.write(header)
         for d in data:
             name = short(d[hdr.index("Kernel Name")])
             f.write(f"\n== {name}\n")
@@ -85,9 +90,18 @@ if os.path.exists(rep):
             base = re.sub(r"<.*", "", name).replace("void ", "")
             traffic[base] = {"dram_bytes_per_launch": val("dram__bytes_read.sum") + val("dram__bytes_write.sum"),
                              "kernel": name}
-    json.dump({"source": f"profiles/{tag}_ncu_step_summary.txt", "workload": "C3 1024^2 x 64, chunk 64", "kernels": traffic},
-              open(os.path.join(out_dir, f"{tag}_ncu_traffic.json"), "w"), indent=1)
+    json.dump({"source": f"profiles/{tag}_ncu_{stem}_summary.txt", "workload": traffic_workload, "chunk": chunk, "kernels": traffic},
+              open(os.path.join(out_dir, f"{tag}_ncu_traffic.json" if stem == "step" else f"{tag}_ncu_{stem}_traffic.json"), "w"), indent=1)
     print("wrote ncu summary", {k: round(v["dram_bytes_per_launch"] / 1e6) for k, v in traffic.items()})
+
+
+
+summarize_full("step", "# ncu --set full --clock-control none --import-source on --profile-from-start off -c 3 python tools/profile_c3.py\n"
+               "# one ETDRK2 step of C3 (1024^2 x 64, library defaults: 2 lanes x 32 samples per launch): first evaluation's IX, PHYS, FX\n",
+               "C3 1024^2 x 64, 2 lanes x 32 samples per launch (library default)", 32)
+summarize_full("c5", "# FSM_NCU_WINDOW=1 ncu --set full --clock-control none --import-source on --profile-from-start off -c 20 python tools/bench_configs.py c5\n"
+               "# one SETDRK4 step of C5 (512^3, one GPU): IX, MID inverse, PHYS, MID forward, FX of each of the four evaluations\n",
+               "C5 512^3 x 1", 1)
 
 for name in (f"bench_{tag}.json", f"bench_ref_{tag}.json", f"configs_{tag}.jsonl"):
     src = os.path.join(go, name)

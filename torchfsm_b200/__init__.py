@@ -11,7 +11,7 @@ from .operator import (Operator, LinearOperator, NonlinearOperator, Laplacian, B
                        SpatialDerivative, ImplicitSource, ExplicitSource, Convection, KSConvection,
                        VorticityConvection, NSPressureConvection, FusedStepper, Grad, Div, Curl,
                        Vorticity2Velocity, Vorticity2Pressure, Velocity2Pressure, ConservativeConvection,
-                       run_operators, HostComposedStepper)
+                       run_operators, HostComposedStepper, DynamicForceStepper)
 from .traj_recorder import AutoRecorder, CPURecorder, IntervalController  # noqa: F401
 from . import pde, field  # noqa: F401
 

@@ -25,7 +25,7 @@ class FsmDesc(ctypes.Structure):
         ("program", ctypes.c_int32), ("integrator", ctypes.c_int32), ("kmax", ctypes.c_int32 * 3),
         ("ks_remove_mean", ctypes.c_int32), ("tab_channels", ctypes.c_int32), ("chunk", ctypes.c_int32),
         ("dt", ctypes.c_double), ("nl_coef", ctypes.c_double), ("ks_ext_sum", ctypes.c_double),
-        ("ks_ext_count", ctypes.c_int32), ("tab_complex", ctypes.c_int32),
+        ("dynamic_force", ctypes.c_int32), ("tab_complex", ctypes.c_int32),
         ("dk", ctypes.c_void_p * 3), ("dkraw", ctypes.c_void_p * 3),
         ("tab_exp", ctypes.c_void_p), ("tab_half_exp", ctypes.c_void_p), ("tab_coef", ctypes.c_void_p * 6),
         ("tab_lin", ctypes.c_void_p), ("source_hat", ctypes.c_void_p),
@@ -42,7 +42,7 @@ class FsmMapTerm(ctypes.Structure):
 
 
 EXPORTS = ["fsm_plan_create", "fsm_plan_destroy", "fsm_workspace_bytes", "fsm_step", "fsm_rhs", "fsm_r2c",
-           "fsm_c2r", "fsm_spectral_map", "fsm_stage_input", "fsm_stage_combine", "fsm_mask_state", "fsm_sym_outer", "fsm_half_to_full", "fsm_full_to_half", "fsm_plan_info", "fsm_stage_kinds", "fsm_slab_phase", "fsm_slab_info", "fsm_slab_peers", "fsm_ks_log", "fsm_profile_enable", "fsm_profile_read", "fsm_last_error",
+           "fsm_c2r", "fsm_spectral_map", "fsm_stage_input", "fsm_stage_combine", "fsm_stage_run", "fsm_mask_state", "fsm_sym_outer", "fsm_half_to_full", "fsm_full_to_half", "fsm_plan_info", "fsm_plan_traffic", "fsm_stage_kinds", "fsm_slab_phase", "fsm_slab_info", "fsm_slab_peers", "fsm_ks_log", "fsm_profile_enable", "fsm_profile_read", "fsm_last_error",
            "fsm_abi_version", "fsm_backend"]
 
 _lib = None
@@ -71,6 +71,8 @@ def _declare(lib):
     lib.fsm_stage_input.restype = i32
     lib.fsm_stage_combine.argtypes = [vp, i32, vp, vp, vp, vp, sz, vp]
     lib.fsm_stage_combine.restype = i32
+    lib.fsm_stage_run.argtypes = [vp, i32, vp, vp, vp, vp, sz, vp]
+    lib.fsm_stage_run.restype = i32
     lib.fsm_mask_state.argtypes = [vp, vp, i32, vp]
     lib.fsm_mask_state.restype = i32
     lib.fsm_sym_outer.argtypes = [vp, vp, vp, i32, vp]
@@ -81,6 +83,8 @@ def _declare(lib):
     lib.fsm_full_to_half.restype = i32
     lib.fsm_plan_info.argtypes = [vp, i64p, i64p, i64p, ctypes.POINTER(ctypes.c_int32)]
     lib.fsm_plan_info.restype = i32
+    lib.fsm_plan_traffic.argtypes = [vp, i64p]
+    lib.fsm_plan_traffic.restype = i32
     lib.fsm_stage_kinds.argtypes = [vp, ctypes.POINTER(ctypes.c_int32), i32]
     lib.fsm_stage_kinds.restype = i32
     lib.fsm_slab_phase.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, vp, sz, vp, vp, vp]

@@ -946,6 +946,9 @@ __global__ void __launch_bounds__(kKL * Cfg::TL, FSM_MINB(kKL * Cfg::TL)) k_pass
 // ------------------------------------------------------------------------------------------
 #ifndef FSM_PHYS_PARK
 #define FSM_PHYS_PARK 1
+#ifndef FSM_PHYS_PARK3
+#define FSM_PHYS_PARK3 1
+#endif
 #endif
 template <int PROG, int NDIM>
 struct PhysTraits;
@@ -1247,12 +1250,22 @@ __global__ void __launch_bounds__(NLP * Cfg::TL, FSM_MINB(NLP * Cfg::TL)) k_pass
             line_fft<Cfg, -1, T>(v, mybuf, tw, tau, sync);
             FSM_UNROLL
             for (int m = 0; m < EPT; ++m) stage[(r == 0 ? 0 : 2) * Cfg::LINE_PITCH + tau + m * TL] = v[m];
+            // the third component of row 0 waits for row 1: parked in staging line 1 (written only after row 1) as real
+            // values instead of EPT registers held across the six inverse transforms of row 1 (the kernel sits at the
+            // 128-register cap: cuobjdump showed 72 B of spills without this)
+            // (measured: C5, 512-point lines, last-axis pass 9.98 -> 9.82 ms per step; at 256 points the registers are
+            // there and parking costs 5 % of the pass, so shorter lines keep the registers)
+            constexpr bool kPark3 = FSM_PHYS_PARK3 && (N >= 512);
+            T* park3 = reinterpret_cast<T*>(stage + 1 * Cfg::LINE_PITCH);
             if constexpr (r == 0) {
                 FSM_UNROLL
-                for (int m = 0; m < EPT; ++m) keep2[m] = acc[2][m];
+                for (int m = 0; m < EPT; ++m) {
+                    if constexpr (kPark3) park3[tau + m * TL] = acc[2][m];
+                    else keep2[m] = acc[2][m];
+                }
             } else {
                 FSM_UNROLL
-                for (int m = 0; m < EPT; ++m) v[m] = mk<T>(keep2[m], acc[2][m]);
+                for (int m = 0; m < EPT; ++m) v[m] = mk<T>(kPark3 ? park3[tau + m * TL] : keep2[m], acc[2][m]);
                 sync();
                 line_fft<Cfg, -1, T>(v, mybuf, tw, tau, sync);
                 FSM_UNROLL
@@ -1533,6 +1546,9 @@ struct FxEpilogue {
     int project;                   // NS pressure projection (2-D and 3-D velocity form)
     const cplx<T>* force;          // optional constant term added BEFORE the projection [C][nmodes]: -coef * f_hat of
                                    // NSPressureConvection(external_force) (_navier_stokes.py:237-254)
+    const cplx<T>* force_dyn;      // optional per-evaluation force spectrum f_hat(u) [B][C][nmodes] (a force operator that
+                                   // depends on the state, evaluated by the caller on the stage input): -coef * f before the
+                                   // projection and +coef * f after it (the reference adds the force twice, :241-254)
 };
 
 // ---- compile-time combine structures ---------------------------------------------------------------------
@@ -1559,9 +1575,9 @@ struct CShape {   // generic: structure read from the Combine at run time
     }
 // u' = c1 N + E u                                               (ETDRK1 / SETDRK1)
 FSM_CSHAPE(0, 1, 1, 2, {{0, 1, -2, -2}, {-2, -2, -2, -2}, {-2, -2, -2, -2}});
-// a = c1 N + E u ; N0 = N                                       (ETDRK2 / SETDRK2 stage 1)
-FSM_CSHAPE(1, 1, 2, 2, {{0, 1, -2, -2}, {-1, -2, -2, -2}, {-2, -2, -2, -2}});
-// u' = c2 N + a - c2 N0                                         (ETDRK2 / SETDRK2 stage 2)
+// a = c1 N + E u ; d = (c1 - c2) N + E u                        (ETDRK2 / SETDRK2 stage 1; stage 2 is shape 6, u' = c2 N + d)
+FSM_CSHAPE(1, 1, 2, 3, {{0, 1, -2, -2}, {2, 1, -2, -2}, {-2, -2, -2, -2}});
+// u' = c2 N + a - c2 N0                                         (ETDRK2 / SETDRK2 stage 2 when no c1 - c2 table is supplied)
 FSM_CSHAPE(2, 2, 1, 1, {{0, -1, 0, -2}, {-2, -2, -2, -2}, {-2, -2, -2, -2}});
 // a = c1 N + E2 u ; N0 = N ; sum = c4 N + E u                   (SETDRK3 / SETDRK4 stage 1)
 FSM_CSHAPE(3, 1, 3, 4, {{0, 1, -2, -2}, {-1, -2, -2, -2}, {2, 3, -2, -2}});
@@ -1823,6 +1839,11 @@ k_pass_fx(Geom<T> g, const cplx<T>* __restrict__ win, long win_fstride,
                         FSM_UNROLL
                         for (int c = 0; c < C; ++c) f[c][j] = f[c][j] + ep.force[(long)c * g.nmodes + line_mode0 + p];
                     }
+                    if (ep.force_dyn) {
+                        FSM_UNROLL
+                        for (int c = 0; c < C; ++c)
+                            f[c][j] = f[c][j] - cscale(ep.force_dyn[(b * C + c) * g.nmodes + line_mode0 + p], ep.nl_coef);
+                    }
                     const int kk[3] = {p, ky, kz};
                     T dd[C];
                     bool qq[C];
@@ -1857,6 +1878,16 @@ k_pass_fx(Geom<T> g, const cplx<T>* __restrict__ win, long win_fstride,
                 FSM_UNROLL
                 for (int j = 0; j < NB; ++j)
                     f[c][j] = f[c][j] + ep.source[(long)c * g.nmodes + line_mode0 + tau + (mb + j) * TL];
+            }
+        }
+        if constexpr (C == 3 || C == 2) {
+            if (ep.project && ep.force_dyn) {
+                FSM_UNROLL
+                for (int c = 0; c < C; ++c) {
+                    FSM_UNROLL
+                    for (int j = 0; j < NB; ++j)
+                        f[c][j] = f[c][j] + cscale(ep.force_dyn[(b * C + c) * g.nmodes + line_mode0 + tau + (mb + j) * TL], ep.nl_coef);
+                }
             }
         }
         if (ep.dc_out && line == 0 && g.ky0 == 0 && tau == 0 && mb == 0) {

@@ -87,6 +87,8 @@ struct Stage {
     int n_in = 0, in[FSM_MAX_IN] = {0, 0, 0};
     int n_out = 0, out[FSM_MAX_OUT] = {0, 0, 0};
     bool has_next = false;      // row FSM_MAX_OUT = next stage state handed over in registers (fused FX+IX)
+    int model_io = -1;          // arrays the reference's stage formula reads + writes (SURVEY.md section 8d byte model) when
+                                // that differs from n_in + n_out of this formulation
     Coef c[FSM_MAX_OUT + 1][FSM_MAX_IN + 1];
 };
 static Coef tabc(int tab, double b = 1.0) { Coef c; c.tab = tab; c.a = 0; c.b = b; return c; }
@@ -94,7 +96,7 @@ static Coef scal(double a) { Coef c; c.tab = SCALAR; c.a = a; c.b = 0; return c;
 static Coef affine(double a, int tab, double b) { Coef c; c.tab = tab; c.a = a; c.b = b; return c; }
 static Coef tab2c(int tab, double b, int tab2, double b2) { Coef c; c.tab = tab; c.a = 0; c.b = b; c.tab2 = tab2; c.b2 = b2; return c; }
 
-static std::vector<Stage> build_stages(int integ, double dt, bool has_lin) {
+static std::vector<Stage> build_stages(int integ, double dt, bool has_lin, bool has_c12) {
     std::vector<Stage> st;
     auto mk_stage = [](int input, std::initializer_list<int> ins, std::initializer_list<int> outs) {
         Stage s;
@@ -120,6 +122,20 @@ static std::vector<Stage> build_stages(int integ, double dt, bool has_lin) {
         }
         case FSM_INT_ETDRK2:
         case FSM_INT_SETDRK2: {  // a = E u + c1 N0; u' = a + c2 (N(a) - N0)   (_etdrk.py:72-82)
+            if (has_c12) {
+                // the same step with one array read less: stage 1 also writes d = a - c2 N0 = E u + (c1 - c2) N0 (table
+                // coef_1 - coef_2 supplied in the coef_3 slot) in place of N0, stage 2 is u' = d + c2 N(a) and never
+                // reads a again. Rounding differs from the reference's grouping by ~1 ulp of c2 N0.
+                Stage s1 = mk_stage(ARR_U, {ARR_U}, {ARR_S1, ARR_S2});
+                s1.c[0][0] = tabc(TAB_C1); s1.c[0][1] = tabc(TAB_EXP);
+                s1.c[1][0] = tabc(TAB_C3); s1.c[1][1] = tabc(TAB_EXP);
+                Stage s2 = mk_stage(ARR_S1, {ARR_S2}, {ARR_U});
+                s2.c[0][0] = tabc(TAB_C2); s2.c[0][1] = scal(1.0);
+                s2.model_io = 3;
+                st.push_back(s1);
+                st.push_back(s2);
+                break;
+            }
             Stage s1 = mk_stage(ARR_U, {ARR_U}, {ARR_S1, ARR_S2});
             s1.c[0][0] = tabc(TAB_C1);
             s1.c[0][1] = tabc(TAB_EXP);
@@ -210,6 +226,7 @@ struct fsm_plan {
     size_t cap_fields;  // how many independent fields the W buffers can hold at once (r2c/c2r)
     int64_t launches_per_step, algo_bytes_per_step;
     int64_t pass_units[4];  // algorithmic field-units moved per step by each pass class (IX, MID, PHYS, FX)
+    int64_t pass_touched[4];  // bytes the passes of each class really read + write per step (kept modes only, tables excluded)
     // optional per-pass device timing
     bool profile = false;
 #ifndef FSM_EMU
@@ -435,8 +452,9 @@ int run_forward_tail(const fsm_plan* p, const Buffers<T>& bf, const Geom<T>& g, 
 // the one-stage schemes, whose `exp * u` is formed before the evaluation runs (_etdrk.py:47-51, _setdrk_step.py:5-11), and
 // in the right-hand side (operator/_base.py:425-433: `linear_coef * u_fft` first).
 template <typename T>
-int mask_stage_input(const fsm_plan* p, const Geom<T>& g, const Stage& s, cplx<T>* arr, int b_lo, int b_hi, cudaStream_t st) {
-    if (!p->d.force_hat || &s == &p->rhs_stage || p->stages.size() < 2) return 0;
+int mask_stage_input(const fsm_plan* p, const Geom<T>& g, const Stage& s, cplx<T>* arr, int b_lo, int b_hi, cudaStream_t st,
+                     bool dyn_force = false) {
+    if ((!p->d.force_hat && !dyn_force) || &s == &p->rhs_stage || p->stages.size() < 2) return 0;
     const long total = (long)(b_hi - b_lo) * p->C * p->nmodes;
     auto kern = k_mask_state<T>;
     FSM_LAUNCH(kern, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, g, arr + (long)b_lo * p->C * p->nmodes, total);
@@ -462,7 +480,7 @@ int run_stage(const fsm_plan* p, const Buffers<T>& bf, const Stage& s, cudaStrea
     }
     const Geom<T> g = make_geom<T>(p, false);
     const cplx<T>* stage_in = bf.arr[s.input];
-    if (int e = mask_stage_input<T>(p, g, s, bf.arr[s.input], b_lo, b_hi, st)) return e;
+    if (int e = mask_stage_input<T>(p, g, s, bf.arr[s.input], b_lo, b_hi, st, ext_fresh != nullptr)) return e;
     const LaunchTable<T>* tx = launch_table<T>(p->n[0]);
     const LaunchTable<T>* tl = launch_table<T>(p->n[p->ndim - 1]);
     const LaunchTable<T>* ty = (p->ndim == 3) ? launch_table<T>(p->n[1]) : nullptr;
@@ -472,6 +490,7 @@ int run_stage(const fsm_plan* p, const Buffers<T>& bf, const Stage& s, cudaStrea
     ep.dc_out = (p->prog == FSM_PROG_KS && p->d.ks_remove_mean) ? bf.dc : nullptr;
     ep.project = (p->prog == FSM_PROG_NS3D) ? 1 : 0;
     ep.force = static_cast<const cplx<T>*>(p->d.force_hat);
+    ep.force_dyn = ext_fresh;     // fused programs: the externally evaluated array is the state-dependent force (fsm_stage_run)
     for (int b0 = b_lo; b0 < b_hi; b0 += p->chunk) {
         const int nb = (b_hi - b0 < p->chunk) ? (b_hi - b0) : p->chunk;
         IxArgs<T> a;
@@ -538,6 +557,7 @@ int run_1d(const fsm_plan* p, const Buffers<T>& bf, const Stage* stages, int n_s
     a.ep.dc_out = nullptr;
     a.ep.project = 0;
     a.ep.force = nullptr;
+    a.ep.force_dyn = nullptr;
     a.n_steps = n_steps;
     a.nb = p->B;
     const LaunchTable<T>* tx = launch_table<T>(p->n[0]);
@@ -636,7 +656,7 @@ int do_r2c(fsm_plan* p, const void* u, void* u_hat, void* ws, cudaStream_t st) {
         tmp.d.tab_channels = 1;
         if (int e = make_combine<T>(&tmp, s, arr, true, &cb)) return e;
         FxEpilogue<T> ep;
-        ep.nl_coef = T(1); ep.source = nullptr; ep.dc_out = nullptr; ep.project = 0; ep.force = nullptr;
+        ep.nl_coef = T(1); ep.source = nullptr; ep.dc_out = nullptr; ep.project = 0; ep.force = nullptr; ep.force_dyn = nullptr;
         if (int e = run_forward_tail<T>(p, bf, g, 1, 1, cb, ep, 0, nf, st)) return e;
     }
     return 0;
@@ -838,6 +858,7 @@ int do_slab_phase(fsm_plan* p, int op, int stage, int phase, int sub, int nsub, 
         ep.dc_out = nullptr;
         ep.project = (p->prog == FSM_PROG_NS3D) ? 1 : 0;
         ep.force = static_cast<const cplx<T>*>(p->d.force_hat);
+        ep.force_dyn = nullptr;
         return slab_fx<T>(p, g, rcv, p->C, p->B, cb, ep, nsub, st);
     }
     if (nsub != 1) return fail(-EINVAL, "the plain transforms run with one sub-slab");
@@ -856,7 +877,7 @@ int do_slab_phase(fsm_plan* p, int op, int stage, int phase, int sub, int nsub, 
         tmp.d.tab_channels = 1;
         if (int e = make_combine<T>(&tmp, s, bf.arr, true, &cb)) return e;
         FxEpilogue<T> ep;
-        ep.nl_coef = T(1); ep.source = nullptr; ep.dc_out = nullptr; ep.project = 0; ep.force = nullptr;
+        ep.nl_coef = T(1); ep.source = nullptr; ep.dc_out = nullptr; ep.project = 0; ep.force = nullptr; ep.force_dyn = nullptr;
         return slab_fx<T>(p, g, rcv, 1, nf, cb, ep, 1, st);
     }
     if (op == FSM_SLAB_C2R) {
@@ -996,7 +1017,9 @@ int fsm_plan_create(fsm_plan** out, const fsm_desc* d) {
         const int e = p->f64 ? launch_table<double>(p->n[i])->prepare() : launch_table<float>(p->n[i])->prepare();
         if (e) { delete p; return fail(e, "could not initialise the twiddle tables"); }
     }
-    p->stages = build_stages(d->integrator, d->dt, d->tab_lin != nullptr);
+    p->stages = build_stages(d->integrator, d->dt, d->tab_lin != nullptr,
+                             (d->integrator == FSM_INT_ETDRK2 || d->integrator == FSM_INT_SETDRK2) && d->tab_coef[2] != nullptr &&
+                                 !d->force_hat && !d->dynamic_force);   // with a force the reference masks a in place but not N0
     if (p->stages.empty()) { delete p; return fail(-ENOSYS, "unknown integrator %d", d->integrator); }
     p->pf = FSM_PF_DEFAULT;
     // right-hand side L u + N(u)
@@ -1123,7 +1146,36 @@ int fsm_plan_create(fsm_plan** out, const fsm_desc* d) {
                 p->pass_units[PASS_FX] += p->nout;
                 if (p->ndim == 3) p->pass_units[PASS_MID] += (cnf + p->nfi) + 2 * p->nout;
             }
-            p->pass_units[PASS_FX] += (int64_t)(s.n_in + s.n_out) * p->C;
+            p->pass_units[PASS_FX] += (int64_t)(s.model_io >= 0 ? s.model_io : s.n_in + s.n_out) * p->C;
+        }
+        // bytes really touched: the inverse side moves kept (dealiased) modes only
+        for (int i = 0; i < 4; ++i) p->pass_touched[i] = 0;
+        if (p->prog != FSM_PROG_LINEAR && p->ndim >= 2) {
+            const int64_t esz8 = p->f64 ? 16 : 8;
+            const int64_t n0 = p->n[0], n1 = p->n[1], nh = p->nh;
+            const int64_t kx = (2 * d->kmax[0] + 1 < n0) ? 2 * d->kmax[0] + 1 : n0;
+            const int64_t cnf = (int64_t)p->C * p->nf_ix;
+            int64_t t_ix, t_mid = 0, t_phys;
+            if (p->ndim == 2) {
+                const int64_t ly = (d->kmax[1] + 1 < nh) ? d->kmax[1] + 1 : nh;
+                const bool zl = (p->kprog == PROG_NS2D || p->kprog == PROG_KS2D);
+                const int64_t w1 = zl ? (int64_t)(p->nfi / 2) * n0 * (2 * ly - 1) : cnf * n0 * ly;
+                t_ix = p->C * ly * kx + w1;
+                t_phys = w1 + (int64_t)p->nout * nh * n0;
+            } else {
+                const int64_t ky = (2 * d->kmax[1] + 1 < n1) ? 2 * d->kmax[1] + 1 : n1;
+                const int64_t kz = (d->kmax[2] + 1 < nh) ? d->kmax[2] + 1 : nh;
+                t_ix = p->C * ky * kz * kx + cnf * kz * n0 * ky;
+                t_mid = (int64_t)p->nfi * kz * n0 * ky + (int64_t)p->nfi * n0 * n1 * kz + 2 * (int64_t)p->nout * nh * n0 * n1;
+                t_phys = (int64_t)p->nfi * n0 * n1 * kz + (int64_t)p->nout * nh * n0 * n1;
+            }
+            const int64_t full = (p->P > 1) ? p->nmodes * p->P : p->nmodes;   // modes of one field of the whole grid
+            for (const Stage& s : p->stages) {
+                p->pass_touched[PASS_IX] += t_ix * esz8 * p->B;
+                p->pass_touched[PASS_MID] += t_mid * esz8 * p->B;
+                p->pass_touched[PASS_PHYS] += t_phys * esz8 * p->B;
+                p->pass_touched[PASS_FX] += ((int64_t)p->nout + (int64_t)(s.n_in + s.n_out) * p->C) * full * esz8 * p->B;
+            }
         }
         for (int i = 0; i < 4; ++i) units += p->pass_units[i];
         p->launches_per_step = launches;
@@ -1414,6 +1466,33 @@ int fsm_sym_outer(fsm_plan* plan, const void* u, void* out, int32_t channels, vo
         FSM_LAUNCH(kern, grid, block, 0, st, (const float*)u, (float*)out, (int)channels, npts, total);
     }
     return launch_status("symmetric products");
+}
+
+int fsm_plan_traffic(const fsm_plan* plan, int64_t* touched_bytes_per_step4) {
+    if (!plan || !touched_bytes_per_step4) return fail(-EINVAL, "bad argument");
+    for (int i = 0; i < 4; ++i) touched_bytes_per_step4[i] = plan->pass_touched[i];
+    return 0;
+}
+
+int fsm_stage_run(fsm_plan* plan, int32_t stage, void* u_hat, const void* force_hat, void* rhs_out, void* workspace,
+                  size_t ws_bytes, void* stream) {
+    FSM_CHECK_WS(plan, workspace, ws_bytes);
+    if (!u_hat || !force_hat) return fail(-EINVAL, "bad argument");
+    if (plan->prog != FSM_PROG_NS3D || !plan->d.dynamic_force)
+        return fail(-EINVAL, "fsm_stage_run belongs to NS pressure-convection plans created with dynamic_force = 1");
+    if (plan->P > 1) return fail(-ENOSYS, "state-dependent forces are not available on slab-decomposed grids");
+    if (plan->d.integrator == FSM_INT_RK4 && stage >= 0)
+        return fail(-ENOSYS, "NS pressure convection with an external force is not supported with the RK integrators");
+    if (stage < -1 || stage >= (int)plan->stages.size()) return fail(-EINVAL, "bad stage %d", stage);
+    if (stage < 0 && (!rhs_out || rhs_out == u_hat)) return fail(-EINVAL, "the right-hand side needs its own output array");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const Stage& s = (stage < 0) ? plan->rhs_stage : plan->stages[stage];
+    if (plan->f64) {
+        Buffers<double> bf = carve<double>(plan, u_hat, workspace, rhs_out);
+        return run_stage<double>(plan, bf, s, st, 0, -1, static_cast<const cplx<double>*>(force_hat));
+    }
+    Buffers<float> bf = carve<float>(plan, u_hat, workspace, rhs_out);
+    return run_stage<float>(plan, bf, s, st, 0, -1, static_cast<const cplx<float>*>(force_hat));
 }
 
 }  // extern "C"

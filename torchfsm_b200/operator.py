@@ -118,7 +118,7 @@ class FusedStepper:
                  linear_coef: Optional[torch.Tensor], nl_coef: float, source_hat: Optional[torch.Tensor],
                  kmax: Sequence[int], ks_remove_mean: bool, integrator_cfg: dict, chunk: int = 0,
                  tables: Optional[dict] = None, slab=None, lanes: int = 0, allocate: bool = True,
-                 force_hat: Optional[torch.Tensor] = None):
+                 force_hat: Optional[torch.Tensor] = None, dynamic_force: bool = False):
         lib = _GuardedLib(_cabi.lib(), f_mesh.device)
         # slab = (rank, nranks, process_group): ONE 3-D grid decomposed over nranks GPUs
         self.slab = slab
@@ -190,6 +190,7 @@ class FusedStepper:
         desc.lanes = int(lanes)
         desc.dt = float(dt)
         desc.nl_coef = float(nl_coef)
+        desc.dynamic_force = 1 if dynamic_force else 0
         dk, dkraw = f_mesh.wavenumber_tables()
         for i in range(self.n_dim):
             self._keep += [dk[i], dkraw[i]]
@@ -203,6 +204,10 @@ class FusedStepper:
             if L is None:                                    # operator/_base.py:473-478
                 L = torch.tensor([0.0], dtype=self.cdtype, device=self.device).reshape([1] * (self.n_dim + 2))
             tables = build_tables(integrator, dt, L, **integrator_cfg)
+        if integrator in ("ETDRK2", "SETDRK2") and "coef_3" not in tables:
+            # derived table for the one-read-less form of the two-stage step (include/fsm_b200.h, tab_coef)
+            tables = dict(tables)
+            tables["coef_3"] = tables["coef_1"] - tables["coef_2"]
         self.tables_full = tables
         # odd-order linear terms (KdV dispersion, advection) make exp(L dt) complex: 1-D kernels take complex tables
         self.complex_tables = self.n_dim == 1 and (has_imag(linear_coef) or any(has_imag(t) for t in tables.values()))
@@ -430,6 +435,12 @@ class FusedStepper:
         return {"launches_per_step": a.value, "algo_bytes_per_step": b.value, "modes_per_field": c.value,
                 "chunk": d.value}
 
+    def touched_bytes(self):
+        """Bytes each pass class really reads + writes per step (kept modes only), ``fsm_plan_traffic``."""
+        by = (ctypes.c_int64 * 4)()
+        _cabi.check(self._lib.fsm_plan_traffic(self._plan, by), "plan_traffic")
+        return dict(zip(("IX", "MID", "PHYS", "FX"), [int(x) for x in by]))
+
     def stage_kinds(self):
         """Per integrator stage: index of the compile-time combine structure used by the forward-x epilogue
         (-1 = generic data-driven path)."""
@@ -623,17 +634,14 @@ class FusedStepper:
         return self.step(u_hat_full)
 
 
-class HostComposedStepper(FusedStepper):
-    """Integrator for nonlinear cores without a fused program (``_EXTERNAL_KINDS``): the plan carries the linear part
-    and the stage formulas; each stage's nonlinear term is evaluated by ``nonlinear(stepper, stage_state_hat)`` from
-    the library's own passes and combined by ``fsm_stage_combine`` (same tables, same stage algebra as the fused
-    path; integrator/_etdrk.py:47-82, _setdrk_step.py:5-82, _rk.py:43-58)."""
+class _StageLoopStepper(FusedStepper):
+    """A stepper whose integrator stages are driven one by one from the host: between two stages the caller evaluates
+    something on the stage state with the library's own passes (``_evaluate``) and hands it to ``_run_stage``."""
 
-    def __init__(self, *args, nonlinear=None, **kwargs):
+    def __init__(self, *args, **kwargs):
         super().__init__(*args, **kwargs)
         if self.P > 1:
-            raise NotImplementedError("host-composed nonlinear terms are not available on slab-decomposed grids")
-        self._nonlinear = nonlinear
+            raise NotImplementedError("host-driven stages are not available on slab-decomposed grids")
         self._stage_off = []
         off = ctypes.c_int64()
         n = self._lib.fsm_stage_input(self._plan, -1, ctypes.byref(off))
@@ -664,18 +672,56 @@ class HostComposedStepper(FusedStepper):
     def step_half(self, u_hat: torch.Tensor, n_steps: int = 1) -> torch.Tensor:
         for _ in range(int(n_steps)):
             for s in range(len(self._stage_off)):
-                fresh = self._nonlinear(self, self._stage_state(s, u_hat))
-                _cabi.check(self._lib.fsm_stage_combine(self._plan, s, u_hat.data_ptr(), fresh.data_ptr(), None,
-                                                        self.workspace.data_ptr(), self.ws_bytes, self._stream()),
-                            "stage_combine")
+                self._run_stage(s, u_hat, self._evaluate(self._stage_state(s, u_hat)), None)
         return u_hat
 
     def rhs_half(self, u_hat: torch.Tensor) -> torch.Tensor:
         out = self.empty_half()
-        fresh = self._nonlinear(self, u_hat)
-        _cabi.check(self._lib.fsm_stage_combine(self._plan, -1, u_hat.data_ptr(), fresh.data_ptr(), out.data_ptr(),
-                                                self.workspace.data_ptr(), self.ws_bytes, self._stream()), "stage_combine")
+        self._run_stage(-1, u_hat, self._evaluate(u_hat), out)
         return out
+
+
+class HostComposedStepper(_StageLoopStepper):
+    """Integrator for nonlinear cores without a fused program (``_EXTERNAL_KINDS``): the plan carries the linear part
+    and the stage formulas; each stage's nonlinear term is evaluated by ``nonlinear(stepper, stage_state_hat)`` from
+    the library's own passes and combined by ``fsm_stage_combine`` (same tables, same stage algebra as the fused
+    path; integrator/_etdrk.py:47-82, _setdrk_step.py:5-82, _rk.py:43-58)."""
+
+    def __init__(self, *args, nonlinear=None, **kwargs):
+        super().__init__(*args, **kwargs)
+        self._nonlinear = nonlinear
+
+    def _evaluate(self, x_hat):
+        return self._nonlinear(self, x_hat)
+
+    def _run_stage(self, s, u_hat, fresh, out):
+        _cabi.check(self._lib.fsm_stage_combine(self._plan, s, u_hat.data_ptr(), fresh.data_ptr(),
+                                                out.data_ptr() if out is not None else None,
+                                                self.workspace.data_ptr(), self.ws_bytes, self._stream()), "stage_combine")
+
+
+class DynamicForceStepper(_StageLoopStepper):
+    """``NSPressureConvection(external_force)`` with a force operator that depends on the state
+    (dedicated/_navier_stokes.py:237-254): before every stage the force is evaluated on the stage state (un-dealiased,
+    as the reference does) by the force operator's own lowering -- any operator this package can evaluate -- and the
+    fused convection + projection + combine of the stage runs with it (``fsm_stage_run``)."""
+
+    def __init__(self, *args, force=None, **kwargs):
+        super().__init__(*args, dynamic_force=True, **kwargs)
+        self._force = force
+
+    def _evaluate(self, x_hat):
+        f_hat, c = self._force._eval_half(x_hat, self.f_mesh, self.C)
+        if c != self.C:
+            if c != 1:
+                raise ValueError("the external force must have one channel or as many as the velocity")
+            f_hat = f_hat.expand(self.B, self.C, self.nmodes)
+        return f_hat.contiguous()
+
+    def _run_stage(self, s, u_hat, f_hat, out):
+        _cabi.check(self._lib.fsm_stage_run(self._plan, s, u_hat.data_ptr(), f_hat.data_ptr(),
+                                            out.data_ptr() if out is not None else None,
+                                            self.workspace.data_ptr(), self.ws_bytes, self._stream()), "stage_run")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -851,7 +897,7 @@ class OperatorLike:
             return
         lin = []
         program, nl_coef, ks_remove_mean = _cabi.PROG_LINEAR, 0.0, True
-        source_hat = force_hat = None
+        source_hat = force_hat = dyn_force = None
         external = []
         for t in self.terms:
             if t.kind in _LINEAR_KINDS:
@@ -880,8 +926,9 @@ class OperatorLike:
                         # adds -coef * f_hat to coef * conv_hat before the projection. The force is evaluated once:
                         # it must not depend on the state (explicit sources only).
                         if any(ft.kind != "explicit_source" for ft in force.terms):
-                            raise NotImplementedError("NSPressureConvection takes state-independent external forces only "
-                                                      "(sums of ExplicitSource) on the fused CUDA path")
+                            # the force depends on the state: evaluated before every stage by its own lowering
+                            dyn_force = force
+                            continue
                         f_hat = None
                         for ft in force.terms:
                             fs = ft.params["source"].to(device=f_mesh.device)
@@ -921,7 +968,7 @@ class OperatorLike:
                                       "(rate < 1) on the fused CUDA path")
         self._state_dict["linear_coef"] = L
         self._lowered = dict(program=program, nl_coef=nl_coef, ks_remove_mean=ks_remove_mean,
-                             source_hat=source_hat, force_hat=force_hat, kmax=kmax, external=external)
+                             source_hat=source_hat, force_hat=force_hat, kmax=kmax, external=external, dyn_force=dyn_force)
 
     def _lower_map(self, f_mesh: FourierMesh, n_channel: int):
         """Operators made of symbol products only (Grad, Div, Curl, Vorticity2Velocity, optionally summed with linear
@@ -1130,6 +1177,20 @@ class OperatorLike:
             cls = FusedStepper
             if lo["external"]:
                 cls, extra = HostComposedStepper, {"nonlinear": self._external_nonlinear(lo["external"], sd["n_channel"])}
+            elif lo["dyn_force"] is not None:
+                if name == "RK4" and not rhs_only:
+                    raise NotImplementedError("NSPressureConvection with an external force is not supported with the RK integrators")
+                if self._slab is not None:
+                    raise NotImplementedError("state-dependent external forces are not available on slab-decomposed grids")
+                if sd["f_mesh"].dtype == torch.float64:
+                    # the force acts on the un-dealiased state, Nyquist planes included, where the reference's full C2C
+                    # state carries anti-Hermitian content that the pressure symbol turns into real-space output
+                    # (SURVEY.md H1); a half-spectrum state cannot hold it. Measured against the reference: 1e-8 relative
+                    # after three steps -- below fp32 rounding, four orders above the fp64 tolerance.
+                    raise NotImplementedError("NSPressureConvection with a state-dependent external force reproduces the "
+                                              "reference to ~1e-8 only (Nyquist-plane content of its full spectrum): "
+                                              "available in fp32, refused in fp64")
+                cls, extra = DynamicForceStepper, {"force": lo["dyn_force"]}
             st = cls(sd["f_mesh"], batch, sd["n_channel"], lo["program"], name, dt, sd["linear_coef"],
                      lo["nl_coef"], lo["source_hat"], lo["kmax"], lo["ks_remove_mean"], cfg,
                      chunk=self._chunk, tables=tables, slab=self._slab, lanes=self._lanes,

@@ -109,10 +109,9 @@ def lower(ref_op, dt: float) -> LoweredIntegrator:
             source_hat = s_hat if source_hat is None else source_hat + s_hat
         else:
             raise NotImplementedError(f"nonlinear core {cls} has no fused program")
-    if program == _cabi.PROG_LINEAR and source_hat is not None:
-        raise NotImplementedError("an explicit source without a convective term is not supported")
     L = sd.get("linear_coef")
-    name = _integrator_name(ref_op, program == _cabi.PROG_LINEAR)
+    # an explicit source is a nonlinear core in the reference: "auto" picks SETDRK4 for it (operator/_base.py:451-455)
+    name = _integrator_name(ref_op, program == _cabi.PROG_LINEAR and source_hat is None)
     if name == "ETDRK0" and program != _cabi.PROG_LINEAR:
         raise AssertionError("The ETDRK0 integrator only supports linear term")
     rate = getattr(ref_op, "_de_aliasing_rate", 2 / 3)
@@ -123,7 +122,7 @@ def lower(ref_op, dt: float) -> LoweredIntegrator:
            if k in ("n_integration_points", "integration_radius", "cpu_cached")}
     low = LoweredIntegrator(f_mesh, n_channel, program, name, dt, L, nl_coef, source_hat, kmax, ks_remove_mean, cfg)
     # plan creation validates the configuration now (NotImplementedError if unsupported); no workspace is allocated
-    low.stepper(1, allocate=False)
+    low.stepper(L.shape[0] if (L is not None and L.shape[0] > 1) else 1, allocate=False)   # per-sample coefficients fix the batch
     return low
 
 
