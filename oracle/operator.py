@@ -37,7 +37,13 @@ class OracleOperator:
             if kind in LINEAR_KINDS:
                 lin.append((coef, linear_core(kind, mesh, n_channel, params)))
             elif kind in NONLINEAR_KINDS:
-                non.append((coef, nonlinear_core(kind, mesh, n_channel, params)))
+                if isinstance(params.get("force"), OracleOperator):      # a force operator sees the same mesh and state
+                    fop = params["force"]
+                    fop.de_aliasing_rate = self.de_aliasing_rate
+                    fop.register_mesh(mesh, n_channel)
+                core = nonlinear_core(kind, mesh, n_channel, params)
+                core.rate = self.de_aliasing_rate
+                non.append((coef, core))
             else:
                 raise ValueError(f"Operator {kind} is not supported")
         # _base.py:339-357 — python sum() => 0 + c_0*core_0 + c_1*core_1 ...

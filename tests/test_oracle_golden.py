@@ -95,3 +95,64 @@ def test_ks_batch_mean_only_shifts_dc():
     alone = oracle_from_golden(g).integrate(g["u0"][:1], dt=spec["dt"], step=3)
     diff = both[:1] - alone
     assert diff.std() < 1e-12 and abs(diff.mean()) > 1e-8
+
+
+# ---------------------------------------------------------------- the operators around the path (tests/golden_ops)
+def _oracle_terms(terms, spec, dtype):
+    """ops_util term lists -> oracle term lists (numpy sources, numpy callables, nested force operators)."""
+    import torch
+    from ops_util import FUNCS, source_field
+    from oracle import OracleOperator
+    tdt = torch.float32 if dtype == "float32" else torch.float64
+    out = []
+    for kind, coef, params in terms:
+        p = {k: v for k, v in dict(params).items() if k != "_ndim"}
+        if "source" in p:
+            p["source"] = source_field(p["source"], [tuple(m) for m in spec["mesh"]], tdt).numpy()
+        if "func" in p:
+            f = FUNCS[p["func"]]
+            p["func"] = lambda u, f=f: f(torch.from_numpy(np.ascontiguousarray(u))).numpy()
+        if p.get("force") is not None:
+            p["force"] = OracleOperator(_oracle_terms(p["force"], spec, dtype))
+        if isinstance(coef, (list, tuple)):
+            coef = np.asarray(coef, dtype=dtype).reshape([len(coef), 1] + [1] * len(spec["mesh"]))
+        out.append((kind, coef, p))
+    return out
+
+
+def _ops_names():
+    from ops_util import ops_names
+    return ops_names()
+
+
+@pytest.mark.parametrize("name", _ops_names())
+def test_oracle_matches_reference_ops(name):
+    """The oracle's restatement of the cores around the path against vectors generated from the unmodified reference."""
+    from ops_util import load_ops
+    from oracle import OracleOperator
+    g = load_ops(name)
+    spec = g["spec"]
+    tol = 1e-5 if name.endswith("f32") else 1e-12
+    mesh_info = [tuple(m) for m in spec["mesh"]]
+    u0 = g["u0"]
+
+    def build(terms):
+        op = OracleOperator(_oracle_terms(terms, spec, spec["dtype"]))
+        op.register_mesh(mesh_info, spec["C"], dtype=spec["dtype"])
+        return op
+    if spec["mode"] == "call":
+        assert rel_l2(build(spec["terms"])(u0.copy()), g["y"]) <= tol
+    elif spec["mode"] == "run_operators":
+        for i, terms in enumerate(spec["operators"]):
+            assert rel_l2(build(terms)(u0.copy()), g[f"y{i}"]) <= tol
+    elif spec["mode"] == "solve":
+        op = build(spec["terms"])
+        L = op.linear_coef
+        inv = np.where(L == 0, 1.0, 1 / np.where(L == 0, 1, L))          # operator/_base.py:250-255
+        assert rel_l2(op.mesh.ifft(op.mesh.fft(u0) * inv).real, g["y"]) <= tol
+    else:
+        op = build(spec["terms"])
+        op.set_integrator(spec["integrator"])
+        assert rel_l2(op.integrate(u0.copy(), dt=spec["dt"], step=1), g["u1"]) <= tol
+        assert rel_l2(op.integrate(u0.copy(), dt=spec["dt"], step=spec["steps"]), g["uT"]) <= tol * (3 if name.endswith("f32") else 1)
+        assert rel_l2(op(u0.copy()), g["rhs0"]) <= 10 * tol      # one evaluation of stiff symbols (k^4): as in the product tests
