@@ -442,7 +442,7 @@ def run_b200(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    st.step_half(u_hat, max(args.warmup, 3) + 40)      # warm-up + load for the clock record
+    st.step_half(u_hat, max(args.warmup, 3) + 300)     # warm-up + ~0.5 s of load for the clock record (50 ms samples)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -450,7 +450,7 @@ def run_b200(args):
     e1.record()
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    st.step_half(u_hat, 20)                            # keep the load on while the sampler takes its last samples
+    st.step_half(u_hat, 100)                           # keep the load on while the sampler takes its last samples
     torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     assert torch.isfinite(u_hat.real).all(), "state blew up"
@@ -602,7 +602,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)     # 200 timed steps (0.3 s on one B200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--chunk", type=int, default=0, help="samples per pass launch (0 = library default)")

@@ -207,7 +207,18 @@ struct FftCfg {
     static constexpr int TLG = (N_ / EPT_ < PADG) ? N_ / EPT_ : PADG;   // granularity of tau's low bits
     // complex elements per line buffer, rounded so that LINE_PITCH % 16 == 2: eight lines
     // read "column-wise" by consecutive lanes (transposed stores) hit distinct banks.
-    static constexpr int RAWLEN = N_ + (N_ >> PADSHIFT) + 1;
+    // Layout of the LAST stage's input when the middle stage writes it (NST == 3). With R0 = R1 = 8 the middle stage's
+    // half-warp stores two 8-slot runs (lanes 0-7 and 8-15: butterfly groups g and g+1) whose bases are pad(64) = 68
+    // slots apart: 4 of 16 bank pairs collide (ncu: every excess shared-memory wavefront of the 3-D last-axis pass
+    // sat on these STS.64, profiles/r2f_phys3d_shared_wavefronts.txt). Four extra slots in front of every odd group
+    // of 64 (and, to stay injective, of everything behind it: 4 * ceil(g / 2) slots before group g) put the two runs
+    // 72 = 8 (mod 16) apart; the loads of the last stage (consecutive lanes, consecutive slots) do not care. The
+    // offset depends on the group index i >> 6 only, which comes from the thread part in the stores and from the
+    // compile-time part in the loads, so the affine splits below stay exact.
+    static constexpr int XTRA = (R2_ > 1 && R0_ == 8 && R1_ == 8 && PADSHIFT == 4) ? 4 : 0;
+    static_assert(XTRA == 0 || EPT_ == R1_, "pad_last: one butterfly per thread in the middle stage");
+    static FSM_HD constexpr int pad_last(int i) { return pad(i) + XTRA * (((i >> 6) + 1) >> 1); }
+    static constexpr int RAWLEN = N_ + (N_ >> PADSHIFT) + 1 + XTRA * (((N_ >> 6) + 1) >> 1);
     static constexpr int LINE_PITCH = RAWLEN + ((2 - RAWLEN % 16) + 16) % 16;
     // twiddle tables (complex entries): stage 1 uses (R1-1)*R0, stage 2 uses (R2-1)*R0*R1 -- or only their
     // first rows (R0, R0*R1 entries) when the other rows are formed by recurrence
@@ -285,7 +296,7 @@ __device__ __forceinline__ void line_fft_head(cplx<T>* v, cplx<T>* buf, const cp
         constexpr bool kAffSt = (TL % Ns == 0) && (Cfg::PADG % Ns == 0) && ((Ns * R1) % Cfg::PADG == 0) &&
                                 ((TL * R1) % Cfg::PADG == 0);
         const int jt = tau & (Ns - 1);
-        cplx<T>* stb = buf + Cfg::pad((tau / Ns) * Ns * R1 + jt);
+        cplx<T>* stb = buf + Cfg::pad_last((tau / Ns) * Ns * R1 + jt);   // XTRA: the thread part carries bit 6
         cplx<T> pw[R1];   // twiddle row of this thread (same for every q when the split is affine)
         if constexpr (Cfg::RECUR && kAffSt) twiddle_powers<R1, T>(tw[jt], pw);
         static_for<0, EPT / R1>([&](auto qc) FSM_INLINE_LAMBDA {
@@ -307,7 +318,7 @@ __device__ __forceinline__ void line_fft_head(cplx<T>* v, cplx<T>* buf, const cp
             static_for<0, R1>([&](auto tc) FSM_INLINE_LAMBDA {
                 constexpr int t = decltype(tc)::value;
                 if constexpr (kAffSt) stb[Cfg::pad(q * TL * R1 + t * Ns)] = a[t];
-                else buf[Cfg::pad(base + t * Ns)] = a[t];
+                else buf[Cfg::pad_last(base + t * Ns)] = a[t];
             });
         });
     }
@@ -327,16 +338,20 @@ __device__ __forceinline__ void fft_last_item(const cplx<T>* buf, const cplx<T>*
     // NST == 2: Ns = R0 = NS and j = w; NST == 3: Ns = R0*R1 = NS and j = w
     constexpr bool kAff = (WC % Cfg::TLG == 0) && (NS % Cfg::TLG == 0);
     const int w = wt + WC;
+    // NST == 3: the buffer was written by the middle stage in the pad_last layout; wt + (WC mod 64) < 64 whenever the
+    // affine split is taken with XTRA != 0 (TL <= 64, WC a multiple of TL), so bit 6 comes from the compile-time part
+    constexpr bool kLast = (Cfg::NST == 3);
+    static_assert(Cfg::XTRA == 0 || (Cfg::TL <= 64 && (64 % Cfg::TL) == 0), "pad_last split");
     const cplx<T>* ldb = buf + Cfg::pad(wt);
-    if constexpr (kAff) a[0] = ldb[Cfg::pad(WC)];
-    else a[0] = buf[Cfg::pad(w)];
+    if constexpr (kAff) a[0] = ldb[kLast ? Cfg::pad_last(WC) : Cfg::pad(WC)];
+    else a[0] = buf[kLast ? Cfg::pad_last(w) : Cfg::pad(w)];
     cplx<T> pw[RL];
     if constexpr (Cfg::RECUR) twiddle_powers<RL, T>(twl[WC], pw);
     static_for<1, RL>([&](auto tc) FSM_INLINE_LAMBDA {
         constexpr int t = decltype(tc)::value;
         cplx<T> x;
-        if constexpr (kAff) x = ldb[Cfg::pad(WC + t * NS)];
-        else x = buf[Cfg::pad(w + t * NS)];
+        if constexpr (kAff) x = ldb[kLast ? Cfg::pad_last(WC + t * NS) : Cfg::pad(WC + t * NS)];
+        else x = buf[kLast ? Cfg::pad_last(w + t * NS) : Cfg::pad(w + t * NS)];
         cplx<T> wv;
         if constexpr (Cfg::RECUR) wv = pw[t];
         else wv = twl[(t - 1) * NS + WC];
