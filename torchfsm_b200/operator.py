@@ -145,7 +145,7 @@ class FusedStepper:
         self._keep = []  # tensors referenced by the plan descriptor
         if self.rdtype == torch.float64 and not _cabi.is_emulator():
             # line buffers of one CTA must fit the 227 KB of shared memory of an SM (8 lines x 2 buffers, 16 B/point)
-            if max(self.shape) > 512:
+            if max(self.shape) > 512 and self.n_dim > 1:      # 1-D kernels hold one line per CTA
                 raise NotImplementedError("fp64 grids are limited to 512 points per axis on the fused CUDA path "
                                           "(shared memory per SM); use fp32 or a smaller grid")
             if self.n_dim == 3 and program in (_cabi.PROG_CONVECTION, _cabi.PROG_NS3D) and self.shape[-1] > 256:
