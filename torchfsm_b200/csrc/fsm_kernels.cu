@@ -192,16 +192,22 @@ static int launch_mid(int dir, const MidArgs<T>& a, cudaStream_t s) {
 }
 
 #ifndef FSM_PHYS3D_NL512
-// thread-lines per CTA of the 3-D convection last-axis pass at 512 points. Measured on C5: 4 (two 256-thread CTAs per
-// SM, 64-byte store segments, 80 B of spills) 9.68 ms/step against 9.75 with 8 (one CTA per SM): no gain, kept at 8.
-#define FSM_PHYS3D_NL512 8
+// thread-lines per CTA of the 3-D convection last-axis pass at 512 points. Round 1 measured 4 (two 256-thread CTAs per
+// SM, 32-byte store segments, 80 B of spills) 9.68 ms/step against 9.75 with 8: no gain. With the third component parked
+// in shared memory and the conflict-free last-stage layout (round 2) 4 lines win: 9.68 -> 9.39 ms per C5 step
+// (profiles/r2_kernel_variants.md).
+#define FSM_PHYS3D_NL512 4
+#endif
+#ifndef FSM_PHYS3D_NL256
+#define FSM_PHYS3D_NL256 8
 #endif
 template <typename T, int N, int PROG, int NDIM>
 static int launch_phys_p(const PhysArgs<T>& a, cudaStream_t s) {
     using Cfg = typename CfgPhys<N, NDIM>::type;
     using PT = PhysTraits<PROG, NDIM>;
     constexpr int NFW = (PT::NOUT * PT::RPT + 1) / 2;
-    constexpr int NLP = (PROG == PROG_CONV && NDIM == 3 && N == 512 && sizeof(T) == 4) ? FSM_PHYS3D_NL512 : kKL;
+    constexpr int NLP = (PROG == PROG_CONV && NDIM == 3 && N == 512 && sizeof(T) == 4) ? FSM_PHYS3D_NL512
+                        : ((PROG == PROG_CONV && NDIM == 3 && N == 256 && sizeof(T) == 4) ? FSM_PHYS3D_NL256 : kKL);
     auto kern = k_pass_phys<T, Cfg, PROG, NDIM, NLP>;
     const int K = NLP * PT::RPT;
     const size_t smem = Smem<Cfg, T>::bytes(NLP * (1 + (NFW > 0 ? NFW : 0)));
