@@ -6,7 +6,6 @@ same torch expressions on the same device, so the comparison is apples to apples
 import os
 import sys
 
-import numpy as np
 import pytest
 import torch
 

@@ -15,7 +15,6 @@ on the REFERENCE side of the boundary, as INTEGRATION.md §2 describes; this pac
 
 Nothing here imports ``torchfsm``: the adapter only looks at attributes of the objects it is handed.
 """
-from typing import Optional
 
 import torch
 
