@@ -727,6 +727,25 @@ class DynamicForceStepper(_StageLoopStepper):
 # ------------------------------------------------------------------------------------------------
 # Operators
 # ------------------------------------------------------------------------------------------------
+class _LinearFn(torch.autograd.Function):
+    """y = A u for a real-linear A evaluated by the library (no graph inside); backward applies A^T, which for
+    A = ifft . S . fft on real fields is ifft . S^H . fft: the same kernels with the conjugate-transposed symbol."""
+
+    @staticmethod
+    def forward(ctx, u, fwd, bwd):
+        ctx.bwd = bwd
+        return fwd(u.detach())
+
+    @staticmethod
+    def backward(ctx, g):
+        return ctx.bwd(g.detach().contiguous()), None, None
+
+
+def _adjoint_map_terms(terms):
+    """(out, in, powers, inverse-Laplacian power, coef) of S -> terms of S^H: channels swapped, (i k)^p conjugated."""
+    return [(ci, co, pw, q, coef * (-1.0) ** (sum(pw) % 2)) for (co, ci, pw, q, coef) in terms]
+
+
 class OperatorLike:
     """Sum of generator terms (mirror of ``OperatorLike``/``Operator``, operator/_base.py:286-850)."""
 
@@ -1107,8 +1126,10 @@ class OperatorLike:
             assert u.shape == u_fft.shape, "The shape of u and u_fft should be the same"
         assert mesh is not None, "Mesh should be given"
         value = u if u is not None else u_fft
-        if value.requires_grad:
-            raise NotImplementedError("the fused CUDA path is forward-only; detach the input first")
+        if value.requires_grad and not getattr(self, "_autograd_ok", False):
+            raise NotImplementedError("the fused CUDA path differentiates linear operators and point-wise spectral maps "
+                                      "only (their adjoint is the same kernels with the conjugate symbol); detach the "
+                                      "input of a nonlinear operator first")
         if not isinstance(mesh, FourierMesh):
             if isinstance(mesh, MeshGrid):
                 mesh = FourierMesh(mesh, device=value.device, dtype=mesh.dtype)
@@ -1227,6 +1248,9 @@ class OperatorLike:
                   step: int = 1, mesh=None, progressive: bool = False, trajectory_recorder=None,
                   return_in_fourier: bool = False):
         """operator/_base.py:676-751 — same signature and return conventions."""
+        if u_0 is not None and u_0.requires_grad and u_0_fft is None and trajectory_recorder is None \
+                and not return_in_fourier and not progressive:
+            return self._integrate_with_grad(u_0, dt, step, mesh)
         st = self._stepper_for((u_0, u_0_fft), mesh, dt)
         try:
             u_hat = st.r2c(u_0) if u_0_fft is None else st.full_to_half(u_0_fft)
@@ -1353,6 +1377,8 @@ class OperatorLike:
     def __call__(self, u: Optional[torch.Tensor] = None, u_fft: Optional[torch.Tensor] = None, mesh=None,
                  return_in_fourier: bool = False):
         """operator/_base.py:753-790 — evaluate L u + N(u) once."""
+        if u is not None and u.requires_grad and u_fft is None and not return_in_fourier:
+            return self._call_with_grad(u, mesh)
         if self._state_dict["f_mesh"] is None or mesh is not None or self._lowered is None:
             m, n_channel = self._pre_check(u, u_fft, mesh if mesh is not None else self._state_dict["f_mesh"])
             self.register_mesh(m, n_channel)
@@ -1374,6 +1400,53 @@ class OperatorLike:
         u_hat = st_in.r2c(u) if u_fft is None else st_in.full_to_half(u_fft)
         out, _ = self._eval_half(u_hat, f_mesh, n_channel)
         return st_out.half_to_full(out) if return_in_fourier else st_out.c2r(out)
+
+
+    # ---- differentiable linear paths ------------------------------------------------------------
+    def _call_with_grad(self, u, mesh):
+        """``operator(u)`` with ``u.requires_grad``: linear operators and point-wise spectral maps (Grad, Div, Curl,
+        Vorticity2Velocity, sums with linear cores) are differentiated by running the adjoint map on the cotangent."""
+        self._autograd_ok = True
+        try:
+            if self._state_dict["f_mesh"] is None or mesh is not None or self._lowered is None:
+                m, n_channel = self._pre_check(u, None, mesh if mesh is not None else self._state_dict["f_mesh"])
+                self.register_mesh(m, n_channel)
+            else:
+                self._pre_check(u, None, self._state_dict["f_mesh"])
+        finally:
+            self._autograd_ok = False
+        lo, n_channel, B = self._lowered, self._state_dict["n_channel"], u.shape[0]
+        if "map" in lo:
+            c_out, terms = lo["c_out"], lo["map"]
+        elif "composite" not in lo and self.is_linear and not any(isinstance(t.coef, torch.Tensor) for t in self.terms):
+            c_out, terms = self._lower_map(self._state_dict["f_mesh"], n_channel)
+        else:
+            raise NotImplementedError("only linear operators and point-wise spectral maps are differentiable on the fused "
+                                      "CUDA path; detach the input of a nonlinear operator first")
+        adj = _adjoint_map_terms(terms)
+
+        def run(x, c_in, c_to, tt):
+            st_in, st_to = self._tf(B, c_in), self._tf(B, c_to)
+            return st_to.c2r(st_in.spectral_map(st_in.r2c(x), c_to, tt))
+        return _LinearFn.apply(u, lambda x: run(x, n_channel, c_out, terms), lambda g: run(g, c_out, n_channel, adj))
+
+    def _integrate_with_grad(self, u_0, dt, step, mesh):
+        """``integrate(u_0)`` of a purely linear operator with real tables (exp(L dt) real: even-order terms): the step
+        is self-adjoint, so the cotangent is integrated by the same plan."""
+        self._autograd_ok = True
+        try:
+            st = self._stepper_for((u_0, None), mesh, dt)
+        finally:
+            self._autograd_ok = False
+        lo = self._lowered
+        if lo.get("program") != _cabi.PROG_LINEAR or lo.get("source_hat") is not None or lo.get("external") or st.complex_tables \
+                or st.integrator != "ETDRK0":
+            raise NotImplementedError("only linear operators (ETDRK0, real symbol) are differentiable through integrate() "
+                                      "on the fused CUDA path; detach the input of a nonlinear operator first")
+
+        def run(x):
+            return st.c2r(st.step_half(st.r2c(x), step))
+        return _LinearFn.apply(u_0, run, run)
 
 
 class Operator(OperatorLike):
