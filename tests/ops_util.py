@@ -199,6 +199,8 @@ OPS_CASES = [
          terms=[("laplacian", 0.01, {}), ("conservative_convection", -1, {})], integrator="ETDRK2", dt=0.002, steps=3),
     dict(name="conscon1d_rk4", mode="integrate", mesh=_m((64,), 1.0), B=2, C=1,
          terms=[("laplacian", 0.01, {}), ("conservative_convection", -0.5, {})], integrator="RK4", dt=0.0005, steps=3),
+    dict(name="ksconv1d_setdrk4", mode="integrate", mesh=_m((64,), 32.0), B=3, C=1,
+         terms=[("laplacian", -1, {}), ("biharmonic", -1, {}), ("ks_convection", -1, {})], integrator="auto", dt=0.05, steps=3),
     dict(name="allen_cahn2d_etdrk2", mode="integrate", mesh=_m((32, 32), TWO_PI, TWO_PI), B=2, C=1,
          terms=[("laplacian", 0.05, {}), ("implicit_func_source", 1, {"func": "allen_cahn"})],
          integrator="ETDRK2", dt=0.01, steps=3),

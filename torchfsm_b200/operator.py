@@ -921,6 +921,13 @@ class OperatorLike:
         for t in self.terms:
             if t.kind in _LINEAR_KINDS:
                 lin.append(t)
+            elif t.kind == "ks_convection" and f_mesh.n_dim == 1:
+                # no fused 1-D program for 1/2 (phi_x)^2: composed on the host from the library's passes
+                if n_channel != 1:
+                    raise NotImplementedError("KSConvection only supports scalar field")
+                if isinstance(t.coef, torch.Tensor):
+                    raise NotImplementedError("tensor-valued coefficients on nonlinear terms are not supported")
+                external.append(t)
             elif t.kind in _PROGRAM_OF:
                 if program != _cabi.PROG_LINEAR:
                     raise NotImplementedError("only one convective nonlinear term per operator is supported "
@@ -1154,7 +1161,8 @@ class OperatorLike:
         """sum_t coef_t * core_t(u_hat) for the host-composed cores (operator/_base.py:375-403): dealiased input for the
         cores that ask for it, one inverse transform shared by all of them, every transform on the library's passes."""
         d = self._state_dict["f_mesh"].n_dim
-        need_masked = any(t.kind == "conservative_convection" or t.params.get("non_linear", True) for t in terms)
+        need_masked = any(t.kind == "conservative_convection" or (t.kind == "implicit_func_source" and t.params.get("non_linear", True))
+                          for t in terms)
         need_plain = any(t.kind == "implicit_func_source" and not t.params.get("non_linear", True) for t in terms)
         pairs = [(a, c) for a in range(n_channel) for c in range(a, n_channel)]
 
@@ -1169,6 +1177,12 @@ class OperatorLike:
                         raise ValueError("ImplicitSource: source_func must keep the shape of its argument")
                     r = st.r2c(v)
                     r = r * float(t.coef) if float(t.coef) != 1.0 else r
+                elif t.kind == "ks_convection":                          # dedicated/_ks_convection.py:18-38 on a 1-D grid
+                    g_hat = st.spectral_map(x_hat, 1, [(0, 0, (1, 0, 0), 0, 1.0)], dealias=True)      # i k phi_hat, dealiased
+                    r = st.r2c(st.sym_outer(st.c2r(g_hat)))              # (phi_x)^2
+                    if t.params.get("remove_mean", True):                # the mean spans batch and space: zero modes only
+                        r[:, :, 0] -= r[:, :, 0].mean()
+                    r = r * (0.5 * float(t.coef))
                 else:                                                    # generic/_conservative_convection.py:18-27
                     uu_hat = self._tf(st.B, len(pairs)).r2c(st.sym_outer(u_d))
                     e = [tuple(1 if i == a else 0 for i in range(3)) for a in range(d)]
