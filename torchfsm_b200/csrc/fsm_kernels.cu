@@ -288,7 +288,7 @@ template <typename T, int N>
 static int launch_step1d(const Step1dArgs<T>& a, cudaStream_t s) {
     using Cfg = typename CfgFor<N>::type;
     auto kern = k_step1d<T, Cfg>;
-    const size_t smem = Smem<Cfg, T>::bytes(1);
+    const size_t smem = Smem<Cfg, T>::bytes(1) + sizeof(cplx<T>) * (size_t)FSM_1D_ARRAYS * (N / 2 + 2);   // + resident arrays
     if (int e = set_smem(kern, smem)) return e;
     FSM_LAUNCH(kern, dim3(a.nb), dim3(Cfg::TL), smem, s, a.g, a.sl, a.ep, a.n_steps);
     return check_launch();

@@ -1920,12 +1920,19 @@ struct StageList {
     Combine<T> cb[FSM_MAX_STAGES];
 };
 
+// The state and stage arrays of the sample (at most FSM_1D_ARRAYS distinct ones, N/2+1 modes each) are copied into shared
+// memory once, every stage of every step works on those copies (the Combine descriptors are re-pointed at them), and
+// all of them are written back at the end: between two stages nothing but the coefficient tables is read from global
+// memory. (First version: every stage re-read its input and operands from L2 and wrote its outputs there, ~1 us per
+// dependent round trip; C1 ran at 44 us per step.)
+#define FSM_1D_ARRAYS 6
 template <typename T, class Cfg>
 __global__ void __launch_bounds__(Cfg::TL) k_step1d(Geom<T> g, StageList<T> sl, FxEpilogue<T> ep, int n_steps) {
-    constexpr int N = Cfg::N, EPT = Cfg::EPT, TL = Cfg::TL;
+    constexpr int N = Cfg::N, EPT = Cfg::EPT, TL = Cfg::TL, NH = N / 2 + 1, APITCH = NH + 1;
     FSM_DYN_SMEM(smem_raw);
     cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);
     cplx<T>* buf = tw + Smem<Cfg, T>::TWPAD;
+    cplx<T>* arrs = buf + Cfg::LINE_PITCH;
     make_twiddles<Cfg, T>(tw);
     const int tau = threadIdx.x;
     const long b = blockIdx.x;
@@ -1933,9 +1940,35 @@ __global__ void __launch_bounds__(Cfg::TL) k_step1d(Geom<T> g, StageList<T> sl, 
     const int kmax = g.kmax[0];
     const T* dk = g.dk[0];
     LineSync<TL> sync{1};
+    // distinct global arrays touched by the stage list (every thread builds the same list)
+    const cplx<T>* base[FSM_1D_ARRAYS];
+    int nbase = 0;
+    auto slot_of = [&](const cplx<T>* p) FSM_INLINE_LAMBDA {
+        for (int i = 0; i < nbase; ++i)
+            if (base[i] == p) return i;
+        if (nbase < FSM_1D_ARRAYS) base[nbase] = p;
+        return nbase++;
+    };
+    for (int si = 0; si < sl.n_stages; ++si) {
+        slot_of(sl.input[si]);
+        for (int i = 0; i < sl.cb[si].n_in; ++i) slot_of(sl.cb[si].in[i]);
+        for (int r = 0; r < sl.cb[si].n_out; ++r) slot_of(sl.cb[si].out[r]);
+    }
+    const bool resident = nbase <= FSM_1D_ARRAYS;     // always true for the stage programs of fsm_plan.cu
+    if (resident) {
+        for (int a = 0; a < nbase; ++a)
+            for (int k = tau; k < NH; k += TL) arrs[a * APITCH + k] = base[a][boff + k];
+    }
+    __syncthreads();
     for (int step = 0; step < n_steps; ++step) {
         for (int si = 0; si < sl.n_stages; ++si) {
+            Combine<T> cb = sl.cb[si];
             const cplx<T>* in = sl.input[si] + boff;
+            if (resident) {        // re-point the descriptor: element [boff + k] of an array is arrs[slot * APITCH + k]
+                in = arrs + slot_of(sl.input[si]) * APITCH;
+                for (int i = 0; i < cb.n_in; ++i) cb.in[i] = arrs + slot_of(cb.in[i]) * APITCH - boff;
+                for (int r = 0; r < cb.n_out; ++r) cb.out[r] = arrs + slot_of(sl.cb[si].out[r]) * APITCH - boff;
+            }
             cplx<T> v[EPT];
             FSM_UNROLL
             for (int m = 0; m < EPT; ++m) {
@@ -1959,10 +1992,16 @@ __global__ void __launch_bounds__(Cfg::TL) k_step1d(Geom<T> g, StageList<T> sl, 
                 if (p <= N / 2) {
                     cplx<T> f = cscale(v[m], ep.nl_coef);
                     if (ep.source) f = f + ep.source[p];
-                    combine_mode<T>(sl.cb[si], f, boff, b * sl.cb[si].tab_bstride, p);
+                    combine_mode<T>(cb, f, boff, b * cb.tab_bstride, p);
                 }
             }
             __syncthreads();
+        }
+    }
+    if (resident) {
+        for (int a = 0; a < nbase; ++a) {
+            cplx<T>* dst = const_cast<cplx<T>*>(base[a]);
+            for (int k = tau; k < NH; k += TL) dst[boff + k] = arrs[a * APITCH + k];
         }
     }
 }
