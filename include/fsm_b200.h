@@ -175,6 +175,11 @@ int fsm_mask_state(fsm_plan* plan, void* state_hat, int32_t channels, void* stre
 int fsm_stage_run(fsm_plan* plan, int32_t stage, void* u_hat, const void* force_hat, void* rhs_out, void* workspace,
                   size_t ws_bytes, void* stream);
 int fsm_sym_outer(fsm_plan* plan, const void* u, void* out, int32_t channels, void* stream);
+/* out = base + sum_j coefs[j] * terms[j] over `count` complex elements of the plan dtype (n_terms <= 8, out may alias
+ * base): the stage states and the update of the explicit Runge-Kutta family other than RK4, whose right-hand sides come
+ * from fsm_rhs (replaces `x_t + dt * sum([a_i * k for a_i, k in zip(ca_i[1:], ks)])`, integrator/_rk.py:43-58). */
+int fsm_lincomb(fsm_plan* plan, void* out, const void* base, const void* const* terms, const double* coefs, int32_t n_terms,
+                int64_t count, void* stream);
 
 /* introspection for benchmarks: kernels launched per step, algorithmic bytes per step
  * (transform-pass model), modes per field, chunk size */

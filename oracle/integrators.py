@@ -219,4 +219,36 @@ class RK4:
         return x + dt * sum(b * k for b, k in zip(self.b, ks))
 
 
+# the other fixed-step members of the explicit Runge-Kutta family: rows [c_i, a_i1, ...] and weights b as the reference
+# holds them (_rk.py:82-255), stepped by the same loop (_rk.py:43-58)
+RK_FAMILY = {
+    "Euler": ([[1.0]], [1.0]),                                                                       # _rk.py:82-87
+    "Midpoint": ([[1 / 2, 1 / 2]], [0, 1]),                                                          # :90-95
+    "Heun12": ([[1, 1]], [1 / 2, 1 / 2]),                                                            # :98-105
+    "Ralston12": ([[2 / 3, 2 / 3]], [1 / 4, 3 / 4]),                                                 # :108-120
+    "BogackiShampine23": ([[1 / 2, 1 / 2], [3 / 4, 0, 3 / 4], [1, 2 / 9, 1 / 3, 4 / 9]], [2 / 9, 1 / 3, 4 / 9, 0]),   # :123-139
+    "RK4_38Rule": ([[1 / 3, 1 / 3], [2 / 3, -1 / 3, 1], [1, -1, 1, 1]], [1 / 8, 3 / 8, 3 / 8, 1 / 8]),               # :158-171
+    "Dorpi45": ([[1 / 5, 1 / 5], [3 / 10, 3 / 40, 9 / 40], [4 / 5, 44 / 45, -56 / 15, 32 / 9],      # :174-202
+                 [8 / 9, 19372 / 6561, -25360 / 2187, 64448 / 6561, -212 / 729],
+                 [1, 9017 / 3168, -355 / 33, 46732 / 5247, 49 / 176, -5103 / 18656],
+                 [1, 35 / 384, 0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84]],
+                [35 / 384, 0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84]),
+    "Fehlberg45": ([[1 / 4, 1 / 4], [3 / 8, 3 / 32, 9 / 32], [12 / 13, 1932 / 2197, -7200 / 2197, 7296 / 2197],     # :205-225
+                    [1, 439 / 216, -8, 3680 / 513, -845 / 4104], [1 / 2, -8 / 27, 2, -3544 / 2565, 1859 / 4104, -11 / 40]],
+                   [16 / 135, 0, 6656 / 12825, 28561 / 56430, -9 / 50, 2 / 55]),
+    "CashKarp45": ([[1 / 5, 1 / 5], [3 / 10, 3 / 40, 9 / 40], [3 / 5, 3 / 10, -9 / 10, 6 / 5],      # :228-255
+                    [1, -11 / 54, 5 / 2, -70 / 27, 35 / 27],
+                    [7 / 8, 1631 / 55296, 175 / 512, 575 / 13824, 44275 / 110592, 253 / 4096]],
+                   [37 / 378, 0, 250 / 621, 125 / 594, 0, 512 / 1771]),
+}
+
+
+def explicit_rk(name, dt, rhs):
+    """An RK4-style stepper with the tableau of ``name``."""
+    r = RK4(dt, rhs)
+    r.order_name = name
+    r.ca, r.b = RK_FAMILY[name]
+    return r
+
+
 INTEGRATORS = {c.order_name: c for c in (ETDRK0, ETDRK1, ETDRK2, SETDRK1, SETDRK2, SETDRK3, SETDRK4)}

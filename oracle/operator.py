@@ -97,6 +97,9 @@ class OracleOperator:
         if name == "RK4":
             self.integrator = _int.RK4(dt, self.rhs)
             return self.integrator
+        if name in _int.RK_FAMILY:
+            self.integrator = _int.explicit_rk(name, dt, self.rhs)
+            return self.integrator
         cls = _int.INTEGRATORS[name]
         L = self.linear_coef
         if L is None:                                                   # _base.py:473-478

@@ -32,7 +32,8 @@ OUT = os.path.join(os.path.dirname(HERE), "golden_ops")
 torch.set_num_threads(4)
 INTEGRATORS = {"ETDRK0": ETDRKIntegrator.ETDRK0, "ETDRK1": ETDRKIntegrator.ETDRK1, "ETDRK2": ETDRKIntegrator.ETDRK2,
                "SETDRK1": SETDRKIntegrator.SETDRK1, "SETDRK2": SETDRKIntegrator.SETDRK2,
-               "SETDRK3": SETDRKIntegrator.SETDRK3, "SETDRK4": SETDRKIntegrator.SETDRK4, "RK4": RKIntegrator.RK4}
+               "SETDRK3": SETDRKIntegrator.SETDRK3, "SETDRK4": SETDRKIntegrator.SETDRK4}
+INTEGRATORS.update({m.name: m for m in RKIntegrator})
 
 
 def run_case(case, dtype):

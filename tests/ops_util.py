@@ -184,6 +184,27 @@ OPS_CASES = [
     dict(name="ns3d_drag_force_etdrk1", mode="integrate", dtypes=["float32"], mesh=_m((8, 16, 16), TWO_PI, TWO_PI, TWO_PI), B=1, C=3,
          terms=[("ns_pressure_convection", 1, {"force": [("implicit_unit_source", -0.1, {})]}),
                 ("laplacian", 1 / 100, {})], integrator="ETDRK1", dt=0.0025, steps=3),
+    # the explicit Runge-Kutta family other than RK4 (integrator/_rk.py:82-255), non-adaptive
+    dict(name="burgers1d_euler", mode="integrate", mesh=_m((64,), 1.0), B=2, C=1,
+         terms=[("laplacian", 0.02, {}), ("convection", -1, {})], integrator="Euler", dt=0.0002, steps=3),
+    dict(name="burgers1d_midpoint", mode="integrate", mesh=_m((64,), 1.0), B=2, C=1,
+         terms=[("laplacian", 0.02, {}), ("convection", -1, {})], integrator="Midpoint", dt=0.0002, steps=3),
+    dict(name="kdv1d_ralston12", mode="integrate", mesh=_m((64,), 20.0), B=2, C=1,
+         terms=[("spatial_derivative", -1, {"dim_index": 0, "order": 3}), ("convection", 6.0, {})], integrator="Ralston12",
+         dt=0.00005, steps=3),
+    dict(name="burgers2d_heun12", mode="integrate", mesh=_m((32, 16), 1.0, 1.0), B=2, C=2,
+         terms=[("laplacian", 0.01, {}), ("convection", -1, {})], integrator="Heun12", dt=0.0005, steps=3),
+    dict(name="ks2d_bogacki_shampine23", mode="integrate", mesh=_m((32, 32), 30.0, 30.0), B=2, C=1,
+         terms=[("laplacian", -1, {}), ("biharmonic", -1, {}), ("ks_convection", -1, {})], integrator="BogackiShampine23",
+         dt=0.002, steps=3),
+    dict(name="ns2d_kolm_rk4_38rule", mode="integrate", mesh=_m((32, 32), TWO_PI, TWO_PI), B=2, C=1,
+         terms=[("vorticity_convection", -1, {}), ("laplacian", 0.01, {})] + KOLM, integrator="RK4_38Rule", dt=0.002, steps=3),
+    dict(name="burgers3d_dorpi45", mode="integrate", mesh=_m((16, 8, 8), 1.0, 1.0, 1.0), B=1, C=3,
+         terms=[("laplacian", 0.01, {}), ("convection", -1, {})], integrator="Dorpi45", dt=0.0005, steps=3),
+    dict(name="ns3d_fehlberg45", mode="integrate", mesh=_m((16, 16, 8), TWO_PI, TWO_PI, TWO_PI), B=1, C=3,
+         terms=[("ns_pressure_convection", 1, {}), ("laplacian", 1 / 100, {})], integrator="Fehlberg45", dt=0.002, steps=3),
+    dict(name="conscon2d_cashkarp45", mode="integrate", mesh=_m((32, 32), 1.0, 1.0), B=2, C=2,
+         terms=[("laplacian", 0.01, {}), ("conservative_convection", -1, {})], integrator="CashKarp45", dt=0.0005, steps=3),
     dict(name="burgers2d_batched_nu_etdrk2", mode="integrate", mesh=_m((32, 16), 1.0, 1.0), B=3, C=2,
          terms=[("laplacian", [0.01, 0.02, 0.05], {"_ndim": 2}), ("convection", -1, {})], integrator="ETDRK2", dt=0.002, steps=3),
     dict(name="burgers1d_batched_nu_setdrk4", mode="integrate", mesh=_m((64,), 1.0), B=3, C=1,

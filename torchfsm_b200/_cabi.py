@@ -42,7 +42,7 @@ class FsmMapTerm(ctypes.Structure):
 
 
 EXPORTS = ["fsm_plan_create", "fsm_plan_destroy", "fsm_workspace_bytes", "fsm_step", "fsm_rhs", "fsm_r2c",
-           "fsm_c2r", "fsm_spectral_map", "fsm_stage_input", "fsm_stage_combine", "fsm_stage_run", "fsm_mask_state", "fsm_sym_outer", "fsm_half_to_full", "fsm_full_to_half", "fsm_plan_info", "fsm_plan_traffic", "fsm_stage_kinds", "fsm_slab_phase", "fsm_slab_info", "fsm_slab_peers", "fsm_ks_log", "fsm_profile_enable", "fsm_profile_read", "fsm_last_error",
+           "fsm_c2r", "fsm_spectral_map", "fsm_stage_input", "fsm_stage_combine", "fsm_stage_run", "fsm_mask_state", "fsm_sym_outer", "fsm_lincomb", "fsm_half_to_full", "fsm_full_to_half", "fsm_plan_info", "fsm_plan_traffic", "fsm_stage_kinds", "fsm_slab_phase", "fsm_slab_info", "fsm_slab_peers", "fsm_ks_log", "fsm_profile_enable", "fsm_profile_read", "fsm_last_error",
            "fsm_abi_version", "fsm_backend"]
 
 _lib = None
@@ -77,6 +77,8 @@ def _declare(lib):
     lib.fsm_mask_state.restype = i32
     lib.fsm_sym_outer.argtypes = [vp, vp, vp, i32, vp]
     lib.fsm_sym_outer.restype = i32
+    lib.fsm_lincomb.argtypes = [vp, vp, vp, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_double), i32, ctypes.c_int64, vp]
+    lib.fsm_lincomb.restype = i32
     lib.fsm_half_to_full.argtypes = [vp, vp, vp, vp]
     lib.fsm_half_to_full.restype = i32
     lib.fsm_full_to_half.argtypes = [vp, vp, vp, vp]

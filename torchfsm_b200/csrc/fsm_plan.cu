@@ -1495,4 +1495,27 @@ int fsm_stage_run(fsm_plan* plan, int32_t stage, void* u_hat, const void* force_
     return run_stage<float>(plan, bf, s, st, 0, -1, static_cast<const cplx<float>*>(force_hat));
 }
 
+int fsm_lincomb(fsm_plan* plan, void* out, const void* base, const void* const* terms, const double* coefs, int32_t n_terms,
+                int64_t count, void* stream) {
+    if (!plan || !out || !base || (n_terms > 0 && (!terms || !coefs)) || count < 0) return fail(-EINVAL, "bad argument");
+    if (n_terms < 0 || n_terms > FSM_LINCOMB_MAX) return fail(-EINVAL, "at most %d terms", FSM_LINCOMB_MAX);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    dim3 grid((unsigned)((count + 255) / 256)), block(256);
+    if (count == 0) return 0;
+    if (plan->f64) {
+        LinComb<double> lc;
+        lc.n = n_terms;
+        for (int j = 0; j < n_terms; ++j) { lc.term[j] = static_cast<const cplx<double>*>(terms[j]); lc.coef[j] = coefs[j]; }
+        auto kern = k_lincomb<double>;
+        FSM_LAUNCH(kern, grid, block, 0, st, (cplx<double>*)out, (const cplx<double>*)base, lc, (long)count);
+    } else {
+        LinComb<float> lc;
+        lc.n = n_terms;
+        for (int j = 0; j < n_terms; ++j) { lc.term[j] = static_cast<const cplx<float>*>(terms[j]); lc.coef[j] = (float)coefs[j]; }
+        auto kern = k_lincomb<float>;
+        FSM_LAUNCH(kern, grid, block, 0, st, (cplx<float>*)out, (const cplx<float>*)base, lc, (long)count);
+    }
+    return launch_status("linear combination");
+}
+
 }  // extern "C"

@@ -154,4 +154,24 @@ __global__ void __launch_bounds__(256) k_sym_outer(const T* __restrict__ u, T* _
         for (int c = a; c < C; ++c, ++idx) out[(b * npair + idx) * npts + x] = v[a] * v[c];
 }
 
+// out = base + sum_j coef_j * term_j over complex arrays: the state combinations of the explicit Runge-Kutta family
+// (`x_t + dt * sum([a_i * k for ...])`, integrator/_rk.py:43-58) without a chain of separate axpy kernels.
+#define FSM_LINCOMB_MAX 8
+template <typename T>
+struct LinComb {
+    int n;
+    const cplx<T>* term[FSM_LINCOMB_MAX];
+    T coef[FSM_LINCOMB_MAX];
+};
+template <typename T>
+__global__ void __launch_bounds__(256) k_lincomb(cplx<T>* __restrict__ out, const cplx<T>* __restrict__ base, LinComb<T> lc, long total) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    cplx<T> acc = base[i];
+    FSM_UNROLL
+    for (int j = 0; j < FSM_LINCOMB_MAX; ++j)
+        if (j < lc.n) acc = cfma_s(lc.coef[j], lc.term[j][i], acc);
+    out[i] = acc;
+}
+
 }  // namespace fsm

@@ -27,7 +27,43 @@ class SETDRKIntegrator(Enum):
 
 
 class RKIntegrator(Enum):
+    """integrator/_rk.py:257-282. RK4 runs as fused stages inside the library; the other members run as right-hand-side
+    evaluations (``fsm_rhs``) combined by ``fsm_lincomb`` (non-adaptive stepping, the reference's default)."""
+    Euler = "Euler"
+    Midpoint = "Midpoint"
+    Heun12 = "Heun12"
+    Ralston12 = "Ralston12"
+    BogackiShampine23 = "BogackiShampine23"
     RK4 = "RK4"
+    RK4_38Rule = "RK4_38Rule"
+    Dorpi45 = "Dorpi45"
+    Fehlberg45 = "Fehlberg45"
+    CashKarp45 = "CashKarp45"
+
+
+# Butcher tableaus in the reference's row format [c_i, a_i1, a_i2, ...] (integrator/_rk.py:82-255; textbook constants) and
+# the weights b. _RKBase._rk_step evaluates k_0 = f(x), then one k per row, and x' = x + dt * sum(b_i k_i) over
+# zip(b, ks): a row may be evaluated and not used (Euler's, Dormand-Prince's last).
+RK_TABLEAUS = {
+    "Euler": ([[1.0]], [1.0]),
+    "Midpoint": ([[1 / 2, 1 / 2]], [0, 1]),
+    "Heun12": ([[1, 1]], [1 / 2, 1 / 2]),
+    "Ralston12": ([[2 / 3, 2 / 3]], [1 / 4, 3 / 4]),
+    "BogackiShampine23": ([[1 / 2, 1 / 2], [3 / 4, 0, 3 / 4], [1, 2 / 9, 1 / 3, 4 / 9]], [2 / 9, 1 / 3, 4 / 9, 0]),
+    "RK4_38Rule": ([[1 / 3, 1 / 3], [2 / 3, -1 / 3, 1], [1, -1, 1, 1]], [1 / 8, 3 / 8, 3 / 8, 1 / 8]),
+    "Dorpi45": ([[1 / 5, 1 / 5], [3 / 10, 3 / 40, 9 / 40], [4 / 5, 44 / 45, -56 / 15, 32 / 9],
+                 [8 / 9, 19372 / 6561, -25360 / 2187, 64448 / 6561, -212 / 729],
+                 [1, 9017 / 3168, -355 / 33, 46732 / 5247, 49 / 176, -5103 / 18656],
+                 [1, 35 / 384, 0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84]],
+                [35 / 384, 0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84]),
+    "Fehlberg45": ([[1 / 4, 1 / 4], [3 / 8, 3 / 32, 9 / 32], [12 / 13, 1932 / 2197, -7200 / 2197, 7296 / 2197],
+                    [1, 439 / 216, -8, 3680 / 513, -845 / 4104], [1 / 2, -8 / 27, 2, -3544 / 2565, 1859 / 4104, -11 / 40]],
+                   [16 / 135, 0, 6656 / 12825, 28561 / 56430, -9 / 50, 2 / 55]),
+    "CashKarp45": ([[1 / 5, 1 / 5], [3 / 10, 3 / 40, 9 / 40], [3 / 5, 3 / 10, -9 / 10, 6 / 5],
+                    [1, -11 / 54, 5 / 2, -70 / 27, 35 / 27],
+                    [7 / 8, 1631 / 55296, 175 / 512, 575 / 13824, 44275 / 110592, 253 / 4096]],
+                   [37 / 378, 0, 250 / 621, 125 / 594, 0, 512 / 1771]),
+}
 
 
 def integrator_name(integrator, is_linear):

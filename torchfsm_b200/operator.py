@@ -16,7 +16,7 @@ from typing import Callable, List, Optional, Sequence
 import torch
 
 from . import _cabi
-from .integrator import (ETDRKIntegrator, SETDRKIntegrator, RKIntegrator, integrator_name, build_tables)
+from .integrator import (ETDRKIntegrator, SETDRKIntegrator, RKIntegrator, RK_TABLEAUS, integrator_name, build_tables)
 from .mesh import FourierMesh, MeshGrid
 
 _LINEAR_KINDS = ("laplacian", "biharmonic", "spatial_derivative", "implicit_unit_source")
@@ -724,6 +724,50 @@ class DynamicForceStepper(_StageLoopStepper):
                                             self.workspace.data_ptr(), self.ws_bytes, self._stream()), "stage_run")
 
 
+class ExplicitRKStepper:
+    """The explicit Runge-Kutta family other than RK4 (integrator/_rk.py:43-58, 82-255; non-adaptive): every k_i is one
+    right-hand-side evaluation of the wrapped plan (``fsm_rhs``: the fused program, or the host-composed / forced
+    variants), the stage states and the update are ``fsm_lincomb`` launches. Everything else (transforms, layout
+    converters, introspection) is the wrapped stepper's."""
+
+    def __init__(self, inner: FusedStepper, name: str, dt: float):
+        self._inner, self.integrator, self.dt = inner, name, dt
+        self._rows, self._b = RK_TABLEAUS[name]
+
+    def __getattr__(self, item):
+        return getattr(self._inner, item)
+
+    def _lincomb(self, base, coefs, ks):
+        terms = [(c, k) for c, k in zip(coefs, ks) if c != 0]
+        out = torch.empty_like(base)
+        n = len(terms)
+        ptrs = (ctypes.c_void_p * max(1, n))(*[k.data_ptr() for _, k in terms])
+        cf = (ctypes.c_double * max(1, n))(*[float(c) for c, _ in terms])
+        st = self._inner
+        _cabi.check(st._lib.fsm_lincomb(st._plan, out.data_ptr(), base.data_ptr(), ptrs, cf, n, base.numel(), st._stream()),
+                    "lincomb")
+        return out
+
+    def step_half(self, u_hat: torch.Tensor, n_steps: int = 1) -> torch.Tensor:
+        st, dt = self._inner, self.dt
+        x = u_hat
+        for _ in range(int(n_steps)):
+            ks = [st.rhs_half(x)]
+            for row in self._rows:                                  # _rk.py:50-52
+                ks.append(st.rhs_half(self._lincomb(x, [dt * a for a in row[1:]], ks)))
+            x = self._lincomb(x, [dt * b for b in self._b], ks)    # _rk.py:53 (zip stops at the shorter list)
+        if x is not u_hat:
+            u_hat.copy_(x)
+        return u_hat
+
+    def step(self, u_hat_full: torch.Tensor) -> torch.Tensor:
+        st = self._inner
+        return st.half_to_full(self.step_half(st.full_to_half(u_hat_full), 1))
+
+    def forward(self, u_hat_full: torch.Tensor, dt: float) -> torch.Tensor:
+        return self.step(u_hat_full)
+
+
 # ------------------------------------------------------------------------------------------------
 # Operators
 # ------------------------------------------------------------------------------------------------
@@ -1204,6 +1248,15 @@ class OperatorLike:
             # an explicit source is a nonlinear core in the reference (operator/_base.py:994-1015): "auto" -> SETDRK4
             name, cfg = integrator_name(self._integrator, lo["program"] == _cabi.PROG_LINEAR and lo["source_hat"] is None
                                         and not lo["external"]), self._integrator_config
+        generic_rk = None
+        if name in RK_TABLEAUS:               # explicit RK other than RK4: right-hand sides of an RK4-type plan + fsm_lincomb
+            if cfg.get("adaptive"):
+                raise NotImplementedError("adaptive Runge-Kutta stepping is host-synchronous and not part of the fused CUDA path")
+            if lo.get("dyn_force") is not None or lo.get("force_hat") is not None:
+                raise NotImplementedError("NSPressureConvection with an external force is not supported with the RK integrators")
+            if self._slab is not None:
+                raise NotImplementedError("only RK4 of the Runge-Kutta family runs on slab-decomposed grids")
+            generic_rk, name, cfg = name, "RK4", {}
         if name == "ETDRK0":
             assert lo["program"] == _cabi.PROG_LINEAR and ((lo["source_hat"] is None and not lo["external"]) or rhs_only), \
                 "The ETDRK0 integrator only supports linear term"
@@ -1236,6 +1289,8 @@ class OperatorLike:
                 "Original error message: {}".format(str(e)),
                 "Please try to use a smaller mesh or a low-order integrator."]))
         st.ks_group = getattr(self, "_ensemble_group", None)
+        if generic_rk is not None:
+            st = ExplicitRKStepper(st, generic_rk, dt)
         if rhs_only:
             self._rhs_stepper = st
         else:
