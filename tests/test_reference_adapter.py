@@ -94,3 +94,26 @@ def test_unsupported_reference_operators_fall_back_to_torch():
     assert type(op._state_dict["integrator"]).__name__ != "LoweredIntegrator" and torch.isfinite(out).all()
     with pytest.raises(NotImplementedError):
         reference_adapter.install(Burgers(0.01), strict=True).integrate(u0, mesh=mesh, dt=1e-3, step=1)
+
+
+def test_truncated_fourier_series_equals_the_reference_for_a_seed():
+    """The IC helper of the batched-parameter tutorial (field.py:62-125): same draws from torch's generator, inverse
+    transform on the library (emulator build here) -> the same field as the reference."""
+    torchfsm = _reference()
+    if torchfsm is None:
+        pytest.skip("reference not importable")
+    from product_util import build_emulator
+    from torchfsm_b200 import _cabi
+    import torchfsm_b200 as fsm
+    _cabi.use_library(build_emulator())
+    try:
+        for info, kw in [([(0, 1.0, 128)], dict(batch_size=3, freq_threshold=2)),
+                         ([(0, 2.0, 32), (0, 1.0, 16)], dict(batch_size=2, n_channel=2, freq_threshold=5, unit_magnitude=False,
+                                                            unit_variance=True))]:
+            torch.manual_seed(5)
+            want = torchfsm.field.truncated_fourier_series(torchfsm.mesh.MeshGrid(info, dtype=torch.float64), **kw)
+            torch.manual_seed(5)
+            got = fsm.field.truncated_fourier_series(fsm.MeshGrid(info, dtype=torch.float64), **kw)
+            assert got.shape == want.shape and float((got - want).abs().max()) < 1e-12
+    finally:
+        _cabi._lib = None

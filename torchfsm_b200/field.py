@@ -5,7 +5,8 @@ from typing import Optional
 import torch
 
 from .mesh import FourierMesh, MeshGrid
-from .operator import Operator, Laplacian, ImplicitSource, ExplicitSource
+from . import _cabi
+from .operator import Operator, Laplacian, ImplicitSource, ExplicitSource, FusedStepper
 
 
 def diffused_noise(mesh, diffusion_coef: float = 1.0, zero_centered: bool = True, unit_variance: bool = False,
@@ -36,3 +37,36 @@ def diffused_noise(mesh, diffusion_coef: float = 1.0, zero_centered: bool = True
 def kolm_force(x: torch.Tensor, drag_coef: float = -0.1, k: float = 4.0, length_scale: float = 1.0) -> Operator:
     """Kolmogorov forcing in vorticity form: drag*w - k cos(k l x)   (field.py:128-148)"""
     return drag_coef * ImplicitSource() - ExplicitSource(k * torch.cos(k * length_scale * x))
+
+
+def truncated_fourier_series(mesh, freq_threshold: int = 5, amplitude_range=(-1.0, 1.0), angle_range=(0.0, 2.0 * torch.pi),
+                             zero_centered: bool = True, unit_variance: bool = False, unit_magnitude: bool = True,
+                             device=None, dtype=None, batch_size: int = 1, n_channel: int = 1) -> torch.Tensor:
+    """Random field with a truncated Fourier spectrum (field.py:62-125): random magnitudes and phases on the modes with
+    |f_i| <= freq_threshold, the real part of the inverse transform (Hermitian projection + C2R on the library), then the
+    same normalisations. Draws from torch's global generator in the reference's order, so a seed gives the same field."""
+    if unit_magnitude and unit_variance:
+        raise ValueError("Cannot set both unit_magnitude and unit_variance to True.")
+    if device is None and isinstance(mesh, (FourierMesh, MeshGrid)):
+        device = mesh.device
+    if dtype is None and isinstance(mesh, (FourierMesh, MeshGrid)):
+        dtype = mesh.dtype
+    f_mesh = mesh if isinstance(mesh, FourierMesh) else FourierMesh(mesh, device=device, dtype=dtype)
+    shape = [batch_size, n_channel] + list(f_mesh.shape)
+    magnitude = torch.rand(*shape, device=device, dtype=dtype) * (amplitude_range[1] - amplitude_range[0]) + amplitude_range[0]
+    angle = torch.rand(*shape, device=device, dtype=dtype) * (angle_range[1] - angle_range[0]) + angle_range[0]
+    mask = torch.ones(shape[2:], device=f_mesh.device, dtype=f_mesh.dtype)
+    for i in range(f_mesh.n_dim):                                       # mesh.py:463-479 (absolute frequency threshold)
+        mask = mask * torch.where(f_mesh.bf(i)[0, 0].abs() > freq_threshold, 0, 1)
+    noise_hat = (magnitude * torch.exp(1j * angle) * mask).to(f_mesh.device)
+    st = FusedStepper(f_mesh, batch_size, n_channel, _cabi.PROG_LINEAR, "RK4", 1.0, None, 0.0, None,
+                      [n // 2 for n in f_mesh.shape], True, {})
+    noise = st.c2r(st.full_to_half(noise_hat))
+    dims = list(range(1, noise.ndim))
+    if zero_centered:
+        noise = noise - noise.mean(dim=dims, keepdim=True)
+    if unit_variance:
+        noise = noise / noise.std(dim=dims, keepdim=True)
+    if unit_magnitude:
+        noise = noise / noise.abs().amax(dim=dims, keepdim=True)
+    return noise
