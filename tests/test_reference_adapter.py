@@ -102,9 +102,12 @@ def test_truncated_fourier_series_equals_the_reference_for_a_seed():
     torchfsm = _reference()
     if torchfsm is None:
         pytest.skip("reference not importable")
+    import torchfsm.field      # noqa: F401  (the reference's package does not import its submodules)
+    import torchfsm.mesh       # noqa: F401
     from product_util import build_emulator
     from torchfsm_b200 import _cabi
     import torchfsm_b200 as fsm
+    prev = (_cabi._lib, _cabi._lib_path)          # another module's fixture may own the loaded library (xdist)
     _cabi.use_library(build_emulator())
     try:
         for info, kw in [([(0, 1.0, 128)], dict(batch_size=3, freq_threshold=2)),
@@ -116,4 +119,4 @@ def test_truncated_fourier_series_equals_the_reference_for_a_seed():
             got = fsm.field.truncated_fourier_series(fsm.MeshGrid(info, dtype=torch.float64), **kw)
             assert got.shape == want.shape and float((got - want).abs().max()) < 1e-12
     finally:
-        _cabi._lib = None
+        _cabi._lib, _cabi._lib_path = prev
