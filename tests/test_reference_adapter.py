@@ -47,7 +47,28 @@ def reference_cases(torchfsm, device, dtype):
     m5 = MeshGrid([(0, 2 * np.pi, 16)] * 3, device=device, dtype=dtype)            # C5 shape
     op5 = NavierStokes(Re=100)
     op5.set_integrator(SETDRKIntegrator.SETDRK4)
-    out.append(("c5_ns3d", op5, m5, 0.3 * torch.randn(1, 3, 16, 16, 16, generator=g, dtype=dtype).to(device), 0.01, 3))
+    u5 = 0.3 * torch.randn(1, 3, 16, 16, 16, generator=g, dtype=dtype).to(device)
+    out.append(("c5_ns3d", op5, m5, u5, 0.01, 3))
+    # around the path: what the adapter translates through this package's own lowering
+    from torchfsm.operator import (Laplacian, Convection, ConservativeConvection, ImplicitSource, ExplicitSource,
+                                   NSPressureConvection)
+    from torchfsm.integrator import RKIntegrator
+    m4 = MeshGrid([(0, 1, 32), (0, 1, 16)], device=device, dtype=dtype)
+    u4 = 0.5 * torch.randn(2, 2, 32, 16, generator=g, dtype=dtype).to(device)
+    out.append(("conservative_convection2d", 0.01 * Laplacian() - ConservativeConvection(), m4, u4, 1e-3, 3))
+    out.append(("allen_cahn2d", 0.05 * Laplacian() + ImplicitSource(lambda u: u - u ** 3), m3,
+                torch.randn(2, 1, 32, 32, generator=g, dtype=dtype).to(device), 0.01, 3))
+    xx, yy, zz = m5.bc_mesh_grid()
+    body = torch.cat([0.3 * torch.sin(yy) * torch.cos(2 * zz) + 0 * xx, 0.2 * torch.cos(xx + zz) + 0 * yy,
+                      0.1 * torch.sin(2 * xx) * torch.sin(yy) + 0 * zz], dim=1)
+    opf = NSPressureConvection(ExplicitSource(body)) + 0.01 * Laplacian()
+    opf.set_integrator(ETDRKIntegrator.ETDRK2)
+    out.append(("ns3d_body_force", opf, m5, u5, 0.005, 3))
+    opr = 0.01 * Laplacian() - Convection()
+    opr.set_integrator(RKIntegrator.Dorpi45)
+    out.append(("burgers2d_dorpi45", opr, m4, u4, 2e-4, 3))
+    nu = torch.tensor([0.01, 0.03], dtype=dtype, device=device).reshape(2, 1, 1, 1)
+    out.append(("burgers2d_batched_nu", nu * Laplacian() - Convection(), m4, u4, 1e-3, 3))
     return out
 
 

@@ -19,7 +19,9 @@ from . import _cabi
 from .integrator import (ETDRKIntegrator, SETDRKIntegrator, RKIntegrator, RK_TABLEAUS, integrator_name, build_tables)
 from .mesh import FourierMesh, MeshGrid
 
-_LINEAR_KINDS = ("laplacian", "biharmonic", "spatial_derivative", "implicit_unit_source")
+# "linear_tensor": a ready-made L(k) tensor in the reference layout (what a genuine torchfsm operator registered,
+# reference_adapter.lower); time stepping only
+_LINEAR_KINDS = ("laplacian", "biharmonic", "spatial_derivative", "implicit_unit_source", "linear_tensor")
 # channel-changing cores that are pure symbol products: evaluated by the point-wise spectral map (fsm_spectral_map)
 _MAP_KINDS = ("grad", "div", "curl", "vorticity2velocity")
 # diagnostics composed of a map, one convection evaluation and a pressure solve
@@ -1002,7 +1004,7 @@ class OperatorLike:
                         f_hat = None
                         for ft in force.terms:
                             fs = ft.params["source"].to(device=f_mesh.device)
-                            fh = ft.coef * torch.fft.fftn(fs, dim=list(range(2, fs.dim())))
+                            fh = ft.coef * (fs if ft.params.get("in_fourier") else torch.fft.fftn(fs, dim=list(range(2, fs.dim()))))
                             f_hat = fh if f_hat is None else f_hat + fh
                         # the reference subtracts the force from the convection in place and then adds it once more
                         # (:241-254: `convection -= force` ... `- convection + force`): coef * (P(conv - f) + f) with
@@ -1017,7 +1019,7 @@ class OperatorLike:
                 external.append(t)
             elif t.kind == "explicit_source":
                 src = t.params["source"].to(device=f_mesh.device)
-                s_hat = torch.fft.fftn(src, dim=list(range(2, src.dim())))        # operator/_base.py:1002-1005
+                s_hat = src if t.params.get("in_fourier") else torch.fft.fftn(src, dim=list(range(2, src.dim())))   # _base.py:1002-1005
                 s_hat = t.coef * s_hat
                 source_hat = s_hat if source_hat is None else source_hat + s_hat
             else:
@@ -1087,6 +1089,8 @@ class OperatorLike:
                 per_term.append((1, [(0, 0, e(t.params["dim_index"], t.params["order"]), 0, c)]))
             elif k == "implicit_unit_source":
                 per_term.append((C, [(ch, ch, (0, 0, 0), 0, c) for ch in range(C)]))
+            elif k == "linear_tensor":
+                raise NotImplementedError("a tabulated linear symbol has no point-wise map form")
             else:
                 raise NotImplementedError(f"{k} cannot be summed with a channel-changing operator on the fused CUDA path")
         c_out = per_term[0][0]
@@ -1122,7 +1126,7 @@ class OperatorLike:
             return self._tf(B, n_channel).spectral_map(u_hat, lo["c_out"], lo["map"]), lo["c_out"]
         if "composite" in lo:
             return self._eval_composite(lo["composite"], u_hat, f_mesh, n_channel), 1
-        if self.is_linear and not any(isinstance(t.coef, torch.Tensor) for t in self.terms):
+        if self.is_linear and not any(isinstance(t.coef, torch.Tensor) or t.kind == "linear_tensor" for t in self.terms):
             # a purely linear operator is a point-wise map too; this route also takes odd-order derivatives on 2-D/3-D
             # grids, whose complex symbol the time-stepping tables refuse
             if "linear_map" not in lo:
@@ -1167,6 +1171,8 @@ class OperatorLike:
             return f_mesh.grad(t.params["dim_index"], t.params["order"])
         if t.kind == "implicit_unit_source":                                      # generic/_source.py:14-17
             return torch.ones_like(f_mesh.bf(0))
+        if t.kind == "linear_tensor":
+            return t.params["L"].to(f_mesh.device)
         raise ValueError(t.kind)
 
     def _pre_check(self, u, u_fft, mesh):
@@ -1459,7 +1465,7 @@ class OperatorLike:
         lo = self._lowered
         if "map" in lo or "composite" in lo:
             st_in, st_out = self._tf(B, n_channel), self._tf(B, lo["c_out"])
-        elif self.is_linear and not any(isinstance(t.coef, torch.Tensor) for t in self.terms):
+        elif self.is_linear and not any(isinstance(t.coef, torch.Tensor) or t.kind == "linear_tensor" for t in self.terms):
             st_in = st_out = self._tf(B, n_channel)
         else:
             st_in = getattr(self, "_rhs_stepper", None)

@@ -3,8 +3,9 @@
 ``lower(ref_operator, dt)`` inspects what the reference's own ``register_mesh`` produced (operator/_base.py:581-624)
 — the linear coefficient tensor it built with its own expressions (``_state_dict["linear_coef"]``, :339-357) and the
 nonlinear cores it collected (``_nonlinear_funcs``, pattern-matched by class: ``_ConvectionCore``,
-``_VorticityConvectionCore``, ``_KSConvectionCore``, ``_NSPressureConvectionCore``, ``_ExplicitSourceCore``) — and
-returns an object that speaks the integrator protocol the hot loop expects (``.dt``, ``.step(u_hat)``,
+``_ConservativeConvectionCore``, ``_VorticityConvectionCore``, ``_KSConvectionCore``, ``_NSPressureConvectionCore`` with its
+external force, ``_ExplicitSourceCore``, ``_ImplicitFuncSourceCore``) —, translates them into an operator of this
+package and lowers that with the package's own machinery. It returns an object that speaks the integrator protocol the hot loop expects (``.dt``, ``.step(u_hat)``,
 ``.forward(u_hat, dt)`` on full C2C spectra, operator/_base.py:462-491, 732-735) but advances the state with the
 fused sm_100a kernels through the C ABI (include/fsm_b200.h).
 
@@ -18,49 +19,63 @@ Nothing here imports ``torchfsm``: the adapter only looks at attributes of the o
 
 import torch
 
-from . import _cabi
-from .integrator import build_tables
+from .integrator import ETDRKIntegrator, SETDRKIntegrator, RKIntegrator
 from .mesh import FourierMesh
-from .operator import FusedStepper
+from .operator import Operator, _Term
 
-_PROGRAM_OF_CORE = {"_ConvectionCore": _cabi.PROG_CONVECTION, "_KSConvectionCore": _cabi.PROG_KS,
-                    "_VorticityConvectionCore": _cabi.PROG_NS2D_VORT, "_NSPressureConvectionCore": _cabi.PROG_NS3D}
+# reference core class -> term kind of this package (operator/generic/*.py, operator/dedicated/*.py, operator/_base.py)
+_KIND_OF_CORE = {"_ConvectionCore": "convection", "_ConservativeConvectionCore": "conservative_convection",
+                 "_KSConvectionCore": "ks_convection", "_VorticityConvectionCore": "vorticity_convection",
+                 "_NSPressureConvectionCore": "ns_pressure_convection", "_ExplicitSourceCore": "explicit_source",
+                 "_ImplicitFuncSourceCore": "implicit_func_source"}
 
 
-def _integrator_name(ref_op, linear: bool) -> str:
-    solver = ref_op._integrator
-    if isinstance(solver, str):                      # "auto": operator/_base.py:451-455
-        return "ETDRK0" if linear else "SETDRK4"
-    name = getattr(solver, "name", None)
-    if name not in _cabi.INTEGRATOR_IDS:
-        raise NotImplementedError(f"integrator {solver!r} is not supported by the fused CUDA path")
-    return name
+def translate(ref_op, f_mesh: FourierMesh, n_channel: int) -> Operator:
+    """A registered reference operator as an operator of this package: its linear coefficient tensor as it stands
+    (``_state_dict["linear_coef"]``, built by the reference's own expressions, operator/_base.py:339-357) plus one term per
+    nonlinear core it collected (``_nonlinear_funcs``, :359-406), recognised by class. An external force handed to
+    ``NSPressureConvection`` is itself a reference operator and is translated the same way."""
+    terms = []
+    L = ref_op._state_dict.get("linear_coef")
+    if L is not None:
+        terms.append(_Term("linear_tensor", 1, {"L": L}))
+    for coef, core in getattr(ref_op, "_nonlinear_funcs", []) or []:
+        cls = type(core).__name__
+        kind = _KIND_OF_CORE.get(cls)
+        if kind is None:
+            raise NotImplementedError(f"nonlinear core {cls} has no counterpart on the fused CUDA path")
+        params = {}
+        if kind == "ks_convection":
+            params["remove_mean"] = bool(core.remove_mean)
+        elif kind == "explicit_source":
+            params.update(source=core.source, in_fourier=True)          # already fftn(source), operator/_base.py:1002-1005
+        elif kind == "implicit_func_source":
+            params.update(source_func=core.source_func, non_linear=bool(getattr(core, "_dealiasing_swtich", True)))
+        elif kind == "ns_pressure_convection":
+            force = getattr(core, "external_force", None)
+            if force is not None:
+                if force._state_dict.get("f_mesh") is None:             # the reference registers it at its first evaluation
+                    force.register_mesh(ref_op._state_dict["f_mesh"], n_channel)
+                params["external_force"] = translate(force, f_mesh, n_channel)
+        elif not getattr(core, "_dealiasing_swtich", True):
+            raise NotImplementedError("convective cores without de-aliasing are not supported")
+        terms.append(_Term(kind, coef, params))
+    if not terms:
+        raise NotImplementedError("empty operator")
+    return Operator(terms)
 
 
 class LoweredIntegrator:
     """What ``install`` puts into ``_state_dict['integrator']`` of a reference operator. The reference's integrators
     are batch-agnostic; a plan is bound to a batch size, so steppers are created on first use per batch size."""
 
-    def __init__(self, f_mesh: FourierMesh, n_channel: int, program: int, integrator: str, dt: float, linear_coef,
-                 nl_coef: float, source_hat, kmax, ks_remove_mean: bool, cfg: dict):
-        self.dt = dt
-        self._args = (f_mesh, n_channel, program, integrator, dt, linear_coef, nl_coef, source_hat, kmax, ks_remove_mean, cfg)
-        self._steppers = {}
-        self._tables = None
+    def __init__(self, op: Operator, dt: float):
+        self.dt, self._op, self._steppers = dt, op, {}
 
-    def stepper(self, batch: int, allocate: bool = True) -> FusedStepper:
-        st = self._steppers.get(batch) if allocate else None
+    def stepper(self, batch: int):
+        st = self._steppers.get(batch)
         if st is None:
-            f_mesh, c, program, integ, dt, L, nl_coef, src, kmax, ks_mean, cfg = self._args
-            if self._tables is None:                 # built once with the reference's expressions (SURVEY.md H2)
-                Lt = L
-                if Lt is None:                        # operator/_base.py:473-478
-                    Lt = torch.tensor([0.0], dtype=f_mesh.cdtype, device=f_mesh.device).reshape([1] * (f_mesh.n_dim + 2))
-                self._tables = build_tables(integ, dt, Lt, **cfg)
-            st = FusedStepper(f_mesh, batch, c, program, integ, dt, L, nl_coef, src, kmax, ks_mean, cfg,
-                              tables=self._tables, allocate=allocate)
-            if allocate:
-                self._steppers[batch] = st
+            st = self._steppers[batch] = self._op._build_integrator(self.dt, batch)
         return st
 
     def step(self, u_hat_full: torch.Tensor) -> torch.Tensor:
@@ -77,51 +92,39 @@ class LoweredIntegrator:
 
 
 def lower(ref_op, dt: float) -> LoweredIntegrator:
-    """Pattern-match a registered reference operator into a fused step program. Raises ``NotImplementedError`` for
-    anything outside the fused programs (user ``NonlinearFunc`` subclasses, ``ImplicitSource(func)``, tensor
-    coefficients on nonlinear terms, adaptive RK, ...)."""
+    """Translate a registered reference operator (``translate``) and lower it with this package's own machinery: fused
+    programs, host-composed cores, external forces, per-sample coefficients, every ETD / RK integrator it supports. Raises
+    ``NotImplementedError`` for anything outside (user ``NonlinearFunc`` subclasses, adaptive RK, unsupported grids, ...)."""
     sd = ref_op._state_dict
     ref_mesh = sd.get("f_mesh")
     if ref_mesh is None:
         raise ValueError("register_mesh must run before lowering (operator/_base.py:581-624)")
     n_channel = sd["n_channel"]
     f_mesh = FourierMesh([tuple(m) for m in ref_mesh.mesh_info], device=ref_mesh.device, dtype=ref_mesh.dtype)
-    if getattr(ref_op, "_integrator_config", {}).get("adaptive"):
+    cfg = dict(getattr(ref_op, "_integrator_config", {}) or {})
+    if cfg.get("adaptive"):
         raise NotImplementedError("adaptive Runge-Kutta stepping is host-synchronous and stays on the torch path")
-    program, nl_coef, ks_remove_mean, source_hat = _cabi.PROG_LINEAR, 0.0, True, None
-    for coef, core in getattr(ref_op, "_nonlinear_funcs", []):
-        cls = type(core).__name__
-        if cls in _PROGRAM_OF_CORE:
-            if program != _cabi.PROG_LINEAR:
-                raise NotImplementedError("only one convective nonlinear term per operator is supported")
-            if isinstance(coef, torch.Tensor):
-                raise NotImplementedError("tensor-valued coefficients on nonlinear terms are not supported")
-            program, nl_coef = _PROGRAM_OF_CORE[cls], float(coef)
-            if cls == "_KSConvectionCore":
-                ks_remove_mean = bool(core.remove_mean)
-            if cls == "_NSPressureConvectionCore" and core.external_force is not None:
-                raise NotImplementedError("NSPressureConvection with an external force is not supported")
-            if not getattr(core, "_dealiasing_swtich", True):
-                raise NotImplementedError("convective cores without de-aliasing are not supported")
-        elif cls == "_ExplicitSourceCore":
-            s_hat = coef * core.source.to(f_mesh.device)             # operator/_base.py:1002-1015
-            source_hat = s_hat if source_hat is None else source_hat + s_hat
+    op = translate(ref_op, f_mesh, n_channel)
+    op._de_aliasing_rate = getattr(ref_op, "_de_aliasing_rate", 2 / 3)
+    solver = ref_op._integrator
+    if isinstance(solver, str):
+        op.set_integrator("auto")
+    else:
+        name = getattr(solver, "name", None)
+        for enum in (ETDRKIntegrator, SETDRKIntegrator, RKIntegrator):
+            if name in enum.__members__:
+                op.set_integrator(enum[name], **{k: v for k, v in cfg.items()
+                                                 if k in ("n_integration_points", "integration_radius", "cpu_cached")})
+                break
         else:
-            raise NotImplementedError(f"nonlinear core {cls} has no fused program")
+            raise NotImplementedError(f"integrator {solver!r} is not supported by the fused CUDA path")
+    op.register_mesh(f_mesh, n_channel)
+    low = LoweredIntegrator(op, dt)
+    # building a plan validates the configuration now (NotImplementedError if unsupported); per-sample coefficients fix
+    # the batch, otherwise one sample is enough for the check
     L = sd.get("linear_coef")
-    # an explicit source is a nonlinear core in the reference: "auto" picks SETDRK4 for it (operator/_base.py:451-455)
-    name = _integrator_name(ref_op, program == _cabi.PROG_LINEAR and source_hat is None)
-    if name == "ETDRK0" and program != _cabi.PROG_LINEAR:
-        raise AssertionError("The ETDRK0 integrator only supports linear term")
-    rate = getattr(ref_op, "_de_aliasing_rate", 2 / 3)
-    kmax = f_mesh.low_pass_kmax(rate) if program != _cabi.PROG_LINEAR else [n // 2 for n in f_mesh.shape]
-    if program == _cabi.PROG_NS3D and any(k >= n // 2 and n % 2 == 0 for k, n in zip(kmax, f_mesh.shape)):
-        raise NotImplementedError("NSPressureConvection needs a de-aliasing rate below 1 on the fused path")
-    cfg = {k: v for k, v in getattr(ref_op, "_integrator_config", {}).items()
-           if k in ("n_integration_points", "integration_radius", "cpu_cached")}
-    low = LoweredIntegrator(f_mesh, n_channel, program, name, dt, L, nl_coef, source_hat, kmax, ks_remove_mean, cfg)
-    # plan creation validates the configuration now (NotImplementedError if unsupported); no workspace is allocated
-    low.stepper(L.shape[0] if (L is not None and L.shape[0] > 1) else 1, allocate=False)   # per-sample coefficients fix the batch
+    nb = L.shape[0] if (L is not None and L.shape[0] > 1) else 1
+    low._steppers[nb] = op._build_integrator(dt, nb)
     return low
 
 
