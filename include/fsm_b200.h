@@ -102,6 +102,8 @@ typedef struct fsm_desc {
     const void* force_hat;    /* FSM_PROG_NS3D only: constant spectrum added to coef * conv_hat BEFORE the pressure
                                  projection, complex [C][modes] = -coef * f_hat of NSPressureConvection(external_force)
                                  for a force that does not depend on u (_navier_stokes.py:237-254) */
+    const void* nl_coef_b;    /* optional per-sample coefficient of the convective term, real [batch] in the plan dtype
+                                 (tensor-valued coefficient, operator/_base.py:375-403); replaces nl_coef when set */
 } fsm_desc;
 
 /* replaces: OperatorLike._build_integrator (operator/_base.py:441-526) */

@@ -209,6 +209,14 @@ OPS_CASES = [
          terms=[("laplacian", [0.01, 0.02, 0.05], {"_ndim": 2}), ("convection", -1, {})], integrator="ETDRK2", dt=0.002, steps=3),
     dict(name="burgers1d_batched_nu_setdrk4", mode="integrate", mesh=_m((64,), 1.0), B=3, C=1,
          terms=[("laplacian", [0.01, 0.02, 0.05], {"_ndim": 1}), ("convection", -1, {})], integrator="auto", dt=0.002, steps=3),
+    dict(name="burgers2d_batched_convection_coef", mode="integrate", mesh=_m((32, 16), 1.0, 1.0), B=3, C=2,
+         terms=[("laplacian", 0.01, {}), ("convection", [-1.0, -0.5, -2.0], {"_ndim": 2})], integrator="ETDRK2", dt=0.002, steps=3),
+    dict(name="kdv1d_batched_convection_coef", mode="integrate", mesh=_m((64,), 20.0), B=2, C=1,
+         terms=[("spatial_derivative", -1, {"dim_index": 0, "order": 3}), ("convection", [6.0, 3.0], {"_ndim": 1})],
+         integrator="auto", dt=0.001, steps=3),
+    dict(name="ns3d_batched_coef_setdrk4", mode="integrate", mesh=_m((16, 8, 16), TWO_PI, TWO_PI, TWO_PI), B=2, C=3,
+         terms=[("ns_pressure_convection", [1.0, 0.5], {"_ndim": 3}), ("laplacian", 1 / 100, {})], integrator="auto",
+         dt=0.0025, steps=3),
     dict(name="ks2d_batched_setdrk4", mode="integrate", mesh=_m((32, 32), 30.0, 30.0), B=2, C=1,
          terms=[("laplacian", [-1.0, -0.9], {"_ndim": 2}), ("biharmonic", -1, {}), ("ks_convection", -1, {})],
          integrator="SETDRK4", dt=0.05, steps=3),

@@ -31,7 +31,7 @@ class FsmDesc(ctypes.Structure):
         ("tab_lin", ctypes.c_void_p), ("source_hat", ctypes.c_void_p),
         ("slab_rank", ctypes.c_int32), ("slab_nranks", ctypes.c_int32),
         ("lanes", ctypes.c_int32), ("tab_batched", ctypes.c_int32),
-        ("force_hat", ctypes.c_void_p),
+        ("force_hat", ctypes.c_void_p), ("nl_coef_b", ctypes.c_void_p),
     ]
 
 

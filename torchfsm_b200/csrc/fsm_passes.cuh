@@ -1541,6 +1541,8 @@ struct Combine {
 template <typename T>
 struct FxEpilogue {
     T nl_coef;                     // scalar coefficient of the convective term
+    const T* nl_coef_b;            // optional per-sample coefficient [B] (tensor-valued coefficient on the nonlinear term,
+                                   // operator/_base.py:375-403: `result += coef * fun(...)`); replaces nl_coef
     const cplx<T>* source;         // optional constant source spectrum [C][nmodes] (coef folded in)
     T* dc_out;                     // KS: per-sample zero-mode of the nonlinear term (captured, then zeroed)
     int project;                   // NS pressure projection (2-D and 3-D velocity form)
@@ -1825,11 +1827,12 @@ k_pass_fx(Geom<T> g, const cplx<T>* __restrict__ win, long win_fstride,
         if constexpr (kPipe && mb + NB < EPT)
             combine_load<T, NB, KIND>(cb, b * g.nmodes, b * cb.tab_bstride, line_mode0 + tau + (mb + NB) * TL, TL, opq[cur ^ 1]);
         cplx<T> f[C][NB];
+        const T nlc = ep.nl_coef_b ? ep.nl_coef_b[b] : ep.nl_coef;
         FSM_UNROLL
         for (int j = 0; j < NB; ++j) {
             const int p = tau + (mb + j) * TL;
             FSM_UNROLL
-            for (int c = 0; c < C; ++c) f[c][j] = cscale(nhat[c][mb + j], ep.nl_coef);
+            for (int c = 0; c < C; ++c) f[c][j] = cscale(nhat[c][mb + j], nlc);
             if constexpr (C == 3 || C == 2) {
                 if (ep.project) {
                     // result_i = (ik_i) lap^-1 sum_j (ik_j) c_j - c_i   (_navier_stokes.py:249-254), with the
@@ -1990,7 +1993,7 @@ __global__ void __launch_bounds__(Cfg::TL) k_step1d(Geom<T> g, StageList<T> sl, 
             for (int m = 0; m < EPT; ++m) {
                 const int p = tau + m * TL;
                 if (p <= N / 2) {
-                    cplx<T> f = cscale(v[m], ep.nl_coef);
+                    cplx<T> f = cscale(v[m], ep.nl_coef_b ? ep.nl_coef_b[b] : ep.nl_coef);
                     if (ep.source) f = f + ep.source[p];
                     combine_mode<T>(cb, f, boff, b * cb.tab_bstride, p);
                 }

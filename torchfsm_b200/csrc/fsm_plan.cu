@@ -439,7 +439,7 @@ int run_forward_tail(const fsm_plan* p, const Buffers<T>& bf, const Geom<T>& g, 
     f.nlines = (int)(p->nmodes / p->n[0]); f.b0 = b0; f.nb = nb;
     // independent channels (no projection, no per-channel table or source): run them as separate
     // single-channel fields -> no three-channel register tile, C times the parallelism
-    if (C > 1 && !ep.project && !ep.source && !ep.dc_out && cb.tab_cstride == 0 && cb.tab_bstride == 0) {
+    if (C > 1 && !ep.project && !ep.source && !ep.dc_out && !ep.nl_coef_b && cb.tab_cstride == 0 && cb.tab_bstride == 0) {
         f.b0 = b0 * C; f.nb = nb * C;
         C = 1;
     }
@@ -486,6 +486,7 @@ int run_stage(const fsm_plan* p, const Buffers<T>& bf, const Stage& s, cudaStrea
     const LaunchTable<T>* ty = (p->ndim == 3) ? launch_table<T>(p->n[1]) : nullptr;
     FxEpilogue<T> ep;
     ep.nl_coef = (T)p->d.nl_coef;
+    ep.nl_coef_b = static_cast<const T*>(p->d.nl_coef_b);
     ep.source = static_cast<const cplx<T>*>(p->d.source_hat);
     ep.dc_out = (p->prog == FSM_PROG_KS && p->d.ks_remove_mean) ? bf.dc : nullptr;
     ep.project = (p->prog == FSM_PROG_NS3D) ? 1 : 0;
@@ -553,6 +554,7 @@ int run_1d(const fsm_plan* p, const Buffers<T>& bf, const Stage* stages, int n_s
         if (int e = make_combine<T>(p, stages[i], bf.arr, true, &a.sl.cb[i])) return e;
     }
     a.ep.nl_coef = (T)p->d.nl_coef;
+    a.ep.nl_coef_b = static_cast<const T*>(p->d.nl_coef_b);
     a.ep.source = static_cast<const cplx<T>*>(p->d.source_hat);
     a.ep.dc_out = nullptr;
     a.ep.project = 0;
@@ -656,7 +658,7 @@ int do_r2c(fsm_plan* p, const void* u, void* u_hat, void* ws, cudaStream_t st) {
         tmp.d.tab_channels = 1;
         if (int e = make_combine<T>(&tmp, s, arr, true, &cb)) return e;
         FxEpilogue<T> ep;
-        ep.nl_coef = T(1); ep.source = nullptr; ep.dc_out = nullptr; ep.project = 0; ep.force = nullptr; ep.force_dyn = nullptr;
+        ep.nl_coef = T(1); ep.nl_coef_b = nullptr; ep.source = nullptr; ep.dc_out = nullptr; ep.project = 0; ep.force = nullptr; ep.force_dyn = nullptr;
         if (int e = run_forward_tail<T>(p, bf, g, 1, 1, cb, ep, 0, nf, st)) return e;
     }
     return 0;
@@ -854,6 +856,7 @@ int do_slab_phase(fsm_plan* p, int op, int stage, int phase, int sub, int nsub, 
         if (int e = make_combine<T>(p, s, bf.arr, true, &cb)) return e;
         FxEpilogue<T> ep;
         ep.nl_coef = (T)p->d.nl_coef;
+        ep.nl_coef_b = static_cast<const T*>(p->d.nl_coef_b);
         ep.source = static_cast<const cplx<T>*>(p->d.source_hat);
         ep.dc_out = nullptr;
         ep.project = (p->prog == FSM_PROG_NS3D) ? 1 : 0;
@@ -877,7 +880,7 @@ int do_slab_phase(fsm_plan* p, int op, int stage, int phase, int sub, int nsub, 
         tmp.d.tab_channels = 1;
         if (int e = make_combine<T>(&tmp, s, bf.arr, true, &cb)) return e;
         FxEpilogue<T> ep;
-        ep.nl_coef = T(1); ep.source = nullptr; ep.dc_out = nullptr; ep.project = 0; ep.force = nullptr; ep.force_dyn = nullptr;
+        ep.nl_coef = T(1); ep.nl_coef_b = nullptr; ep.source = nullptr; ep.dc_out = nullptr; ep.project = 0; ep.force = nullptr; ep.force_dyn = nullptr;
         return slab_fx<T>(p, g, rcv, 1, nf, cb, ep, 1, st);
     }
     if (op == FSM_SLAB_C2R) {
@@ -1004,6 +1007,10 @@ int fsm_plan_create(fsm_plan** out, const fsm_desc* d) {
     if (p->prog != FSM_PROG_LINEAR && d->integrator == FSM_INT_ETDRK0) {
         delete p;
         return fail(-EINVAL, "The ETDRK0 integrator only supports linear term");
+    }
+    if (d->nl_coef_b && (d->force_hat || d->dynamic_force)) {
+        delete p;
+        return fail(-ENOSYS, "a per-sample coefficient on NS pressure convection cannot be combined with an external force");
     }
     if (d->force_hat && p->prog != FSM_PROG_NS3D) {
         delete p;

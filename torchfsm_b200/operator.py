@@ -120,7 +120,8 @@ class FusedStepper:
                  linear_coef: Optional[torch.Tensor], nl_coef: float, source_hat: Optional[torch.Tensor],
                  kmax: Sequence[int], ks_remove_mean: bool, integrator_cfg: dict, chunk: int = 0,
                  tables: Optional[dict] = None, slab=None, lanes: int = 0, allocate: bool = True,
-                 force_hat: Optional[torch.Tensor] = None, dynamic_force: bool = False):
+                 force_hat: Optional[torch.Tensor] = None, dynamic_force: bool = False,
+                 nl_coef_b: Optional[torch.Tensor] = None):
         lib = _GuardedLib(_cabi.lib(), f_mesh.device)
         # slab = (rank, nranks, process_group): ONE 3-D grid decomposed over nranks GPUs
         self.slab = slab
@@ -193,6 +194,12 @@ class FusedStepper:
         desc.dt = float(dt)
         desc.nl_coef = float(nl_coef)
         desc.dynamic_force = 1 if dynamic_force else 0
+        if nl_coef_b is not None:             # tensor-valued coefficient of the convective term: one value per sample
+            nl_coef_b = nl_coef_b.to(device=f_mesh.device, dtype=self.rdtype).reshape(-1).contiguous()
+            if nl_coef_b.numel() != batch:
+                raise ValueError("a batched coefficient must have one entry per sample")
+            self._keep.append(nl_coef_b)
+            desc.nl_coef_b = nl_coef_b.data_ptr()
         dk, dkraw = f_mesh.wavenumber_tables()
         for i in range(self.n_dim):
             self._keep += [dk[i], dkraw[i]]
@@ -962,7 +969,7 @@ class OperatorLike:
             return
         lin = []
         program, nl_coef, ks_remove_mean = _cabi.PROG_LINEAR, 0.0, True
-        source_hat = force_hat = dyn_force = None
+        source_hat = force_hat = dyn_force = nl_coef_b = None
         external = []
         for t in self.terms:
             if t.kind in _LINEAR_KINDS:
@@ -978,9 +985,15 @@ class OperatorLike:
                 if program != _cabi.PROG_LINEAR:
                     raise NotImplementedError("only one convective nonlinear term per operator is supported "
                                               "by the fused CUDA path")
-                if isinstance(t.coef, torch.Tensor):
-                    raise NotImplementedError("tensor-valued coefficients on nonlinear terms are not supported")
-                program, nl_coef = _PROGRAM_OF[t.kind], float(t.coef)
+                if isinstance(t.coef, torch.Tensor):          # one coefficient per sample (operator/_base.py:375-403)
+                    if t.coef.numel() != t.coef.shape[0]:
+                        raise NotImplementedError("tensor-valued coefficients on nonlinear terms must be per-sample scalars")
+                    if t.kind == "ns_pressure_convection" and t.params.get("external_force") is not None:
+                        raise NotImplementedError("a per-sample coefficient on NSPressureConvection cannot be combined "
+                                                  "with an external force")
+                    program, nl_coef, nl_coef_b = _PROGRAM_OF[t.kind], 1.0, t.coef
+                else:
+                    program, nl_coef = _PROGRAM_OF[t.kind], float(t.coef)
                 if t.kind == "convection" and f_mesh.n_dim != n_channel:
                     raise ValueError("convection operator only works for vector field with the same dimension as mesh")
                 if t.kind == "vorticity_convection" and (f_mesh.n_dim != 2 or n_channel != 1):
@@ -1013,7 +1026,7 @@ class OperatorLike:
                         source_hat = float(t.coef) * f_hat if source_hat is None else source_hat + float(t.coef) * f_hat
             elif t.kind in _EXTERNAL_KINDS:
                 if isinstance(t.coef, torch.Tensor):
-                    raise NotImplementedError("tensor-valued coefficients on nonlinear terms are not supported")
+                    raise NotImplementedError("tensor-valued coefficients on host-composed nonlinear terms are not supported")
                 if t.kind == "conservative_convection" and f_mesh.n_dim != n_channel:
                     raise ValueError("div operator only works for vector field with the same dimension as mesh")
                 external.append(t)
@@ -1040,7 +1053,8 @@ class OperatorLike:
                                       "(rate < 1) on the fused CUDA path")
         self._state_dict["linear_coef"] = L
         self._lowered = dict(program=program, nl_coef=nl_coef, ks_remove_mean=ks_remove_mean,
-                             source_hat=source_hat, force_hat=force_hat, kmax=kmax, external=external, dyn_force=dyn_force)
+                             source_hat=source_hat, force_hat=force_hat, kmax=kmax, external=external, dyn_force=dyn_force,
+                             nl_coef_b=nl_coef_b)
 
     def _lower_map(self, f_mesh: FourierMesh, n_channel: int):
         """Operators made of symbol products only (Grad, Div, Curl, Vorticity2Velocity, optionally summed with linear
@@ -1288,7 +1302,7 @@ class OperatorLike:
             st = cls(sd["f_mesh"], batch, sd["n_channel"], lo["program"], name, dt, sd["linear_coef"],
                      lo["nl_coef"], lo["source_hat"], lo["kmax"], lo["ks_remove_mean"], cfg,
                      chunk=self._chunk, tables=tables, slab=self._slab, lanes=self._lanes,
-                     force_hat=lo["force_hat"], **extra)
+                     force_hat=lo["force_hat"], nl_coef_b=lo.get("nl_coef_b"), **extra)
         except torch.cuda.OutOfMemoryError as e:
             raise RuntimeError(os.linesep.join([
                 "Cuda out of memory when building the integrator.",
