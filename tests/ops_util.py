@@ -117,7 +117,7 @@ def build_operator(ops, terms, sources, dtype, device="cpu"):
         else:
             raise ValueError(kind)
         if isinstance(coef, (list, tuple)):
-            nd = params.get("_ndim")
+            nd = params.pop("_ndim")
             c = torch.tensor(coef, dtype=dtype, device=device)
             coef = c.reshape([len(coef), 1] + [1] * nd)
         t = coef * t
@@ -217,6 +217,9 @@ OPS_CASES = [
     dict(name="ns3d_batched_coef_setdrk4", mode="integrate", mesh=_m((16, 8, 16), TWO_PI, TWO_PI, TWO_PI), B=2, C=3,
          terms=[("ns_pressure_convection", [1.0, 0.5], {"_ndim": 3}), ("laplacian", 1 / 100, {})], integrator="auto",
          dt=0.0025, steps=3),
+    dict(name="conscon2d_batched_coef_etdrk2", mode="integrate", mesh=_m((32, 16), 1.0, 1.0), B=2, C=2,
+         terms=[("laplacian", 0.01, {}), ("conservative_convection", [-1.0, -0.5], {"_ndim": 2})], integrator="ETDRK2",
+         dt=0.002, steps=3),
     dict(name="ks2d_batched_setdrk4", mode="integrate", mesh=_m((32, 32), 30.0, 30.0), B=2, C=1,
          terms=[("laplacian", [-1.0, -0.9], {"_ndim": 2}), ("biharmonic", -1, {}), ("ks_convection", -1, {})],
          integrator="SETDRK4", dt=0.05, steps=3),

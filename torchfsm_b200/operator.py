@@ -978,8 +978,8 @@ class OperatorLike:
                 # no fused 1-D program for 1/2 (phi_x)^2: composed on the host from the library's passes
                 if n_channel != 1:
                     raise NotImplementedError("KSConvection only supports scalar field")
-                if isinstance(t.coef, torch.Tensor):
-                    raise NotImplementedError("tensor-valued coefficients on nonlinear terms are not supported")
+                if isinstance(t.coef, torch.Tensor) and t.coef.numel() != t.coef.shape[0]:
+                    raise NotImplementedError("tensor-valued coefficients on nonlinear terms must be per-sample scalars")
                 external.append(t)
             elif t.kind in _PROGRAM_OF:
                 if program != _cabi.PROG_LINEAR:
@@ -1025,8 +1025,8 @@ class OperatorLike:
                         force_hat = -float(t.coef) * f_hat
                         source_hat = float(t.coef) * f_hat if source_hat is None else source_hat + float(t.coef) * f_hat
             elif t.kind in _EXTERNAL_KINDS:
-                if isinstance(t.coef, torch.Tensor):
-                    raise NotImplementedError("tensor-valued coefficients on host-composed nonlinear terms are not supported")
+                if isinstance(t.coef, torch.Tensor) and t.coef.numel() != t.coef.shape[0]:
+                    raise NotImplementedError("tensor-valued coefficients on nonlinear terms must be per-sample scalars")
                 if t.kind == "conservative_convection" and f_mesh.n_dim != n_channel:
                     raise ValueError("div operator only works for vector field with the same dimension as mesh")
                 external.append(t)
@@ -1230,6 +1230,13 @@ class OperatorLike:
         need_plain = any(t.kind == "implicit_func_source" and not t.params.get("non_linear", True) for t in terms)
         pairs = [(a, c) for a in range(n_channel) for c in range(a, n_channel)]
 
+        def scaled(r, coef, extra=1.0):
+            """coef * r for a number or a per-sample tensor (B, 1, 1, ..) -> (B, 1, 1) on the half-spectrum layout"""
+            if isinstance(coef, torch.Tensor):
+                return r * (coef.reshape(-1, 1, 1).to(device=r.device, dtype=r.real.dtype) * extra)
+            c = float(coef) * extra
+            return r if c == 1.0 else r * c
+
         def evaluate(st, x_hat):
             u_d = st.c2r(st.mask_state(x_hat.clone())) if need_masked else None
             u = st.c2r(x_hat) if need_plain else None
@@ -1239,20 +1246,19 @@ class OperatorLike:
                     v = t.params["source_func"](u_d if t.params.get("non_linear", True) else u)
                     if v.shape != (st.B, st.C) + tuple(st.local_shape):
                         raise ValueError("ImplicitSource: source_func must keep the shape of its argument")
-                    r = st.r2c(v)
-                    r = r * float(t.coef) if float(t.coef) != 1.0 else r
+                    r = scaled(st.r2c(v), t.coef)
                 elif t.kind == "ks_convection":                          # dedicated/_ks_convection.py:18-38 on a 1-D grid
                     g_hat = st.spectral_map(x_hat, 1, [(0, 0, (1, 0, 0), 0, 1.0)], dealias=True)      # i k phi_hat, dealiased
                     r = st.r2c(st.sym_outer(st.c2r(g_hat)))              # (phi_x)^2
                     if t.params.get("remove_mean", True):                # the mean spans batch and space: zero modes only
                         r[:, :, 0] -= r[:, :, 0].mean()
-                    r = r * (0.5 * float(t.coef))
+                    r = scaled(r, t.coef, 0.5)
                 else:                                                    # generic/_conservative_convection.py:18-27
                     uu_hat = self._tf(st.B, len(pairs)).r2c(st.sym_outer(u_d))
                     e = [tuple(1 if i == a else 0 for i in range(3)) for a in range(d)]
-                    m = [(c, pairs.index((min(i, c), max(i, c))), e[i], 0, float(t.coef))
+                    m = [(c, pairs.index((min(i, c), max(i, c))), e[i], 0, 1.0)
                          for c in range(n_channel) for i in range(d)]
-                    r = self._tf(st.B, len(pairs)).spectral_map(uu_hat, n_channel, m)
+                    r = scaled(self._tf(st.B, len(pairs)).spectral_map(uu_hat, n_channel, m), t.coef)
                 out = r if out is None else out.add_(r)
             return out
         return evaluate
