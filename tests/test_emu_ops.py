@@ -77,5 +77,7 @@ def test_linear_operators_and_maps_are_differentiable():
     assert torch.autograd.gradcheck(lambda x: fsm.Grad()(x, mesh=small), (u,), eps=1e-6, atol=1e-7)
     diff = 0.05 * fsm.Laplacian()
     assert torch.autograd.gradcheck(lambda x: diff.integrate(x, mesh=small, dt=0.1, step=3), (u,), eps=1e-6, atol=1e-7)
-    with pytest.raises(NotImplementedError):
-        fsm.pde.Burgers(0.01).integrate(torch.zeros(1, 2, 8, 8, dtype=torch.float64, requires_grad=True), mesh=small, dt=0.1, step=1)
+    # nonlinear operators are differentiated by gradient mode (tests/test_autograd_nonlinear.py)
+    ub = (0.1 * torch.randn(1, 2, 8, 8, dtype=torch.float64)).requires_grad_(True)
+    assert torch.autograd.gradcheck(lambda x: fsm.pde.Burgers(0.01).integrate(x, mesh=small, dt=0.01, step=2), (ub,),
+                                    eps=1e-6, atol=1e-7)

@@ -1198,9 +1198,8 @@ class OperatorLike:
         assert mesh is not None, "Mesh should be given"
         value = u if u is not None else u_fft
         if value.requires_grad and not getattr(self, "_autograd_ok", False):
-            raise NotImplementedError("the fused CUDA path differentiates linear operators and point-wise spectral maps "
-                                      "only (their adjoint is the same kernels with the conjugate symbol); detach the "
-                                      "input of a nonlinear operator first")
+            raise NotImplementedError("gradients are available through integrate(u_0) and operator(u) with real-space "
+                                      "inputs only (no u_fft / return_in_fourier / recorder); detach the input first")
         if not isinstance(mesh, FourierMesh):
             if isinstance(mesh, MeshGrid):
                 mesh = FourierMesh(mesh, device=value.device, dtype=mesh.dtype)
@@ -1251,15 +1250,22 @@ class OperatorLike:
                     g_hat = st.spectral_map(x_hat, 1, [(0, 0, (1, 0, 0), 0, 1.0)], dealias=True)      # i k phi_hat, dealiased
                     r = st.r2c(st.sym_outer(st.c2r(g_hat)))              # (phi_x)^2
                     if t.params.get("remove_mean", True):                # the mean spans batch and space: zero modes only
-                        r[:, :, 0] -= r[:, :, 0].mean()
+                        if r.requires_grad:
+                            dc = torch.zeros_like(r)
+                            dc[:, :, 0] = 1.0
+                            r = r - dc * r[:, :, 0].mean()
+                        else:
+                            r[:, :, 0] -= r[:, :, 0].mean()
                     r = scaled(r, t.coef, 0.5)
                 else:                                                    # generic/_conservative_convection.py:18-27
-                    uu_hat = self._tf(st.B, len(pairs)).r2c(st.sym_outer(u_d))
+                    # gradient mode hands in a differentiable view of the same passes (autograd._HostView)
+                    tf = st.other(len(pairs)) if hasattr(st, "other") else self._tf(st.B, len(pairs))
+                    uu_hat = tf.r2c(st.sym_outer(u_d))
                     e = [tuple(1 if i == a else 0 for i in range(3)) for a in range(d)]
                     m = [(c, pairs.index((min(i, c), max(i, c))), e[i], 0, 1.0)
                          for c in range(n_channel) for i in range(d)]
-                    r = scaled(self._tf(st.B, len(pairs)).spectral_map(uu_hat, n_channel, m), t.coef)
-                out = r if out is None else out.add_(r)
+                    r = scaled(tf.spectral_map(uu_hat, n_channel, m), t.coef)
+                out = r if out is None else (out + r if r.requires_grad else out.add_(r))
             return out
         return evaluate
 
@@ -1500,7 +1506,8 @@ class OperatorLike:
     # ---- differentiable linear paths ------------------------------------------------------------
     def _call_with_grad(self, u, mesh):
         """``operator(u)`` with ``u.requires_grad``: linear operators and point-wise spectral maps (Grad, Div, Curl,
-        Vorticity2Velocity, sums with linear cores) are differentiated by running the adjoint map on the cotangent."""
+        Vorticity2Velocity, sums with linear cores) are differentiated by running the adjoint map on the cotangent;
+        nonlinear operators through gradient mode (autograd.py)."""
         self._autograd_ok = True
         try:
             if self._state_dict["f_mesh"] is None or mesh is not None or self._lowered is None:
@@ -1515,9 +1522,15 @@ class OperatorLike:
             c_out, terms = lo["c_out"], lo["map"]
         elif "composite" not in lo and self.is_linear and not any(isinstance(t.coef, torch.Tensor) for t in self.terms):
             c_out, terms = self._lower_map(self._state_dict["f_mesh"], n_channel)
-        else:
-            raise NotImplementedError("only linear operators and point-wise spectral maps are differentiable on the fused "
-                                      "CUDA path; detach the input of a nonlinear operator first")
+        elif "composite" in lo:
+            raise NotImplementedError("Velocity2Pressure / Vorticity2Pressure are not differentiable on the CUDA path; "
+                                      "detach their input first")
+        else:                       # nonlinear (or per-sample linear) right-hand side: unrolled on the library's passes
+            from .autograd import GradientMode
+            st = getattr(self, "_rhs_stepper", None)
+            if st is None or st.B != B or st.f_mesh is not self._state_dict["f_mesh"]:
+                st = self._build_integrator(1.0, B, rhs_only=True)
+            return GradientMode(self, st).evaluate(u)
         adj = _adjoint_map_terms(terms)
 
         def run(x, c_in, c_to, tt):
@@ -1526,8 +1539,9 @@ class OperatorLike:
         return _LinearFn.apply(u, lambda x: run(x, n_channel, c_out, terms), lambda g: run(g, c_out, n_channel, adj))
 
     def _integrate_with_grad(self, u_0, dt, step, mesh):
-        """``integrate(u_0)`` of a purely linear operator with real tables (exp(L dt) real: even-order terms): the step
-        is self-adjoint, so the cotangent is integrated by the same plan."""
+        """``integrate(u_0)`` with ``u_0.requires_grad``. A purely linear operator with real tables (exp(L dt) real:
+        even-order terms) is self-adjoint, so the cotangent is integrated by the same fused plan; everything else goes
+        through gradient mode (autograd.py)."""
         self._autograd_ok = True
         try:
             st = self._stepper_for((u_0, None), mesh, dt)
@@ -1536,8 +1550,10 @@ class OperatorLike:
         lo = self._lowered
         if lo.get("program") != _cabi.PROG_LINEAR or lo.get("source_hat") is not None or lo.get("external") or st.complex_tables \
                 or st.integrator != "ETDRK0":
-            raise NotImplementedError("only linear operators (ETDRK0, real symbol) are differentiable through integrate() "
-                                      "on the fused CUDA path; detach the input of a nonlinear operator first")
+            # nonlinear operators: the step is unrolled on the library's transform and symbol kernels, each with its
+            # adjoint pass as backward (torchfsm_b200/autograd.py)
+            from .autograd import GradientMode
+            return GradientMode(self, st).integrate(u_0, step)
 
         def run(x):
             return st.c2r(st.step_half(st.r2c(x), step))
