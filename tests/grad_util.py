@@ -28,6 +28,9 @@ GRAD_CASES = [
     dict(name="ns2d_velocity_setdrk1", op="ns3d", mesh=[(0, 1, 16), (0, 1, 16)], C=2, integrator="SETDRK1", dt=0.005),
     dict(name="allen_cahn2d_etdrk2", op="allen_cahn", mesh=[(0, 1, 16), (0, 1, 16)], C=1, integrator="ETDRK2", dt=0.01),
     dict(name="conservative2d_setdrk2", op="conservative", mesh=[(0, 1, 16), (0, 1, 16)], C=2, integrator="SETDRK2", dt=0.005),
+    # complex linear symbol on a 2-D grid (paired half spectra, torchfsm_b200/unrolled.py); rough data: Nyquist planes matter
+    dict(name="beta_plane2d_setdrk4", op="beta_plane", mesh=[(0, TWO_PI, 16), (0, TWO_PI, 16)], C=1, integrator="SETDRK4",
+         dt=0.01, rough=0.2),
     dict(name="burgers2d_rk4", op="burgers", mesh=[(0, 1, 16), (0, 1, 16)], C=2, integrator="RK4", dt=0.001),
     dict(name="burgers2d_dorpi45", op="burgers", mesh=[(0, 1, 16), (0, 1, 16)], C=2, integrator="Dorpi45", dt=0.001),
 ]
@@ -74,6 +77,8 @@ def build(ns, case, mesh, dtype, device="cpu"):
         y = mesh.bc_mesh_grid()[1]
         force = -0.1 * ns.ImplicitSource() - ns.ExplicitSource(4.0 * torch.cos(4.0 * y))
         op = 0.01 * ns.Laplacian() - ns.VorticityConvection() + force
+    elif k == "beta_plane":
+        op = 0.01 * ns.Laplacian() - ns.VorticityConvection() + 0.5 * ns.SpatialDerivative(0, 1)
     elif k == "ns3d":
         op = 0.01 * ns.Laplacian() + ns.NSPressureConvection()
     elif k == "allen_cahn":
@@ -100,6 +105,8 @@ def inputs(case, dtype):
         u_hat = u_hat * (f <= 3).to(u_hat.dtype).reshape([1, 1] + [n if i == a else 1 for i in range(len(shape))])
     u = torch.fft.ifftn(u_hat, dim=list(range(2, u.dim()))).real
     u = u / u.abs().amax()
+    if case.get("rough"):
+        u = u + case["rough"] * torch.randn(BATCH, case["C"], *shape, dtype=torch.float64, generator=g)
     w = torch.randn(BATCH, case["C"], *shape, dtype=torch.float64, generator=g)
     return u.to(dtype).contiguous(), w.to(dtype).contiguous()
 

@@ -36,6 +36,9 @@ def source_field(recipe, mesh_info, dtype, device="cpu"):
     if recipe == "force2d":
         x, y = g
         return torch.cat([0.3 * torch.sin(2 * y) + 0 * x, 0.2 * torch.cos(x + y)], dim=1).contiguous()
+    if recipe == "heat3d":
+        x, y, z = g
+        return (torch.sin(x) * torch.cos(2 * y) * torch.cos(z)).contiguous()
     if recipe == "heat2d":
         x, y = g
         return (torch.sin(x) * torch.cos(2 * y)).contiguous()
@@ -68,6 +71,8 @@ def smooth_field(case, dtype):
         u_hat = u_hat * (f <= max(2, int(0.3 * n / 2))).to(u_hat.dtype).reshape(view)
     u = torch.fft.ifftn(u_hat, dim=dims).real
     u = u / u.abs().amax(dim=tuple(range(1, u.ndim)), keepdim=True)
+    if case.get("rough"):                      # white noise on top: every mode populated, the Nyquist planes included
+        u = u + case["rough"] * torch.randn(*shape, generator=g, dtype=torch.float64)
     return u.to(dtype)
 
 
@@ -220,6 +225,33 @@ OPS_CASES = [
     dict(name="conscon2d_batched_coef_etdrk2", mode="integrate", mesh=_m((32, 16), 1.0, 1.0), B=2, C=2,
          terms=[("laplacian", 0.01, {}), ("conservative_convection", [-1.0, -0.5], {"_ndim": 2})], integrator="ETDRK2",
          dt=0.002, steps=3),
+    # ---- complex linear symbol (odd-order terms) on 2-D/3-D grids: the reference's state leaves the Hermitian subspace on
+    # the Nyquist planes; rough initial data so that those planes matter (torchfsm_b200/unrolled.py)
+    dict(name="advdiff2d_complex_etdrk0", mode="integrate", mesh=_m((16, 32), 1.0, 1.0), B=2, C=1, rough=0.3,
+         terms=[("laplacian", 0.01, {}), ("spatial_derivative", 0.7, {"dim_index": 0, "order": 1}),
+                ("spatial_derivative", -0.3, {"dim_index": 1, "order": 1})], integrator="auto", dt=0.01, steps=4),
+    dict(name="advdiff2d_complex_rk4", mode="integrate", mesh=_m((16, 16), 1.0, 1.0), B=2, C=1, rough=0.3,
+         terms=[("laplacian", 0.01, {}), ("spatial_derivative", 0.7, {"dim_index": 0, "order": 1})],
+         integrator="RK4", dt=0.0005, steps=3),
+    dict(name="dispersion3d_source_setdrk4", mode="integrate", mesh=_m((8, 16, 8), TWO_PI, TWO_PI, TWO_PI), B=1, C=1, rough=0.3,
+         terms=[("laplacian", 0.01, {}), ("spatial_derivative", 0.7, {"dim_index": 2, "order": 1}),
+                ("spatial_derivative", -0.05, {"dim_index": 0, "order": 3}), ("explicit_source", 1, {"source": "heat3d"})],
+         integrator="auto", dt=0.002, steps=3),
+    dict(name="beta_plane2d_etdrk2", mode="integrate", mesh=_m((32, 16), TWO_PI, TWO_PI), B=2, C=1, rough=0.2,
+         terms=[("laplacian", 0.01, {}), ("vorticity_convection", -1, {}),
+                ("spatial_derivative", 0.5, {"dim_index": 0, "order": 1})] + KOLM, integrator="ETDRK2", dt=0.01, steps=3),
+    dict(name="beta_plane2d_setdrk4", mode="integrate", mesh=_m((16, 16), TWO_PI, TWO_PI), B=2, C=1, rough=0.2,
+         terms=[("laplacian", 0.01, {}), ("vorticity_convection", -1, {}),
+                ("spatial_derivative", 0.5, {"dim_index": 0, "order": 1})], integrator="SETDRK4", dt=0.01, steps=3),
+    dict(name="ks2d_dispersion_setdrk3", mode="integrate", mesh=_m((16, 16), 10.0, 10.0), B=2, C=1, rough=0.2,
+         terms=[("laplacian", -1, {}), ("biharmonic", -1, {}), ("ks_convection", -1, {}),
+                ("spatial_derivative", 0.3, {"dim_index": 0, "order": 3})], integrator="SETDRK3", dt=0.02, steps=3),
+    dict(name="allen_cahn2d_advection_setdrk2", mode="integrate", mesh=_m((16, 16), 1.0, 1.0), B=2, C=1, rough=0.2,
+         terms=[("laplacian", 0.05, {}), ("implicit_func_source", 1, {"func": "allen_cahn"}),
+                ("spatial_derivative", 0.4, {"dim_index": 1, "order": 1})], integrator="SETDRK2", dt=0.01, steps=3),
+    dict(name="beta_plane2d_dorpi45", mode="integrate", mesh=_m((16, 16), TWO_PI, TWO_PI), B=2, C=1, rough=0.2,
+         terms=[("laplacian", 0.01, {}), ("vorticity_convection", -1, {}),
+                ("spatial_derivative", 0.5, {"dim_index": 0, "order": 1})], integrator="Dorpi45", dt=0.002, steps=3),
     dict(name="ks2d_batched_setdrk4", mode="integrate", mesh=_m((32, 32), 30.0, 30.0), B=2, C=1,
          terms=[("laplacian", [-1.0, -0.9], {"_ndim": 2}), ("biharmonic", -1, {}), ("ks_convection", -1, {})],
          integrator="SETDRK4", dt=0.05, steps=3),

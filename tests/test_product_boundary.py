@@ -96,10 +96,20 @@ def test_multi_gpu_options_are_validated_before_any_work():
     ptrs = (ctypes.c_void_p * 2)(1, 2)
     assert st._lib.fsm_slab_peers(st._plan, 1, ptrs, 2) != 0           # no slab decomposition on this plan
     assert b"slab" in st._lib.fsm_last_error()
-    # complex linear symbols are a 1-D feature: a 2-D advection term must be refused, not silently dropped
+    # a complex linear symbol on a 2-D grid runs as a pair of half spectra (unrolled.py) -- never silently dropped; with
+    # a nonlinear term it needs the Nyquist planes dealiased away, and it does not run multi-GPU
     adv = -1.0 * fsm.SpatialDerivative(0, 1) + 0.01 * fsm.Laplacian()
+    moved = adv.integrate(u0, mesh=mesh, dt=1e-2, step=1)
+    still = (0.01 * fsm.Laplacian()).integrate(u0, mesh=mesh, dt=1e-2, step=1)
+    assert float((moved - still).abs().max()) > 1e-3
+    full = fsm.pde.KuramotoSivashinskyHighDim() + 0.1 * fsm.SpatialDerivative(0, 3)
+    full.set_de_aliasing_rate(1.0)
     with pytest.raises(NotImplementedError):
-        adv.integrate(u0, mesh=mesh, dt=1e-2, step=1)
+        full.integrate(u0, mesh=mesh, dt=1e-3, step=1)
+    sharded = fsm.pde.KuramotoSivashinskyHighDim() + 0.1 * fsm.SpatialDerivative(0, 3)
+    sharded.set_ensemble_group(object())
+    with pytest.raises(NotImplementedError):
+        sharded.integrate(u0, mesh=mesh, dt=1e-3, step=1)
 
 
 def test_no_tuning_hooks_in_the_product_path():

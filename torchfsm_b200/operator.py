@@ -1280,6 +1280,21 @@ class OperatorLike:
             # an explicit source is a nonlinear core in the reference (operator/_base.py:994-1015): "auto" -> SETDRK4
             name, cfg = integrator_name(self._integrator, lo["program"] == _cabi.PROG_LINEAR and lo["source_hat"] is None
                                         and not lo["external"]), self._integrator_config
+        if sd["f_mesh"].n_dim > 1:
+            from .unrolled import PairedSpectrumStepper, has_imag
+            if has_imag(sd["linear_coef"]) or (tables is not None and any(has_imag(t) for t in tables.values())):
+                # odd-order linear terms on a 2-D/3-D grid: the state leaves the Hermitian subspace on the Nyquist planes;
+                # stepped as a pair of half spectra on the library's transform kernels (unrolled.py)
+                if cfg.get("adaptive"):
+                    raise NotImplementedError("adaptive Runge-Kutta stepping is host-synchronous and not part of the fused CUDA path")
+                assert name != "ETDRK0" or rhs_only or (lo["program"] == _cabi.PROG_LINEAR and lo["source_hat"] is None
+                                                        and not lo["external"]), "The ETDRK0 integrator only supports linear term"
+                st = PairedSpectrumStepper(self, batch, name, dt, cfg, tables=tables)
+                if rhs_only:
+                    self._rhs_stepper = st
+                else:
+                    sd["integrator"] = st
+                return st
         generic_rk = None
         if name in RK_TABLEAUS:               # explicit RK other than RK4: right-hand sides of an RK4-type plan + fsm_lincomb
             if cfg.get("adaptive"):
@@ -1530,6 +1545,8 @@ class OperatorLike:
             st = getattr(self, "_rhs_stepper", None)
             if st is None or st.B != B or st.f_mesh is not self._state_dict["f_mesh"]:
                 st = self._build_integrator(1.0, B, rhs_only=True)
+            if hasattr(st, "evaluate_with_grad"):
+                return st.evaluate_with_grad(u)
             return GradientMode(self, st).evaluate(u)
         adj = _adjoint_map_terms(terms)
 
@@ -1548,6 +1565,8 @@ class OperatorLike:
         finally:
             self._autograd_ok = False
         lo = self._lowered
+        if hasattr(st, "integrate_with_grad"):          # complex symbol on a 2-D/3-D grid (unrolled.py)
+            return st.integrate_with_grad(u_0, step)
         if lo.get("program") != _cabi.PROG_LINEAR or lo.get("source_hat") is not None or lo.get("external") or st.complex_tables \
                 or st.integrator != "ETDRK0":
             # nonlinear operators: the step is unrolled on the library's transform and symbol kernels, each with its
