@@ -67,6 +67,11 @@ def reference_cases(torchfsm, device, dtype):
     opr = 0.01 * Laplacian() - Convection()
     opr.set_integrator(RKIntegrator.Dorpi45)
     out.append(("burgers2d_dorpi45", opr, m4, u4, 2e-4, 3))
+    # complex linear symbol on a 2-D grid: the reference's loop hands its (non-Hermitian) full spectrum to every step
+    from torchfsm.operator import SpatialDerivative, VorticityConvection
+    opb = 0.01 * Laplacian() - VorticityConvection() + 0.5 * SpatialDerivative(0, 1)
+    opb.set_integrator(ETDRKIntegrator.ETDRK2)
+    out.append(("beta_plane2d", opb, m3, torch.randn(2, 1, 32, 32, generator=g, dtype=dtype).to(device), 0.01, 4))
     nu = torch.tensor([0.01, 0.03], dtype=dtype, device=device).reshape(2, 1, 1, 1)
     out.append(("burgers2d_batched_nu", nu * Laplacian() - Convection(), m4, u4, 1e-3, 3))
     return out

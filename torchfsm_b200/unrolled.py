@@ -51,6 +51,18 @@ def _rot(t: torch.Tensor, shape) -> torch.Tensor:
     return t.reshape(*t.shape[:len(lead)], -1).contiguous()
 
 
+def _unrot(t: torch.Tensor, shape) -> torch.Tensor:
+    """(..., rot-half modes) -> (..., *shape[:-1], nh) full-layout half."""
+    nd, nh = len(shape), shape[-1] // 2 + 1
+    lead = t.shape[:-1]
+    n = len(lead)
+    if nd == 1:
+        return t.reshape(*lead, nh)
+    if nd == 2:
+        return t.reshape(*lead, nh, shape[0]).permute(*range(n), n + 1, n)
+    return t.reshape(*lead, shape[1], nh, shape[0]).permute(*range(n), n + 2, n, n + 1)
+
+
 class _PairMode(GradientMode):
     def table(self, k):
         return self.st.pair_tables.get(k)
@@ -115,14 +127,22 @@ class PairedSpectrumStepper:
         return self._tf.c2r(((x[0] + x[1]) * 0.5).contiguous(), out)
 
     def full_to_half(self, full_hat: torch.Tensor) -> torch.Tensor:
+        """Any full spectrum, Hermitian or not (the reference's state between two steps), without loss: the stored half
+        of S and of S~ (``fsm_full_to_half`` would project onto the Hermitian subspace)."""
         full_hat = full_hat.to(self.cdtype)
-        return torch.stack([self._tf.full_to_half(full_hat), self._tf.full_to_half(_mirror(full_hat, self.n_dim))])
+        return torch.stack([_rot(full_hat, self.shape), _rot(_mirror(full_hat, self.n_dim), self.shape)])
 
     def half_to_full(self, x: torch.Tensor) -> torch.Tensor:
-        """The reference's (non-Hermitian) full spectrum: stored half from S, mirrored half from S~."""
-        full, other = self._tf.half_to_full(x[0].contiguous()), self._tf.half_to_full(x[1].contiguous())
-        nh = self.shape[-1] // 2 + 1
-        full[..., nh:] = other[..., nh:]
+        """The reference's (non-Hermitian) full spectrum: S(k) on the stored half; S(k) = conj S~(-k) on the other."""
+        nh, nl = self.shape[-1] // 2 + 1, self.shape[-1]
+        s, sm = _unrot(x[0], self.shape), _unrot(x[1], self.shape)
+        full = torch.empty((self.B, self.C) + self.shape, dtype=self.cdtype, device=self.device)
+        full[..., :nh] = s
+        rest = sm[..., 1:nl - nh + 1].flip(-1).conj()                   # last-axis index j > n/2 <- n - j of S~
+        if self.n_dim > 1:
+            dims = list(range(2, 1 + self.n_dim))
+            rest = torch.roll(torch.flip(rest, dims), [1] * len(dims), dims)
+        full[..., nh:] = rest
         return full
 
     def step_half(self, x: torch.Tensor, n_steps: int = 1) -> torch.Tensor:
