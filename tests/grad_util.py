@@ -31,6 +31,13 @@ GRAD_CASES = [
     # complex linear symbol on a 2-D grid (paired half spectra, torchfsm_b200/unrolled.py); rough data: Nyquist planes matter
     dict(name="beta_plane2d_setdrk4", op="beta_plane", mesh=[(0, TWO_PI, 16), (0, TWO_PI, 16)], C=1, integrator="SETDRK4",
          dt=0.01, rough=0.2),
+    # gradients with respect to PARAMETERS (inverse problems): per-sample viscosity and convection coefficient, a source
+    dict(name="burgers2d_learned_coefs_setdrk4", op="burgers_learned", mesh=[(0, 1, 16), (0, 1, 16)], C=2,
+         integrator="SETDRK4", dt=0.005),
+    dict(name="burgers2d_learned_coefs_rk4", op="burgers_learned", mesh=[(0, 1, 16), (0, 1, 16)], C=2,
+         integrator="RK4", dt=0.001),
+    dict(name="heat2d_learned_source_setdrk2", op="heat_learned_source", mesh=[(0, 1, 16), (0, 1, 16)], C=1,
+         integrator="SETDRK2", dt=0.01),
     dict(name="burgers2d_rk4", op="burgers", mesh=[(0, 1, 16), (0, 1, 16)], C=2, integrator="RK4", dt=0.001),
     dict(name="burgers2d_dorpi45", op="burgers", mesh=[(0, 1, 16), (0, 1, 16)], C=2, integrator="Dorpi45", dt=0.001),
 ]
@@ -61,12 +68,25 @@ def namespace(kind):
 
 
 def build(ns, case, mesh, dtype, device="cpu"):
+    """-> (operator, [parameter tensors that require grad])"""
     k = case["op"]
+    params = []
     if k == "burgers":
         op = 0.01 * ns.Laplacian() - ns.Convection()
     elif k == "burgers_batched":
         c = torch.tensor([-1.0, -0.5], dtype=dtype, device=device).reshape(BATCH, 1, *([1] * len(case["mesh"])))
         op = 0.01 * ns.Laplacian() + c * ns.Convection()
+    elif k == "burgers_learned":
+        ones = [1] * len(case["mesh"])
+        nu = torch.tensor([0.01, 0.03], dtype=dtype, device=device).reshape(BATCH, 1, *ones).requires_grad_(True)
+        c = torch.tensor([-1.0, -0.5], dtype=dtype, device=device).reshape(BATCH, 1, *ones).requires_grad_(True)
+        params = [nu, c]
+        op = nu * ns.Laplacian() + c * ns.Convection()
+    elif k == "heat_learned_source":
+        x, y = mesh.bc_mesh_grid()
+        src = (torch.sin(TWO_PI * x) * torch.cos(2 * TWO_PI * y)).to(dtype).contiguous().requires_grad_(True)
+        params = [src]
+        op = 0.05 * ns.Laplacian() + ns.ExplicitSource(src)
     elif k == "ks":
         op = -ns.Laplacian() - ns.Biharmonic() - ns.KSConvection()
     elif k == "kdv":
@@ -91,7 +111,7 @@ def build(ns, case, mesh, dtype, device="cpu"):
     enum = ns.ETDRKIntegrator if name.startswith("ETDRK") else ns.SETDRKIntegrator if name.startswith("SETDRK") \
         else ns.RKIntegrator
     op.set_integrator(getattr(enum, name))
-    return op
+    return op, params
 
 
 def inputs(case, dtype):
@@ -117,19 +137,32 @@ def run(ns, case, dtype, device="cpu"):
     u0, w = inputs(case, dtype)
     u0, w = u0.to(device), w.to(device)
     mesh = ns.MeshGrid(mesh_info, dtype=dtype, device=device)
-    op = build(ns, case, mesh, dtype, device)
+    op, params = build(ns, case, mesh, dtype, device)
     x = u0.clone().requires_grad_(True)
     y = op.integrate(x, mesh=mesh, dt=case["dt"], step=STEPS)
     (y * w).sum().backward()
+    out = {"y": y.detach(), "grad_y": x.grad}
+    for i, p in enumerate(params):
+        out[f"grad_y_p{i}"] = p.grad.detach().clone()
+    if params:      # the reference caches L (and its graph) in the operator: a fresh operator per differentiated call
+        op, params = build(ns, case, mesh, dtype, device)
     x2 = u0.clone().requires_grad_(True)
     z = op(x2, mesh=mesh)
     (z * w).sum().backward()
-    return {"y": y.detach(), "grad_y": x.grad, "z": z.detach(), "grad_z": x2.grad}
+    out.update({"z": z.detach(), "grad_z": x2.grad})
+    for i, p in enumerate(params):
+        out[f"grad_z_p{i}"] = p.grad.detach().clone()
+    if params:      # parameters alone: the state does not require grad
+        op, params = build(ns, case, mesh, dtype, device)
+        (op.integrate(u0.clone(), mesh=mesh, dt=case["dt"], step=STEPS) * w).sum().backward()
+        for i, p in enumerate(params):
+            out[f"grad_only_p{i}"] = p.grad.detach().clone()
+    return out
 
 
 def load(name, dtype):
     tag = "f32" if dtype == torch.float32 else "f64"
     with np.load(os.path.join(GRAD_DIR, f"{name}_{tag}.npz")) as z:
-        out = {k: torch.from_numpy(z[k]) for k in ("y", "grad_y", "z", "grad_z")}
+        out = {k: torch.from_numpy(z[k]) for k in z.files if k != "spec"}
         out["spec"] = json.loads(str(z["spec"]))
     return out

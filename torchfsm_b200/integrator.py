@@ -66,6 +66,17 @@ RK_TABLEAUS = {
 }
 
 
+def has_imag(t) -> bool:
+    """Does a table / symbol carry a genuine imaginary part? (2j*pi*f)**4 and **6 carry ~1e-13 of rounding in the
+    imaginary part although the symbol is real (generic/_spatial_derivative.py:7-20 accepts them): compare against the
+    magnitude, not against 0."""
+    if t is None or not t.is_complex():
+        return False
+    t = t.detach()
+    eps = torch.finfo(t.real.dtype).eps
+    return float(t.imag.abs().max()) > 8 * eps * float(t.abs().max())
+
+
 def integrator_name(integrator, is_linear):
     if isinstance(integrator, str):
         if integrator != "auto":

@@ -16,7 +16,10 @@ from typing import Callable, List, Optional, Sequence
 import torch
 
 from . import _cabi
-from .integrator import (ETDRKIntegrator, SETDRKIntegrator, RKIntegrator, RK_TABLEAUS, integrator_name, build_tables)
+from .autograd import GradientMode, _adjoint_terms
+from .integrator import (ETDRKIntegrator, SETDRKIntegrator, RKIntegrator, RK_TABLEAUS, integrator_name, build_tables,
+                         has_imag)
+from .unrolled import PairedSpectrumStepper
 from .mesh import FourierMesh, MeshGrid
 
 # "linear_tensor": a ready-made L(k) tensor in the reference layout (what a genuine torchfsm operator registered,
@@ -40,6 +43,8 @@ class _Term:
         self.kind, self.coef, self.params = kind, coef, dict(params or {})
 
     def scaled(self, s):
+        if isinstance(s, torch.Tensor) and not isinstance(self.coef, torch.Tensor) and self.coef == 1:
+            return _Term(self.kind, s, self.params)        # the parameter itself: no graph node made at construction
         return _Term(self.kind, self.coef * s, self.params)
 
 
@@ -154,14 +159,6 @@ class FusedStepper:
             if self.n_dim == 3 and program in (_cabi.PROG_CONVECTION, _cabi.PROG_NS3D) and self.shape[-1] > 256:
                 raise NotImplementedError("fp64 3-D convection is limited to 256 points along the last axis on the "
                                           "fused CUDA path (shared memory per SM); use fp32 or a smaller grid")
-
-        def has_imag(t):
-            # (2j*pi*f)**4 and **6 carry ~1e-13 of rounding in the imaginary part although the symbol is real
-            # (generic/_spatial_derivative.py:7-20 accepts them): compare against the magnitude, not against 0
-            if t is None or not t.is_complex():
-                return False
-            eps = torch.finfo(t.real.dtype).eps
-            return float(t.imag.abs().max()) > 8 * eps * float(t.abs().max())
 
         def real_table(t):
             t = _expand_table(t, self.shape)
@@ -794,11 +791,6 @@ class _LinearFn(torch.autograd.Function):
         return ctx.bwd(g.detach().contiguous()), None, None
 
 
-def _adjoint_map_terms(terms):
-    """(out, in, powers, inverse-Laplacian power, coef) of S -> terms of S^H: channels swapped, (i k)^p conjugated."""
-    return [(ci, co, pw, q, coef * (-1.0) ** (sum(pw) % 2)) for (co, ci, pw, q, coef) in terms]
-
-
 class OperatorLike:
     """Sum of generator terms (mirror of ``OperatorLike``/``Operator``, operator/_base.py:286-850)."""
 
@@ -1281,7 +1273,6 @@ class OperatorLike:
             name, cfg = integrator_name(self._integrator, lo["program"] == _cabi.PROG_LINEAR and lo["source_hat"] is None
                                         and not lo["external"]), self._integrator_config
         if sd["f_mesh"].n_dim > 1:
-            from .unrolled import PairedSpectrumStepper, has_imag
             if has_imag(sd["linear_coef"]) or (tables is not None and any(has_imag(t) for t in tables.values())):
                 # odd-order linear terms on a 2-D/3-D grid: the state leaves the Hermitian subspace on the Nyquist planes;
                 # stepped as a pair of half spectra on the library's transform kernels (unrolled.py)
@@ -1364,7 +1355,7 @@ class OperatorLike:
                   step: int = 1, mesh=None, progressive: bool = False, trajectory_recorder=None,
                   return_in_fourier: bool = False):
         """operator/_base.py:676-751 — same signature and return conventions."""
-        if u_0 is not None and u_0.requires_grad and u_0_fft is None and trajectory_recorder is None \
+        if u_0 is not None and self._needs_graph(u_0) and u_0_fft is None and trajectory_recorder is None \
                 and not return_in_fourier and not progressive:
             return self._integrate_with_grad(u_0, dt, step, mesh)
         st = self._stepper_for((u_0, u_0_fft), mesh, dt)
@@ -1493,7 +1484,7 @@ class OperatorLike:
     def __call__(self, u: Optional[torch.Tensor] = None, u_fft: Optional[torch.Tensor] = None, mesh=None,
                  return_in_fourier: bool = False):
         """operator/_base.py:753-790 — evaluate L u + N(u) once."""
-        if u is not None and u.requires_grad and u_fft is None and not return_in_fourier:
+        if u is not None and self._needs_graph(u) and u_fft is None and not return_in_fourier:
             return self._call_with_grad(u, mesh)
         if self._state_dict["f_mesh"] is None or mesh is not None or self._lowered is None:
             m, n_channel = self._pre_check(u, u_fft, mesh if mesh is not None else self._state_dict["f_mesh"])
@@ -1518,11 +1509,35 @@ class OperatorLike:
         return st_out.half_to_full(out) if return_in_fourier else st_out.c2r(out)
 
 
-    # ---- differentiable linear paths ------------------------------------------------------------
+    # ---- differentiable paths -------------------------------------------------------------------
+    def _params_require_grad(self) -> bool:
+        """Tensor-valued coefficients or explicit sources that are being optimised (inverse problems)."""
+        for t in self.terms:
+            if isinstance(t.coef, torch.Tensor) and t.coef.requires_grad:
+                return True
+            src = t.params.get("source")
+            if isinstance(src, torch.Tensor) and src.requires_grad:
+                return True
+        return False
+
+    def _needs_graph(self, u) -> bool:
+        return torch.is_grad_enabled() and (u.requires_grad or self._params_require_grad())
+
+    def _fresh_graph(self):
+        """Parameters that require grad: symbol, tables and sources are rebuilt for every call, so that each result
+        carries its own graph to them (a cached plan would hold the graph of an earlier call)."""
+        if self._params_require_grad():
+            self._lowered = None
+            self._state_dict["integrator"] = None
+            self._rhs_stepper = None
+            return True
+        return False
+
     def _call_with_grad(self, u, mesh):
         """``operator(u)`` with ``u.requires_grad``: linear operators and point-wise spectral maps (Grad, Div, Curl,
         Vorticity2Velocity, sums with linear cores) are differentiated by running the adjoint map on the cotangent;
         nonlinear operators through gradient mode (autograd.py)."""
+        params = self._fresh_graph()
         self._autograd_ok = True
         try:
             if self._state_dict["f_mesh"] is None or mesh is not None or self._lowered is None:
@@ -1534,6 +1549,9 @@ class OperatorLike:
             self._autograd_ok = False
         lo, n_channel, B = self._lowered, self._state_dict["n_channel"], u.shape[0]
         if "map" in lo:
+            if params:
+                raise NotImplementedError("gradients with respect to the coefficients of Grad/Div/Curl-type operators are "
+                                          "not available on the CUDA path")
             c_out, terms = lo["c_out"], lo["map"]
         elif "composite" not in lo and self.is_linear and not any(isinstance(t.coef, torch.Tensor) for t in self.terms):
             c_out, terms = self._lower_map(self._state_dict["f_mesh"], n_channel)
@@ -1541,14 +1559,13 @@ class OperatorLike:
             raise NotImplementedError("Velocity2Pressure / Vorticity2Pressure are not differentiable on the CUDA path; "
                                       "detach their input first")
         else:                       # nonlinear (or per-sample linear) right-hand side: unrolled on the library's passes
-            from .autograd import GradientMode
             st = getattr(self, "_rhs_stepper", None)
             if st is None or st.B != B or st.f_mesh is not self._state_dict["f_mesh"]:
                 st = self._build_integrator(1.0, B, rhs_only=True)
             if hasattr(st, "evaluate_with_grad"):
                 return st.evaluate_with_grad(u)
             return GradientMode(self, st).evaluate(u)
-        adj = _adjoint_map_terms(terms)
+        adj = _adjoint_terms(terms)
 
         def run(x, c_in, c_to, tt):
             st_in, st_to = self._tf(B, c_in), self._tf(B, c_to)
@@ -1559,19 +1576,21 @@ class OperatorLike:
         """``integrate(u_0)`` with ``u_0.requires_grad``. A purely linear operator with real tables (exp(L dt) real:
         even-order terms) is self-adjoint, so the cotangent is integrated by the same fused plan; everything else goes
         through gradient mode (autograd.py)."""
+        params = self._fresh_graph()
         self._autograd_ok = True
         try:
             st = self._stepper_for((u_0, None), mesh, dt)
         finally:
             self._autograd_ok = False
         lo = self._lowered
+        if params:
+            self._state_dict["integrator"] = None       # the plan's tables carry this call's graph: not reused
         if hasattr(st, "integrate_with_grad"):          # complex symbol on a 2-D/3-D grid (unrolled.py)
             return st.integrate_with_grad(u_0, step)
         if lo.get("program") != _cabi.PROG_LINEAR or lo.get("source_hat") is not None or lo.get("external") or st.complex_tables \
-                or st.integrator != "ETDRK0":
+                or st.integrator != "ETDRK0" or params:
             # nonlinear operators: the step is unrolled on the library's transform and symbol kernels, each with its
             # adjoint pass as backward (torchfsm_b200/autograd.py)
-            from .autograd import GradientMode
             return GradientMode(self, st).integrate(u_0, step)
 
         def run(x):

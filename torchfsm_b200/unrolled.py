@@ -21,16 +21,7 @@ import torch
 
 from . import _cabi
 from .autograd import GradientMode
-from .integrator import build_tables
-
-
-def has_imag(t: Optional[torch.Tensor]) -> bool:
-    """(2j*pi*f)**4 and **6 carry ~1e-13 of rounding in the imaginary part although the symbol is real
-    (generic/_spatial_derivative.py:7-20 accepts them): compare against the magnitude, not against 0."""
-    if t is None or not t.is_complex():
-        return False
-    eps = torch.finfo(t.real.dtype).eps
-    return float(t.imag.abs().max()) > 8 * eps * float(t.abs().max())
+from .integrator import build_tables, has_imag  # noqa: F401
 
 
 def _mirror(t: torch.Tensor, n_dim: int) -> torch.Tensor:
