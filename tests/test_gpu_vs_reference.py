@@ -58,6 +58,14 @@ CASES = [
          terms=[("ns_pressure_convection", 1, {"force": [("implicit_unit_source", -0.1, {}),
                                                         ("explicit_source", 1, {"source": "force2d"})]}),
                 ("laplacian", 1 / 400, {})]),
+    # complex linear symbol on 2-D/3-D grids (paired half spectra, torchfsm_b200/unrolled.py), rough data
+    dict(name="beta_plane2d_256_etdrk2", mesh=_m((256, 256), TWO_PI, TWO_PI), B=2, C=1, dt=0.005, steps=3, integrator="ETDRK2",
+         rough=0.05, terms=[("vorticity_convection", -1, {}), ("laplacian", 0.01, {}),
+                            ("spatial_derivative", 0.5, {"dim_index": 0, "order": 1})]),
+    dict(name="advection_dispersion3d_64_setdrk4", mesh=_m((64, 32, 64), TWO_PI, TWO_PI, TWO_PI), B=2, C=1, dt=0.002, steps=3,
+         integrator="SETDRK4", rough=0.05,
+         terms=[("laplacian", 0.01, {}), ("spatial_derivative", 0.7, {"dim_index": 2, "order": 1}),
+                ("spatial_derivative", -0.01, {"dim_index": 0, "order": 3}), ("ks_convection", -1, {})]),
     dict(name="conscon2d_256_setdrk4", mesh=_m((256, 256), 1.0, 1.0), B=2, C=2, dt=1e-3, steps=3, integrator="SETDRK4",
          terms=[("laplacian", 0.01, {}), ("conservative_convection", -1, {})]),
     dict(name="allen_cahn3d_32_etdrk2", mesh=_m((32, 64, 32), TWO_PI, TWO_PI, TWO_PI), B=2, C=1, dt=0.01, steps=3,
