@@ -160,6 +160,8 @@ OPS_CASES = [
          terms=[("conservative_convection", 1, {})]),
     dict(name="run_operators2d", mode="run_operators", mesh=_m((16, 32), TWO_PI, 3.0), B=2, C=2,
          operators=[[("div", 1, {})], [("curl", 1, {})], [("laplacian", 0.1, {}), ("convection", -1, {})]]),
+    dict(name="solve_third_derivative2d", mode="solve", mesh=_m((16, 32), TWO_PI, 3.0), B=2, C=1, rough=0.3,
+         terms=[("spatial_derivative", 0.7, {"dim_index": 1, "order": 3})]),
     dict(name="solve_poisson2d", mode="solve", mesh=_m((32, 16), TWO_PI, 3.0), B=2, C=1, terms=[("laplacian", 1, {})]),
     # ---- time stepping
     dict(name="ns3d_force_setdrk4", mode="integrate", mesh=_m((16, 16, 16), TWO_PI, TWO_PI, TWO_PI), B=1, C=3,

@@ -1619,8 +1619,11 @@ def _solve(self, b: Optional[torch.Tensor] = None, b_fft: Optional[torch.Tensor]
     self.register_mesh(f_mesh, n_channel)
     L = self._state_dict["linear_coef"]
     inv = torch.where(L == 0, 1.0, 1 / L)                                   # operator/_base.py:250-255
-    st = FusedStepper(f_mesh, value.shape[0], n_channel, _cabi.PROG_LINEAR, "ETDRK0", 1.0, None, 0.0, None,
-                      [n // 2 for n in f_mesh.shape], True, {}, tables={"exp": inv})
+    if f_mesh.n_dim > 1 and has_imag(inv):        # odd-order terms on a 2-D/3-D grid: 1/L(k) and 1/L(-k) are no conjugates
+        st = PairedSpectrumStepper(self, value.shape[0], "ETDRK0", 1.0, {}, tables={"exp": inv})
+    else:
+        st = FusedStepper(f_mesh, value.shape[0], n_channel, _cabi.PROG_LINEAR, "ETDRK0", 1.0, None, 0.0, None,
+                          [n // 2 for n in f_mesh.shape], True, {}, tables={"exp": inv})
     x_hat = st.r2c(b) if b_fft is None else st.full_to_half(b_fft)
     st.step_half(x_hat, 1)
     return st.half_to_full(x_hat) if return_in_fourier else st.c2r(x_hat)
