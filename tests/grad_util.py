@@ -36,6 +36,8 @@ GRAD_CASES = [
          integrator="SETDRK4", dt=0.005),
     dict(name="burgers2d_learned_coefs_rk4", op="burgers_learned", mesh=[(0, 1, 16), (0, 1, 16)], C=2,
          integrator="RK4", dt=0.001),
+    dict(name="burgers2d_learned_scalars_setdrk4", op="burgers_learned_scalar", mesh=[(0, 1, 16), (0, 1, 16)], C=2,
+         integrator="SETDRK4", dt=0.005),
     dict(name="heat2d_learned_source_setdrk2", op="heat_learned_source", mesh=[(0, 1, 16), (0, 1, 16)], C=1,
          integrator="SETDRK2", dt=0.01),
     dict(name="burgers2d_rk4", op="burgers", mesh=[(0, 1, 16), (0, 1, 16)], C=2, integrator="RK4", dt=0.001),
@@ -80,6 +82,11 @@ def build(ns, case, mesh, dtype, device="cpu"):
         ones = [1] * len(case["mesh"])
         nu = torch.tensor([0.01, 0.03], dtype=dtype, device=device).reshape(BATCH, 1, *ones).requires_grad_(True)
         c = torch.tensor([-1.0, -0.5], dtype=dtype, device=device).reshape(BATCH, 1, *ones).requires_grad_(True)
+        params = [nu, c]
+        op = nu * ns.Laplacian() + c * ns.Convection()
+    elif k == "burgers_learned_scalar":               # 0-dim tensors: one learnable value shared by the batch
+        nu = torch.tensor(0.02, dtype=dtype, device=device).requires_grad_(True)
+        c = torch.tensor(-0.8, dtype=dtype, device=device).requires_grad_(True)
         params = [nu, c]
         op = nu * ns.Laplacian() + c * ns.Convection()
     elif k == "heat_learned_source":

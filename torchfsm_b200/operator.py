@@ -51,6 +51,11 @@ class _Term:
 # ------------------------------------------------------------------------------------------------
 # rot-half layout helpers (see include/fsm_b200.h)
 # ------------------------------------------------------------------------------------------------
+def _per_sample(coef: torch.Tensor) -> bool:
+    """A tensor-valued coefficient the nonlinear terms accept: one value, or one value per sample ((B, 1, 1, ..))."""
+    return coef.dim() == 0 or coef.numel() == coef.shape[0]
+
+
 def _rot_half(t: torch.Tensor, shape) -> torch.Tensor:
     """(X, n0[, n1[, n2]]) full-layout tensor -> (X, rot-half modes) contiguous."""
     nd = len(shape)
@@ -192,7 +197,10 @@ class FusedStepper:
         desc.nl_coef = float(nl_coef)
         desc.dynamic_force = 1 if dynamic_force else 0
         if nl_coef_b is not None:             # tensor-valued coefficient of the convective term: one value per sample
-            nl_coef_b = nl_coef_b.to(device=f_mesh.device, dtype=self.rdtype).reshape(-1).contiguous()
+            nl_coef_b = nl_coef_b.to(device=f_mesh.device, dtype=self.rdtype).reshape(-1)
+            if nl_coef_b.numel() == 1:        # a scalar tensor (e.g. a learnable coefficient): the same for every sample
+                nl_coef_b = nl_coef_b.expand(batch)
+            nl_coef_b = nl_coef_b.contiguous()
             if nl_coef_b.numel() != batch:
                 raise ValueError("a batched coefficient must have one entry per sample")
             self._keep.append(nl_coef_b)
@@ -970,7 +978,7 @@ class OperatorLike:
                 # no fused 1-D program for 1/2 (phi_x)^2: composed on the host from the library's passes
                 if n_channel != 1:
                     raise NotImplementedError("KSConvection only supports scalar field")
-                if isinstance(t.coef, torch.Tensor) and t.coef.numel() != t.coef.shape[0]:
+                if isinstance(t.coef, torch.Tensor) and not _per_sample(t.coef):
                     raise NotImplementedError("tensor-valued coefficients on nonlinear terms must be per-sample scalars")
                 external.append(t)
             elif t.kind in _PROGRAM_OF:
@@ -978,7 +986,7 @@ class OperatorLike:
                     raise NotImplementedError("only one convective nonlinear term per operator is supported "
                                               "by the fused CUDA path")
                 if isinstance(t.coef, torch.Tensor):          # one coefficient per sample (operator/_base.py:375-403)
-                    if t.coef.numel() != t.coef.shape[0]:
+                    if not _per_sample(t.coef):
                         raise NotImplementedError("tensor-valued coefficients on nonlinear terms must be per-sample scalars")
                     if t.kind == "ns_pressure_convection" and t.params.get("external_force") is not None:
                         raise NotImplementedError("a per-sample coefficient on NSPressureConvection cannot be combined "
@@ -1017,7 +1025,7 @@ class OperatorLike:
                         force_hat = -float(t.coef) * f_hat
                         source_hat = float(t.coef) * f_hat if source_hat is None else source_hat + float(t.coef) * f_hat
             elif t.kind in _EXTERNAL_KINDS:
-                if isinstance(t.coef, torch.Tensor) and t.coef.numel() != t.coef.shape[0]:
+                if isinstance(t.coef, torch.Tensor) and not _per_sample(t.coef):
                     raise NotImplementedError("tensor-valued coefficients on nonlinear terms must be per-sample scalars")
                 if t.kind == "conservative_convection" and f_mesh.n_dim != n_channel:
                     raise ValueError("div operator only works for vector field with the same dimension as mesh")
