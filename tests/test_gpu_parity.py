@@ -514,3 +514,35 @@ def test_linear_operators_and_maps_are_differentiable_on_gpu():
     out = (0.05 * fsm.Laplacian()).integrate(u, mesh=mesh2, dt=0.1, step=3)
     (gu,) = torch.autograd.grad(out.sum(), u)
     assert float((gu - 1.0).abs().max()) < 1e-12          # d/du sum(exp(L t) u) = exp(L t)^T 1 = 1 (the mean mode is kept)
+
+
+@pytest.mark.gpu
+def test_functional_forms_and_batch_wise_recorders_on_gpu(tmp_path):
+    """functional.py, DiskRecorder and RandomBatchWisedRecorder through the CUDA library (the CPU twin of this test,
+    tests/test_functional_recorders.py, also checks them against the unmodified reference)."""
+    import numpy as np
+    import torchfsm_b200 as fsm
+    import torchfsm_b200.functional as F
+    dev = "cuda"
+    mesh = fsm.MeshGrid([(0, 6.28, 64), (0, 3.0, 128)], device=dev, dtype=torch.float32)
+    g = torch.Generator().manual_seed(3)
+    w = torch.randn(2, 1, 64, 128, generator=g).to(dev)
+    w = (0.002 * fsm.Laplacian()).integrate(w, mesh=mesh, dt=1.0, step=1)
+    assert float((F.grad(w, mesh=mesh) - fsm.Grad()(w, mesh=mesh)).abs().max()) == 0.0
+    assert float((F.vorticity2velocity(w, mesh=mesh) - fsm.Vorticity2Velocity()(w, mesh=mesh)).abs().max()) == 0.0
+    p = F.vorticity2pressure(w, mesh=mesh, external_force=-0.1 * fsm.ImplicitSource())
+    assert p.shape == (2, 1, 64, 128) and torch.isfinite(p).all()
+    op = 0.01 * fsm.Laplacian() - fsm.VorticityConvection()
+    whole = op.integrate(w, mesh=mesh, dt=0.01, step=12, trajectory_recorder=fsm.AutoRecorder())
+    rec = fsm.DiskRecorder(cache_dir=str(tmp_path) + "/", cache_freq=5)
+    assert op.integrate(w, mesh=mesh, dt=0.01, step=12, trajectory_recorder=rec) is None
+    parts = [torch.load(f) for f in rec.files]
+    assert [q.shape[1] for q in parts] == [5, 5, 3]
+    assert float((torch.cat(parts, dim=1) - whole.cpu()).abs().max()) == 0.0
+    np.random.seed(5)
+    rnd = fsm.RandomBatchWisedRecorder(simulation_steps=12, recorder_interval=2, n_recorded_frames=2)
+    traj = op.integrate(w, mesh=mesh, dt=0.01, step=12, trajectory_recorder=rnd)
+    ids = rnd._recorded_frame_id
+    for b in range(2):
+        for j in range(2):
+            assert float((traj[b, j] - whole[b, ids[b, j]]).abs().max()) < 1e-5

@@ -12,7 +12,8 @@ from .operator import (Operator, LinearOperator, NonlinearOperator, Laplacian, B
                        VorticityConvection, NSPressureConvection, FusedStepper, Grad, Div, Curl,
                        Vorticity2Velocity, Vorticity2Pressure, Velocity2Pressure, ConservativeConvection,
                        run_operators, HostComposedStepper, DynamicForceStepper)
-from .traj_recorder import AutoRecorder, CPURecorder, IntervalController  # noqa: F401
-from . import pde, field  # noqa: F401
+from .traj_recorder import (AutoRecorder, CPURecorder, DiskRecorder, RandomBatchWisedRecorder,  # noqa: F401
+                            IntervalController)
+from . import pde, field, functional  # noqa: F401
 
 __version__ = "0.1.0"

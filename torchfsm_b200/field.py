@@ -70,3 +70,24 @@ def truncated_fourier_series(mesh, freq_threshold: int = 5, amplitude_range=(-1.
     if unit_magnitude:
         noise = noise / noise.abs().amax(dim=dims, keepdim=True)
     return noise
+
+
+def wave_1d(x: torch.Tensor, min_k: int = 1, max_k: int = 5, min_amplitude: float = 0.5, max_amplitude: float = 1.0,
+            n_polynomial: int = 5, zero_mean: bool = False, mean_shift_coef=0.3, batched: bool = False) -> torch.Tensor:
+    """Sum of ``n_polynomial`` sines with random integer wavenumbers, amplitudes and phases on the coordinate field ``x``
+    (field.py:151-207); draws from torch's global generator in the reference's order, so a seed gives the same field."""
+    x_new = x / x.max() * torch.pi * 2
+    y = torch.zeros_like(x)
+    if not batched:
+        x_new, y = x_new.unsqueeze(0), y.unsqueeze(0)
+    batch = x_new.shape[0]
+    shape = [batch, n_polynomial] + [1] * (x_new.dim() - 2)
+    k = torch.randint(min_k, max_k + 1, shape, device=x.device, dtype=x.dtype)
+    amplitude = torch.rand(*shape, device=x.device, dtype=x.dtype) * (max_amplitude - min_amplitude) + min_amplitude
+    shift = torch.rand(*shape, device=x.device, dtype=x.dtype) * torch.pi * 2
+    for i in range(n_polynomial):
+        y = y + amplitude[:, i:i + 1] * torch.sin(k[:, i:i + 1] * (x_new + shift[:, i:i + 1]))
+    if not zero_mean:
+        value_shift = torch.rand([batch] + [1] * (x_new.dim() - 1), device=x.device, dtype=x.dtype)
+        y = y + ((value_shift - 0.5) * 2 * (max_amplitude - min_amplitude) * mean_shift_coef + min_amplitude)
+    return y if batched else y.squeeze(0)

@@ -1377,6 +1377,8 @@ class OperatorLike:
                 st.step_half(u_hat, step)
             else:
                 i = 0
+                if hasattr(trajectory_recorder, "prepare"):          # per-sample frame draws need the batch size
+                    trajectory_recorder.prepare(st.B)
                 control = getattr(trajectory_recorder, "control_func", None) if trajectory_recorder is not None else None
                 # recorders of this package take physical frames straight from the C2R pass; anything else gets
                 # the reference's full-spectrum frame (traj_recorder.py:46-55)
