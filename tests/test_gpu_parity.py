@@ -546,3 +546,25 @@ def test_functional_forms_and_batch_wise_recorders_on_gpu(tmp_path):
     for b in range(2):
         for j in range(2):
             assert float((traj[b, j] - whole[b, ids[b, j]]).abs().max()) < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["f32", "f64"])
+def test_fourier_mesh_transforms_on_gpu(dtype):
+    """FourierMesh.fft / .ifft (the reference's transform choke point, mesh.py:481-491) on the CUDA library's passes
+    against cuFFT, for real fields, complex fields and non-Hermitian spectra."""
+    import torchfsm_b200 as fsm
+    tol = 2e-5 if dtype == torch.float32 else 1e-12
+    cd = torch.complex64 if dtype == torch.float32 else torch.complex128
+    g = torch.Generator().manual_seed(9)
+    for mesh_info in ([(0, 1, 256)], [(0, 1, 128), (0, 2, 256)], [(0, 1, 32), (0, 2, 64), (0, 3, 32)]):
+        f = fsm.FourierMesh(mesh_info, device="cuda", dtype=dtype)
+        shape = [m[2] for m in mesh_info]
+        dims = list(range(-len(shape), 0))
+        u = torch.randn(2, 3, *shape, dtype=dtype, generator=g).cuda()
+        spec = torch.randn(2, 3, *shape, dtype=cd, generator=g).cuda()
+        scale = float(torch.fft.fftn(u, dim=dims).abs().max())
+        assert float((f.fft(u) - torch.fft.fftn(u, dim=dims)).abs().max()) < tol * scale
+        assert float((f.fft(spec) - torch.fft.fftn(spec, dim=dims)).abs().max()) < tol * scale * 2
+        assert float((f.ifft(spec) - torch.fft.ifftn(spec, dim=dims)).abs().max()) < tol
+        assert float((f.ifft(f.fft(u)).real - u).abs().max()) < tol * 10
