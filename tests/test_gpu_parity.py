@@ -568,3 +568,31 @@ def test_fourier_mesh_transforms_on_gpu(dtype):
         assert float((f.fft(spec) - torch.fft.fftn(spec, dim=dims)).abs().max()) < tol * scale * 2
         assert float((f.ifft(spec) - torch.fft.ifftn(spec, dim=dims)).abs().max()) < tol
         assert float((f.ifft(f.fft(u)).real - u).abs().max()) < tol * 10
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["f32", "f64"])
+def test_user_defined_cores_on_gpu(dtype):
+    """The reference's extension protocol (LinearCoef / NonlinearFunc / CoreGenerator, operator/_base.py:16-131) through
+    the CUDA library: the user core's ``f_mesh.fft`` / ``f_mesh.ifft`` are the library's passes. Checked against the same
+    physics written with built-in operators (tests/test_custom_cores.py checks the reference itself on CPU)."""
+    import torchfsm_b200 as fsm
+    from test_custom_cores import make_cores
+    Cubic, GradientSquared, HyperViscosity, ByChannels = make_cores(fsm)
+    tol = 2e-5 if dtype == torch.float32 else 1e-12
+    mesh = fsm.MeshGrid([(0, 1, 128), (0, 1, 256)], device="cuda", dtype=dtype)
+    g = torch.Generator().manual_seed(17)
+    u0 = torch.randn(2, 1, 128, 256, dtype=dtype, generator=g).cuda()
+    u0 = (0.0005 * fsm.Laplacian()).integrate(u0, mesh=mesh, dt=1.0, step=1)
+    u0 = u0 / u0.abs().max()
+    builtin = 0.05 * fsm.Laplacian() - 1e-6 * fsm.Biharmonic() + fsm.ImplicitSource(lambda u: -u ** 3)
+    custom = 0.05 * fsm.Laplacian() + fsm.LinearOperator(HyperViscosity(1e-6)) + fsm.Operator(ByChannels())
+    for op in (builtin, custom):
+        op.set_integrator(fsm.SETDRKIntegrator.SETDRK4)
+    want = builtin.integrate(u0, mesh=mesh, dt=0.002, step=4)
+    got = custom.integrate(u0, mesh=mesh, dt=0.002, step=4)
+    assert float((got - want).norm() / want.norm()) < tol
+    gs = fsm.NonlinearOperator(GradientSquared())(u0, mesh=mesh)
+    gx, gy = fsm.Grad()(u0, mesh=mesh).unbind(dim=1)
+    ref = gx * gx + gy * gy
+    assert float((gs[:, 0] - ref).norm() / ref.norm()) < 10 * tol

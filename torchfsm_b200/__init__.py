@@ -11,7 +11,8 @@ from .operator import (Operator, LinearOperator, NonlinearOperator, Laplacian, B
                        SpatialDerivative, ImplicitSource, ExplicitSource, Convection, KSConvection,
                        VorticityConvection, NSPressureConvection, FusedStepper, Grad, Div, Curl,
                        Vorticity2Velocity, Vorticity2Pressure, Velocity2Pressure, ConservativeConvection,
-                       run_operators, HostComposedStepper, DynamicForceStepper)
+                       run_operators, HostComposedStepper, DynamicForceStepper, LinearCoef, NonlinearFunc,
+                       CoreGenerator)
 from .traj_recorder import (AutoRecorder, CPURecorder, DiskRecorder, RandomBatchWisedRecorder,  # noqa: F401
                             IntervalController)
 from . import pde, field, functional  # noqa: F401

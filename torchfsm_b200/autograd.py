@@ -135,6 +135,12 @@ class _HostView:
     def other(self, n_channel):
         return _HostView(self.ops, n_channel)
 
+    def half_to_full(self, x_hat):
+        raise NotImplementedError("user-defined NonlinearFunc cores are not available in the unrolled modes (gradients, "
+                                  "complex symbols on 2-D/3-D grids)")
+
+    full_to_half = half_to_full
+
 
 class GradientMode:
     """One operator on one mesh, batch size and time step, unrolled for autograd. ``st`` is the stepper the forward

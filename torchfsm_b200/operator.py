@@ -31,7 +31,9 @@ _MAP_KINDS = ("grad", "div", "curl", "vorticity2velocity")
 _COMPOSITE_KINDS = ("velocity2pressure", "vorticity2pressure")
 # nonlinear cores without a fused program: evaluated by composing the library's passes on the host (c2r, a point-wise
 # physical-space function, r2c, spectral map) and handed to the integrator stage (fsm_stage_combine)
-_EXTERNAL_KINDS = ("implicit_func_source", "conservative_convection")
+# "custom_nonlinear": a user-defined NonlinearFunc (the reference's core protocol, operator/_base.py:56-103) called on
+# full spectra that the library's passes produce and consume
+_EXTERNAL_KINDS = ("implicit_func_source", "conservative_convection", "custom_nonlinear")
 _PROGRAM_OF = {"convection": _cabi.PROG_CONVECTION, "ks_convection": _cabi.PROG_KS,
                "vorticity_convection": _cabi.PROG_NS2D_VORT, "ns_pressure_convection": _cabi.PROG_NS3D}
 
@@ -799,11 +801,55 @@ class _LinearFn(torch.autograd.Function):
         return ctx.bwd(g.detach().contiguous()), None, None
 
 
-class OperatorLike:
-    """Sum of generator terms (mirror of ``OperatorLike``/``Operator``, operator/_base.py:286-850)."""
+class LinearCoef:
+    """User-defined linear symbol (the reference's core protocol, operator/_base.py:16-54): ``__call__(f_mesh, n_channel)``
+    returns L(k) in the reference layout ``(1|B, C, N...)``, built from the tables of ``FourierMesh``."""
 
-    def __init__(self, terms: Optional[List[_Term]] = None):
-        self.terms: List[_Term] = list(terms or [])
+    def __call__(self, f_mesh: FourierMesh, n_channel: int) -> torch.Tensor:
+        raise NotImplementedError
+
+    def nonlinear_like(self, u_fft, f_mesh, u=None):
+        return self(f_mesh, u_fft.shape[1]) * u_fft
+
+
+class NonlinearFunc:
+    """User-defined nonlinear core (operator/_base.py:56-103): ``__call__(u_fft, f_mesh, u)`` takes the full spectrum
+    ``(B, C, N...)`` (dealiased when ``dealiasing_swtich``) and the matching physical field and returns the full
+    spectrum of the term. ``f_mesh.fft`` / ``f_mesh.ifft`` inside it run on the library's passes."""
+
+    def __init__(self, dealiasing_swtich: bool = True) -> None:
+        self._dealiasing_swtich = dealiasing_swtich
+
+    def __call__(self, u_fft, f_mesh, u=None) -> torch.Tensor:
+        raise NotImplementedError
+
+    def spatial_value(self, u_fft, f_mesh, u=None):
+        return f_mesh.ifft(self(u_fft, f_mesh, u)).real
+
+
+class CoreGenerator:
+    """``__call__(f_mesh, n_channel) -> LinearCoef | NonlinearFunc`` (operator/_base.py:106-126): decides the core once
+    the mesh and the channel count are known."""
+
+    def __call__(self, f_mesh: FourierMesh, n_channel: int):
+        raise NotImplementedError
+
+
+class OperatorLike:
+    """Sum of generator terms (mirror of ``OperatorLike``/``Operator``, operator/_base.py:286-850).
+
+    ``OperatorLike(operator_generators, coefs)`` as in the reference (:297-307): every generator is a ``LinearCoef``, a
+    ``NonlinearFunc``, a ``CoreGenerator`` or a callable ``(f_mesh, n_channel) -> core``. The built-in operators pass
+    ready-made terms instead."""
+
+    def __init__(self, terms=None, coefs: Optional[List] = None):
+        terms = [] if terms is None else (list(terms) if isinstance(terms, (list, tuple)) else [terms])
+        coefs = list(coefs) if coefs is not None else [1] * len(terms)
+        if len(coefs) != len(terms):
+            raise ValueError("The length of coefs should match the number of operator generators")
+        self.terms: List[_Term] = [t if isinstance(t, _Term) and c == 1 else (t.scaled(c) if isinstance(t, _Term) else
+                                   _Term("custom", c, {"generator": t})) for t, c in zip(terms, coefs)]
+        self._rt = None               # terms with the user-defined generators resolved for the registered mesh
         self._de_aliasing_rate = 2 / 3
         self._integrator = "auto"
         self._integrator_config = {}
@@ -941,8 +987,31 @@ class OperatorLike:
         self._value_mesh_check_func = func
 
     @property
+    def _terms_now(self) -> List[_Term]:
+        return self._rt if self._rt is not None else self.terms
+
+    def _resolve_terms(self, f_mesh: FourierMesh, n_channel: int) -> List[_Term]:
+        """User-defined generators -> what they produce on this mesh (operator/_base.py:611-624): a ``LinearCoef``
+        becomes a tabulated symbol, a ``NonlinearFunc`` a host-composed nonlinear term."""
+        out = []
+        for t in self.terms:
+            if t.kind != "custom":
+                out.append(t)
+                continue
+            core = t.params["generator"]
+            if not isinstance(core, (LinearCoef, NonlinearFunc)):
+                core = core(f_mesh, n_channel)
+            if isinstance(core, LinearCoef) or (hasattr(core, "nonlinear_like") and not hasattr(core, "_dealiasing_swtich")):
+                out.append(_Term("linear_tensor", t.coef, {"L": core(f_mesh, n_channel)}))
+            elif isinstance(core, NonlinearFunc) or hasattr(core, "_dealiasing_swtich"):
+                out.append(_Term("custom_nonlinear", t.coef, {"func": core}))
+            else:
+                raise TypeError("a core generator must produce a LinearCoef or a NonlinearFunc")
+        return out
+
+    @property
     def is_linear(self) -> bool:
-        return all(t.kind in _LINEAR_KINDS for t in self.terms)
+        return all(t.kind in _LINEAR_KINDS for t in self._terms_now)
 
     # ---- lowering ----------------------------------------------------------------------------------
     def register_mesh(self, mesh, n_channel: int, device=None, dtype=None):
@@ -951,12 +1020,14 @@ class OperatorLike:
             else FourierMesh(mesh, device=device, dtype=dtype)
         self._state_dict = {"f_mesh": f_mesh, "n_channel": n_channel, "linear_coef": None, "integrator": None}
         self._rhs_stepper = None
-        kinds = {t.kind for t in self.terms}
+        self._rt = self._resolve_terms(f_mesh, n_channel) if any(t.kind == "custom" for t in self.terms) else None
+        terms = self._terms_now
+        kinds = {t.kind for t in terms}
         if kinds & set(_COMPOSITE_KINDS):
-            if len(self.terms) != 1 or isinstance(self.terms[0].coef, torch.Tensor):
+            if len(terms) != 1 or isinstance(terms[0].coef, torch.Tensor):
                 raise NotImplementedError("Velocity2Pressure / Vorticity2Pressure cannot be summed with other operators "
                                           "on the fused CUDA path")
-            t = self.terms[0]
+            t = terms[0]
             if t.kind == "vorticity2pressure" and (f_mesh.n_dim != 2 or n_channel != 1):
                 raise ValueError("Only vorticity in 2Dmesh is supported")
             if t.kind == "velocity2pressure" and f_mesh.n_dim != n_channel:
@@ -971,7 +1042,7 @@ class OperatorLike:
         program, nl_coef, ks_remove_mean = _cabi.PROG_LINEAR, 0.0, True
         source_hat = force_hat = dyn_force = nl_coef_b = None
         external = []
-        for t in self.terms:
+        for t in terms:
             if t.kind in _LINEAR_KINDS:
                 lin.append(t)
             elif t.kind == "ks_convection" and f_mesh.n_dim == 1:
@@ -1066,7 +1137,7 @@ class OperatorLike:
             return tuple(order if i == a else 0 for i in range(3))
 
         per_term = []
-        for t in self.terms:
+        for t in self._terms_now:
             if isinstance(t.coef, torch.Tensor):
                 raise NotImplementedError("tensor-valued coefficients are not supported on channel-changing operators")
             k, c = t.kind, float(t.coef)
@@ -1140,7 +1211,7 @@ class OperatorLike:
             return self._tf(B, n_channel).spectral_map(u_hat, lo["c_out"], lo["map"]), lo["c_out"]
         if "composite" in lo:
             return self._eval_composite(lo["composite"], u_hat, f_mesh, n_channel), 1
-        if self.is_linear and not any(isinstance(t.coef, torch.Tensor) or t.kind == "linear_tensor" for t in self.terms):
+        if self.is_linear and not any(isinstance(t.coef, torch.Tensor) or t.kind == "linear_tensor" for t in self._terms_now):
             # a purely linear operator is a point-wise map too; this route also takes odd-order derivatives on 2-D/3-D
             # grids, whose complex symbol the time-stepping tables refuse
             if "linear_map" not in lo:
@@ -1224,9 +1295,16 @@ class OperatorLike:
         """sum_t coef_t * core_t(u_hat) for the host-composed cores (operator/_base.py:375-403): dealiased input for the
         cores that ask for it, one inverse transform shared by all of them, every transform on the library's passes."""
         d = self._state_dict["f_mesh"].n_dim
-        need_masked = any(t.kind == "conservative_convection" or (t.kind == "implicit_func_source" and t.params.get("non_linear", True))
-                          for t in terms)
-        need_plain = any(t.kind == "implicit_func_source" and not t.params.get("non_linear", True) for t in terms)
+        def wants_dealiased(t):
+            """True: the core reads the dealiased state; False: the state as it is; None: it masks on its own"""
+            if t.kind == "custom_nonlinear":
+                return bool(getattr(t.params["func"], "_dealiasing_swtich", True))
+            if t.kind == "implicit_func_source":
+                return bool(t.params.get("non_linear", True))
+            return True if t.kind == "conservative_convection" else None
+        need_masked = any(wants_dealiased(t) is True for t in terms)
+        need_plain = any(wants_dealiased(t) is False for t in terms)
+        f_mesh = self._state_dict["f_mesh"]
         pairs = [(a, c) for a in range(n_channel) for c in range(a, n_channel)]
 
         def scaled(r, coef, extra=1.0):
@@ -1237,7 +1315,8 @@ class OperatorLike:
             return r if c == 1.0 else r * c
 
         def evaluate(st, x_hat):
-            u_d = st.c2r(st.mask_state(x_hat.clone())) if need_masked else None
+            x_d = st.mask_state(x_hat.clone()) if need_masked else None
+            u_d = st.c2r(x_d) if need_masked else None
             u = st.c2r(x_hat) if need_plain else None
             out = None
             for t in terms:
@@ -1246,6 +1325,12 @@ class OperatorLike:
                     if v.shape != (st.B, st.C) + tuple(st.local_shape):
                         raise ValueError("ImplicitSource: source_func must keep the shape of its argument")
                     r = scaled(st.r2c(v), t.coef)
+                elif t.kind == "custom_nonlinear":                       # operator/_base.py:375-403 with a user core
+                    deal = wants_dealiased(t)
+                    full = t.params["func"](st.half_to_full(x_d if deal else x_hat), f_mesh, u_d if deal else u)
+                    if tuple(full.shape) != (st.B, st.C) + tuple(st.local_shape):
+                        raise ValueError("NonlinearFunc: the returned spectrum must keep the shape of its argument")
+                    r = scaled(st.full_to_half(full), t.coef)
                 elif t.kind == "ks_convection":                          # dedicated/_ks_convection.py:18-38 on a 1-D grid
                     g_hat = st.spectral_map(x_hat, 1, [(0, 0, (1, 0, 0), 0, 1.0)], dealias=True)      # i k phi_hat, dealiased
                     r = st.r2c(st.sym_outer(st.c2r(g_hat)))              # (phi_x)^2
@@ -1507,7 +1592,7 @@ class OperatorLike:
         lo = self._lowered
         if "map" in lo or "composite" in lo:
             st_in, st_out = self._tf(B, n_channel), self._tf(B, lo["c_out"])
-        elif self.is_linear and not any(isinstance(t.coef, torch.Tensor) or t.kind == "linear_tensor" for t in self.terms):
+        elif self.is_linear and not any(isinstance(t.coef, torch.Tensor) or t.kind == "linear_tensor" for t in self._terms_now):
             st_in = st_out = self._tf(B, n_channel)
         else:
             st_in = getattr(self, "_rhs_stepper", None)
@@ -1563,7 +1648,7 @@ class OperatorLike:
                 raise NotImplementedError("gradients with respect to the coefficients of Grad/Div/Curl-type operators are "
                                           "not available on the CUDA path")
             c_out, terms = lo["c_out"], lo["map"]
-        elif "composite" not in lo and self.is_linear and not any(isinstance(t.coef, torch.Tensor) for t in self.terms):
+        elif "composite" not in lo and self.is_linear and not any(isinstance(t.coef, torch.Tensor) for t in self._terms_now):
             c_out, terms = self._lower_map(self._state_dict["f_mesh"], n_channel)
         elif "composite" in lo:
             raise NotImplementedError("Velocity2Pressure / Vorticity2Pressure are not differentiable on the CUDA path; "
@@ -1616,8 +1701,6 @@ def _solve(self, b: Optional[torch.Tensor] = None, b_fft: Optional[torch.Tensor]
            n_channel: Optional[int] = None, return_in_fourier: bool = False):
     """Solve the linear equation ``A x = b`` (mirror of ``_InverseSolveMixin.solve``, operator/_base.py:217-262):
     ``x_hat = b_hat * where(L == 0, 1, 1/L)``. Runs on the CUDA library: r2c, one table multiply, c2r."""
-    if not self.is_linear:
-        raise NotImplementedError("solve is only defined for linear operators")
     value = b if b is not None else b_fft
     if value is None:
         raise ValueError("Either b or b_fft should be given")
@@ -1626,7 +1709,9 @@ def _solve(self, b: Optional[torch.Tensor] = None, b_fft: Optional[torch.Tensor]
         mesh = self._state_dict["f_mesh"]
     f_mesh, c = self._pre_check(b, b_fft, mesh)
     n_channel = c if n_channel is None else n_channel
-    self.register_mesh(f_mesh, n_channel)
+    self.register_mesh(f_mesh, n_channel)            # user-defined generators are resolved here
+    if not self.is_linear:
+        raise NotImplementedError("solve is only defined for linear operators")
     L = self._state_dict["linear_coef"]
     inv = torch.where(L == 0, 1.0, 1 / L)                                   # operator/_base.py:250-255
     if f_mesh.n_dim > 1 and has_imag(inv):        # odd-order terms on a 2-D/3-D grid: 1/L(k) and 1/L(-k) are no conjugates

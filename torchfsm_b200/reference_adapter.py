@@ -43,7 +43,12 @@ def translate(ref_op, f_mesh: FourierMesh, n_channel: int) -> Operator:
         cls = type(core).__name__
         kind = _KIND_OF_CORE.get(cls)
         if kind is None:
-            raise NotImplementedError(f"nonlinear core {cls} has no counterpart on the fused CUDA path")
+            # a user-defined NonlinearFunc (operator/_base.py:56-103): called as it is, on full spectra the library's passes
+            # produce, with this package's FourierMesh (same table and fft/ifft names); `lower` dry-runs it once
+            if not callable(core) or not hasattr(core, "_dealiasing_swtich"):
+                raise NotImplementedError(f"nonlinear core {cls} has no counterpart on the fused CUDA path")
+            terms.append(_Term("custom_nonlinear", coef, {"func": core}))
+            continue
         params = {}
         if kind == "ks_convection":
             params["remove_mean"] = bool(core.remove_mean)
@@ -125,6 +130,14 @@ def lower(ref_op, dt: float) -> LoweredIntegrator:
     L = sd.get("linear_coef")
     nb = L.shape[0] if (L is not None and L.shape[0] > 1) else 1
     low._steppers[nb] = op._build_integrator(dt, nb)
+    if any(t.kind == "custom_nonlinear" for t in op.terms):
+        st = low._steppers[nb]
+        try:                                       # a user core may lean on reference internals this package does not have
+            st.rhs_half(st.empty_half().zero_())
+        except NotImplementedError:
+            raise
+        except Exception as e:                     # noqa: BLE001
+            raise NotImplementedError(f"user-defined core failed on the CUDA path: {e!r}")
     return low
 
 
