@@ -847,8 +847,9 @@ class OperatorLike:
         coefs = list(coefs) if coefs is not None else [1] * len(terms)
         if len(coefs) != len(terms):
             raise ValueError("The length of coefs should match the number of operator generators")
-        self.terms: List[_Term] = [t if isinstance(t, _Term) and c == 1 else (t.scaled(c) if isinstance(t, _Term) else
-                                   _Term("custom", c, {"generator": t})) for t, c in zip(terms, coefs)]
+        unit = lambda c: not isinstance(c, torch.Tensor) and c == 1      # noqa: E731
+        self.terms: List[_Term] = [(t if unit(c) else t.scaled(c)) if isinstance(t, _Term) else
+                                   _Term("custom", c, {"generator": t}) for t, c in zip(terms, coefs)]
         self._rt = None               # terms with the user-defined generators resolved for the registered mesh
         self._de_aliasing_rate = 2 / 3
         self._integrator = "auto"
