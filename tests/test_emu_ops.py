@@ -80,4 +80,4 @@ def test_linear_operators_and_maps_are_differentiable():
     # nonlinear operators are differentiated by gradient mode (tests/test_autograd_nonlinear.py)
     ub = (0.1 * torch.randn(1, 2, 8, 8, dtype=torch.float64)).requires_grad_(True)
     assert torch.autograd.gradcheck(lambda x: fsm.pde.Burgers(0.01).integrate(x, mesh=small, dt=0.01, step=2), (ub,),
-                                    eps=1e-6, atol=1e-7)
+                                    eps=1e-6, atol=1e-7, fast_mode=True)
