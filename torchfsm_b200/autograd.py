@@ -108,6 +108,42 @@ class DiffOps:
     def e(self, a):
         return self._e[a]
 
+    # ---- layout converters as torch ops (what fsm_half_to_full / fsm_full_to_half compute) ---------------------
+    def _unrot(self, x_hat):
+        """(B, C, modes) rot-half -> (B, C, *shape[:-1], nh)"""
+        shape, nh = self.shape, self.shape[-1] // 2 + 1
+        lead = x_hat.shape[:-1]
+        if self.d == 1:
+            return x_hat.reshape(*lead, nh)
+        if self.d == 2:
+            return x_hat.reshape(*lead, nh, shape[0]).permute(0, 1, 3, 2)
+        return x_hat.reshape(*lead, shape[1], nh, shape[0]).permute(0, 1, 4, 2, 3)
+
+    def _mirror(self, t):
+        """t(k) -> conj t(-k) over the grid axes"""
+        dims = list(range(2, 2 + self.d))
+        return torch.roll(torch.flip(t, dims), [1] * self.d, dims).conj()
+
+    def half_to_full(self, x_hat):
+        """Hermitian extension of a half spectrum: (B, C, modes) -> (B, C, N...)"""
+        nh, nl = self.shape[-1] // 2 + 1, self.shape[-1]
+        s = self._unrot(x_hat)
+        rest = s[..., 1:nl - nh + 1].flip(-1).conj()
+        if self.d > 1:
+            dims = list(range(2, 1 + self.d))
+            rest = torch.roll(torch.flip(rest, dims), [1] * len(dims), dims)
+        return torch.cat([s, rest], dim=-1)
+
+    def full_to_half(self, full_hat):
+        """Hermitian projection of ANY full spectrum, stored half in the rot-half layout"""
+        nh = self.shape[-1] // 2 + 1
+        h = (0.5 * (full_hat + self._mirror(full_hat)))[..., :nh]
+        if self.d == 2:
+            h = h.permute(0, 1, 3, 2)
+        elif self.d == 3:
+            h = h.permute(0, 1, 3, 4, 2)
+        return h.reshape(h.shape[0], h.shape[1], -1)
+
 
 class _HostView:
     """What a host-composed core (``OperatorLike._external_nonlinear``) sees in place of the stepper: the same method
@@ -135,11 +171,56 @@ class _HostView:
     def other(self, n_channel):
         return _HostView(self.ops, n_channel)
 
+    # full spectra for user-defined NonlinearFunc cores, as torch ops so that autograd sees them
     def half_to_full(self, x_hat):
-        raise NotImplementedError("user-defined NonlinearFunc cores are not available in the unrolled modes (gradients, "
-                                  "complex symbols on 2-D/3-D grids)")
+        return self.ops.half_to_full(x_hat)
 
-    full_to_half = half_to_full
+    def full_to_half(self, full_hat):
+        return self.ops.full_to_half(full_hat)
+
+    @property
+    def mesh(self):
+        """What a user core receives as ``f_mesh`` in gradient mode: the same tables, differentiable transforms."""
+        return _DiffMesh(self.ops)
+
+
+class _DiffMesh:
+    """``FourierMesh`` as seen by a user-defined core while a graph is being recorded: every table attribute is the
+    mesh's own; ``fft`` / ``ifft`` (mesh.py:481-491) go through the differentiable passes of ``DiffOps``."""
+
+    def __init__(self, ops: "DiffOps"):
+        self._ops, self._mesh = ops, ops.op._state_dict["f_mesh"]
+
+    def __getattr__(self, name):
+        return getattr(self._mesh, name)
+
+    def fft(self, u):
+        if u.is_complex():
+            return self.fft(u.real) + 1j * self.fft(u.imag)
+        o, shape = self._ops, self._mesh.shape
+        lead = u.shape[:u.dim() - len(shape)]
+        flat = u.reshape(-1, 1, *shape)
+        return _ForBatch(o, flat.shape[0]).fft(flat).reshape(*lead, *shape)
+
+    def ifft(self, u_fft):
+        o, shape = self._ops, self._mesh.shape
+        lead = u_fft.shape[:u_fft.dim() - len(shape)]
+        flat = u_fft.reshape(-1, 1, *shape)
+        return _ForBatch(o, flat.shape[0]).ifft(flat).reshape(*lead, *shape)
+
+
+class _ForBatch:
+    """Differentiable full-spectrum transforms of ``n`` scalar fields (leading axes of a user core's argument flattened)."""
+
+    def __init__(self, ops: "DiffOps", n: int):
+        self.ops = ops if n == ops.B else DiffOps(ops.op, n)
+
+    def fft(self, u):
+        return self.ops.half_to_full(self.ops.r2c(u))
+
+    def ifft(self, full):
+        o = self.ops
+        return torch.complex(o.c2r(o.full_to_half(full)), o.c2r(o.full_to_half(-1j * full)))
 
 
 class GradientMode:

@@ -1328,7 +1328,8 @@ class OperatorLike:
                     r = scaled(st.r2c(v), t.coef)
                 elif t.kind == "custom_nonlinear":                       # operator/_base.py:375-403 with a user core
                     deal = wants_dealiased(t)
-                    full = t.params["func"](st.half_to_full(x_d if deal else x_hat), f_mesh, u_d if deal else u)
+                    full = t.params["func"](st.half_to_full(x_d if deal else x_hat), getattr(st, "mesh", f_mesh),
+                                            u_d if deal else u)
                     if tuple(full.shape) != (st.B, st.C) + tuple(st.local_shape):
                         raise ValueError("NonlinearFunc: the returned spectrum must keep the shape of its argument")
                     r = scaled(st.full_to_half(full), t.coef)
@@ -1613,6 +1614,9 @@ class OperatorLike:
                 return True
             src = t.params.get("source")
             if isinstance(src, torch.Tensor) and src.requires_grad:
+                return True
+            core = t.params.get("generator")          # a user-defined core that is an nn.Module (learned closure)
+            if isinstance(core, torch.nn.Module) and any(p.requires_grad for p in core.parameters()):
                 return True
         return False
 
