@@ -213,3 +213,22 @@ def test_learned_closure_is_differentiable(mesh_info, shape):
         want = _closure_run(rop, rbase, RefMesh(mesh_info, dtype=torch.float64), rint.ETDRKIntegrator, u0, w)
         for g, r in zip(got, want):
             assert _rel(g, r) < 1e-11
+
+
+def test_custom_core_with_a_complex_symbol_on_a_2d_grid():
+    """User core + odd-order linear term on a 2-D grid: the paired half spectra of unrolled.py; a core that reads the
+    un-dealiased state is refused there (it would see the non-Hermitian Nyquist planes)."""
+    import torchfsm_b200 as fsm
+    Cubic, GradientSquared, _, _ = make_cores(fsm)
+    mesh = fsm.MeshGrid([(0, 1, 16), (0, 1, 32)], dtype=torch.float64)
+    u0 = _u0(2, 1, 16, 32)
+    adv = 0.4 * fsm.SpatialDerivative(1, 1)
+    custom = 0.05 * fsm.Laplacian() + adv + fsm.NonlinearOperator(Cubic())
+    builtin = 0.05 * fsm.Laplacian() + adv + fsm.ImplicitSource(lambda u: -u ** 3)
+    for op in (custom, builtin):
+        op.set_integrator(fsm.SETDRKIntegrator.SETDRK2)
+    got, want = (op.integrate(u0, mesh=mesh, dt=0.01, step=3) for op in (custom, builtin))
+    assert type(custom._state_dict["integrator"]).__name__ == "PairedSpectrumStepper"
+    assert _rel(got, want) < 1e-13
+    with pytest.raises(NotImplementedError):
+        (0.05 * fsm.Laplacian() + adv + fsm.NonlinearOperator(GradientSquared())).integrate(u0, mesh=mesh, dt=0.01, step=1)

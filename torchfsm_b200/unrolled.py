@@ -82,8 +82,11 @@ class PairedSpectrumStepper:
             raise NotImplementedError("a complex linear symbol (odd-order linear terms) with a nonlinear term needs a "
                                       "de-aliasing rate below 1 on 2-D/3-D grids: the nonlinear cores must not see the "
                                       "non-Hermitian content of the Nyquist planes")
-        if any(t.kind == "implicit_func_source" and not t.params.get("non_linear", True) for t in lo["external"]):
-            raise NotImplementedError("ImplicitSource(func, non_linear=False) reads the un-dealiased state: not available "
+        if any((t.kind == "implicit_func_source" and not t.params.get("non_linear", True)) or
+               (t.kind == "custom_nonlinear" and not getattr(t.params["func"], "_dealiasing_swtich", True))
+               for t in lo["external"]):
+            raise NotImplementedError("a nonlinear core that reads the un-dealiased state (ImplicitSource(func, "
+                                      "non_linear=False), NonlinearFunc(dealiasing_swtich=False)) is not available "
                                       "together with a complex linear symbol on 2-D/3-D grids")
         if getattr(op, "_ensemble_group", None) is not None or getattr(op, "_slab", None) is not None:
             raise NotImplementedError("complex linear symbols on 2-D/3-D grids run on one GPU only")
