@@ -113,6 +113,9 @@ class PairedSpectrumStepper:
         self._mode = _PairMode(op, self)
 
     # ---- native entry points on the pair ----------------------------------------------------------------------
+    def empty_half(self) -> torch.Tensor:
+        return torch.empty((2, self.B, self.C, self.nmodes), dtype=self.cdtype, device=self.device)
+
     def r2c(self, u: torch.Tensor) -> torch.Tensor:
         h = self._tf.r2c(u)
         return torch.stack([h, h])
