@@ -1269,7 +1269,7 @@ class OperatorLike:
             assert u.shape == u_fft.shape, "The shape of u and u_fft should be the same"
         assert mesh is not None, "Mesh should be given"
         value = u if u is not None else u_fft
-        if value.requires_grad and not getattr(self, "_autograd_ok", False):
+        if value.requires_grad and torch.is_grad_enabled() and not getattr(self, "_autograd_ok", False):
             raise NotImplementedError("gradients are available through integrate(u_0) and operator(u) with real-space "
                                       "inputs only (no u_fft / return_in_fourier / recorder); detach the input first")
         if not isinstance(mesh, FourierMesh):
