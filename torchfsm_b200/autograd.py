@@ -331,11 +331,20 @@ class GradientMode:
             return T("exp") * x + T("coef_4") * n0 + T("coef_5") * (2 * (n1 + n2)) + T("coef_6") * n3
         raise NotImplementedError(name)
 
-    def integrate(self, u_0, n_steps: int):
-        x = self.ops.r2c(u_0.to(self.st.rdtype))
+    def advance(self, x, n_steps: int):
+        """``n_steps`` unrolled steps; with ``Operator.set_gradient_checkpointing(True)`` only the state at every step
+        boundary is kept and each step is recomputed during backward (long rollouts on large grids)."""
+        if getattr(self.op, "_grad_checkpoint", False) and torch.is_grad_enabled():
+            from torch.utils.checkpoint import checkpoint
+            for _ in range(int(n_steps)):
+                x = checkpoint(self.step, x, use_reentrant=False)
+            return x
         for _ in range(int(n_steps)):
             x = self.step(x)
-        return self.ops.c2r(x)
+        return x
+
+    def integrate(self, u_0, n_steps: int):
+        return self.ops.c2r(self.advance(self.ops.r2c(u_0.to(self.st.rdtype)), n_steps))
 
     def evaluate(self, u):
         return self.ops.c2r(self.rhs(self.ops.r2c(u.to(self.st.rdtype))))

@@ -984,6 +984,12 @@ class OperatorLike:
         self._lanes = int(lanes)
         self._state_dict["integrator"] = None
 
+    def set_gradient_checkpointing(self, enabled: bool = True):
+        """Gradient mode (autograd.py) keeps every intermediate of every step, as the reference's autograd does; with
+        checkpointing only the state at step boundaries is kept and each step is recomputed in backward."""
+        self._grad_checkpoint = bool(enabled)
+        return self
+
     def register_additional_check(self, func: Callable[[int, int], bool]):
         self._value_mesh_check_func = func
 

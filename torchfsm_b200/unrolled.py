@@ -165,9 +165,7 @@ class PairedSpectrumStepper:
     def integrate_with_grad(self, u_0: torch.Tensor, n_steps: int) -> torch.Tensor:
         ops = self._mode.ops
         h = ops.r2c(u_0.to(self.rdtype))
-        x = torch.stack([h, h])
-        for _ in range(int(n_steps)):
-            x = self._mode.step(x)
+        x = self._mode.advance(torch.stack([h, h]), n_steps)
         return ops.c2r((x[0] + x[1]) * 0.5)
 
     def evaluate_with_grad(self, u: torch.Tensor) -> torch.Tensor:
